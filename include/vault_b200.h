@@ -1,0 +1,215 @@
+/*
+ * vault_b200 -- C ABI of the B200 (sm_100a) kernels behind the VAuLT hot path.
+ *
+ * The reference (gchochla/VAuLT) has no FFI/plugin layer: its hot path is Python glue
+ * (ref:vault/models/vault/model.py:151-218, 512-570) over HuggingFace ViLT/BERT modules that dispatch to ATen.  This
+ * header is the boundary the new implementation introduces *below* that Python class API: plain
+ * `extern "C"` functions, raw device pointers and sizes, no torch types.  Each entry point names the reference
+ * computation it replaces (`ref:` = /root/reference, `HF:` = transformers==4.48.0 modelling code the reference calls).
+ *
+ * Conventions
+ *   - every pointer is a DEVICE pointer owned by the caller (outputs and workspaces included); nothing is allocated,
+ *     freed or retained;
+ *   - `stream` is a cudaStream_t passed as void*; calls enqueue and return (no device synchronisation);
+ *   - return 0 on success, a negative VAULT_ERR_* otherwise; text via vault_last_error();
+ *   - activations bf16 unless stated, statistics / residual stream / master weights / gradients fp32;
+ *   - there is NO CPU fallback: a missing device or a non-sm_100 device is an error.
+ */
+#ifndef VAULT_B200_H_
+#define VAULT_B200_H_
+
+#include <stddef.h>
+#include <stdint.h>
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+#define VAULT_OK 0
+#define VAULT_ERR_INVALID (-1) /* bad shape / alignment / argument */
+#define VAULT_ERR_LAUNCH (-2)  /* cudaGetLastError() after a launch */
+#define VAULT_ERR_DRIVER (-3)  /* tensor-map encode / driver entry point */
+#define VAULT_ERR_ARCH (-4)    /* device is not sm_100 */
+
+int vault_version(void);
+/* copies the last error message of the calling thread; returns its length */
+size_t vault_last_error(char* buf, size_t cap);
+/* 0 if device `dev` is an sm_100 part, VAULT_ERR_ARCH otherwise */
+int vault_check_device(int dev);
+
+/* ------------------------------------------------------------------------------------------------------------------
+ * Dense contractions on tcgen05 / TMEM, operands fed by TMA.
+ * Replaces every nn.Linear on the path and its autograd:
+ *   ViLT  HF:models/vilt/modeling_vilt.py:306-428 (query/key/value, attention.output.dense, intermediate, output)
+ *   BERT  HF:models/bert/modeling_bert.py:143-356
+ * forward   y = x W^T + b      : A = x [M,K] (a_mn=0), B = W [N,K] (b_mn=0)
+ * dgrad     dx = dy W          : A = dy [M,N'] (a_mn=0), B = W stored [N',K'] read as MN-major (b_mn=1)
+ * wgrad     dW = dy^T x        : A = dy stored [M',N] read MN-major (a_mn=1), B = x stored [M',K] read MN-major (b_mn=1)
+ * ------------------------------------------------------------------------------------------------------------------ */
+enum {
+  VAULT_EPI_BIAS_BF16 = 0,       /* out(bf16) = acc + bias                                                   */
+  VAULT_EPI_BIAS_GELU_BF16 = 1,  /* out2(bf16, optional) = acc + bias ; out(bf16) = gelu_erf(acc + bias)    */
+  VAULT_EPI_BIAS_RESID_F32 = 2,  /* out(f32) = resid(f32) + dropout_p(acc + bias)                            */
+  VAULT_EPI_PLAIN_BF16 = 3,      /* out(bf16) = acc                                                          */
+  VAULT_EPI_DGELU_BF16 = 4,      /* out(bf16) = acc * gelu_erf'(aux(bf16))                                   */
+  VAULT_EPI_ATOMIC_F32 = 5,      /* out(f32) += acc   (split-K partial sums; caller zero-fills)               */
+  VAULT_EPI_BIAS_F32 = 6,        /* out(f32) = acc + bias (bias optional)                                    */
+  VAULT_EPI_STORE_F32 = 7        /* out(f32) = acc        (wgrad without split-K)                             */
+};
+
+typedef struct vault_gemm_args {
+  int32_t M, N, K;        /* logical C[M,N] = sum_k A[m,k] * B[n,k] */
+  const void* A;          /* bf16 */
+  int64_t lda;            /* elements between consecutive rows of the STORED matrix */
+  int32_t a_mn;           /* 0: stored [M,K] (K contiguous)   1: stored [K,M] (M contiguous) */
+  const void* B;          /* bf16 */
+  int64_t ldb;
+  int32_t b_mn;           /* 0: stored [N,K] (K contiguous)   1: stored [K,N] (N contiguous) */
+  int32_t epilogue;       /* VAULT_EPI_* */
+  const float* bias;      /* [N] or NULL */
+  const float* resid;     /* [M,N] fp32 (EPI_BIAS_RESID_F32) */
+  int64_t ldr;
+  const void* aux;        /* [M,N] bf16 (EPI_DGELU_BF16) */
+  int64_t ldaux;
+  void* out;
+  int64_t ldo;
+  void* out2;             /* optional */
+  int64_t ldo2;
+  float dropout_p;        /* EPI_BIAS_RESID_F32 only; 0 = off */
+  uint64_t seed;
+  uint32_t site;          /* dropout site id: forward and backward of the same site regenerate the same mask */
+  int32_t split_k;        /* >=1; >1 only with EPI_ATOMIC_F32 */
+  int32_t block_n;        /* 0 = choose; else 64 / 128 / 256 */
+  int32_t max_ctas;       /* 0 = all SMs */
+} vault_gemm_args;
+
+int vault_gemm_bf16(const vault_gemm_args* args, void* stream);
+
+/* Patch embedding, im2col-free: Conv2d(3,H,k=32,s=32) as a TF32 tcgen05 GEMM whose A tiles are TMA boxes taken straight
+ * from the NCHW fp32 pixels.  Replaces ViltPatchEmbeddings.forward, HF:models/vilt/modeling_vilt.py:293-303.
+ *   pixels [B,C,Hi,Wi] fp32, weight [N, C*P*P] fp32 (= projection.weight.view(N,-1)), bias [N] fp32 or NULL
+ *   out [B*(Hi/P)*(Wi/P), N] fp32, row = b*gh*gw + i*gw + j                                                     */
+int vault_patch_embed_fwd(const float* pixels, const float* weight, const float* bias, float* out, int32_t B, int32_t C,
+                          int32_t Hi, int32_t Wi, int32_t P, int32_t N, void* stream);
+
+/* ------------------------------------------------------------------------------------------------------------------
+ * LayerNorm (HF nn.LayerNorm call sites: 25 in the LM, 26 in ViLT).  x fp32 [rows, cols].
+ *   fwd: y = (x - mean) * rstd * gamma + beta -> y_bf16 and/or y_f32 (either may be NULL); saves mean, rstd [rows]
+ *   bwd: dy = (dy_f32 ? dy_f32 : 0) + (dy_bf16 ? dy_bf16 : 0);
+ *        dx = LN'(dy) + (dres_f32 ? dres_f32 : 0) -> dx_f32 (required), dx_bf16 (optional);
+ *        dgamma, dbeta [cols] are ACCUMULATED with atomics (caller zero-fills), either may be NULL (frozen)
+ * ------------------------------------------------------------------------------------------------------------------ */
+int vault_layernorm_fwd(const float* x, const float* gamma, const float* beta, void* y_bf16, float* y_f32, float* mean,
+                        float* rstd, int64_t rows, int32_t cols, float eps, void* stream);
+int vault_layernorm_bwd(const float* dy_f32, const void* dy_bf16, const float* x, const float* mean, const float* rstd,
+                        const float* gamma, const float* dres_f32, float* dx_f32, void* dx_bf16, float* dgamma,
+                        float* dbeta, int64_t rows, int32_t cols, void* stream);
+/* Same with Philox dropout on the LayerNorm OUTPUT (BertEmbeddings: dropout(LayerNorm(.)), HF:models/bert/modeling_bert.py:110-111);
+ * the backward regenerates the mask from (seed, site) and applies it to dy before differentiating the norm. */
+int vault_layernorm_fwd_drop(const float* x, const float* gamma, const float* beta, void* y_bf16, float* y_f32, float* mean,
+                             float* rstd, int64_t rows, int32_t cols, float eps, float dropout_p, uint64_t seed,
+                             uint32_t site, void* stream);
+int vault_layernorm_bwd_drop(const float* dy_f32, const void* dy_bf16, const float* x, const float* mean, const float* rstd,
+                             const float* gamma, const float* dres_f32, float* dx_f32, void* dx_bf16, float* dgamma,
+                             float* dbeta, int64_t rows, int32_t cols, float dropout_p, uint64_t seed, uint32_t site,
+                             void* stream);
+
+/* ------------------------------------------------------------------------------------------------------------------
+ * Fused masked-softmax attention over the variable-length text+image sequence.
+ * Replaces ViltSelfAttention.forward HF:models/vilt/modeling_vilt.py:325-365 and BERT eager_attention_forward
+ * HF:models/bert/modeling_bert.py:115-140 plus the additive mask of HF:modeling_utils.py:902-949 (never materialised).
+ *   qkv  [B*S, 3*heads*64] bf16, row = [q(h0..), k(h0..), v(h0..)]      key_mask [B,S] uint8 (1 = attend)
+ *   ctx  [B*S, heads*64] bf16         lse [B,heads,S] fp32 (natural-log sum-exp of scaled, masked scores)
+ *   dropout on the probabilities (BERT stack in training) is Philox(seed, site) keyed by (b,h,q,k).
+ * ------------------------------------------------------------------------------------------------------------------ */
+int vault_attn_fwd(const void* qkv, const uint8_t* key_mask, void* ctx, float* lse, int32_t B, int32_t S, int32_t heads,
+                   float dropout_p, uint64_t seed, uint32_t site, void* stream);
+/* dqkv [B*S, 3*heads*64] bf16 is fully overwritten; delta [B,heads,S] fp32 is workspace */
+int vault_attn_bwd(const void* qkv, const uint8_t* key_mask, const void* ctx, const void* dctx, const float* lse,
+                   float* delta, void* dqkv, int32_t B, int32_t S, int32_t heads, float dropout_p, uint64_t seed,
+                   uint32_t site, void* stream);
+
+/* ------------------------------------------------------------------------------------------------------------------
+ * Embedding assembly.
+ * LM:    BertEmbeddings.forward HF:models/bert/modeling_bert.py:72-112 / RobertaEmbeddings HF:models/roberta/
+ *        modeling_roberta.py:79-150 (pad-offset position ids when roberta_pad >= 0):
+ *        x = word[ids] + type[tt] + pos[pid]  -> x_sum fp32 [B*T, H] (input of the embedding LayerNorm)
+ * ViLT text: TextEmbeddings.forward with inputs_embeds HF:models/vilt/modeling_vilt.py:240-272 (4.48.0 gate):
+ *        x = inputs_embeds + type[tt] (+ pos[t] if pos != NULL)
+ * ------------------------------------------------------------------------------------------------------------------ */
+int vault_lm_embed_fwd(const int64_t* ids, const int64_t* tt, const float* word, const float* type, const float* pos,
+                       float* x_sum, int32_t B, int32_t T, int32_t H, int32_t roberta_pad, void* stream);
+/* scatter-add dx [B*T,H] fp32 into dword/dtype/dpos (fp32, atomics; caller zero-fills); any table grad may be NULL */
+int vault_lm_embed_bwd(const int64_t* ids, const int64_t* tt, const float* dx, float* dword, float* dtype, float* dpos,
+                       int32_t B, int32_t T, int32_t H, int32_t roberta_pad, void* stream);
+int vault_vilt_text_embed_fwd(const float* inputs_embeds, const int64_t* tt, const float* type, const float* pos,
+                              float* x_sum, int32_t B, int32_t T, int32_t H, void* stream);
+int vault_vilt_text_embed_bwd(const int64_t* tt, const float* dx, float* dtype, float* dpos, int32_t B, int32_t T,
+                              int32_t H, void* stream);
+
+/* Per-sample valid patch grid (h_b, w_b) from the pixel mask: nearest down-sampling, HF:models/vilt/modeling_vilt.py:95-98.
+ * pixel_mask [B,Hi,Wi] int64 (mask_is_f32 = 0) or fp32 (1);  hw [B,2] int32 */
+int vault_patch_grid(const void* pixel_mask, int32_t mask_is_f32, int32_t* hw, int32_t B, int32_t Hi, int32_t Wi, int32_t P,
+                     void* stream);
+
+/* ViLT sequence assembly (ViltEmbeddings.visual_embed :101-175 + ViltEmbeddings.forward :203-216), raster order:
+ *   X[b, t]        = text_ln[b,t] + modality[0]                                   t <  T
+ *   X[b, T]        = cls + pos_table[0] + modality[img_type]
+ *   X[b, T+1+p]    = patch[b, i*gw+j] + bilinear_{align_corners}(pos_table[1:], (h_b,w_b))[i,j] + modality[img_type]
+ *                    for p = i*w_b + j < h_b*w_b, zero rows after; key_mask [B,S] uint8 = [attention_mask, 1, valid]
+ * X fp32 [B,S,H], S = T+1+Pmax;  text_ln fp32 [B*T,H];  patch fp32 [B*gh*gw, H];  pos_table [1+grid*grid, H]        */
+int vault_vilt_assemble_fwd(const float* text_ln, const float* patch, const float* cls, const float* pos_table,
+                            const float* modality, const int64_t* attention_mask, const int32_t* hw, float* X,
+                            uint8_t* key_mask, int32_t B, int32_t T, int32_t Pmax, int32_t gh, int32_t gw, int32_t grid,
+                            int32_t H, int32_t img_type, void* stream);
+/* backward of the assembly: dX fp32 [B,S,H] ->
+ *   dtext_ln fp32 [B*T,H] (= dX text rows), dpatch bf16 [B*gh*gw, H] (zero rows where invalid),
+ *   dcls [H], dpos_table [1+grid*grid, H], dmodality [2.., H]  (fp32, atomics; caller zero-fills) */
+int vault_vilt_assemble_bwd(const float* dX, const int32_t* hw, float* dtext_ln, void* dpatch_bf16, float* dcls,
+                            float* dpos_table, float* dmodality, int32_t B, int32_t T, int32_t Pmax, int32_t gh, int32_t gw,
+                            int32_t grid, int32_t H, int32_t img_type, void* stream);
+
+/* im2col of NCHW fp32 pixels into bf16 patch rows [B*gh*gw, C*P*P] (k = c*P*P + kh*P + kw): the B operand of the
+ * patch-projection wgrad (dW = dpatch^T * patches). */
+int vault_patchify_bf16(const float* pixels, void* out_bf16, int32_t B, int32_t C, int32_t Hi, int32_t Wi, int32_t P,
+                        void* stream);
+
+/* ------------------------------------------------------------------------------------------------------------------
+ * Pooler + TMSC head + loss (ViltPooler HF:models/vilt/modeling_vilt.py:663-675; VaultForTMSC classifier
+ * ref:vault/models/vault/model.py:547-550,569; CE mean ref:vault/tmsc_utils/trainer.py:228-242).  All fp32.
+ * small_linear: y[r,n] = act(sum_k x[r*ldx + k] W[n,k] + b[n]); act 0 none, 1 tanh
+ * ------------------------------------------------------------------------------------------------------------------ */
+int vault_small_linear_fwd(const float* x, int64_t ldx, const float* W, const float* b, float* y, int32_t rows, int32_t N,
+                           int32_t K, int32_t act, void* stream);
+/* dy [rows,N]; if act==1, y is the saved tanh output and dy is multiplied by (1-y^2) first.
+ * dx[r*lddx + k] (+)= sum_n dy W[n,k] (accumulate_dx: add into existing), dW [N,K] = dy^T x, db [N] = colsum(dy): overwritten */
+int vault_small_linear_bwd(const float* dy, const float* y, const float* x, int64_t ldx, const float* W, float* dx,
+                           int64_t lddx, int32_t accumulate_dx, float* dW, float* db, int32_t rows, int32_t N, int32_t K,
+                           int32_t act, void* stream);
+/* dropout on fp32 [n] (head dropout): y = x * keep / (1-p) */
+int vault_dropout_f32(const float* x, float* y, int64_t n, float p, uint64_t seed, uint32_t site, void* stream);
+/* softmax cross-entropy, mean over rows: loss[0] = mean_r(-log softmax(logits[r])[label[r]]);
+ * dlogits = (softmax - onehot) * grad_scale / rows  (dlogits may be NULL) */
+int vault_ce_loss(const float* logits, const int64_t* labels, float* loss, float* dlogits, int32_t rows, int32_t n_classes,
+                  float grad_scale, void* stream);
+
+/* column sums of a bf16 [rows, cols] matrix accumulated into fp32 out[cols] (bias gradients); caller zero-fills */
+int vault_colsum_bf16(const void* x, int64_t ldx, float* out, int64_t rows, int32_t cols, void* stream);
+
+/* ------------------------------------------------------------------------------------------------------------------
+ * One fused AdamW step over a flat fp32 parameter range with the transformers==4.48.0 rule
+ * (transformers.optimization.AdamW, used by ref:vault/tmsc_utils/trainer.py:244-254 with correct_bias=False):
+ *   m = b1 m + (1-b1) g ; v = b2 v + (1-b2) g^2 ; p -= step_size * m / (sqrt(v) + eps) ; p -= lr*wd*p (if wd > 0)
+ *   step_size = lr * sqrt(1-b2^t)/(1-b1^t) if correct_bias else lr.      grad_scale multiplies g first (DP averaging).
+ * Also refreshes the bf16 shadow copy used by the GEMMs (shadow may be NULL).
+ * ------------------------------------------------------------------------------------------------------------------ */
+int vault_adamw_step(float* p, const float* g, float* m, float* v, void* shadow_bf16, int64_t n, float lr, float beta1,
+                     float beta2, float eps, float weight_decay, int32_t correct_bias, int32_t step, float grad_scale,
+                     void* stream);
+/* fp32 -> bf16 cast of a flat range (shadow refresh after an external optimizer touched the masters) */
+int vault_cast_f32_bf16(const float* src, void* dst_bf16, int64_t n, void* stream);
+
+#ifdef __cplusplus
+}
+#endif
+#endif /* VAULT_B200_H_ */

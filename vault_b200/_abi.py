@@ -1,0 +1,104 @@
+"""ctypes binding of include/vault_b200.h (the C-ABI of the sm_100a kernels).
+
+The shared library is built in-tree by ``python -m vault_b200.build`` (also run by ``__graft_entry__.build()``).  There is
+no fallback: if the library is missing, or a call returns non-zero, this raises.
+"""
+from __future__ import annotations
+
+import ctypes as C
+import os
+
+_HERE = os.path.dirname(os.path.abspath(__file__))
+LIB_PATH = os.path.join(_HERE, "lib", "libvault_b200.so")
+
+c_i32, c_i64, c_u32, c_u64, c_f32, c_p = C.c_int32, C.c_int64, C.c_uint32, C.c_uint64, C.c_float, C.c_void_p
+
+EPI_BIAS_BF16, EPI_BIAS_GELU_BF16, EPI_BIAS_RESID_F32, EPI_PLAIN_BF16 = 0, 1, 2, 3
+EPI_DGELU_BF16, EPI_ATOMIC_F32, EPI_BIAS_F32, EPI_STORE_F32 = 4, 5, 6, 7
+
+
+class GemmArgs(C.Structure):
+    _fields_ = [
+        ("M", c_i32), ("N", c_i32), ("K", c_i32),
+        ("A", c_p), ("lda", c_i64), ("a_mn", c_i32),
+        ("B", c_p), ("ldb", c_i64), ("b_mn", c_i32),
+        ("epilogue", c_i32),
+        ("bias", c_p), ("resid", c_p), ("ldr", c_i64),
+        ("aux", c_p), ("ldaux", c_i64),
+        ("out", c_p), ("ldo", c_i64), ("out2", c_p), ("ldo2", c_i64),
+        ("dropout_p", c_f32), ("seed", c_u64), ("site", c_u32),
+        ("split_k", c_i32), ("block_n", c_i32), ("max_ctas", c_i32),
+    ]
+
+
+# name -> argtypes (restype is int unless listed in _RESTYPES); mirrors include/vault_b200.h declaration by declaration
+SIGNATURES = {
+    "vault_version": [],
+    "vault_last_error": [C.c_char_p, C.c_size_t],
+    "vault_check_device": [c_i32],
+    "vault_gemm_bf16": [C.POINTER(GemmArgs), c_p],
+    "vault_patch_embed_fwd": [c_p, c_p, c_p, c_p, c_i32, c_i32, c_i32, c_i32, c_i32, c_i32, c_p],
+    "vault_layernorm_fwd": [c_p, c_p, c_p, c_p, c_p, c_p, c_p, c_i64, c_i32, c_f32, c_p],
+    "vault_layernorm_bwd": [c_p, c_p, c_p, c_p, c_p, c_p, c_p, c_p, c_p, c_p, c_p, c_i64, c_i32, c_p],
+    "vault_layernorm_fwd_drop": [c_p, c_p, c_p, c_p, c_p, c_p, c_p, c_i64, c_i32, c_f32, c_f32, c_u64, c_u32, c_p],
+    "vault_layernorm_bwd_drop": [c_p, c_p, c_p, c_p, c_p, c_p, c_p, c_p, c_p, c_p, c_p, c_i64, c_i32, c_f32, c_u64, c_u32, c_p],
+    "vault_attn_fwd": [c_p, c_p, c_p, c_p, c_i32, c_i32, c_i32, c_f32, c_u64, c_u32, c_p],
+    "vault_attn_bwd": [c_p, c_p, c_p, c_p, c_p, c_p, c_p, c_i32, c_i32, c_i32, c_f32, c_u64, c_u32, c_p],
+    "vault_lm_embed_fwd": [c_p, c_p, c_p, c_p, c_p, c_p, c_i32, c_i32, c_i32, c_i32, c_p],
+    "vault_lm_embed_bwd": [c_p, c_p, c_p, c_p, c_p, c_p, c_i32, c_i32, c_i32, c_i32, c_p],
+    "vault_vilt_text_embed_fwd": [c_p, c_p, c_p, c_p, c_p, c_i32, c_i32, c_i32, c_p],
+    "vault_vilt_text_embed_bwd": [c_p, c_p, c_p, c_p, c_i32, c_i32, c_i32, c_p],
+    "vault_patch_grid": [c_p, c_i32, c_p, c_i32, c_i32, c_i32, c_i32, c_p],
+    "vault_vilt_assemble_fwd": [c_p, c_p, c_p, c_p, c_p, c_p, c_p, c_p, c_p, c_i32, c_i32, c_i32, c_i32, c_i32, c_i32, c_i32, c_i32, c_p],
+    "vault_vilt_assemble_bwd": [c_p, c_p, c_p, c_p, c_p, c_p, c_p, c_i32, c_i32, c_i32, c_i32, c_i32, c_i32, c_i32, c_i32, c_p],
+    "vault_patchify_bf16": [c_p, c_p, c_i32, c_i32, c_i32, c_i32, c_i32, c_p],
+    "vault_small_linear_fwd": [c_p, c_i64, c_p, c_p, c_p, c_i32, c_i32, c_i32, c_i32, c_p],
+    "vault_small_linear_bwd": [c_p, c_p, c_p, c_i64, c_p, c_p, c_i64, c_i32, c_p, c_p, c_i32, c_i32, c_i32, c_i32, c_p],
+    "vault_dropout_f32": [c_p, c_p, c_i64, c_f32, c_u64, c_u32, c_p],
+    "vault_ce_loss": [c_p, c_p, c_p, c_p, c_i32, c_i32, c_f32, c_p],
+    "vault_colsum_bf16": [c_p, c_i64, c_p, c_i64, c_i32, c_p],
+    "vault_adamw_step": [c_p, c_p, c_p, c_p, c_p, c_i64, c_f32, c_f32, c_f32, c_f32, c_f32, c_i32, c_i32, c_f32, c_p],
+    "vault_cast_f32_bf16": [c_p, c_p, c_i64, c_p],
+}
+_RESTYPES = {"vault_last_error": C.c_size_t}
+
+_lib = None
+
+
+def lib() -> C.CDLL:
+    """The loaded C-ABI library.  Raises if it has not been built -- there is no other implementation to fall back to."""
+    global _lib
+    if _lib is None:
+        if not os.path.exists(LIB_PATH):
+            raise RuntimeError(
+                f"{LIB_PATH} is missing: build it with `python -m vault_b200.build` (nvcc, sm_100a). "
+                "vault_b200 has no CPU or eager fallback."
+            )
+        l = C.CDLL(LIB_PATH)
+        partial = os.environ.get("VAULT_B200_ALLOW_PARTIAL") == "1"  # kernel bring-up probes only
+        for name, argtypes in SIGNATURES.items():
+            try:
+                fn = getattr(l, name)  # AttributeError here = header / library mismatch: fail loudly
+            except AttributeError:
+                if partial:
+                    continue
+                raise
+            fn.argtypes = argtypes
+            fn.restype = _RESTYPES.get(name, C.c_int)
+        _lib = l
+    return _lib
+
+
+def last_error() -> str:
+    buf = C.create_string_buffer(512)
+    lib().vault_last_error(buf, 512)
+    return buf.value.decode(errors="replace")
+
+
+def check(rc: int, what: str = "") -> None:
+    if rc != 0:
+        raise RuntimeError(f"vault_b200 {what} failed (code {rc}): {last_error()}")
+
+
+def call(name: str, *args) -> None:
+    check(getattr(lib(), name)(*args), name)

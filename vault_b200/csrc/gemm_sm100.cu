@@ -1,0 +1,414 @@
+// Persistent warp-specialised bf16 GEMM for sm_100a: TMA -> 128B-swizzled smem ring -> tcgen05.mma (accumulators in TMEM,
+// double-buffered) -> 8 epilogue warps (tcgen05.ld, smem transpose, fused epilogue, coalesced global stores).
+//
+//   C[M,N] = sum_k A[m,k] * B[n,k]     A, B bf16, fp32 accumulate
+//
+// Either operand may be stored K-major (k contiguous) or MN-major (m/n contiguous); the only differences are the TMA box
+// walk, the UMMA smem-descriptor strides and two bits of the instruction descriptor, all run-time values.  That one
+// kernel therefore serves forward (K,K), dgrad (K,MN: W is read un-transposed) and wgrad (MN,MN: dy and x read
+// un-transposed, contraction over tokens, optional split-K with fp32 atomics).
+//
+// Warp roles (384 threads, 1 CTA/SM):  warp0 TMA producer | warp1 MMA issuer | warp2 TMEM alloc | warp3 idle | warps4-11 epilogue
+#include "common.cuh"
+
+namespace vb {
+
+constexpr int BM = 128;
+constexpr int BK = 64;  // 64 bf16 = one 128-byte swizzle row
+constexpr int UMMA_K = 16;
+constexpr int kEpiWarps = 8;
+constexpr int kThreads = 128 + kEpiWarps * 32;
+constexpr int kRingBytes = 196608;                 // smem ring for A/B stages
+constexpr int kStagingBytes = kEpiWarps * 4096;    // per-warp 32x32 fp32 transpose buffers
+constexpr int kSmemBytes = kRingBytes + kStagingBytes + 1024 /*align slack*/ + 256 /*barriers*/;
+
+struct GemmParams {
+  int M, N, K;
+  int a_mn, b_mn;
+  int num_m_blocks, num_n_blocks, num_k_blocks, split_k, kb_per_split;
+  const float* bias;
+  const float* resid;
+  long long ldr;
+  const bf16* aux;
+  long long ldaux;
+  void* out;
+  long long ldo;
+  void* out2;
+  long long ldo2;
+  float dropout_p;
+  unsigned long long seed;
+  unsigned site;
+};
+
+template <int EPI>
+__device__ __forceinline__ void epilogue4(const GemmParams& p, float4 acc, const float4& b4, long long row, int col) {
+  if constexpr (EPI == VAULT_EPI_BIAS_BF16) {
+    uint2 o;
+    o.x = pack_bf16x2(acc.x + b4.x, acc.y + b4.y);
+    o.y = pack_bf16x2(acc.z + b4.z, acc.w + b4.w);
+    *reinterpret_cast<uint2*>(reinterpret_cast<bf16*>(p.out) + row * p.ldo + col) = o;
+  } else if constexpr (EPI == VAULT_EPI_BIAS_GELU_BF16) {
+    const float x0 = acc.x + b4.x, x1 = acc.y + b4.y, x2 = acc.z + b4.z, x3 = acc.w + b4.w;
+    if (p.out2) {
+      uint2 o2;
+      o2.x = pack_bf16x2(x0, x1);
+      o2.y = pack_bf16x2(x2, x3);
+      *reinterpret_cast<uint2*>(reinterpret_cast<bf16*>(p.out2) + row * p.ldo2 + col) = o2;
+    }
+    uint2 o;
+    o.x = pack_bf16x2(gelu_erf(x0), gelu_erf(x1));
+    o.y = pack_bf16x2(gelu_erf(x2), gelu_erf(x3));
+    *reinterpret_cast<uint2*>(reinterpret_cast<bf16*>(p.out) + row * p.ldo + col) = o;
+  } else if constexpr (EPI == VAULT_EPI_BIAS_RESID_F32) {
+    float x0 = acc.x + b4.x, x1 = acc.y + b4.y, x2 = acc.z + b4.z, x3 = acc.w + b4.w;
+    if (p.dropout_p > 0.f) {
+      const uint32_t thr = dropout_threshold(p.dropout_p);
+      const float sc = 1.0f / (1.0f - p.dropout_p);
+      const uint4 bits = dropout_bits4(p.seed, p.site, (unsigned long long)(row * p.N + col) >> 2);
+      x0 = bits.x >= thr ? x0 * sc : 0.f;
+      x1 = bits.y >= thr ? x1 * sc : 0.f;
+      x2 = bits.z >= thr ? x2 * sc : 0.f;
+      x3 = bits.w >= thr ? x3 * sc : 0.f;
+    }
+    const float4 r = *reinterpret_cast<const float4*>(p.resid + row * p.ldr + col);
+    float4 o = make_float4(r.x + x0, r.y + x1, r.z + x2, r.w + x3);
+    *reinterpret_cast<float4*>(reinterpret_cast<float*>(p.out) + row * p.ldo + col) = o;
+  } else if constexpr (EPI == VAULT_EPI_PLAIN_BF16) {
+    uint2 o;
+    o.x = pack_bf16x2(acc.x, acc.y);
+    o.y = pack_bf16x2(acc.z, acc.w);
+    *reinterpret_cast<uint2*>(reinterpret_cast<bf16*>(p.out) + row * p.ldo + col) = o;
+  } else if constexpr (EPI == VAULT_EPI_DGELU_BF16) {
+    const uint2 a = *reinterpret_cast<const uint2*>(p.aux + row * p.ldaux + col);
+    const float2 a01 = unpack_bf16x2(a.x), a23 = unpack_bf16x2(a.y);
+    uint2 o;
+    o.x = pack_bf16x2(acc.x * gelu_erf_grad(a01.x), acc.y * gelu_erf_grad(a01.y));
+    o.y = pack_bf16x2(acc.z * gelu_erf_grad(a23.x), acc.w * gelu_erf_grad(a23.y));
+    *reinterpret_cast<uint2*>(reinterpret_cast<bf16*>(p.out) + row * p.ldo + col) = o;
+  } else if constexpr (EPI == VAULT_EPI_ATOMIC_F32) {
+    float* dst = reinterpret_cast<float*>(p.out) + row * p.ldo + col;
+    asm volatile("red.global.add.v4.f32 [%0], {%1, %2, %3, %4};" ::"l"(dst), "f"(acc.x), "f"(acc.y), "f"(acc.z), "f"(acc.w)
+                 : "memory");
+  } else if constexpr (EPI == VAULT_EPI_BIAS_F32) {
+    float4 o = make_float4(acc.x + b4.x, acc.y + b4.y, acc.z + b4.z, acc.w + b4.w);
+    *reinterpret_cast<float4*>(reinterpret_cast<float*>(p.out) + row * p.ldo + col) = o;
+  } else {  // VAULT_EPI_STORE_F32
+    *reinterpret_cast<float4*>(reinterpret_cast<float*>(p.out) + row * p.ldo + col) = acc;
+  }
+}
+
+template <int BN, int EPI>
+__global__ void __launch_bounds__(kThreads, 1)
+gemm_bf16_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CUtensorMap tmB, const GemmParams p) {
+  constexpr int kAStage = BM * BK * 2;
+  constexpr int kBStage = BN * BK * 2;
+  constexpr int kStage = kAStage + kBStage;
+  constexpr int kStages = kRingBytes / kStage;
+  constexpr uint32_t kTmemCols = 2 * BN;  // two accumulator buffers (power of two >= 32 for BN in {64,128,256})
+
+  extern __shared__ uint8_t smem_raw[];
+  const uint32_t smem_base = (smem_u32(smem_raw) + 1023u) & ~1023u;
+  uint8_t* smem_gen = smem_raw + (smem_base - smem_u32(smem_raw));
+  const uint32_t ring = smem_base;
+  uint8_t* staging_gen = smem_gen + kRingBytes;
+  const uint32_t bars = smem_base + kRingBytes + kStagingBytes;
+  // barrier slots (8 bytes each): full[kStages] | empty[kStages] | tmem_full[2] | tmem_empty[2] | tmem ptr
+  auto full_bar = [&](int s) { return bars + 8u * s; };
+  auto empty_bar = [&](int s) { return bars + 8u * (kStages + s); };
+  auto tfull_bar = [&](int s) { return bars + 8u * (2 * kStages + s); };
+  auto tempty_bar = [&](int s) { return bars + 8u * (2 * kStages + 2 + s); };
+  const uint32_t tmem_slot = bars + 8u * (2 * kStages + 4);
+  volatile uint32_t* tmem_slot_gen = reinterpret_cast<volatile uint32_t*>(smem_gen + kRingBytes + kStagingBytes + 8 * (2 * kStages + 4));
+
+  const int warp = threadIdx.x >> 5;
+  const int lane = threadIdx.x & 31;
+
+  if (warp == 0 && lane == 0) {
+    tma_prefetch_desc(&tmA);
+    tma_prefetch_desc(&tmB);
+  }
+  if (warp == 1 && lane == 0) {
+    for (int s = 0; s < kStages; ++s) {
+      mbar_init(full_bar(s), 1);
+      mbar_init(empty_bar(s), 1);
+    }
+    for (int s = 0; s < 2; ++s) {
+      mbar_init(tfull_bar(s), 1);
+      mbar_init(tempty_bar(s), kEpiWarps);
+    }
+    mbar_fence_init();
+  }
+  if (warp == 2) tmem_alloc(tmem_slot, kTmemCols);
+  tc_fence_before();
+  __syncthreads();
+  tc_fence_after();
+  const uint32_t tmem_base = *tmem_slot_gen;
+
+  const int tiles_mn = p.num_m_blocks * p.num_n_blocks;
+  const int total_tiles = tiles_mn * p.split_k;
+
+  if (warp == 0) {
+    // ===================== TMA producer =====================
+    if (lane == 0) {
+      int stage = 0;
+      uint32_t phase = 0;
+      for (int t = blockIdx.x; t < total_tiles; t += gridDim.x) {
+        const int split = t / tiles_mn;
+        const int rem = t - split * tiles_mn;
+        const int m0 = (rem / p.num_n_blocks) * BM;
+        const int n0 = (rem % p.num_n_blocks) * BN;
+        const int kb0 = split * p.kb_per_split;
+        const int kb1 = min(kb0 + p.kb_per_split, p.num_k_blocks);
+        for (int kb = kb0; kb < kb1; ++kb) {
+          mbar_wait(empty_bar(stage), phase ^ 1u);
+          const uint32_t sA = ring + stage * kStage;
+          const uint32_t sB = sA + kAStage;
+          const uint32_t fb = full_bar(stage);
+          mbar_expect_tx(fb, kStage);
+          const int k0 = kb * BK;
+          if (!p.a_mn) {
+            tma_load_2d(sA, &tmA, fb, k0, m0);  // box {64 k, 128 rows}
+          } else {
+#pragma unroll
+            for (int j = 0; j < BM / 64; ++j) tma_load_2d(sA + j * 8192, &tmA, fb, m0 + 64 * j, k0);  // box {64 m, 64 k-rows}
+          }
+          if (!p.b_mn) {
+            tma_load_2d(sB, &tmB, fb, k0, n0);  // box {64 k, BN rows}
+          } else {
+#pragma unroll
+            for (int j = 0; j < BN / 64; ++j) tma_load_2d(sB + j * 8192, &tmB, fb, n0 + 64 * j, k0);
+          }
+          if (++stage == kStages) { stage = 0; phase ^= 1u; }
+        }
+      }
+    }
+  } else if (warp == 1) {
+    // ===================== MMA issuer (single thread) =====================
+    if (lane == 0) {
+      const uint32_t idesc = umma_idesc(1u, BM, BN, (uint32_t)p.a_mn, (uint32_t)p.b_mn);
+      const uint32_t a_lbo = p.a_mn ? 8192u : 16u, b_lbo = p.b_mn ? 8192u : 16u;
+      const uint32_t a_kstep = p.a_mn ? (UMMA_K * 128u) : (UMMA_K * 2u);
+      const uint32_t b_kstep = p.b_mn ? (UMMA_K * 128u) : (UMMA_K * 2u);
+      int stage = 0;
+      uint32_t phase = 0;
+      int as = 0;
+      uint32_t aphase = 0;
+      for (int t = blockIdx.x; t < total_tiles; t += gridDim.x) {
+        const int split = t / tiles_mn;
+        const int kb0 = split * p.kb_per_split;
+        const int kb1 = min(kb0 + p.kb_per_split, p.num_k_blocks);
+        mbar_wait(tempty_bar(as), aphase ^ 1u);
+        tc_fence_after();
+        const uint32_t d_tmem = tmem_base + (uint32_t)(as * BN);
+        for (int kb = kb0; kb < kb1; ++kb) {
+          mbar_wait(full_bar(stage), phase);
+          tc_fence_after();
+          const uint32_t sA = ring + stage * kStage;
+          const uint32_t sB = sA + kAStage;
+#pragma unroll
+          for (int k = 0; k < BK / UMMA_K; ++k) {
+            const uint64_t ad = umma_desc_sw128(sA + k * a_kstep, a_lbo, 1024u);
+            const uint64_t bd = umma_desc_sw128(sB + k * b_kstep, b_lbo, 1024u);
+            tc_mma_f16(d_tmem, ad, bd, idesc, (kb > kb0 || k > 0) ? 1u : 0u);
+          }
+          tc_commit(empty_bar(stage));  // smem slot free once these MMAs have read it
+          if (++stage == kStages) { stage = 0; phase ^= 1u; }
+        }
+        tc_commit(tfull_bar(as));  // accumulator complete
+        as ^= 1;
+        if (as == 0) aphase ^= 1u;
+      }
+    }
+  } else if (warp >= 4) {
+    // ===================== epilogue warps =====================
+    const int ew = warp - 4;
+    const int q = warp & 3;        // TMEM lane quadrant this warp may access
+    const int half = ew >> 2;      // which half of the tile's columns
+    constexpr int kColsPerWarp = BN / 2;
+    float4* stg = reinterpret_cast<float4*>(staging_gen + ew * 4096);
+    int as = 0;
+    uint32_t aphase = 0;
+    for (int t = blockIdx.x; t < total_tiles; t += gridDim.x) {
+      const int split = t / tiles_mn;
+      const int rem = t - split * tiles_mn;
+      const int m0 = (rem / p.num_n_blocks) * BM;
+      const int n0 = (rem % p.num_n_blocks) * BN;
+      mbar_wait(tfull_bar(as), aphase);
+      tc_fence_after();
+#pragma unroll 1
+      for (int c = half * kColsPerWarp; c < (half + 1) * kColsPerWarp; c += 32) {
+        uint32_t r[32];
+        tmem_ld32(tmem_base + ((uint32_t)(q * 32) << 16) + (uint32_t)(as * BN + c), r);
+        tmem_ld_wait();
+        // transpose through smem: thread = row -> (4 rows x 8 column-groups) per pass, XOR-swizzled 16B slots
+#pragma unroll
+        for (int j = 0; j < 8; ++j) {
+          stg[lane * 8 + (j ^ (lane & 7))] =
+              make_float4(__uint_as_float(r[4 * j]), __uint_as_float(r[4 * j + 1]), __uint_as_float(r[4 * j + 2]), __uint_as_float(r[4 * j + 3]));
+        }
+        __syncwarp();
+        const int cg = lane & 7;
+        const int col = n0 + c + cg * 4;
+        float4 b4 = make_float4(0.f, 0.f, 0.f, 0.f);
+        if constexpr (EPI == VAULT_EPI_BIAS_BF16 || EPI == VAULT_EPI_BIAS_GELU_BF16 || EPI == VAULT_EPI_BIAS_RESID_F32 || EPI == VAULT_EPI_BIAS_F32) {
+          if (p.bias != nullptr && col < p.N) b4 = *reinterpret_cast<const float4*>(p.bias + col);
+        }
+#pragma unroll
+        for (int i = 0; i < 8; ++i) {
+          const int rl = 4 * i + (lane >> 3);
+          const float4 acc = stg[rl * 8 + (cg ^ (rl & 7))];
+          const long long row = (long long)m0 + q * 32 + rl;
+          if (row < p.M && col < p.N) epilogue4<EPI>(p, acc, b4, row, col);
+        }
+        __syncwarp();
+      }
+      tc_fence_before();
+      __syncwarp();
+      if (lane == 0) mbar_arrive(tempty_bar(as));
+      as ^= 1;
+      if (as == 0) aphase ^= 1u;
+    }
+  }
+
+  tc_fence_before();
+  __syncthreads();
+  if (warp == 2) {
+    tc_fence_after();
+    tmem_dealloc(tmem_base, kTmemCols);
+  }
+}
+
+// ---- host side -----------------------------------------------------------------------------------------------------
+typedef CUresult (*EncodeTiledFn)(CUtensorMap*, CUtensorMapDataType, cuuint32_t, void*, const cuuint64_t*, const cuuint64_t*,
+                                  const cuuint32_t*, const cuuint32_t*, CUtensorMapInterleave, CUtensorMapSwizzle,
+                                  CUtensorMapL2promotion, CUtensorMapFloatOOBfill);
+
+EncodeTiledFn get_encode_fn() {
+  static EncodeTiledFn fn = nullptr;
+  if (fn) return fn;
+  void* sym = nullptr;
+  cudaDriverEntryPointQueryResult qres;
+  cudaError_t e = cudaGetDriverEntryPoint("cuTensorMapEncodeTiled", &sym, cudaEnableDefault, &qres);
+  if (e != cudaSuccess || qres != cudaDriverEntryPointSuccess || sym == nullptr) {
+    cudaGetLastError();
+    return nullptr;
+  }
+  fn = reinterpret_cast<EncodeTiledFn>(sym);
+  return fn;
+}
+
+// 2-D bf16 tensor [outer rows, inner contiguous], 128B swizzle, zero fill out of bounds
+int encode_tmap_2d(CUtensorMap* tm, CUtensorMapDataType dt, int elem_bytes, const void* base, uint64_t inner, uint64_t outer,
+                   uint64_t ld_elems, uint32_t box_inner, uint32_t box_outer) {
+  EncodeTiledFn fn = get_encode_fn();
+  if (!fn) return fail(VAULT_ERR_DRIVER, "cuTensorMapEncodeTiled entry point not available");
+  if ((reinterpret_cast<uintptr_t>(base) & 15) != 0 || ((ld_elems * elem_bytes) & 15) != 0)
+    return fail(VAULT_ERR_INVALID, "TMA operand must be 16-byte aligned (base %p, ld %llu)", base, (unsigned long long)ld_elems);
+  cuuint64_t gdim[2] = {inner, outer};
+  cuuint64_t gstr[1] = {ld_elems * (uint64_t)elem_bytes};
+  cuuint32_t box[2] = {box_inner, box_outer};
+  cuuint32_t estr[2] = {1, 1};
+  CUresult r = fn(tm, dt, 2, const_cast<void*>(base), gdim, gstr, box, estr, CU_TENSOR_MAP_INTERLEAVE_NONE, CU_TENSOR_MAP_SWIZZLE_128B,
+                  CU_TENSOR_MAP_L2_PROMOTION_L2_256B, CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
+  if (r != CUDA_SUCCESS) return fail(VAULT_ERR_DRIVER, "cuTensorMapEncodeTiled failed (%d): inner %llu outer %llu ld %llu box %ux%u", (int)r,
+                                     (unsigned long long)inner, (unsigned long long)outer, (unsigned long long)ld_elems, box_inner, box_outer);
+  return VAULT_OK;
+}
+
+template <int BN, int EPI>
+int launch_gemm(const CUtensorMap& tmA, const CUtensorMap& tmB, const GemmParams& p, int grid, cudaStream_t st) {
+  static bool attr_set = false;
+  if (!attr_set) {
+    cudaError_t e = cudaFuncSetAttribute(gemm_bf16_kernel<BN, EPI>, cudaFuncAttributeMaxDynamicSharedMemorySize, kSmemBytes);
+    if (e != cudaSuccess) return fail(VAULT_ERR_LAUNCH, "cudaFuncSetAttribute(smem=%d): %s", kSmemBytes, cudaGetErrorString(e));
+    attr_set = true;
+  }
+  gemm_bf16_kernel<BN, EPI><<<grid, kThreads, kSmemBytes, st>>>(tmA, tmB, p);
+  return check_launch("gemm_bf16_kernel");
+}
+
+template <int EPI>
+int dispatch_bn(int bn, const CUtensorMap& tmA, const CUtensorMap& tmB, const GemmParams& p, int grid, cudaStream_t st) {
+  switch (bn) {
+    case 256: return launch_gemm<256, EPI>(tmA, tmB, p, grid, st);
+    case 128: return launch_gemm<128, EPI>(tmA, tmB, p, grid, st);
+    case 64: return launch_gemm<64, EPI>(tmA, tmB, p, grid, st);
+  }
+  return fail(VAULT_ERR_INVALID, "block_n must be 64, 128 or 256 (got %d)", bn);
+}
+
+// Tile-N choice: fill whole waves of SMs; wider tiles amortise the A-tile smem traffic (N=256 runs the MMA at full rate with
+// 96 B/clk of smem reads, N=128 needs 128 B/clk, N=64 is smem-bound).
+static int pick_block_n(int M, int N, int split_k, int sms) {
+  const int cands[3] = {256, 128, 64};
+  const float rate[3] = {1.0f, 0.85f, 0.55f};
+  float best = -1.f;
+  int best_bn = 128;
+  const int mb = (M + BM - 1) / BM;
+  for (int i = 0; i < 3; ++i) {
+    const int bn = cands[i];
+    if (bn > 64 && N < bn) continue;
+    const int nb = (N + bn - 1) / bn;
+    const long long tiles = (long long)mb * nb * split_k;
+    const long long waves = (tiles + sms - 1) / sms;
+    const float util = (float)((double)M * N * split_k / ((double)waves * sms * BM * bn));
+    const float score = util * rate[i];
+    if (score > best) { best = score; best_bn = bn; }
+  }
+  return best_bn;
+}
+
+}  // namespace vb
+
+extern "C" int vault_gemm_bf16(const vault_gemm_args* a, void* stream) {
+  using namespace vb;
+  VB_REQUIRE(a != nullptr, "vault_gemm_bf16: null args");
+  VB_REQUIRE(a->M > 0 && a->N > 0 && a->K > 0, "vault_gemm_bf16: empty problem %dx%dx%d", a->M, a->N, a->K);
+  VB_REQUIRE(a->N % 8 == 0, "vault_gemm_bf16: N=%d must be a multiple of 8", a->N);
+  VB_REQUIRE(a->A && a->B && a->out, "vault_gemm_bf16: null operand");
+  VB_REQUIRE(a->split_k >= 1, "vault_gemm_bf16: split_k must be >= 1");
+  VB_REQUIRE(a->split_k == 1 || a->epilogue == VAULT_EPI_ATOMIC_F32, "vault_gemm_bf16: split_k>1 needs VAULT_EPI_ATOMIC_F32");
+  if (a->epilogue == VAULT_EPI_BIAS_RESID_F32) VB_REQUIRE(a->resid != nullptr, "vault_gemm_bf16: resid required");
+  if (a->epilogue == VAULT_EPI_DGELU_BF16) VB_REQUIRE(a->aux != nullptr, "vault_gemm_bf16: aux required");
+  VB_REQUIRE(a->ldo % 4 == 0, "vault_gemm_bf16: ldo=%lld must be a multiple of 4", (long long)a->ldo);
+  cudaStream_t st = reinterpret_cast<cudaStream_t>(stream);
+  const int sms = a->max_ctas > 0 ? a->max_ctas : device_sm_count();
+  int bn = a->block_n > 0 ? a->block_n : pick_block_n(a->M, a->N, a->split_k, sms);
+
+  CUtensorMap tmA, tmB;
+  int rc;
+  if (!a->a_mn) rc = encode_tmap_2d(&tmA, CU_TENSOR_MAP_DATA_TYPE_BFLOAT16, 2, a->A, (uint64_t)a->K, (uint64_t)a->M, (uint64_t)a->lda, BK, BM);
+  else rc = encode_tmap_2d(&tmA, CU_TENSOR_MAP_DATA_TYPE_BFLOAT16, 2, a->A, (uint64_t)a->M, (uint64_t)a->K, (uint64_t)a->lda, 64, BK);
+  if (rc) return rc;
+  if (!a->b_mn) rc = encode_tmap_2d(&tmB, CU_TENSOR_MAP_DATA_TYPE_BFLOAT16, 2, a->B, (uint64_t)a->K, (uint64_t)a->N, (uint64_t)a->ldb, BK, (uint32_t)bn);
+  else rc = encode_tmap_2d(&tmB, CU_TENSOR_MAP_DATA_TYPE_BFLOAT16, 2, a->B, (uint64_t)a->N, (uint64_t)a->K, (uint64_t)a->ldb, 64, BK);
+  if (rc) return rc;
+
+  GemmParams p;
+  p.M = a->M; p.N = a->N; p.K = a->K;
+  p.a_mn = a->a_mn; p.b_mn = a->b_mn;
+  p.num_m_blocks = (a->M + BM - 1) / BM;
+  p.num_n_blocks = (a->N + bn - 1) / bn;
+  p.num_k_blocks = (a->K + BK - 1) / BK;
+  p.split_k = a->split_k < p.num_k_blocks ? a->split_k : p.num_k_blocks;
+  p.kb_per_split = (p.num_k_blocks + p.split_k - 1) / p.split_k;
+  p.split_k = (p.num_k_blocks + p.kb_per_split - 1) / p.kb_per_split;  // no empty splits
+  p.bias = a->bias; p.resid = a->resid; p.ldr = a->ldr;
+  p.aux = reinterpret_cast<const bf16*>(a->aux); p.ldaux = a->ldaux;
+  p.out = a->out; p.ldo = a->ldo; p.out2 = a->out2; p.ldo2 = a->ldo2;
+  p.dropout_p = a->dropout_p; p.seed = a->seed; p.site = a->site;
+  const long long total = (long long)p.num_m_blocks * p.num_n_blocks * p.split_k;
+  const int grid = (int)(total < sms ? total : sms);
+
+  switch (a->epilogue) {
+    case VAULT_EPI_BIAS_BF16: return dispatch_bn<VAULT_EPI_BIAS_BF16>(bn, tmA, tmB, p, grid, st);
+    case VAULT_EPI_BIAS_GELU_BF16: return dispatch_bn<VAULT_EPI_BIAS_GELU_BF16>(bn, tmA, tmB, p, grid, st);
+    case VAULT_EPI_BIAS_RESID_F32: return dispatch_bn<VAULT_EPI_BIAS_RESID_F32>(bn, tmA, tmB, p, grid, st);
+    case VAULT_EPI_PLAIN_BF16: return dispatch_bn<VAULT_EPI_PLAIN_BF16>(bn, tmA, tmB, p, grid, st);
+    case VAULT_EPI_DGELU_BF16: return dispatch_bn<VAULT_EPI_DGELU_BF16>(bn, tmA, tmB, p, grid, st);
+    case VAULT_EPI_ATOMIC_F32: return dispatch_bn<VAULT_EPI_ATOMIC_F32>(bn, tmA, tmB, p, grid, st);
+    case VAULT_EPI_BIAS_F32: return dispatch_bn<VAULT_EPI_BIAS_F32>(bn, tmA, tmB, p, grid, st);
+    case VAULT_EPI_STORE_F32: return dispatch_bn<VAULT_EPI_STORE_F32>(bn, tmA, tmB, p, grid, st);
+  }
+  return fail(VAULT_ERR_INVALID, "vault_gemm_bf16: unknown epilogue %d", a->epilogue);
+}

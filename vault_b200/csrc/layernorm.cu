@@ -1,0 +1,230 @@
+// LayerNorm forward / backward, HBM-bound: one warp per row, the row lives in registers (128-bit loads), warp-shuffle
+// reductions, two-pass variance.  x is the fp32 residual stream; y goes out as bf16 (GEMM operand) and/or fp32 (BERT's
+// post-LN residual).  Optional Philox dropout on the output (BERT embeddings, HF:models/bert/modeling_bert.py:110-111).
+#include "common.cuh"
+
+namespace vb {
+
+constexpr int kLnWarps = 8;
+
+template <int VPL>  // float4 vectors per lane: cols = 128 * VPL
+__global__ void __launch_bounds__(kLnWarps * 32)
+ln_fwd_kernel(const float* __restrict__ x, const float* __restrict__ gamma, const float* __restrict__ beta, bf16* __restrict__ y_bf16,
+              float* __restrict__ y_f32, float* __restrict__ mean_out, float* __restrict__ rstd_out, long long rows, float eps,
+              float drop_p, unsigned long long seed, unsigned site) {
+  constexpr int cols = 128 * VPL;
+  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+  const long long row = (long long)blockIdx.x * kLnWarps + warp;
+  if (row >= rows) return;
+  const float4* xr = reinterpret_cast<const float4*>(x + row * cols);
+  float4 v[VPL];
+  float s = 0.f;
+#pragma unroll
+  for (int i = 0; i < VPL; ++i) {
+    v[i] = __ldg(xr + lane + 32 * i);
+    s += (v[i].x + v[i].y) + (v[i].z + v[i].w);
+  }
+  const float mean = warp_sum(s) * (1.0f / cols);
+  float ss = 0.f;
+#pragma unroll
+  for (int i = 0; i < VPL; ++i) {
+    const float a = v[i].x - mean, b = v[i].y - mean, c = v[i].z - mean, d = v[i].w - mean;
+    ss += (a * a + b * b) + (c * c + d * d);
+  }
+  const float rstd = rsqrtf(warp_sum(ss) * (1.0f / cols) + eps);
+  if (lane == 0) {
+    if (mean_out) mean_out[row] = mean;
+    if (rstd_out) rstd_out[row] = rstd;
+  }
+  const uint32_t thr = dropout_threshold(drop_p);
+  const float keep_scale = drop_p > 0.f ? 1.0f / (1.0f - drop_p) : 1.0f;
+#pragma unroll
+  for (int i = 0; i < VPL; ++i) {
+    const int c4 = lane + 32 * i;
+    const float4 g = __ldg(reinterpret_cast<const float4*>(gamma) + c4);
+    const float4 b = __ldg(reinterpret_cast<const float4*>(beta) + c4);
+    float4 o;
+    o.x = (v[i].x - mean) * rstd * g.x + b.x;
+    o.y = (v[i].y - mean) * rstd * g.y + b.y;
+    o.z = (v[i].z - mean) * rstd * g.z + b.z;
+    o.w = (v[i].w - mean) * rstd * g.w + b.w;
+    if (drop_p > 0.f) {
+      const uint4 bits = dropout_bits4(seed, site, (unsigned long long)(row * (cols / 4) + c4));
+      o.x = bits.x >= thr ? o.x * keep_scale : 0.f;
+      o.y = bits.y >= thr ? o.y * keep_scale : 0.f;
+      o.z = bits.z >= thr ? o.z * keep_scale : 0.f;
+      o.w = bits.w >= thr ? o.w * keep_scale : 0.f;
+    }
+    if (y_f32) reinterpret_cast<float4*>(y_f32 + row * cols)[c4] = o;
+    if (y_bf16) {
+      uint2 pk;
+      pk.x = pack_bf16x2(o.x, o.y);
+      pk.y = pack_bf16x2(o.z, o.w);
+      reinterpret_cast<uint2*>(y_bf16 + row * cols)[c4] = pk;
+    }
+  }
+}
+
+// Backward.  Persistent grid: each warp strides over rows and keeps its dgamma/dbeta partial sums in registers; one smem
+// reduction and one atomic per column per CTA at the end.
+template <int VPL>
+__global__ void __launch_bounds__(kLnWarps * 32)
+ln_bwd_kernel(const float* __restrict__ dy_f32, const bf16* __restrict__ dy_bf16, const float* __restrict__ x, const float* __restrict__ mean,
+              const float* __restrict__ rstd, const float* __restrict__ gamma, const float* __restrict__ dres, float* __restrict__ dx_f32,
+              bf16* __restrict__ dx_bf16, float* __restrict__ dgamma, float* __restrict__ dbeta, long long rows, float drop_p,
+              unsigned long long seed, unsigned site) {
+  constexpr int cols = 128 * VPL;
+  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+  float4 g[VPL], dg[VPL], db[VPL];
+#pragma unroll
+  for (int i = 0; i < VPL; ++i) {
+    g[i] = __ldg(reinterpret_cast<const float4*>(gamma) + lane + 32 * i);
+    dg[i] = make_float4(0.f, 0.f, 0.f, 0.f);
+    db[i] = make_float4(0.f, 0.f, 0.f, 0.f);
+  }
+  const uint32_t thr = dropout_threshold(drop_p);
+  const float keep_scale = drop_p > 0.f ? 1.0f / (1.0f - drop_p) : 1.0f;
+  for (long long row = (long long)blockIdx.x * kLnWarps + warp; row < rows; row += (long long)gridDim.x * kLnWarps) {
+    const float mu = mean[row], rs = rstd[row];
+    float4 xh[VPL], d[VPL];
+    float s1 = 0.f, s2 = 0.f;
+#pragma unroll
+    for (int i = 0; i < VPL; ++i) {
+      const int c4 = lane + 32 * i;
+      const float4 xv = __ldg(reinterpret_cast<const float4*>(x + row * cols) + c4);
+      float4 dv = make_float4(0.f, 0.f, 0.f, 0.f);
+      if (dy_f32) dv = __ldg(reinterpret_cast<const float4*>(dy_f32 + row * cols) + c4);
+      if (dy_bf16) {
+        const uint2 pk = __ldg(reinterpret_cast<const uint2*>(dy_bf16 + row * cols) + c4);
+        const float2 a = unpack_bf16x2(pk.x), b = unpack_bf16x2(pk.y);
+        dv.x += a.x; dv.y += a.y; dv.z += b.x; dv.w += b.y;
+      }
+      if (drop_p > 0.f) {
+        const uint4 bits = dropout_bits4(seed, site, (unsigned long long)(row * (cols / 4) + c4));
+        dv.x = bits.x >= thr ? dv.x * keep_scale : 0.f;
+        dv.y = bits.y >= thr ? dv.y * keep_scale : 0.f;
+        dv.z = bits.z >= thr ? dv.z * keep_scale : 0.f;
+        dv.w = bits.w >= thr ? dv.w * keep_scale : 0.f;
+      }
+      xh[i] = make_float4((xv.x - mu) * rs, (xv.y - mu) * rs, (xv.z - mu) * rs, (xv.w - mu) * rs);
+      dg[i].x += dv.x * xh[i].x; dg[i].y += dv.y * xh[i].y; dg[i].z += dv.z * xh[i].z; dg[i].w += dv.w * xh[i].w;
+      db[i].x += dv.x; db[i].y += dv.y; db[i].z += dv.z; db[i].w += dv.w;
+      d[i] = make_float4(dv.x * g[i].x, dv.y * g[i].y, dv.z * g[i].z, dv.w * g[i].w);
+      s1 += (d[i].x + d[i].y) + (d[i].z + d[i].w);
+      s2 += (d[i].x * xh[i].x + d[i].y * xh[i].y) + (d[i].z * xh[i].z + d[i].w * xh[i].w);
+    }
+    const float c1 = warp_sum(s1) * (1.0f / cols);
+    const float c2 = warp_sum(s2) * (1.0f / cols);
+#pragma unroll
+    for (int i = 0; i < VPL; ++i) {
+      const int c4 = lane + 32 * i;
+      float4 o;
+      o.x = rs * (d[i].x - c1 - xh[i].x * c2);
+      o.y = rs * (d[i].y - c1 - xh[i].y * c2);
+      o.z = rs * (d[i].z - c1 - xh[i].z * c2);
+      o.w = rs * (d[i].w - c1 - xh[i].w * c2);
+      if (dres) {
+        const float4 r = __ldg(reinterpret_cast<const float4*>(dres + row * cols) + c4);
+        o.x += r.x; o.y += r.y; o.z += r.z; o.w += r.w;
+      }
+      reinterpret_cast<float4*>(dx_f32 + row * cols)[c4] = o;
+      if (dx_bf16) {
+        uint2 pk;
+        pk.x = pack_bf16x2(o.x, o.y);
+        pk.y = pack_bf16x2(o.z, o.w);
+        reinterpret_cast<uint2*>(dx_bf16 + row * cols)[c4] = pk;
+      }
+    }
+  }
+  if (dgamma == nullptr && dbeta == nullptr) return;
+  __shared__ float4 red[kLnWarps][32 * VPL + 1];
+  for (int pass = 0; pass < 2; ++pass) {
+    float* dst = pass == 0 ? dgamma : dbeta;
+    if (dst == nullptr) continue;
+    __syncthreads();
+#pragma unroll
+    for (int i = 0; i < VPL; ++i) red[warp][lane + 32 * i] = pass == 0 ? dg[i] : db[i];
+    __syncthreads();
+    for (int c4 = threadIdx.x; c4 < 32 * VPL; c4 += kLnWarps * 32) {
+      float4 acc = red[0][c4];
+#pragma unroll
+      for (int w = 1; w < kLnWarps; ++w) {
+        const float4 t = red[w][c4];
+        acc.x += t.x; acc.y += t.y; acc.z += t.z; acc.w += t.w;
+      }
+      atomicAdd(dst + 4 * c4 + 0, acc.x);
+      atomicAdd(dst + 4 * c4 + 1, acc.y);
+      atomicAdd(dst + 4 * c4 + 2, acc.z);
+      atomicAdd(dst + 4 * c4 + 3, acc.w);
+    }
+  }
+}
+
+template <int VPL>
+int ln_fwd_launch(const float* x, const float* gamma, const float* beta, void* y_bf16, float* y_f32, float* mean, float* rstd, long long rows,
+                  float eps, float p, unsigned long long seed, unsigned site, cudaStream_t st) {
+  const long long grid = (rows + kLnWarps - 1) / kLnWarps;
+  ln_fwd_kernel<VPL><<<(unsigned)grid, kLnWarps * 32, 0, st>>>(x, gamma, beta, reinterpret_cast<bf16*>(y_bf16), y_f32, mean, rstd, rows, eps, p,
+                                                               seed, site);
+  return check_launch("ln_fwd_kernel");
+}
+template <int VPL>
+int ln_bwd_launch(const float* dy_f32, const void* dy_bf16, const float* x, const float* mean, const float* rstd, const float* gamma,
+                  const float* dres, float* dx_f32, void* dx_bf16, float* dgamma, float* dbeta, long long rows, float p,
+                  unsigned long long seed, unsigned site, cudaStream_t st) {
+  long long grid = (rows + kLnWarps - 1) / kLnWarps;
+  const long long cap = (long long)device_sm_count() * 4;
+  if (grid > cap) grid = cap;
+  ln_bwd_kernel<VPL><<<(unsigned)grid, kLnWarps * 32, 0, st>>>(dy_f32, reinterpret_cast<const bf16*>(dy_bf16), x, mean, rstd, gamma, dres, dx_f32,
+                                                               reinterpret_cast<bf16*>(dx_bf16), dgamma, dbeta, rows, p, seed, site);
+  return check_launch("ln_bwd_kernel");
+}
+
+}  // namespace vb
+
+#define VB_LN_DISPATCH(cols, CALL)                                                                      \
+  switch ((cols) / 128) {                                                                               \
+    case 1: return CALL(1);                                                                             \
+    case 2: return CALL(2);                                                                             \
+    case 4: return CALL(4);                                                                             \
+    case 6: return CALL(6);                                                                             \
+    case 8: return CALL(8);                                                                             \
+    default: return vb::fail(VAULT_ERR_INVALID, "layernorm: cols=%d not in {128,256,512,768,1024}", (int)(cols)); \
+  }
+
+extern "C" int vault_layernorm_fwd_drop(const float* x, const float* gamma, const float* beta, void* y_bf16, float* y_f32, float* mean, float* rstd,
+                                        int64_t rows, int32_t cols, float eps, float dropout_p, uint64_t seed, uint32_t site, void* stream) {
+  using namespace vb;
+  VB_REQUIRE(x && gamma && beta && (y_bf16 || y_f32), "layernorm_fwd: null pointer");
+  VB_REQUIRE(rows >= 0 && cols > 0 && cols % 128 == 0, "layernorm_fwd: bad shape rows=%lld cols=%d", (long long)rows, cols);
+  VB_REQUIRE(dropout_p >= 0.f && dropout_p < 1.f, "layernorm_fwd: dropout_p=%f", dropout_p);
+  if (rows == 0) return VAULT_OK;
+  cudaStream_t st = reinterpret_cast<cudaStream_t>(stream);
+#define CALL(V) ln_fwd_launch<V>(x, gamma, beta, y_bf16, y_f32, mean, rstd, rows, eps, dropout_p, seed, site, st)
+  VB_LN_DISPATCH(cols, CALL)
+#undef CALL
+}
+
+extern "C" int vault_layernorm_fwd(const float* x, const float* gamma, const float* beta, void* y_bf16, float* y_f32, float* mean, float* rstd,
+                                   int64_t rows, int32_t cols, float eps, void* stream) {
+  return vault_layernorm_fwd_drop(x, gamma, beta, y_bf16, y_f32, mean, rstd, rows, cols, eps, 0.f, 0, 0, stream);
+}
+
+extern "C" int vault_layernorm_bwd_drop(const float* dy_f32, const void* dy_bf16, const float* x, const float* mean, const float* rstd,
+                                        const float* gamma, const float* dres_f32, float* dx_f32, void* dx_bf16, float* dgamma, float* dbeta,
+                                        int64_t rows, int32_t cols, float dropout_p, uint64_t seed, uint32_t site, void* stream) {
+  using namespace vb;
+  VB_REQUIRE((dy_f32 || dy_bf16) && x && mean && rstd && gamma && dx_f32, "layernorm_bwd: null pointer");
+  VB_REQUIRE(rows >= 0 && cols > 0 && cols % 128 == 0, "layernorm_bwd: bad shape rows=%lld cols=%d", (long long)rows, cols);
+  if (rows == 0) return VAULT_OK;
+  cudaStream_t st = reinterpret_cast<cudaStream_t>(stream);
+#define CALL(V) ln_bwd_launch<V>(dy_f32, dy_bf16, x, mean, rstd, gamma, dres_f32, dx_f32, dx_bf16, dgamma, dbeta, rows, dropout_p, seed, site, st)
+  VB_LN_DISPATCH(cols, CALL)
+#undef CALL
+}
+
+extern "C" int vault_layernorm_bwd(const float* dy_f32, const void* dy_bf16, const float* x, const float* mean, const float* rstd,
+                                   const float* gamma, const float* dres_f32, float* dx_f32, void* dx_bf16, float* dgamma, float* dbeta,
+                                   int64_t rows, int32_t cols, void* stream) {
+  return vault_layernorm_bwd_drop(dy_f32, dy_bf16, x, mean, rstd, gamma, dres_f32, dx_f32, dx_bf16, dgamma, dbeta, rows, cols, 0.f, 0, 0, stream);
+}

@@ -77,6 +77,7 @@ typedef struct vault_gemm_args {
   int64_t ldo2;
   float dropout_p;        /* EPI_BIAS_RESID_F32 only; 0 = off */
   uint64_t seed;
+  const uint64_t* seed_dev; /* optional DEVICE word added to `seed` at run time (lets a captured CUDA graph advance its masks) */
   uint32_t site;          /* dropout site id: forward and backward of the same site regenerate the same mask */
   int32_t split_k;        /* >=1; >1 only with EPI_ATOMIC_F32 */
   int32_t block_n;        /* 0 = choose; else 64 / 128 / 256 */
@@ -84,13 +85,6 @@ typedef struct vault_gemm_args {
 } vault_gemm_args;
 
 int vault_gemm_bf16(const vault_gemm_args* args, void* stream);
-
-/* Patch embedding, im2col-free: Conv2d(3,H,k=32,s=32) as a TF32 tcgen05 GEMM whose A tiles are TMA boxes taken straight
- * from the NCHW fp32 pixels.  Replaces ViltPatchEmbeddings.forward, HF:models/vilt/modeling_vilt.py:293-303.
- *   pixels [B,C,Hi,Wi] fp32, weight [N, C*P*P] fp32 (= projection.weight.view(N,-1)), bias [N] fp32 or NULL
- *   out [B*(Hi/P)*(Wi/P), N] fp32, row = b*gh*gw + i*gw + j                                                     */
-int vault_patch_embed_fwd(const float* pixels, const float* weight, const float* bias, float* out, int32_t B, int32_t C,
-                          int32_t Hi, int32_t Wi, int32_t P, int32_t N, void* stream);
 
 /* ------------------------------------------------------------------------------------------------------------------
  * LayerNorm (HF nn.LayerNorm call sites: 25 in the LM, 26 in ViLT).  x fp32 [rows, cols].
@@ -104,15 +98,19 @@ int vault_layernorm_fwd(const float* x, const float* gamma, const float* beta, v
 int vault_layernorm_bwd(const float* dy_f32, const void* dy_bf16, const float* x, const float* mean, const float* rstd,
                         const float* gamma, const float* dres_f32, float* dx_f32, void* dx_bf16, float* dgamma,
                         float* dbeta, int64_t rows, int32_t cols, void* stream);
-/* Same with Philox dropout on the LayerNorm OUTPUT (BertEmbeddings: dropout(LayerNorm(.)), HF:models/bert/modeling_bert.py:110-111);
- * the backward regenerates the mask from (seed, site) and applies it to dy before differentiating the norm. */
+/* Dropout-aware variants (BERT stack in training; every mask is Philox(seed + *seed_dev, site) keyed by element index).
+ *   fwd: dropout on the LayerNorm OUTPUT (BertEmbeddings: dropout(LayerNorm(.)), HF:models/bert/modeling_bert.py:110-111)
+ *   bwd: in_*  : that same output mask, applied to dy before differentiating the norm;
+ *        out_* : mask of the dropout that sat on the GEMM output feeding this LayerNorm's input (BertSelfOutput / BertOutput,
+ *                HF:models/bert/modeling_bert.py:294-297, 352-355): applied to the bf16 copy of dx only -- that copy is the dy
+ *                operand of the dgrad / wgrad / bias-grad of that GEMM, while dx_f32 continues down the residual path. */
 int vault_layernorm_fwd_drop(const float* x, const float* gamma, const float* beta, void* y_bf16, float* y_f32, float* mean,
                              float* rstd, int64_t rows, int32_t cols, float eps, float dropout_p, uint64_t seed,
-                             uint32_t site, void* stream);
+                             const uint64_t* seed_dev, uint32_t site, void* stream);
 int vault_layernorm_bwd_drop(const float* dy_f32, const void* dy_bf16, const float* x, const float* mean, const float* rstd,
                              const float* gamma, const float* dres_f32, float* dx_f32, void* dx_bf16, float* dgamma,
-                             float* dbeta, int64_t rows, int32_t cols, float dropout_p, uint64_t seed, uint32_t site,
-                             void* stream);
+                             float* dbeta, int64_t rows, int32_t cols, float in_p, uint32_t in_site, float out_p,
+                             uint32_t out_site, uint64_t seed, const uint64_t* seed_dev, void* stream);
 
 /* ------------------------------------------------------------------------------------------------------------------
  * Fused masked-softmax attention over the variable-length text+image sequence.
@@ -123,11 +121,11 @@ int vault_layernorm_bwd_drop(const float* dy_f32, const void* dy_bf16, const flo
  *   dropout on the probabilities (BERT stack in training) is Philox(seed, site) keyed by (b,h,q,k).
  * ------------------------------------------------------------------------------------------------------------------ */
 int vault_attn_fwd(const void* qkv, const uint8_t* key_mask, void* ctx, float* lse, int32_t B, int32_t S, int32_t heads,
-                   float dropout_p, uint64_t seed, uint32_t site, void* stream);
+                   float dropout_p, uint64_t seed, const uint64_t* seed_dev, uint32_t site, void* stream);
 /* dqkv [B*S, 3*heads*64] bf16 is fully overwritten; delta [B,heads,S] fp32 is workspace */
 int vault_attn_bwd(const void* qkv, const uint8_t* key_mask, const void* ctx, const void* dctx, const float* lse,
                    float* delta, void* dqkv, int32_t B, int32_t S, int32_t heads, float dropout_p, uint64_t seed,
-                   uint32_t site, void* stream);
+                   const uint64_t* seed_dev, uint32_t site, void* stream);
 
 /* ------------------------------------------------------------------------------------------------------------------
  * Embedding assembly.
@@ -137,11 +135,14 @@ int vault_attn_bwd(const void* qkv, const uint8_t* key_mask, const void* ctx, co
  * ViLT text: TextEmbeddings.forward with inputs_embeds HF:models/vilt/modeling_vilt.py:240-272 (4.48.0 gate):
  *        x = inputs_embeds + type[tt] (+ pos[t] if pos != NULL)
  * ------------------------------------------------------------------------------------------------------------------ */
+/* also converts attention_mask int64 [B,T] -> key_mask uint8 [B,T] for the attention kernels (both optional) */
 int vault_lm_embed_fwd(const int64_t* ids, const int64_t* tt, const float* word, const float* type, const float* pos,
-                       float* x_sum, int32_t B, int32_t T, int32_t H, int32_t roberta_pad, void* stream);
+                       float* x_sum, const int64_t* attention_mask, uint8_t* key_mask, int32_t B, int32_t T, int32_t H,
+                       int32_t roberta_pad, void* stream);
 /* scatter-add dx [B*T,H] fp32 into dword/dtype/dpos (fp32, atomics; caller zero-fills); any table grad may be NULL */
+/* word_pad: nn.Embedding(padding_idx=pad_token_id) row that receives no gradient (-1: none) */
 int vault_lm_embed_bwd(const int64_t* ids, const int64_t* tt, const float* dx, float* dword, float* dtype, float* dpos,
-                       int32_t B, int32_t T, int32_t H, int32_t roberta_pad, void* stream);
+                       int32_t B, int32_t T, int32_t H, int32_t roberta_pad, int32_t word_pad, void* stream);
 int vault_vilt_text_embed_fwd(const float* inputs_embeds, const int64_t* tt, const float* type, const float* pos,
                               float* x_sum, int32_t B, int32_t T, int32_t H, void* stream);
 int vault_vilt_text_embed_bwd(const int64_t* tt, const float* dx, float* dtype, float* dpos, int32_t B, int32_t T,
@@ -186,8 +187,9 @@ int vault_small_linear_fwd(const float* x, int64_t ldx, const float* W, const fl
 int vault_small_linear_bwd(const float* dy, const float* y, const float* x, int64_t ldx, const float* W, float* dx,
                            int64_t lddx, int32_t accumulate_dx, float* dW, float* db, int32_t rows, int32_t N, int32_t K,
                            int32_t act, void* stream);
-/* dropout on fp32 [n] (head dropout): y = x * keep / (1-p) */
-int vault_dropout_f32(const float* x, float* y, int64_t n, float p, uint64_t seed, uint32_t site, void* stream);
+/* dropout on fp32 [n] (head dropout): y = x * keep / (1-p); linear, so the same call on dy is its backward */
+int vault_dropout_f32(const float* x, float* y, int64_t n, float p, uint64_t seed, const uint64_t* seed_dev, uint32_t site,
+                      void* stream);
 /* softmax cross-entropy, mean over rows: loss[0] = mean_r(-log softmax(logits[r])[label[r]]);
  * dlogits = (softmax - onehot) * grad_scale / rows  (dlogits may be NULL) */
 int vault_ce_loss(const float* logits, const int64_t* labels, float* loss, float* dlogits, int32_t rows, int32_t n_classes,

@@ -26,7 +26,7 @@ class GemmArgs(C.Structure):
         ("bias", c_p), ("resid", c_p), ("ldr", c_i64),
         ("aux", c_p), ("ldaux", c_i64),
         ("out", c_p), ("ldo", c_i64), ("out2", c_p), ("ldo2", c_i64),
-        ("dropout_p", c_f32), ("seed", c_u64), ("site", c_u32),
+        ("dropout_p", c_f32), ("seed", c_u64), ("seed_dev", c_p), ("site", c_u32),
         ("split_k", c_i32), ("block_n", c_i32), ("max_ctas", c_i32),
     ]
 
@@ -37,15 +37,14 @@ SIGNATURES = {
     "vault_last_error": [C.c_char_p, C.c_size_t],
     "vault_check_device": [c_i32],
     "vault_gemm_bf16": [C.POINTER(GemmArgs), c_p],
-    "vault_patch_embed_fwd": [c_p, c_p, c_p, c_p, c_i32, c_i32, c_i32, c_i32, c_i32, c_i32, c_p],
     "vault_layernorm_fwd": [c_p, c_p, c_p, c_p, c_p, c_p, c_p, c_i64, c_i32, c_f32, c_p],
     "vault_layernorm_bwd": [c_p, c_p, c_p, c_p, c_p, c_p, c_p, c_p, c_p, c_p, c_p, c_i64, c_i32, c_p],
-    "vault_layernorm_fwd_drop": [c_p, c_p, c_p, c_p, c_p, c_p, c_p, c_i64, c_i32, c_f32, c_f32, c_u64, c_u32, c_p],
-    "vault_layernorm_bwd_drop": [c_p, c_p, c_p, c_p, c_p, c_p, c_p, c_p, c_p, c_p, c_p, c_i64, c_i32, c_f32, c_u64, c_u32, c_p],
-    "vault_attn_fwd": [c_p, c_p, c_p, c_p, c_i32, c_i32, c_i32, c_f32, c_u64, c_u32, c_p],
-    "vault_attn_bwd": [c_p, c_p, c_p, c_p, c_p, c_p, c_p, c_i32, c_i32, c_i32, c_f32, c_u64, c_u32, c_p],
-    "vault_lm_embed_fwd": [c_p, c_p, c_p, c_p, c_p, c_p, c_i32, c_i32, c_i32, c_i32, c_p],
-    "vault_lm_embed_bwd": [c_p, c_p, c_p, c_p, c_p, c_p, c_i32, c_i32, c_i32, c_i32, c_p],
+    "vault_layernorm_fwd_drop": [c_p, c_p, c_p, c_p, c_p, c_p, c_p, c_i64, c_i32, c_f32, c_f32, c_u64, c_p, c_u32, c_p],
+    "vault_layernorm_bwd_drop": [c_p, c_p, c_p, c_p, c_p, c_p, c_p, c_p, c_p, c_p, c_p, c_i64, c_i32, c_f32, c_u32, c_f32, c_u32, c_u64, c_p, c_p],
+    "vault_attn_fwd": [c_p, c_p, c_p, c_p, c_i32, c_i32, c_i32, c_f32, c_u64, c_p, c_u32, c_p],
+    "vault_attn_bwd": [c_p, c_p, c_p, c_p, c_p, c_p, c_p, c_i32, c_i32, c_i32, c_f32, c_u64, c_p, c_u32, c_p],
+    "vault_lm_embed_fwd": [c_p, c_p, c_p, c_p, c_p, c_p, c_p, c_p, c_i32, c_i32, c_i32, c_i32, c_p],
+    "vault_lm_embed_bwd": [c_p, c_p, c_p, c_p, c_p, c_p, c_i32, c_i32, c_i32, c_i32, c_i32, c_p],
     "vault_vilt_text_embed_fwd": [c_p, c_p, c_p, c_p, c_p, c_i32, c_i32, c_i32, c_p],
     "vault_vilt_text_embed_bwd": [c_p, c_p, c_p, c_p, c_i32, c_i32, c_i32, c_p],
     "vault_patch_grid": [c_p, c_i32, c_p, c_i32, c_i32, c_i32, c_i32, c_p],
@@ -54,7 +53,7 @@ SIGNATURES = {
     "vault_patchify_bf16": [c_p, c_p, c_i32, c_i32, c_i32, c_i32, c_i32, c_p],
     "vault_small_linear_fwd": [c_p, c_i64, c_p, c_p, c_p, c_i32, c_i32, c_i32, c_i32, c_p],
     "vault_small_linear_bwd": [c_p, c_p, c_p, c_i64, c_p, c_p, c_i64, c_i32, c_p, c_p, c_i32, c_i32, c_i32, c_i32, c_p],
-    "vault_dropout_f32": [c_p, c_p, c_i64, c_f32, c_u64, c_u32, c_p],
+    "vault_dropout_f32": [c_p, c_p, c_i64, c_f32, c_u64, c_p, c_u32, c_p],
     "vault_ce_loss": [c_p, c_p, c_p, c_p, c_i32, c_i32, c_f32, c_p],
     "vault_colsum_bf16": [c_p, c_i64, c_p, c_i64, c_i32, c_p],
     "vault_adamw_step": [c_p, c_p, c_p, c_p, c_p, c_i64, c_f32, c_f32, c_f32, c_f32, c_f32, c_i32, c_i32, c_f32, c_p],

@@ -23,7 +23,7 @@ LIB = os.path.join(LIBDIR, "libvault_b200.so")
 
 NVCC_FLAGS = [
     "-gencode", "arch=compute_100a,code=sm_100a",
-    "-O3", "-std=c++17", "-lineinfo", "--use_fast_math",
+    "-O3", "-std=c++17", "-lineinfo",
     "-Xcompiler", "-fPIC",
     "--expt-relaxed-constexpr", "-Xptxas", "-v",
 ]

@@ -37,6 +37,7 @@ struct GemmParams {
   long long ldo2;
   float dropout_p;
   unsigned long long seed;
+  const unsigned long long* seed_dev;
   unsigned site;
 };
 
@@ -64,7 +65,7 @@ __device__ __forceinline__ void epilogue4(const GemmParams& p, float4 acc, const
     if (p.dropout_p > 0.f) {
       const uint32_t thr = dropout_threshold(p.dropout_p);
       const float sc = 1.0f / (1.0f - p.dropout_p);
-      const uint4 bits = dropout_bits4(p.seed, p.site, (unsigned long long)(row * p.N + col) >> 2);
+      const uint4 bits = dropout_bits4(p.seed + (p.seed_dev ? *p.seed_dev : 0ull), p.site, (unsigned long long)(row * p.N + col) >> 2);
       x0 = bits.x >= thr ? x0 * sc : 0.f;
       x1 = bits.y >= thr ? x1 * sc : 0.f;
       x2 = bits.z >= thr ? x2 * sc : 0.f;
@@ -396,7 +397,7 @@ extern "C" int vault_gemm_bf16(const vault_gemm_args* a, void* stream) {
   p.bias = a->bias; p.resid = a->resid; p.ldr = a->ldr;
   p.aux = reinterpret_cast<const bf16*>(a->aux); p.ldaux = a->ldaux;
   p.out = a->out; p.ldo = a->ldo; p.out2 = a->out2; p.ldo2 = a->ldo2;
-  p.dropout_p = a->dropout_p; p.seed = a->seed; p.site = a->site;
+  p.dropout_p = a->dropout_p; p.seed = a->seed; p.seed_dev = reinterpret_cast<const unsigned long long*>(a->seed_dev); p.site = a->site;
   const long long total = (long long)p.num_m_blocks * p.num_n_blocks * p.split_k;
   const int grid = (int)(total < sms ? total : sms);
 

@@ -1,0 +1,214 @@
+// Pooler / classifier head / loss / bias-gradient kernels.  Everything here is tiny (B rows) and runs in fp32 on CUDA cores:
+// a [B,768]x[768,768] pooler is 38 MFLOP -- not tensor-core work.
+#include "common.cuh"
+
+namespace vb {
+
+// y[r,n] = act(sum_k x[r*ldx+k] * W[n*K+k] + b[n]); one warp per output
+__global__ void __launch_bounds__(256)
+small_linear_fwd_kernel(const float* __restrict__ x, long long ldx, const float* __restrict__ W, const float* __restrict__ b, float* __restrict__ y,
+                        int rows, int N, int K, int act) {
+  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+  const long long o = (long long)blockIdx.x * 8 + warp;
+  if (o >= (long long)rows * N) return;
+  const int r = (int)(o / N), n = (int)(o % N);
+  const float4* xr = reinterpret_cast<const float4*>(x + r * ldx);
+  const float4* wr = reinterpret_cast<const float4*>(W + (long long)n * K);
+  float s = 0.f;
+  for (int c = lane; c < K / 4; c += 32) {
+    const float4 a = __ldg(xr + c), w = __ldg(wr + c);
+    s += a.x * w.x + a.y * w.y + a.z * w.z + a.w * w.w;
+  }
+  s = warp_sum(s);
+  if (lane == 0) {
+    s += b ? b[n] : 0.f;
+    y[(long long)r * N + n] = act == 1 ? tanhf(s) : s;
+  }
+}
+
+__device__ __forceinline__ float act_grad(float dy, const float* y, long long idx, int act) {
+  if (act == 1) {
+    const float t = y[idx];
+    return dy * (1.f - t * t);
+  }
+  return dy;
+}
+
+// dW[n,k] = sum_r g[r,n] x[r,k], db[n] = sum_r g[r,n]; one warp per n
+__global__ void __launch_bounds__(256)
+small_linear_wgrad_kernel(const float* __restrict__ dy, const float* __restrict__ y, const float* __restrict__ x, long long ldx, float* __restrict__ dW,
+                          float* __restrict__ db, int rows, int N, int K, int act) {
+  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+  const int n = blockIdx.x * 8 + warp;
+  if (n >= N) return;
+  float bsum = 0.f;
+  for (int c0 = 0; c0 < K / 4; c0 += 32) {
+    const int c = c0 + lane;
+    float4 acc = make_float4(0.f, 0.f, 0.f, 0.f);
+    for (int r = 0; r < rows; ++r) {
+      const float g = act_grad(dy[(long long)r * N + n], y, (long long)r * N + n, act);
+      if (c0 == 0 && lane == 0) bsum += g;
+      if (c < K / 4) {
+        const float4 a = __ldg(reinterpret_cast<const float4*>(x + r * ldx) + c);
+        acc.x += g * a.x; acc.y += g * a.y; acc.z += g * a.z; acc.w += g * a.w;
+      }
+    }
+    if (dW && c < K / 4) reinterpret_cast<float4*>(dW + (long long)n * K)[c] = acc;
+  }
+  if (db && lane == 0) db[n] = bsum;
+}
+
+// dx[r,k] (+)= sum_n g[r,n] W[n,k]; one warp per (r, 128-column chunk)
+__global__ void __launch_bounds__(256)
+small_linear_dgrad_kernel(const float* __restrict__ dy, const float* __restrict__ y, const float* __restrict__ W, float* __restrict__ dx, long long lddx,
+                          int accumulate, int rows, int N, int K, int act) {
+  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+  const int chunks = (K / 4 + 31) / 32;
+  const long long o = (long long)blockIdx.x * 8 + warp;
+  if (o >= (long long)rows * chunks) return;
+  const int r = (int)(o / chunks), c = (int)(o % chunks) * 32 + lane;
+  if (c >= K / 4) return;
+  float4 acc = make_float4(0.f, 0.f, 0.f, 0.f);
+  for (int n = 0; n < N; ++n) {
+    const float g = act_grad(dy[(long long)r * N + n], y, (long long)r * N + n, act);
+    const float4 w = __ldg(reinterpret_cast<const float4*>(W + (long long)n * K) + c);
+    acc.x += g * w.x; acc.y += g * w.y; acc.z += g * w.z; acc.w += g * w.w;
+  }
+  float4* d = reinterpret_cast<float4*>(dx + r * lddx) + c;
+  if (accumulate) {
+    const float4 old = *d;
+    acc.x += old.x; acc.y += old.y; acc.z += old.z; acc.w += old.w;
+  }
+  *d = acc;
+}
+
+__global__ void dropout_f32_kernel(const float* __restrict__ x, float* __restrict__ y, long long n, float p, unsigned long long seed,
+                                   const unsigned long long* seed_dev, unsigned site) {
+  if (seed_dev) seed += *seed_dev;
+  const uint32_t thr = dropout_threshold(p);
+  const float sc = 1.f / (1.f - p);
+  for (long long q = (long long)blockIdx.x * blockDim.x + threadIdx.x; q * 4 < n; q += (long long)gridDim.x * blockDim.x) {
+    const uint4 bits = dropout_bits4(seed, site, (unsigned long long)q);
+    const uint32_t bb[4] = {bits.x, bits.y, bits.z, bits.w};
+#pragma unroll
+    for (int e = 0; e < 4; ++e) {
+      const long long i = q * 4 + e;
+      if (i < n) y[i] = bb[e] >= thr ? x[i] * sc : 0.f;
+    }
+  }
+}
+
+// mean softmax cross-entropy over rows (nn.CrossEntropyLoss default reduction); one block, thread per row (strided)
+__global__ void __launch_bounds__(256)
+ce_loss_kernel(const float* __restrict__ logits, const int64_t* __restrict__ labels, float* __restrict__ loss, float* __restrict__ dlogits, int rows,
+               int C, float grad_scale) {
+  __shared__ float red[8];
+  float local = 0.f;
+  for (int r = threadIdx.x; r < rows; r += blockDim.x) {
+    const float* z = logits + (long long)r * C;
+    float m = -INFINITY;
+    for (int c = 0; c < C; ++c) m = fmaxf(m, z[c]);
+    float se = 0.f;
+    for (int c = 0; c < C; ++c) se += expf(z[c] - m);
+    const float lse = m + logf(se);
+    const int lab = (int)labels[r];
+    local += lse - z[lab];
+    if (dlogits) {
+      for (int c = 0; c < C; ++c) dlogits[(long long)r * C + c] = (expf(z[c] - lse) - (c == lab ? 1.f : 0.f)) * grad_scale / rows;
+    }
+  }
+  local = warp_sum(local);
+  if ((threadIdx.x & 31) == 0) red[threadIdx.x >> 5] = local;
+  __syncthreads();
+  if (threadIdx.x == 0) {
+    float t = 0.f;
+    for (int w = 0; w < (int)(blockDim.x >> 5); ++w) t += red[w];
+    loss[0] = t / rows;
+  }
+}
+
+// out[c] += sum_r x[r, c]  (bf16 in, fp32 atomics out); lane = 4 columns, warp = 128 columns, 8 warps stride rows
+__global__ void __launch_bounds__(256)
+colsum_bf16_kernel(const bf16* __restrict__ x, long long ldx, float* __restrict__ out, long long rows, int cols) {
+  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+  const int c = blockIdx.x * 128 + lane * 4;
+  float4 acc = make_float4(0.f, 0.f, 0.f, 0.f);
+  if (c < cols) {
+    for (long long r = (long long)blockIdx.y * 8 + warp; r < rows; r += (long long)gridDim.y * 8) {
+      const uint2 pk = __ldg(reinterpret_cast<const uint2*>(x + r * ldx + c));
+      const float2 a = unpack_bf16x2(pk.x), b = unpack_bf16x2(pk.y);
+      acc.x += a.x; acc.y += a.y; acc.z += b.x; acc.w += b.y;
+    }
+  }
+  __shared__ float4 red[8][33];
+  red[warp][lane] = acc;
+  __syncthreads();
+  if (warp == 0 && c < cols) {
+    float4 t = red[0][lane];
+#pragma unroll
+    for (int w = 1; w < 8; ++w) {
+      const float4 u = red[w][lane];
+      t.x += u.x; t.y += u.y; t.z += u.z; t.w += u.w;
+    }
+    atomicAdd(out + c, t.x); atomicAdd(out + c + 1, t.y); atomicAdd(out + c + 2, t.z); atomicAdd(out + c + 3, t.w);
+  }
+}
+
+}  // namespace vb
+
+using namespace vb;
+
+extern "C" int vault_small_linear_fwd(const float* x, int64_t ldx, const float* W, const float* b, float* y, int32_t rows, int32_t N, int32_t K,
+                                      int32_t act, void* stream) {
+  VB_REQUIRE(x && W && y, "small_linear_fwd: null pointer");
+  VB_REQUIRE(rows > 0 && N > 0 && K > 0 && K % 4 == 0 && ldx % 4 == 0, "small_linear_fwd: bad shape rows=%d N=%d K=%d", rows, N, K);
+  const long long outs = (long long)rows * N;
+  small_linear_fwd_kernel<<<(unsigned)((outs + 7) / 8), 256, 0, (cudaStream_t)stream>>>(x, ldx, W, b, y, rows, N, K, act);
+  return check_launch("small_linear_fwd_kernel");
+}
+
+extern "C" int vault_small_linear_bwd(const float* dy, const float* y, const float* x, int64_t ldx, const float* W, float* dx, int64_t lddx,
+                                      int32_t accumulate_dx, float* dW, float* db, int32_t rows, int32_t N, int32_t K, int32_t act, void* stream) {
+  VB_REQUIRE(dy && x && W, "small_linear_bwd: null pointer");
+  VB_REQUIRE(act == 0 || y != nullptr, "small_linear_bwd: tanh backward needs the saved output");
+  VB_REQUIRE(rows > 0 && N > 0 && K > 0 && K % 4 == 0 && ldx % 4 == 0, "small_linear_bwd: bad shape rows=%d N=%d K=%d", rows, N, K);
+  cudaStream_t st = (cudaStream_t)stream;
+  if (dW || db) {
+    small_linear_wgrad_kernel<<<(unsigned)((N + 7) / 8), 256, 0, st>>>(dy, y, x, ldx, dW, db, rows, N, K, act);
+    int rc = check_launch("small_linear_wgrad_kernel");
+    if (rc) return rc;
+  }
+  if (dx) {
+    VB_REQUIRE(lddx % 4 == 0, "small_linear_bwd: lddx must be a multiple of 4");
+    const long long warps = (long long)rows * ((K / 4 + 31) / 32);
+    small_linear_dgrad_kernel<<<(unsigned)((warps + 7) / 8), 256, 0, st>>>(dy, y, W, dx, lddx, accumulate_dx, rows, N, K, act);
+    return check_launch("small_linear_dgrad_kernel");
+  }
+  return VAULT_OK;
+}
+
+extern "C" int vault_dropout_f32(const float* x, float* y, int64_t n, float p, uint64_t seed, const uint64_t* seed_dev, uint32_t site,
+                                 void* stream) {
+  VB_REQUIRE(x && y && n >= 0 && p >= 0.f && p < 1.f, "dropout_f32: bad arguments");
+  if (n == 0) return VAULT_OK;
+  const long long q = (n + 3) / 4;
+  dropout_f32_kernel<<<(unsigned)((q + 255) / 256), 256, 0, (cudaStream_t)stream>>>(x, y, n, p, seed, reinterpret_cast<const unsigned long long*>(seed_dev), site);
+  return check_launch("dropout_f32_kernel");
+}
+
+extern "C" int vault_ce_loss(const float* logits, const int64_t* labels, float* loss, float* dlogits, int32_t rows, int32_t n_classes,
+                             float grad_scale, void* stream) {
+  VB_REQUIRE(logits && labels && loss && rows > 0 && n_classes > 0, "ce_loss: bad arguments");
+  ce_loss_kernel<<<1, 256, 0, (cudaStream_t)stream>>>(logits, labels, loss, dlogits, rows, n_classes, grad_scale);
+  return check_launch("ce_loss_kernel");
+}
+
+extern "C" int vault_colsum_bf16(const void* x, int64_t ldx, float* out, int64_t rows, int32_t cols, void* stream) {
+  VB_REQUIRE(x && out && rows >= 0 && cols > 0 && cols % 4 == 0 && ldx % 4 == 0, "colsum: bad arguments");
+  if (rows == 0) return VAULT_OK;
+  long long gy = (rows + 63) / 64;
+  if (gy > 64) gy = 64;
+  dim3 grid((cols + 127) / 128, (unsigned)gy);
+  colsum_bf16_kernel<<<grid, 256, 0, (cudaStream_t)stream>>>(reinterpret_cast<const bf16*>(x), ldx, out, rows, cols);
+  return check_launch("colsum_bf16_kernel");
+}

@@ -11,11 +11,12 @@ template <int VPL>  // float4 vectors per lane: cols = 128 * VPL
 __global__ void __launch_bounds__(kLnWarps * 32)
 ln_fwd_kernel(const float* __restrict__ x, const float* __restrict__ gamma, const float* __restrict__ beta, bf16* __restrict__ y_bf16,
               float* __restrict__ y_f32, float* __restrict__ mean_out, float* __restrict__ rstd_out, long long rows, float eps,
-              float drop_p, unsigned long long seed, unsigned site) {
+              float drop_p, unsigned long long seed, const unsigned long long* seed_dev, unsigned site) {
   constexpr int cols = 128 * VPL;
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
   const long long row = (long long)blockIdx.x * kLnWarps + warp;
   if (row >= rows) return;
+  if (drop_p > 0.f && seed_dev) seed += *seed_dev;
   const float4* xr = reinterpret_cast<const float4*>(x + row * cols);
   float4 v[VPL];
   float s = 0.f;
@@ -71,9 +72,12 @@ template <int VPL>
 __global__ void __launch_bounds__(kLnWarps * 32)
 ln_bwd_kernel(const float* __restrict__ dy_f32, const bf16* __restrict__ dy_bf16, const float* __restrict__ x, const float* __restrict__ mean,
               const float* __restrict__ rstd, const float* __restrict__ gamma, const float* __restrict__ dres, float* __restrict__ dx_f32,
-              bf16* __restrict__ dx_bf16, float* __restrict__ dgamma, float* __restrict__ dbeta, long long rows, float drop_p,
-              unsigned long long seed, unsigned site) {
+              bf16* __restrict__ dx_bf16, float* __restrict__ dgamma, float* __restrict__ dbeta, long long rows, float drop_p, unsigned site,
+              float out_p, unsigned out_site, unsigned long long seed, const unsigned long long* seed_dev) {
   constexpr int cols = 128 * VPL;
+  if ((drop_p > 0.f || out_p > 0.f) && seed_dev) seed += *seed_dev;
+  const uint32_t out_thr = dropout_threshold(out_p);
+  const float out_scale = out_p > 0.f ? 1.0f / (1.0f - out_p) : 1.0f;
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
   float4 g[VPL], dg[VPL], db[VPL];
 #pragma unroll
@@ -129,6 +133,13 @@ ln_bwd_kernel(const float* __restrict__ dy_f32, const bf16* __restrict__ dy_bf16
       }
       reinterpret_cast<float4*>(dx_f32 + row * cols)[c4] = o;
       if (dx_bf16) {
+        if (out_p > 0.f) {
+          const uint4 bits = dropout_bits4(seed, out_site, (unsigned long long)(row * (cols / 4) + c4));
+          o.x = bits.x >= out_thr ? o.x * out_scale : 0.f;
+          o.y = bits.y >= out_thr ? o.y * out_scale : 0.f;
+          o.z = bits.z >= out_thr ? o.z * out_scale : 0.f;
+          o.w = bits.w >= out_thr ? o.w * out_scale : 0.f;
+        }
         uint2 pk;
         pk.x = pack_bf16x2(o.x, o.y);
         pk.y = pack_bf16x2(o.z, o.w);
@@ -162,21 +173,21 @@ ln_bwd_kernel(const float* __restrict__ dy_f32, const bf16* __restrict__ dy_bf16
 
 template <int VPL>
 int ln_fwd_launch(const float* x, const float* gamma, const float* beta, void* y_bf16, float* y_f32, float* mean, float* rstd, long long rows,
-                  float eps, float p, unsigned long long seed, unsigned site, cudaStream_t st) {
+                  float eps, float p, unsigned long long seed, const unsigned long long* seed_dev, unsigned site, cudaStream_t st) {
   const long long grid = (rows + kLnWarps - 1) / kLnWarps;
   ln_fwd_kernel<VPL><<<(unsigned)grid, kLnWarps * 32, 0, st>>>(x, gamma, beta, reinterpret_cast<bf16*>(y_bf16), y_f32, mean, rstd, rows, eps, p,
-                                                               seed, site);
+                                                               seed, seed_dev, site);
   return check_launch("ln_fwd_kernel");
 }
 template <int VPL>
 int ln_bwd_launch(const float* dy_f32, const void* dy_bf16, const float* x, const float* mean, const float* rstd, const float* gamma,
-                  const float* dres, float* dx_f32, void* dx_bf16, float* dgamma, float* dbeta, long long rows, float p,
-                  unsigned long long seed, unsigned site, cudaStream_t st) {
+                  const float* dres, float* dx_f32, void* dx_bf16, float* dgamma, float* dbeta, long long rows, float p, unsigned site,
+                  float out_p, unsigned out_site, unsigned long long seed, const unsigned long long* seed_dev, cudaStream_t st) {
   long long grid = (rows + kLnWarps - 1) / kLnWarps;
   const long long cap = (long long)device_sm_count() * 4;
   if (grid > cap) grid = cap;
   ln_bwd_kernel<VPL><<<(unsigned)grid, kLnWarps * 32, 0, st>>>(dy_f32, reinterpret_cast<const bf16*>(dy_bf16), x, mean, rstd, gamma, dres, dx_f32,
-                                                               reinterpret_cast<bf16*>(dx_bf16), dgamma, dbeta, rows, p, seed, site);
+                                                               reinterpret_cast<bf16*>(dx_bf16), dgamma, dbeta, rows, p, site, out_p, out_site, seed, seed_dev);
   return check_launch("ln_bwd_kernel");
 }
 
@@ -193,32 +204,34 @@ int ln_bwd_launch(const float* dy_f32, const void* dy_bf16, const float* x, cons
   }
 
 extern "C" int vault_layernorm_fwd_drop(const float* x, const float* gamma, const float* beta, void* y_bf16, float* y_f32, float* mean, float* rstd,
-                                        int64_t rows, int32_t cols, float eps, float dropout_p, uint64_t seed, uint32_t site, void* stream) {
+                                        int64_t rows, int32_t cols, float eps, float dropout_p, uint64_t seed, const uint64_t* seed_dev, uint32_t site,
+                                        void* stream) {
   using namespace vb;
   VB_REQUIRE(x && gamma && beta && (y_bf16 || y_f32), "layernorm_fwd: null pointer");
   VB_REQUIRE(rows >= 0 && cols > 0 && cols % 128 == 0, "layernorm_fwd: bad shape rows=%lld cols=%d", (long long)rows, cols);
   VB_REQUIRE(dropout_p >= 0.f && dropout_p < 1.f, "layernorm_fwd: dropout_p=%f", dropout_p);
   if (rows == 0) return VAULT_OK;
   cudaStream_t st = reinterpret_cast<cudaStream_t>(stream);
-#define CALL(V) ln_fwd_launch<V>(x, gamma, beta, y_bf16, y_f32, mean, rstd, rows, eps, dropout_p, seed, site, st)
+#define CALL(V) ln_fwd_launch<V>(x, gamma, beta, y_bf16, y_f32, mean, rstd, rows, eps, dropout_p, seed, reinterpret_cast<const unsigned long long*>(seed_dev), site, st)
   VB_LN_DISPATCH(cols, CALL)
 #undef CALL
 }
 
 extern "C" int vault_layernorm_fwd(const float* x, const float* gamma, const float* beta, void* y_bf16, float* y_f32, float* mean, float* rstd,
                                    int64_t rows, int32_t cols, float eps, void* stream) {
-  return vault_layernorm_fwd_drop(x, gamma, beta, y_bf16, y_f32, mean, rstd, rows, cols, eps, 0.f, 0, 0, stream);
+  return vault_layernorm_fwd_drop(x, gamma, beta, y_bf16, y_f32, mean, rstd, rows, cols, eps, 0.f, 0, nullptr, 0, stream);
 }
 
 extern "C" int vault_layernorm_bwd_drop(const float* dy_f32, const void* dy_bf16, const float* x, const float* mean, const float* rstd,
                                         const float* gamma, const float* dres_f32, float* dx_f32, void* dx_bf16, float* dgamma, float* dbeta,
-                                        int64_t rows, int32_t cols, float dropout_p, uint64_t seed, uint32_t site, void* stream) {
+                                        int64_t rows, int32_t cols, float in_p, uint32_t in_site, float out_p, uint32_t out_site, uint64_t seed,
+                                        const uint64_t* seed_dev, void* stream) {
   using namespace vb;
   VB_REQUIRE((dy_f32 || dy_bf16) && x && mean && rstd && gamma && dx_f32, "layernorm_bwd: null pointer");
   VB_REQUIRE(rows >= 0 && cols > 0 && cols % 128 == 0, "layernorm_bwd: bad shape rows=%lld cols=%d", (long long)rows, cols);
   if (rows == 0) return VAULT_OK;
   cudaStream_t st = reinterpret_cast<cudaStream_t>(stream);
-#define CALL(V) ln_bwd_launch<V>(dy_f32, dy_bf16, x, mean, rstd, gamma, dres_f32, dx_f32, dx_bf16, dgamma, dbeta, rows, dropout_p, seed, site, st)
+#define CALL(V) ln_bwd_launch<V>(dy_f32, dy_bf16, x, mean, rstd, gamma, dres_f32, dx_f32, dx_bf16, dgamma, dbeta, rows, in_p, in_site, out_p, out_site, seed, reinterpret_cast<const unsigned long long*>(seed_dev), st)
   VB_LN_DISPATCH(cols, CALL)
 #undef CALL
 }
@@ -226,5 +239,5 @@ extern "C" int vault_layernorm_bwd_drop(const float* dy_f32, const void* dy_bf16
 extern "C" int vault_layernorm_bwd(const float* dy_f32, const void* dy_bf16, const float* x, const float* mean, const float* rstd,
                                    const float* gamma, const float* dres_f32, float* dx_f32, void* dx_bf16, float* dgamma, float* dbeta,
                                    int64_t rows, int32_t cols, void* stream) {
-  return vault_layernorm_bwd_drop(dy_f32, dy_bf16, x, mean, rstd, gamma, dres_f32, dx_f32, dx_bf16, dgamma, dbeta, rows, cols, 0.f, 0, 0, stream);
+  return vault_layernorm_bwd_drop(dy_f32, dy_bf16, x, mean, rstd, gamma, dres_f32, dx_f32, dx_bf16, dgamma, dbeta, rows, cols, 0.f, 0, 0.f, 0, 0, nullptr, stream);
 }

@@ -1,0 +1,677 @@
+"""Host-side engine of the VAuLT hot path on one B200: owns the flat parameter / gradient / bf16-shadow buffers and enqueues
+the sm_100a kernels (through the C ABI, include/vault_b200.h) for the whole forward and backward of
+
+    LM (BERT / RoBERTa, post-LN)  ->  ViLT text embed + im2col-free patch embed + sequence assembly
+    ->  12 x ViLT layer (pre-LN)  ->  final LayerNorm  ->  pooler
+
+mirroring ref:vault/models/vault/model.py:151-218 (VaultMixin.lm_preprocess / forward) and the HF modules it drives
+(HF:models/vilt/modeling_vilt.py:67-675, HF:models/bert/modeling_bert.py:53-453).  Only kernel launches, pointer arithmetic
+and buffer allocation happen here; every FLOP is in vault_b200/csrc.  There is no torch-op fallback.
+
+Precision plan: bf16 GEMM/attention operands with fp32 accumulation; the residual stream, LayerNorm statistics, softmax,
+pooler/head and all parameter gradients are fp32; master weights fp32 with a bf16 shadow for the tensor-core operands.
+"""
+from __future__ import annotations
+
+import ctypes as C
+import math
+from typing import Dict, List, Optional, Tuple
+
+import torch
+
+from . import _abi
+from ._abi import (EPI_ATOMIC_F32, EPI_BIAS_BF16, EPI_BIAS_F32, EPI_BIAS_GELU_BF16, EPI_BIAS_RESID_F32, EPI_DGELU_BF16,
+                   EPI_PLAIN_BF16, EPI_STORE_F32, GemmArgs)
+
+ALIGN = 64  # elements; every slot starts on a 256-byte (fp32) / 128-byte (bf16) boundary -> TMA- and float4-safe
+
+
+def _round_up(x: int, a: int) -> int:
+    return (x + a - 1) // a * a
+
+
+class Slot:
+    __slots__ = ("name", "off", "numel", "shape", "trainable")
+
+    def __init__(self, name, off, numel, shape, trainable):
+        self.name, self.off, self.numel, self.shape, self.trainable = name, off, numel, shape, trainable
+
+
+class Tape:
+    """Activations saved by a training-mode forward for its backward."""
+
+    def __init__(self):
+        self.t: Dict[str, torch.Tensor] = {}
+        self.meta: Dict[str, object] = {}
+        self.done = False
+
+
+class VaultEngine:
+    # dropout site ids: (stack, layer, kind)
+    SITE_LM_EMB = 1
+    SITE_HEAD = 2
+
+    @staticmethod
+    def _site(layer: int, kind: int) -> int:  # kind 0 attn-probs, 1 attn-out, 2 ffn-out
+        return 16 + layer * 4 + kind
+
+    def __init__(self, model):
+        self.model = model  # the nn.Module (VaultModel / VaultForTMSC) whose Parameters this engine serves
+        cfg = model.config
+        self.H = cfg.hidden_size
+        self.L = cfg.num_hidden_layers
+        self.heads = cfg.num_attention_heads
+        self.I = cfg.intermediate_size
+        self.patch = cfg.patch_size
+        self.grid = cfg.image_size // cfg.patch_size
+        self.C = cfg.num_channels
+        self.vilt_eps = float(cfg.layer_norm_eps)
+        if self.H // self.heads != 64:
+            raise RuntimeError("vault_b200 attention kernels are built for head_dim 64")
+        if self.H % 128 != 0 or self.H > 1024:
+            raise RuntimeError("vault_b200 LayerNorm kernels need hidden_size in {128,256,512,768,1024}")
+        self.lm = getattr(model, "bert", None)
+        if self.lm is not None:
+            lc = self.lm.config
+            if lc.hidden_size != self.H or lc.num_attention_heads != self.heads or lc.intermediate_size != self.I:
+                raise RuntimeError("vault_b200 needs LM and ViLT of the same width (bert-base / vilt-b32 family)")
+            self.lm_L = lc.num_hidden_layers
+            self.lm_eps = float(lc.layer_norm_eps)
+            self.lm_p = float(lc.hidden_dropout_prob)
+            self.lm_p_attn = float(lc.attention_probs_dropout_prob)
+            self.lm_roberta_pad = int(lc.pad_token_id) if lc.model_type in ("roberta", "xlm-roberta", "camembert") else -1
+            self.lm_word_pad = -1 if lc.pad_token_id is None else int(lc.pad_token_id)
+            self.lm_type_vocab = int(lc.type_vocab_size)
+        self.device = None
+        self.slots: Dict[str, Slot] = {}
+        self._sig = None
+        self._versions = None
+        self._g = GemmArgs()
+        self.seed = 0x5EED5EED
+        self.seed_dev: Optional[torch.Tensor] = None  # device counter added to the seed (advanced once per training step)
+        self.sms = 0
+
+    # ------------------------------------------------------------------------------------------------------------
+    # parameter packing
+    # ------------------------------------------------------------------------------------------------------------
+    def _param_order(self) -> Tuple[List[str], List[str]]:
+        """(trainable names in reverse-topological order, static names).  QKV weights/biases are adjacent so their
+        concatenation is one contiguous [3H,H] / [3H] slice (fused QKV GEMM and its wgrad write straight into it)."""
+        m = self.model
+        named = dict(m.named_parameters())
+        order: List[str] = []
+
+        def add(*names):
+            for n in names:
+                if n in named and n not in order:
+                    order.append(n)
+
+        add("classifier.1.weight", "classifier.1.bias")
+        add("pooler.dense.weight", "pooler.dense.bias", "layernorm.weight", "layernorm.bias")
+        for i in reversed(range(self.L)):
+            p = f"encoder.layer.{i}."
+            a = p + "attention.attention."
+            add(a + "query.weight", a + "key.weight", a + "value.weight", a + "query.bias", a + "key.bias", a + "value.bias")
+            add(p + "attention.output.dense.weight", p + "attention.output.dense.bias")
+            add(p + "layernorm_before.weight", p + "layernorm_before.bias", p + "layernorm_after.weight", p + "layernorm_after.bias")
+            add(p + "intermediate.dense.weight", p + "intermediate.dense.bias", p + "output.dense.weight", p + "output.dense.bias")
+        e = "embeddings."
+        add(e + "cls_token", e + "position_embeddings", e + "token_type_embeddings.weight", e + "patch_embeddings.projection.weight",
+            e + "patch_embeddings.projection.bias", e + "text_embeddings.token_type_embeddings.weight",
+            e + "text_embeddings.LayerNorm.weight", e + "text_embeddings.LayerNorm.bias",
+            e + "text_embeddings.position_embeddings.weight", e + "text_embeddings.word_embeddings.weight")
+        if self.lm is not None:
+            for i in reversed(range(self.lm_L)):
+                p = f"bert.encoder.layer.{i}."
+                a = p + "attention.self."
+                add(a + "query.weight", a + "key.weight", a + "value.weight", a + "query.bias", a + "key.bias", a + "value.bias")
+                add(p + "attention.output.dense.weight", p + "attention.output.dense.bias", p + "attention.output.LayerNorm.weight",
+                    p + "attention.output.LayerNorm.bias")
+                add(p + "intermediate.dense.weight", p + "intermediate.dense.bias", p + "output.dense.weight", p + "output.dense.bias",
+                    p + "output.LayerNorm.weight", p + "output.LayerNorm.bias")
+            b = "bert.embeddings."
+            add(b + "word_embeddings.weight", b + "position_embeddings.weight", b + "token_type_embeddings.weight",
+                b + "LayerNorm.weight", b + "LayerNorm.bias")
+        for n in named:  # anything else the subclass added (other heads): packed, never touched by this engine's kernels
+            add(n)
+        never = self.never_grad_names()
+        train = [n for n in order if named[n].requires_grad and n not in never]
+        static = [n for n in order if n not in train]
+        return train, static
+
+    def never_grad_names(self):
+        """ViLT parameters that receive grad=None whenever an LM is attached."""
+        if self.lm is None:
+            return set()
+        s = {"embeddings.text_embeddings.word_embeddings.weight"}
+        if not self.use_text_pos():
+            s.add("embeddings.text_embeddings.position_embeddings.weight")
+        return s
+
+    def use_text_pos(self) -> bool:
+        # transformers==4.48.0 gate (HF:models/vilt/modeling_vilt.py:240-272): add position embeddings iff "absolute"
+        te = self.model.embeddings.text_embeddings
+        return getattr(te, "position_embedding_type", "absolute") == "absolute"
+
+    def _signature(self):
+        return tuple((id(p), p.requires_grad) for p in self.model.parameters()) + (self.use_text_pos(),)
+
+    def ensure_packed(self, device: torch.device):
+        if device.type != "cuda":
+            raise RuntimeError("vault_b200 runs on CUDA (sm_100a) only -- there is no CPU path")
+        sig = self._signature()
+        if self._sig == sig and self.device == device and self._params_in_place():
+            return
+        _abi.check(_abi.lib().vault_check_device(device.index if device.index is not None else torch.cuda.current_device()), "check_device")
+        self.device = device
+        self.sms = torch.cuda.get_device_properties(device).multi_processor_count
+        named = dict(self.model.named_parameters())
+        train, static = self._param_order()
+        off = 0
+        slots: Dict[str, Slot] = {}
+        for n in train:
+            slots[n] = Slot(n, off, named[n].numel(), tuple(named[n].shape), True)
+            off += _round_up(named[n].numel(), ALIGN)
+        self.n_train = off
+        for n in static:
+            slots[n] = Slot(n, off, named[n].numel(), tuple(named[n].shape), False)
+            off += _round_up(named[n].numel(), ALIGN)
+        self.n_total = off
+        master = torch.zeros(self.n_total, device=device, dtype=torch.float32)
+        with torch.no_grad():
+            for n, s in slots.items():
+                view = master[s.off:s.off + s.numel].view(s.shape)
+                view.copy_(named[n].detach())
+                named[n].data = view  # the nn.Parameter now aliases the flat master buffer
+        self.master = master
+        self.shadow = torch.empty(self.n_total, device=device, dtype=torch.bfloat16)
+        self.grad = torch.zeros(max(self.n_train, ALIGN), device=device, dtype=torch.float32)
+        self.slots = slots
+        self._sig = sig
+        self._ptrs = {n: named[n].data_ptr() for n in slots}
+        self._params = [named[n] for n in slots]
+        self._grad_views = [(n, named[n], self.grad[s.off:s.off + s.numel].view(s.shape)) for n, s in slots.items() if s.trainable]
+        self._versions = None
+        self.seed_dev = torch.zeros(1, device=device, dtype=torch.int64)
+        # gradient ranges that are ACCUMULATED into (atomics): zero-filled at the start of every backward
+        self._zero_ranges = self._compute_zero_ranges()
+        self.opt_state = None
+
+    def _params_in_place(self) -> bool:
+        named = dict(self.model.named_parameters())
+        return all(named[n].data_ptr() == p for n, p in self._ptrs.items()) if len(named) == len(self._ptrs) else False
+
+    def refresh_shadow(self, force: bool = False):
+        """bf16 shadow <- fp32 masters, if any Parameter was modified in place since the last refresh."""
+        v = sum(p._version for p in self._params)
+        if force or v != self._versions:
+            _abi.call("vault_cast_f32_bf16", self.master.data_ptr(), self.shadow.data_ptr(), self.n_total, self._stream())
+            self._versions = v
+
+    def mark_shadow_fresh(self):
+        self._versions = sum(p._version for p in self._params)
+
+    # pointers ---------------------------------------------------------------------------------------------------
+    def w16(self, name):  # bf16 shadow of a weight
+        return self.shadow.data_ptr() + 2 * self.slots[name].off
+
+    def w32(self, name):
+        return self.master.data_ptr() + 4 * self.slots[name].off
+
+    def g32(self, name):  # gradient slot, or 0 (NULL) if the parameter is not trainable
+        s = self.slots.get(name)
+        if s is None or not s.trainable:
+            return 0
+        return self.grad.data_ptr() + 4 * s.off
+
+    def grad_view(self, name) -> Optional[torch.Tensor]:
+        s = self.slots[name]
+        if not s.trainable:
+            return None
+        return self.grad[s.off:s.off + s.numel].view(s.shape)
+
+    def _wgrad_split(self, n_out: int, k_out: int, tokens: int) -> int:
+        tiles = ((n_out + 127) // 128) * ((k_out + 127) // 128)
+        nkb = (tokens + 63) // 64
+        if tiles * 2 > self.sms:
+            return 1
+        return max(1, min(8, self.sms // tiles, max(1, nkb // 4)))
+
+    def _compute_zero_ranges(self):
+        """Everything except the big dense weights (whose wgrad GEMM overwrites them, unless it runs split-K -- decided per
+        call and zeroed there) is accumulated with atomics: biases, LayerNorm affine, embedding tables, cls/pos/modality."""
+        big = set()
+        for n, s in self.slots.items():
+            if not s.trainable:
+                continue
+            if n.endswith("dense.weight") and "pooler" not in n:
+                big.add(n)
+            if any(n.endswith(k + ".weight") for k in ("query", "key", "value")):
+                big.add(n)
+            if n.endswith("projection.weight"):
+                big.add(n)
+        ranges = []
+        for n, s in sorted(self.slots.items(), key=lambda kv: kv[1].off):
+            if not s.trainable or n in big or n.startswith("classifier.") or n.startswith("pooler."):
+                continue  # big weights, pooler and classifier gradients are overwritten by their kernels
+            a, b = s.off, s.off + _round_up(s.numel, ALIGN)
+            if ranges and ranges[-1][1] == a:
+                ranges[-1][1] = b
+            else:
+                ranges.append([a, b])
+        return [(a, b) for a, b in ranges]
+
+    # ------------------------------------------------------------------------------------------------------------
+    # kernel launch helpers
+    # ------------------------------------------------------------------------------------------------------------
+    def _stream(self) -> int:
+        return torch.cuda.current_stream(self.device).cuda_stream
+
+    def _new(self, shape, dtype) -> torch.Tensor:
+        return torch.empty(shape, device=self.device, dtype=dtype)
+
+    def gemm(self, A, lda, a_mn, B, ldb, b_mn, M, N, K, epi, out, ldo, bias=0, resid=0, ldr=0, aux=0, ldaux=0, out2=0, ldo2=0, p=0.0, site=0,
+             split_k=1, block_n=0):
+        g = self._g
+        g.M, g.N, g.K = M, N, K
+        g.A, g.lda, g.a_mn = A, lda, a_mn
+        g.B, g.ldb, g.b_mn = B, ldb, b_mn
+        g.epilogue = epi
+        g.bias, g.resid, g.ldr = bias or None, resid or None, ldr
+        g.aux, g.ldaux = aux or None, ldaux
+        g.out, g.ldo, g.out2, g.ldo2 = out, ldo, out2 or None, ldo2
+        g.dropout_p, g.seed, g.site = p, self.seed, site
+        g.seed_dev = self.seed_dev.data_ptr() if p > 0.0 else None
+        g.split_k, g.block_n, g.max_ctas = split_k, block_n, 0
+        rc = self._lib.vault_gemm_bf16(C.byref(g), self._st)
+        if rc:
+            _abi.check(rc, "vault_gemm_bf16")
+
+    def linear_fwd(self, x16, M, wname, bname, N, K, epi, out, **kw):
+        """y = x W^T + b : A = x [M,K], B = W [N,K] (bf16 shadow), fp32 bias."""
+        self.gemm(x16.data_ptr(), K, 0, self.w16(wname), K, 0, M, N, K, epi, out.data_ptr(), N, bias=self.w32(bname), **kw)
+
+    def linear_dgrad(self, dy16, M, wname, N_out, K_in, epi, out, **kw):
+        """dx[M,K_in] = dy[M,N_out] W[N_out,K_in] : contraction over N_out, W read un-transposed as the MN-major operand."""
+        self.gemm(dy16.data_ptr(), N_out, 0, self.w16(wname), K_in, 1, M, K_in, N_out, epi, out.data_ptr(), K_in, **kw)
+
+    def linear_wgrad(self, dy16, x16, M, wname, bname, N_out, K_in):
+        """dW[N_out,K_in] = dy^T x (contraction over the M tokens, both operands read un-transposed), db = colsum(dy)."""
+        gw = self.g32(wname)
+        if gw:
+            split = self._wgrad_split(N_out, K_in, M)
+            if split > 1:
+                off = self.slots[wname].off
+                self.grad[off:off + N_out * K_in].zero_()  # the whole fused slice (q,k,v adjacent), not just the first tensor
+                self.gemm(dy16.data_ptr(), N_out, 1, x16.data_ptr(), K_in, 1, N_out, K_in, M, EPI_ATOMIC_F32, gw, K_in, split_k=split, block_n=128)
+            else:
+                self.gemm(dy16.data_ptr(), N_out, 1, x16.data_ptr(), K_in, 1, N_out, K_in, M, EPI_STORE_F32, gw, K_in, block_n=128)
+        gb = self.g32(bname)
+        if gb:
+            rc = self._lib.vault_colsum_bf16(dy16.data_ptr(), N_out, gb, M, N_out, self._st)
+            if rc:
+                _abi.check(rc, "vault_colsum_bf16")
+
+    def ln_fwd(self, x32, rows, gname, bname, eps, want16=True, want32=False, p=0.0, site=0):
+        y16 = self._new((rows, self.H), torch.bfloat16) if want16 else None
+        y32 = self._new((rows, self.H), torch.float32) if want32 else None
+        stats = self._new((2, rows), torch.float32)
+        rc = self._lib.vault_layernorm_fwd_drop(x32.data_ptr(), self.w32(gname), self.w32(bname), y16.data_ptr() if want16 else None,
+                                                y32.data_ptr() if want32 else None, stats.data_ptr(), stats.data_ptr() + 4 * rows, rows, self.H, eps,
+                                                p, self.seed, self.seed_dev.data_ptr() if p > 0 else None, site, self._st)
+        if rc:
+            _abi.check(rc, "vault_layernorm_fwd")
+        return y16, y32, stats
+
+    def ln_bwd(self, dy32, dy16, x32, stats, rows, gname, bname, dres32=None, want16=True, in_p=0.0, in_site=0, out_p=0.0, out_site=0):
+        dx32 = self._new((rows, self.H), torch.float32)
+        dx16 = self._new((rows, self.H), torch.bfloat16) if want16 else None
+        use_seed = in_p > 0 or out_p > 0
+        rc = self._lib.vault_layernorm_bwd_drop(dy32.data_ptr() if dy32 is not None else None, dy16.data_ptr() if dy16 is not None else None,
+                                                x32.data_ptr(), stats.data_ptr(), stats.data_ptr() + 4 * rows, self.w32(gname),
+                                                dres32.data_ptr() if dres32 is not None else None, dx32.data_ptr(),
+                                                dx16.data_ptr() if want16 else None, self.g32(gname) or None, self.g32(bname) or None, rows, self.H,
+                                                in_p, in_site, out_p, out_site, self.seed, self.seed_dev.data_ptr() if use_seed else None, self._st)
+        if rc:
+            _abi.check(rc, "vault_layernorm_bwd")
+        return dx32, dx16
+
+    def attn_fwd(self, qkv, key_mask, B, S, p=0.0, site=0, want_lse=True):
+        ctx = self._new((B * S, self.H), torch.bfloat16)
+        lse = self._new((B, self.heads, S), torch.float32) if want_lse else None
+        rc = self._lib.vault_attn_fwd(qkv.data_ptr(), key_mask.data_ptr(), ctx.data_ptr(), lse.data_ptr() if want_lse else None, B, S, self.heads, p,
+                                      self.seed, self.seed_dev.data_ptr() if p > 0 else None, site, self._st)
+        if rc:
+            _abi.check(rc, "vault_attn_fwd")
+        return ctx, lse
+
+    def attn_bwd(self, qkv, key_mask, ctx, dctx, lse, B, S, p=0.0, site=0):
+        dqkv = self._new((B * S, 3 * self.H), torch.bfloat16)
+        delta = self._new((B, self.heads, S), torch.float32)
+        rc = self._lib.vault_attn_bwd(qkv.data_ptr(), key_mask.data_ptr(), ctx.data_ptr(), dctx.data_ptr(), lse.data_ptr(), delta.data_ptr(),
+                                      dqkv.data_ptr(), B, S, self.heads, p, self.seed, self.seed_dev.data_ptr() if p > 0 else None, site, self._st)
+        if rc:
+            _abi.check(rc, "vault_attn_bwd")
+        return dqkv
+
+    # ------------------------------------------------------------------------------------------------------------
+    # transformer layers (shared by the LM and ViLT stacks)
+    # ------------------------------------------------------------------------------------------------------------
+    def _names(self, prefix: str, i: int, vilt: bool):
+        p = f"{prefix}encoder.layer.{i}."
+        a = p + ("attention.attention." if vilt else "attention.self.")
+        return dict(
+            qkv_w=a + "query.weight", qkv_b=a + "query.bias", o_w=p + "attention.output.dense.weight", o_b=p + "attention.output.dense.bias",
+            w1=p + "intermediate.dense.weight", b1=p + "intermediate.dense.bias", w2=p + "output.dense.weight", b2=p + "output.dense.bias",
+            ln1=p + ("layernorm_before" if vilt else "attention.output.LayerNorm"), ln2=p + ("layernorm_after" if vilt else "output.LayerNorm"),
+        )
+
+    def _attn_block_fwd(self, x16, M, B, S, nm, key_mask, p_attn, site, save: Optional[dict], li):
+        H = self.H
+        qkv = self._new((M, 3 * H), torch.bfloat16)
+        self.linear_fwd(x16, M, nm["qkv_w"], nm["qkv_b"], 3 * H, H, EPI_BIAS_BF16, qkv)
+        ctx, lse = self.attn_fwd(qkv, key_mask, B, S, p=p_attn, site=site, want_lse=save is not None)
+        if save is not None:
+            save[f"{li}.qkv"], save[f"{li}.ctx"], save[f"{li}.lse"] = qkv, ctx, lse
+        return ctx
+
+    def _mlp_fwd(self, n16, M, nm, resid32, p_out, site, save: Optional[dict], li):
+        H, I = self.H, self.I
+        act = self._new((M, I), torch.bfloat16)
+        pre = self._new((M, I), torch.bfloat16) if save is not None else None
+        self.linear_fwd(n16, M, nm["w1"], nm["b1"], I, H, EPI_BIAS_GELU_BF16, act, out2=pre.data_ptr() if pre is not None else 0, ldo2=I)
+        y32 = self._new((M, H), torch.float32)
+        self.linear_fwd(act, M, nm["w2"], nm["b2"], H, I, EPI_BIAS_RESID_F32, y32, resid=resid32.data_ptr(), ldr=H, p=p_out, site=site)
+        if save is not None:
+            save[f"{li}.pre"], save[f"{li}.act"] = pre, act
+        return y32
+
+    # ---- ViLT (pre-LN) -----------------------------------------------------------------------------------------
+    def vilt_layer_fwd(self, i, x32, M, B, S, key_mask, save):
+        nm = self._names("", i, True)
+        li = f"v{i}"
+        n1, _, st1 = self.ln_fwd(x32, M, nm["ln1"] + ".weight", nm["ln1"] + ".bias", self.vilt_eps)
+        ctx = self._attn_block_fwd(n1, M, B, S, nm, key_mask, 0.0, 0, save, li)
+        h32 = self._new((M, self.H), torch.float32)
+        self.linear_fwd(ctx, M, nm["o_w"], nm["o_b"], self.H, self.H, EPI_BIAS_RESID_F32, h32, resid=x32.data_ptr(), ldr=self.H)
+        n2, _, st2 = self.ln_fwd(h32, M, nm["ln2"] + ".weight", nm["ln2"] + ".bias", self.vilt_eps)
+        y32 = self._mlp_fwd(n2, M, nm, h32, 0.0, 0, save, li)
+        if save is not None:
+            save[f"{li}.x"], save[f"{li}.st1"], save[f"{li}.n1"] = x32, st1, n1
+            save[f"{li}.h"], save[f"{li}.st2"], save[f"{li}.n2"] = h32, st2, n2
+        return y32
+
+    def vilt_layer_bwd(self, i, g32, g16, M, B, S, key_mask, sv):
+        nm = self._names("", i, True)
+        li = f"v{i}"
+        H, I = self.H, self.I
+        dpre = self._new((M, I), torch.bfloat16)
+        self.linear_dgrad(g16, M, nm["w2"], H, I, EPI_DGELU_BF16, dpre, aux=sv[f"{li}.pre"].data_ptr(), ldaux=I)
+        self.linear_wgrad(g16, sv[f"{li}.act"], M, nm["w2"], nm["b2"], H, I)
+        dn2 = self._new((M, H), torch.bfloat16)
+        self.linear_dgrad(dpre, M, nm["w1"], I, H, EPI_PLAIN_BF16, dn2)
+        self.linear_wgrad(dpre, sv[f"{li}.n2"], M, nm["w1"], nm["b1"], I, H)
+        g2_32, g2_16 = self.ln_bwd(None, dn2, sv[f"{li}.h"], sv[f"{li}.st2"], M, nm["ln2"] + ".weight", nm["ln2"] + ".bias", dres32=g32)
+        dctx = self._new((M, H), torch.bfloat16)
+        self.linear_dgrad(g2_16, M, nm["o_w"], H, H, EPI_PLAIN_BF16, dctx)
+        self.linear_wgrad(g2_16, sv[f"{li}.ctx"], M, nm["o_w"], nm["o_b"], H, H)
+        dqkv = self.attn_bwd(sv[f"{li}.qkv"], key_mask, sv[f"{li}.ctx"], dctx, sv[f"{li}.lse"], B, S)
+        dn1 = self._new((M, H), torch.bfloat16)
+        self.linear_dgrad(dqkv, M, nm["qkv_w"], 3 * H, H, EPI_PLAIN_BF16, dn1)
+        self.linear_wgrad(dqkv, sv[f"{li}.n1"], M, nm["qkv_w"], nm["qkv_b"], 3 * H, H)
+        return self.ln_bwd(None, dn1, sv[f"{li}.x"], sv[f"{li}.st1"], M, nm["ln1"] + ".weight", nm["ln1"] + ".bias", dres32=g2_32)
+
+    # ---- LM (post-LN, dropout when training) ---------------------------------------------------------------------
+    def lm_layer_fwd(self, i, r32, x16, M, B, T, key_mask, save, train):
+        nm = self._names("bert.", i, False)
+        li = f"l{i}"
+        p, pa = (self.lm_p, self.lm_p_attn) if train else (0.0, 0.0)
+        ctx = self._attn_block_fwd(x16, M, B, T, nm, key_mask, pa, self._site(i, 0), save, li)
+        t32 = self._new((M, self.H), torch.float32)
+        self.linear_fwd(ctx, M, nm["o_w"], nm["o_b"], self.H, self.H, EPI_BIAS_RESID_F32, t32, resid=r32.data_ptr(), ldr=self.H, p=p,
+                        site=self._site(i, 1))
+        a16, a32, st1 = self.ln_fwd(t32, M, nm["ln1"] + ".weight", nm["ln1"] + ".bias", self.lm_eps, want32=True)
+        s32 = self._mlp_fwd(a16, M, nm, a32, p, self._site(i, 2), save, li)
+        y16, y32, st2 = self.ln_fwd(s32, M, nm["ln2"] + ".weight", nm["ln2"] + ".bias", self.lm_eps, want32=True)
+        if save is not None:
+            save[f"{li}.x16"], save[f"{li}.t"], save[f"{li}.st1"], save[f"{li}.a16"] = x16, t32, st1, a16
+            save[f"{li}.s"], save[f"{li}.st2"] = s32, st2
+        return y32, y16
+
+    def lm_layer_bwd(self, i, g32, gx16, M, B, T, key_mask, sv, train):
+        """g32 (+ gx16) = gradient w.r.t. the layer's output y = LN_b(s).  Returns (dt32, gx16') for the layer below."""
+        nm = self._names("bert.", i, False)
+        li = f"l{i}"
+        H, I = self.H, self.I
+        p, pa = (self.lm_p, self.lm_p_attn) if train else (0.0, 0.0)
+        ds32, ds16 = self.ln_bwd(g32, gx16, sv[f"{li}.s"], sv[f"{li}.st2"], M, nm["ln2"] + ".weight", nm["ln2"] + ".bias", out_p=p,
+                                 out_site=self._site(i, 2))
+        dpre = self._new((M, I), torch.bfloat16)
+        self.linear_dgrad(ds16, M, nm["w2"], H, I, EPI_DGELU_BF16, dpre, aux=sv[f"{li}.pre"].data_ptr(), ldaux=I)
+        self.linear_wgrad(ds16, sv[f"{li}.act"], M, nm["w2"], nm["b2"], H, I)
+        da16 = self._new((M, H), torch.bfloat16)
+        self.linear_dgrad(dpre, M, nm["w1"], I, H, EPI_PLAIN_BF16, da16)
+        self.linear_wgrad(dpre, sv[f"{li}.a16"], M, nm["w1"], nm["b1"], I, H)
+        dt32, dt16 = self.ln_bwd(ds32, da16, sv[f"{li}.t"], sv[f"{li}.st1"], M, nm["ln1"] + ".weight", nm["ln1"] + ".bias", out_p=p,
+                                 out_site=self._site(i, 1))
+        dctx = self._new((M, H), torch.bfloat16)
+        self.linear_dgrad(dt16, M, nm["o_w"], H, H, EPI_PLAIN_BF16, dctx)
+        self.linear_wgrad(dt16, sv[f"{li}.ctx"], M, nm["o_w"], nm["o_b"], H, H)
+        dqkv = self.attn_bwd(sv[f"{li}.qkv"], key_mask, sv[f"{li}.ctx"], dctx, sv[f"{li}.lse"], B, T, p=pa, site=self._site(i, 0))
+        gx = self._new((M, H), torch.bfloat16)
+        self.linear_dgrad(dqkv, M, nm["qkv_w"], 3 * H, H, EPI_PLAIN_BF16, gx)
+        self.linear_wgrad(dqkv, sv[f"{li}.x16"], M, nm["qkv_w"], nm["qkv_b"], 3 * H, H)
+        return dt32, gx
+
+    # ------------------------------------------------------------------------------------------------------------
+    # whole-model forward / backward
+    # ------------------------------------------------------------------------------------------------------------
+    def patch_hw(self, pixel_mask: Optional[torch.Tensor], B, Hi, Wi) -> Tuple[torch.Tensor, int]:
+        """Per-sample valid patch grid on the device and Pmax = max_b h_b*w_b (HF:models/vilt/modeling_vilt.py:95-98,130-136).
+        A data-dependent output length needs ONE small device->host read, as in the reference; pass pixel_mask=None (all
+        valid) or use TrainStep (static shapes) to avoid it."""
+        gh, gw = Hi // self.patch, Wi // self.patch
+        hw = self._new((B, 2), torch.int32)
+        if pixel_mask is None:
+            hw[:, 0] = gh
+            hw[:, 1] = gw
+            return hw, gh * gw
+        if pixel_mask.dtype not in (torch.int64, torch.float32):
+            pixel_mask = pixel_mask.to(torch.int64)
+        pixel_mask = pixel_mask.contiguous()
+        _abi.call("vault_patch_grid", pixel_mask.data_ptr(), int(pixel_mask.dtype == torch.float32), hw.data_ptr(), B, Hi, Wi, self.patch, self._st)
+        pmax = int((hw[:, 0] * hw[:, 1]).max().item())
+        return hw, pmax
+
+    def forward(self, input_ids, attention_mask, token_type_ids, pixel_values, pixel_mask, image_token_type_idx=1, training=False,
+                need_grad=False, hw: Optional[torch.Tensor] = None, pmax: Optional[int] = None):
+        """Returns (last_hidden_state fp32 [B,S,H], pooler_output fp32 [B,H] or None, key_mask uint8 [B,S], tape or None)."""
+        dev = pixel_values.device
+        self.ensure_packed(dev)
+        self._lib, self._st = _abi.lib(), self._stream()
+        self.refresh_shadow()
+        H = self.H
+        B, T = input_ids.shape
+        Cc, Hi, Wi = pixel_values.shape[1:]
+        if Cc != self.C or Hi % self.patch or Wi % self.patch:
+            raise ValueError(f"pixel_values {tuple(pixel_values.shape)}: need {self.C} channels and sides divisible by {self.patch}")
+        gh, gw = Hi // self.patch, Wi // self.patch
+        input_ids = input_ids.contiguous()
+        if input_ids.dtype != torch.int64:
+            input_ids = input_ids.to(torch.int64)
+        if attention_mask is not None:
+            attention_mask = attention_mask.contiguous() if attention_mask.dtype == torch.int64 else attention_mask.to(torch.int64)
+        if token_type_ids is not None:
+            token_type_ids = token_type_ids.contiguous() if token_type_ids.dtype == torch.int64 else token_type_ids.to(torch.int64)
+        pixel_values = pixel_values.contiguous() if pixel_values.dtype == torch.float32 else pixel_values.float().contiguous()
+        tape = Tape() if need_grad else None
+        sv = tape.t if tape is not None else None
+        Mt = B * T
+        am_ptr = attention_mask.data_ptr() if attention_mask is not None else None
+        tt_ptr = token_type_ids.data_ptr() if token_type_ids is not None else None
+        lib, st = self._lib, self._st
+
+        # ---------------- text: LM or ViLT word embeddings -> inputs_embeds fp32 [Mt,H] ----------------
+        lm_trains = self.lm is not None and not getattr(self.model, "freeze_lm", False) and need_grad
+        if self.lm is not None:
+            # ref:vault/models/vault/model.py:174-180: the LM sees zero type ids when its type vocabulary has < 2 entries
+            lm_tt = None if self.lm_type_vocab < 2 else tt_ptr
+            lm_train_mode = training  # ref :189 only disables grad for a frozen LM; dropout follows module.training
+            lsv = sv if lm_trains else None
+            x_sum = self._new((Mt, H), torch.float32)
+            lm_mask = self._new((B, T), torch.uint8)
+            _abi.check(lib.vault_lm_embed_fwd(input_ids.data_ptr(), lm_tt, self.w32("bert.embeddings.word_embeddings.weight"),
+                                              self.w32("bert.embeddings.token_type_embeddings.weight"),
+                                              self.w32("bert.embeddings.position_embeddings.weight"), x_sum.data_ptr(), am_ptr, lm_mask.data_ptr(), B, T,
+                                              H, self.lm_roberta_pad, st), "lm_embed_fwd")
+            p_emb = self.lm_p if lm_train_mode else 0.0
+            x16, r32, st0 = self.ln_fwd(x_sum, Mt, "bert.embeddings.LayerNorm.weight", "bert.embeddings.LayerNorm.bias", self.lm_eps, want32=True,
+                                        p=p_emb, site=self.SITE_LM_EMB)
+            if lsv is not None:
+                lsv["lm.x_sum"], lsv["lm.st0"], lsv["lm.mask"] = x_sum, st0, lm_mask
+            for i in range(self.lm_L):
+                r32, x16 = self.lm_layer_fwd(i, r32, x16, Mt, B, T, lm_mask, lsv, lm_train_mode)
+            inputs_embeds = r32
+            text_pos = self.w32("embeddings.text_embeddings.position_embeddings.weight") if self.use_text_pos() else None
+            v_sum = self._new((Mt, H), torch.float32)
+            _abi.check(lib.vault_vilt_text_embed_fwd(inputs_embeds.data_ptr(), tt_ptr, self.w32("embeddings.text_embeddings.token_type_embeddings.weight"),
+                                                     text_pos, v_sum.data_ptr(), B, T, H, st), "vilt_text_embed_fwd")
+        else:
+            v_sum = self._new((Mt, H), torch.float32)
+            _abi.check(lib.vault_lm_embed_fwd(input_ids.data_ptr(), tt_ptr, self.w32("embeddings.text_embeddings.word_embeddings.weight"),
+                                              self.w32("embeddings.text_embeddings.token_type_embeddings.weight"),
+                                              self.w32("embeddings.text_embeddings.position_embeddings.weight"), v_sum.data_ptr(), None, None, B, T, H,
+                                              -1, st), "vilt_word_embed_fwd")
+        _, text_ln, st_t = self.ln_fwd(v_sum, Mt, "embeddings.text_embeddings.LayerNorm.weight", "embeddings.text_embeddings.LayerNorm.bias",
+                                       self.vilt_eps, want16=False, want32=True)
+
+        # ---------------- image: patch projection + assembly ----------------
+        G = gh * gw
+        Kp = self.C * self.patch * self.patch
+        patches = self._new((B * G, Kp), torch.bfloat16)
+        _abi.check(lib.vault_patchify_bf16(pixel_values.data_ptr(), patches.data_ptr(), B, self.C, Hi, Wi, self.patch, st), "patchify")
+        patch_out = self._new((B * G, H), torch.float32)
+        self.gemm(patches.data_ptr(), Kp, 0, self.w16("embeddings.patch_embeddings.projection.weight"), Kp, 0, B * G, H, Kp, EPI_BIAS_F32,
+                  patch_out.data_ptr(), H, bias=self.w32("embeddings.patch_embeddings.projection.bias"))
+        if hw is None:
+            hw, pmax = self.patch_hw(pixel_mask, B, Hi, Wi)
+        S = T + 1 + pmax
+        M = B * S
+        X = self._new((B, S, H), torch.float32)
+        key_mask = self._new((B, S), torch.uint8)
+        _abi.check(lib.vault_vilt_assemble_fwd(text_ln.data_ptr(), patch_out.data_ptr(), self.w32("embeddings.cls_token"),
+                                               self.w32("embeddings.position_embeddings"), self.w32("embeddings.token_type_embeddings.weight"), am_ptr,
+                                               hw.data_ptr(), X.data_ptr(), key_mask.data_ptr(), B, T, pmax, gh, gw, self.grid, H,
+                                               int(image_token_type_idx), st), "vilt_assemble_fwd")
+        if sv is not None:
+            sv["v_sum"], sv["st_t"], sv["patches"], sv["hw"], sv["key_mask"] = v_sum, st_t, patches, hw, key_mask
+            sv["ids"], sv["tt"], sv["am"] = input_ids, token_type_ids, attention_mask
+            tape.meta.update(B=B, T=T, S=S, pmax=pmax, gh=gh, gw=gw, Hi=Hi, Wi=Wi, img_type=int(image_token_type_idx), training=training,
+                             lm_trains=lm_trains)
+
+        # ---------------- ViLT encoder, final LN, pooler ----------------
+        x32 = X.view(M, H)
+        for i in range(self.L):
+            x32 = self.vilt_layer_fwd(i, x32, M, B, S, key_mask, sv)
+        _, lhs, st_f = self.ln_fwd(x32, M, "layernorm.weight", "layernorm.bias", self.vilt_eps, want16=False, want32=True)
+        pooled = None
+        if "pooler.dense.weight" in self.slots:
+            pooled = self._new((B, H), torch.float32)
+            _abi.check(lib.vault_small_linear_fwd(lhs.data_ptr(), S * H, self.w32("pooler.dense.weight"), self.w32("pooler.dense.bias"),
+                                                  pooled.data_ptr(), B, H, H, 1, st), "pooler_fwd")
+        if sv is not None:
+            sv["x_final"], sv["st_f"], sv["lhs"], sv["pooled"] = x32, st_f, lhs, pooled
+        return lhs.view(B, S, H), pooled, key_mask, tape
+
+    def attach_grads(self, exclude_prefix: Optional[str] = None, only_prefix: Optional[str] = None):
+        """p.grad <- view of the flat gradient buffer (no copy).  A foreign p.grad tensor is accumulated into instead."""
+        for n, p, view in self._grad_views:
+            if only_prefix is not None and not n.startswith(only_prefix):
+                continue
+            if exclude_prefix is not None and n.startswith(exclude_prefix):
+                continue
+            if p.grad is None:
+                p.grad = view
+            elif p.grad.data_ptr() != view.data_ptr():
+                p.grad.add_(view)
+
+    def zero_accumulated_grads(self):
+        for a, b in self._zero_ranges:
+            self.grad[a:b].zero_()
+
+    def backward(self, tape: Tape, dlhs: Optional[torch.Tensor], dpooled: Optional[torch.Tensor]):
+        """Fills self.grad (fp32, flat) with dL/dparam for every trainable parameter; returns nothing."""
+        if tape.done:
+            raise RuntimeError("vault_b200: backward called twice on the same forward (activations already released)")
+        self._lib, self._st = _abi.lib(), self._stream()
+        lib, st = self._lib, self._st
+        sv, mt = tape.t, tape.meta
+        B, T, S, pmax, gh, gw = mt["B"], mt["T"], mt["S"], mt["pmax"], mt["gh"], mt["gw"]
+        H, M, Mt = self.H, B * S, B * T
+        self.zero_accumulated_grads()
+        if dlhs is not None:
+            g_lhs = dlhs.contiguous().float().clone().view(M, H)
+        else:
+            g_lhs = torch.zeros((M, H), device=self.device, dtype=torch.float32)
+        if dpooled is not None and sv["pooled"] is not None:
+            dpooled = dpooled.contiguous().float()
+            _abi.check(lib.vault_small_linear_bwd(dpooled.data_ptr(), sv["pooled"].data_ptr(), sv["lhs"].data_ptr(), S * H, self.w32("pooler.dense.weight"),
+                                                  g_lhs.data_ptr(), S * H, 1, self.g32("pooler.dense.weight") or None,
+                                                  self.g32("pooler.dense.bias") or None, B, H, H, 1, st), "pooler_bwd")
+        g32, g16 = self.ln_bwd(g_lhs, None, sv["x_final"], sv["st_f"], M, "layernorm.weight", "layernorm.bias")
+        for i in reversed(range(self.L)):
+            g32, g16 = self.vilt_layer_bwd(i, g32, g16, M, B, S, sv["key_mask"], sv)
+        # ---- embeddings ----
+        dtext_ln = self._new((Mt, H), torch.float32)
+        dpatch = self._new((B * gh * gw, H), torch.bfloat16)
+        _abi.check(lib.vault_vilt_assemble_bwd(g32.data_ptr(), sv["hw"].data_ptr(), dtext_ln.data_ptr(), dpatch.data_ptr(),
+                                               self.g32("embeddings.cls_token") or None, self.g32("embeddings.position_embeddings") or None,
+                                               self.g32("embeddings.token_type_embeddings.weight") or None, B, T, pmax, gh, gw, self.grid, H,
+                                               mt["img_type"], st), "vilt_assemble_bwd")
+        Kp = self.C * self.patch * self.patch
+        self.linear_wgrad(dpatch, sv["patches"], B * gh * gw, "embeddings.patch_embeddings.projection.weight",
+                          "embeddings.patch_embeddings.projection.bias", H, Kp)
+        dv_sum, _ = self.ln_bwd(dtext_ln, None, sv["v_sum"], sv["st_t"], Mt, "embeddings.text_embeddings.LayerNorm.weight",
+                                "embeddings.text_embeddings.LayerNorm.bias", want16=False)
+        tt_ptr = sv["tt"].data_ptr() if sv["tt"] is not None else None
+        if self.lm is not None:
+            gpos = self.g32("embeddings.text_embeddings.position_embeddings.weight") if self.use_text_pos() else 0
+            _abi.check(lib.vault_vilt_text_embed_bwd(tt_ptr, dv_sum.data_ptr(), self.g32("embeddings.text_embeddings.token_type_embeddings.weight") or None,
+                                                     gpos or None, B, T, H, st), "vilt_text_embed_bwd")
+            if mt["lm_trains"]:
+                self._lm_backward(dv_sum, sv, B, T, mt["training"])
+        else:
+            _abi.check(lib.vault_lm_embed_bwd(sv["ids"].data_ptr(), tt_ptr, dv_sum.data_ptr(),
+                                              self.g32("embeddings.text_embeddings.word_embeddings.weight") or None,
+                                              self.g32("embeddings.text_embeddings.token_type_embeddings.weight") or None,
+                                              self.g32("embeddings.text_embeddings.position_embeddings.weight") or None, B, T, H, -1,
+                                              int(getattr(self.model.config, "pad_token_id", -1) if getattr(self.model.config, "pad_token_id", None) is not None else -1),
+                                              st), "vilt_word_embed_bwd")
+        tape.done = True
+        tape.t = {}
+
+    def _lm_backward(self, g32, sv, B, T, train):
+        lib, st = self._lib, self._st
+        Mt, H = B * T, self.H
+        gx16 = None
+        for i in reversed(range(self.lm_L)):
+            g32, gx16 = self.lm_layer_bwd(i, g32, gx16, Mt, B, T, sv["lm.mask"], sv, train)
+        p_emb = self.lm_p if train else 0.0
+        dx_sum, _ = self.ln_bwd(g32, gx16, sv["lm.x_sum"], sv["lm.st0"], Mt, "bert.embeddings.LayerNorm.weight", "bert.embeddings.LayerNorm.bias",
+                                want16=False, in_p=p_emb, in_site=self.SITE_LM_EMB)
+        lm_tt = None if (self.lm_type_vocab < 2 or sv["tt"] is None) else sv["tt"].data_ptr()
+        _abi.check(lib.vault_lm_embed_bwd(sv["ids"].data_ptr(), lm_tt, dx_sum.data_ptr(), self.g32("bert.embeddings.word_embeddings.weight") or None,
+                                          self.g32("bert.embeddings.token_type_embeddings.weight") or None,
+                                          self.g32("bert.embeddings.position_embeddings.weight") or None, B, T, H, self.lm_roberta_pad,
+                                          self.lm_word_pad, st), "lm_embed_bwd")
+
+    # ------------------------------------------------------------------------------------------------------------
+    # fused optimizer (transformers==4.48.0 AdamW rule) over the flat trainable range
+    # ------------------------------------------------------------------------------------------------------------
+    def adamw_step(self, lr: float, beta1=0.9, beta2=0.999, eps=1e-8, weight_decay=0.0, correct_bias=False, grad_scale=1.0):
+        if self.opt_state is None:
+            self.opt_state = dict(step=0, m=torch.zeros(self.n_train, device=self.device), v=torch.zeros(self.n_train, device=self.device))
+        s = self.opt_state
+        s["step"] += 1
+        _abi.call("vault_adamw_step", self.master.data_ptr(), self.grad.data_ptr(), s["m"].data_ptr(), s["v"].data_ptr(), self.shadow.data_ptr(),
+                  self.n_train, lr, beta1, beta2, eps, weight_decay, int(correct_bias), s["step"], grad_scale, self._stream())

@@ -1,0 +1,260 @@
+"""Drop-in mirror of the reference's model classes (ref:vault/models/vault/model.py) on top of the sm_100a engine.
+
+Same class names, constructor / ``from_pretrained`` signatures, HF-compatible ``state_dict`` keys and ``forward`` contract:
+
+    VaultModel(vilt_config, bert_config=None, freeze_lm=False, vilt_dropout_prob=0.0, use_vilt_position_embeddings=False)
+    VaultModel.from_pretrained(pretrained_vilt, pretrained_bert=None, freeze_lm=False, use_vilt_position_embeddings=False)
+    VaultForTMSC(vilt_config, n_classes=3, vilt_dropout_prob=0.1, logging_level=None, bert_config=None)
+    model(input_ids, attention_mask, token_type_ids, pixel_values, pixel_mask) -> .last_hidden_state / .pooler_output (or logits)
+
+The HF ``ViltModel`` / ``AutoModel`` classes are inherited / instantiated ONLY as parameter containers (identical keys, working
+``from_pretrained`` / ``save_pretrained`` / ``resize_token_embeddings``); their ``forward`` methods are never called: every
+forward and backward goes through ``vault_b200.engine.VaultEngine`` -> C ABI -> CUDA kernels.  No CPU / eager fallback.
+
+Differences from the reference, all deliberate:
+  * image tokens come out in raster order (valid patches first) instead of a random permutation -- ``pooler_output`` and the
+    text rows are unaffected, image rows match after un-permuting the reference with its ``patch_index``;
+  * ``head_mask``, ``output_attentions``, ``output_hidden_states``, ``image_embeds`` and (with an LM) ``inputs_embeds`` are not
+    on the hot path and raise ``NotImplementedError``;
+  * gradients are written into one flat fp32 buffer and ``p.grad`` are views of it: zero (or ``None``) them between backward
+    calls as the reference trainer does (ref:vault/tmsc_utils/trainer.py:364); accumulation across backwards is not supported.
+"""
+from __future__ import annotations
+
+import logging
+from abc import ABC
+from typing import Optional, Union
+
+import torch
+import torch.nn as nn
+from transformers import AutoModel, PretrainedConfig, ViltModel
+from transformers.modeling_outputs import BaseModelOutputWithPooling
+
+from . import _abi
+from .engine import VaultEngine
+
+
+def set_parameter_requires_grad(model: nn.Module, requires_grad: bool = False):
+    """ref:vault/utils.py:78-88"""
+    for p in model.parameters():
+        p.requires_grad_(requires_grad)
+
+
+class _TrunkFn(torch.autograd.Function):
+    """Whole LM + ViLT + pooler as one autograd node.  Parameters are not inputs: their gradients are written by the kernels
+    into the engine's flat buffer and attached as ``p.grad`` views in ``backward``."""
+
+    @staticmethod
+    def forward(ctx, anchor, engine: VaultEngine, kw: dict):
+        lhs, pooled, key_mask, tape = engine.forward(need_grad=True, **kw)
+        ctx.engine, ctx.tape = engine, tape
+        ctx.has_pooled = pooled is not None
+        ctx.mark_non_differentiable(key_mask)
+        if pooled is None:
+            pooled = lhs.new_zeros(())
+        return lhs, pooled, key_mask
+
+    @staticmethod
+    def backward(ctx, dlhs, dpooled, _dmask):
+        engine: VaultEngine = ctx.engine
+        engine.backward(ctx.tape, dlhs, dpooled if ctx.has_pooled else None)
+        engine.attach_grads(exclude_prefix="classifier.")
+        return None, None, None
+
+
+class _HeadFn(torch.autograd.Function):
+    """VaultForTMSC classifier: Linear(Dropout_p(pooled)) (ref:vault/models/vault/model.py:547-550, 569) in fp32 kernels."""
+
+    @staticmethod
+    def forward(ctx, pooled, engine: VaultEngine, wname: str, bname: str, p: float, n_classes: int):
+        lib, st = _abi.lib(), engine._stream()
+        B, H = pooled.shape
+        pooled = pooled.contiguous()
+        x = pooled
+        if p > 0.0:
+            x = torch.empty_like(pooled)
+            _abi.check(lib.vault_dropout_f32(pooled.data_ptr(), x.data_ptr(), pooled.numel(), p, engine.seed, engine.seed_dev.data_ptr(),
+                                             engine.SITE_HEAD, st), "dropout_f32")
+        logits = torch.empty((B, n_classes), device=pooled.device, dtype=torch.float32)
+        _abi.check(lib.vault_small_linear_fwd(x.data_ptr(), H, engine.w32(wname), engine.w32(bname), logits.data_ptr(), B, n_classes, H, 0, st),
+                   "classifier_fwd")
+        ctx.engine, ctx.names, ctx.p, ctx.x = engine, (wname, bname), p, x
+        return logits
+
+    @staticmethod
+    def backward(ctx, dlogits):
+        engine: VaultEngine = ctx.engine
+        lib, st = _abi.lib(), engine._stream()
+        wname, bname = ctx.names
+        x = ctx.x
+        B, H = x.shape
+        n = dlogits.shape[1]
+        dlogits = dlogits.contiguous().float()
+        dx = torch.empty_like(x)
+        _abi.check(lib.vault_small_linear_bwd(dlogits.data_ptr(), None, x.data_ptr(), H, engine.w32(wname), dx.data_ptr(), H, 0,
+                                              engine.g32(wname) or None, engine.g32(bname) or None, B, n, H, 0, st), "classifier_bwd")
+        if ctx.p > 0.0:
+            _abi.check(lib.vault_dropout_f32(dx.data_ptr(), dx.data_ptr(), dx.numel(), ctx.p, engine.seed, engine.seed_dev.data_ptr(),
+                                             engine.SITE_HEAD, st), "dropout_f32_bwd")
+        engine.attach_grads(only_prefix="classifier.")
+        return dx, None, None, None, None, None
+
+
+class VaultMixin(nn.Module, ABC):
+    """Mirror of ref:vault/models/vault/model.py:20-218 (inherit FIRST from this, then from the ViLT class).
+
+    Attributes:
+        bert: language model (parameter container + config); None -> text goes through ViLT's own word embeddings.
+        freeze_lm: whether the language model is frozen (forward only, no saved activations, no gradients).
+    """
+
+    def __init__(self, vilt_config, bert_config: Optional[PretrainedConfig] = None, freeze_lm: bool = False, vilt_dropout_prob: float = 0.0,
+                 use_vilt_position_embeddings: bool = False, *args, **kwargs):
+        # ref :71-75 -- the reference writes the dropout probability to two MISSPELT config attributes, so ViLT's real
+        # dropout probabilities stay at the config's values (0.0 for vilt-b32-*).  Reproduced: this engine applies
+        # config.hidden_dropout_prob / attention_probs_dropout_prob (and supports only 0 inside ViLT).
+        vilt_config.t_prob = vilt_dropout_prob
+        vilt_config.attention_probshidden_dropou_dropout_prob = vilt_dropout_prob
+        if bert_config is not None and not use_vilt_position_embeddings:  # ref :77-79
+            setattr(vilt_config, "position_embedding_type", "NOT_absolute")
+        super().__init__(vilt_config, *args, **kwargs)
+        # transformers >= 5 dropped the attribute from ViLT's TextEmbeddings; the 4.48.0 gate lives on the module here
+        self.embeddings.text_embeddings.position_embedding_type = getattr(vilt_config, "position_embedding_type", "absolute")
+        self.bert = AutoModel.from_config(config=bert_config, add_pooling_layer=False) if bert_config is not None else None
+        self.freeze_lm = freeze_lm
+        if self.bert is not None and freeze_lm:
+            set_parameter_requires_grad(self.bert, False)
+        self._check_supported(vilt_config)
+        self._engine: Optional[VaultEngine] = None
+        self._anchor = None
+
+    @staticmethod
+    def _check_supported(cfg):
+        if float(getattr(cfg, "hidden_dropout_prob", 0.0)) != 0.0 or float(getattr(cfg, "attention_probs_dropout_prob", 0.0)) != 0.0:
+            raise NotImplementedError("vault_b200: dropout inside the ViLT stack is not on the hot path (vilt-b32-* configs have 0.0)")
+        if int(getattr(cfg, "max_image_length", -1)) >= 0:
+            raise NotImplementedError("vault_b200: max_image_length >= 0 (random patch sub-sampling) is not supported; use -1")
+
+    @classmethod
+    def from_pretrained(cls, pretrained_vilt: str, pretrained_bert: Optional[str] = None, freeze_lm: bool = False,
+                        use_vilt_position_embeddings: bool = False, *args, **kwargs):
+        """ref:vault/models/vault/model.py:92-128"""
+        model = super().from_pretrained(pretrained_vilt, *args, **kwargs)
+        if pretrained_bert is not None and not use_vilt_position_embeddings:
+            model.embeddings.text_embeddings.position_embedding_type = "NOT_absolute"
+        else:
+            model.embeddings.text_embeddings.position_embedding_type = "absolute"
+        model.bert = AutoModel.from_pretrained(pretrained_bert, add_pooling_layer=False) if pretrained_bert is not None else None
+        model.freeze_lm = freeze_lm
+        if model.bert is not None and freeze_lm:
+            set_parameter_requires_grad(model.bert, False)
+        model._engine = None
+        return model
+
+    # ref :130-149 ---------------------------------------------------------------------------------------------
+    def resize_token_embeddings(self, tokenizer_length):
+        if self.bert is not None:
+            return self.bert.resize_token_embeddings(tokenizer_length)
+        return super().resize_token_embeddings(tokenizer_length)
+
+    def get_input_embeddings(self):
+        if self.bert is not None:
+            return self.bert.get_input_embeddings()
+        return super().get_input_embeddings()
+
+    def set_input_embeddings(self, value):
+        if self.bert is not None:
+            self.bert.set_input_embeddings(value)
+        else:
+            super().set_input_embeddings(value)
+
+    # engine ---------------------------------------------------------------------------------------------------
+    @property
+    def engine(self) -> VaultEngine:
+        if self._engine is None or self._engine.lm is not self.bert:
+            self._engine = VaultEngine(self)
+        return self._engine
+
+    def _trunk(self, input_ids=None, attention_mask=None, token_type_ids=None, pixel_values=None, pixel_mask=None, head_mask=None,
+               inputs_embeds=None, image_embeds=None, image_token_type_idx=None, output_attentions=None, output_hidden_states=None,
+               return_dict=None, **extra):
+        if head_mask is not None or output_attentions or output_hidden_states:
+            raise NotImplementedError("vault_b200: head_mask / output_attentions / output_hidden_states are not on the hot path")
+        if image_embeds is not None or inputs_embeds is not None:
+            raise NotImplementedError("vault_b200: image_embeds / inputs_embeds inputs are not built yet (SURVEY.md section 8f)")
+        if input_ids is None or pixel_values is None:
+            raise ValueError("You have to specify input_ids and pixel_values")
+        if not pixel_values.is_cuda:
+            raise RuntimeError("vault_b200 runs on CUDA (sm_100a) only: move the model and the batch to the GPU -- there is no CPU fallback")
+        for p in self.parameters():
+            if p.dtype != torch.float32:
+                raise RuntimeError("vault_b200 keeps fp32 master weights (bf16 tensor-core operands are derived): do not cast the module")
+            break
+        eng = self.engine
+        need_grad = torch.is_grad_enabled() and any(p.requires_grad for p in self.parameters())
+        kw = dict(input_ids=input_ids, attention_mask=attention_mask, token_type_ids=token_type_ids, pixel_values=pixel_values,
+                  pixel_mask=pixel_mask, image_token_type_idx=1 if image_token_type_idx is None else image_token_type_idx,
+                  training=self.training)
+        kw.update({k: v for k, v in extra.items() if k in ("hw", "pmax")})
+        if need_grad:
+            eng.ensure_packed(pixel_values.device)
+            if self.training:
+                eng.seed_dev.add_(1)  # fresh dropout masks per training forward; the backward regenerates them from the same value
+            if self._anchor is None or self._anchor.device != pixel_values.device:
+                self._anchor = torch.zeros(1, device=pixel_values.device, requires_grad=True)
+            lhs, pooled, key_mask = _TrunkFn.apply(self._anchor, eng, kw)
+        else:
+            lhs, pooled, key_mask, _ = eng.forward(need_grad=False, **kw)
+        if self.pooler is None:
+            pooled = None
+        return lhs, pooled, key_mask
+
+    def forward(self, *args, **kwargs):
+        """ref:vault/models/vault/model.py:207-218 (lm_preprocess + vilt_forward, fused).  Positional order follows ViltModel.forward of
+        transformers==4.48.0: input_ids, attention_mask, token_type_ids, pixel_values, pixel_mask, head_mask, inputs_embeds, ..."""
+        lhs, pooled, _ = self._trunk(*args, **kwargs)
+        if kwargs.get("return_dict") is False:
+            return (lhs, pooled)
+        return BaseModelOutputWithPooling(last_hidden_state=lhs, pooler_output=pooled)
+
+
+class VaultModel(VaultMixin, ViltModel):
+    """Vision and Augmented Language Transformer (ref:vault/models/vault/model.py:369-372) on B200 kernels."""
+
+
+class VaultForTMSC(VaultModel):
+    """VAuLT for Target-oriented Multimodal Sentiment Classification (ref:vault/models/vault/model.py:512-570)."""
+
+    def __init__(self, vilt_config: PretrainedConfig, n_classes: int = 3, vilt_dropout_prob: float = 0.1,
+                 logging_level: Optional[Union[int, str]] = None, bert_config: Optional[PretrainedConfig] = None, **kwargs):
+        super().__init__(vilt_config, add_pooling_layer=True, bert_config=bert_config, vilt_dropout_prob=vilt_dropout_prob, **kwargs)
+        self.classifier = nn.Sequential(nn.Dropout(vilt_dropout_prob), nn.Linear(self.config.hidden_size, n_classes))
+        self.logger = logging.getLogger(__name__)
+        self.logger.setLevel(logging_level or logging.WARNING)
+
+    def forward(self, *args, **kwargs) -> torch.Tensor:
+        lhs, pooled, _ = self._trunk(*args, **kwargs)
+        self.logger.debug(f"Output shape: {lhs.shape}")
+        p = float(self.classifier[0].p) if self.training else 0.0
+        n = self.classifier[1].out_features
+        if pooled.requires_grad or (torch.is_grad_enabled() and self.classifier[1].weight.requires_grad):
+            logits = _HeadFn.apply(pooled, self.engine, "classifier.1.weight", "classifier.1.bias", p, n)
+        else:
+            with torch.no_grad():
+                logits = _HeadFn.apply(pooled, self.engine, "classifier.1.weight", "classifier.1.bias", p, n)
+        return logits.squeeze(-1)
+
+
+def _not_built(name):
+    class _Stub:  # keeps `from vault_b200.models.vault import <name>` importable (ref:vault/models/vault/__init__.py)
+        def __init__(self, *a, **k):
+            raise NotImplementedError(f"{name}: head not built yet in vault_b200 (SURVEY.md section 8f, rank 3); the trunk is VaultModel")
+
+    _Stub.__name__ = name
+    return _Stub
+
+
+VaultForImageAndTextRetrieval = _not_built("VaultForImageAndTextRetrieval")
+VaultForImagesAndTextClassification = _not_built("VaultForImagesAndTextClassification")
+VaultForMaskedLM = _not_built("VaultForMaskedLM")
+VaultForQuestionAnswering = _not_built("VaultForQuestionAnswering")

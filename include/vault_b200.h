@@ -204,10 +204,12 @@ int vault_colsum_bf16(const void* x, int64_t ldx, float* out, int64_t rows, int3
  *   m = b1 m + (1-b1) g ; v = b2 v + (1-b2) g^2 ; p -= step_size * m / (sqrt(v) + eps) ; p -= lr*wd*p (if wd > 0)
  *   step_size = lr * sqrt(1-b2^t)/(1-b1^t) if correct_bias else lr.      grad_scale multiplies g first (DP averaging).
  * Also refreshes the bf16 shadow copy used by the GEMMs (shadow may be NULL).
+ * sched_dev (optional, DEVICE float[2] = {step_size, lr*weight_decay}) overrides the host-computed scalars at run time so a
+ * captured CUDA graph can follow the linear-warmup schedule (HF:optimization.py:101-131) without re-capture.
  * ------------------------------------------------------------------------------------------------------------------ */
 int vault_adamw_step(float* p, const float* g, float* m, float* v, void* shadow_bf16, int64_t n, float lr, float beta1,
                      float beta2, float eps, float weight_decay, int32_t correct_bias, int32_t step, float grad_scale,
-                     void* stream);
+                     const float* sched_dev, void* stream);
 /* fp32 -> bf16 cast of a flat range (shadow refresh after an external optimizer touched the masters) */
 int vault_cast_f32_bf16(const float* src, void* dst_bf16, int64_t n, void* stream);
 

@@ -1,0 +1,139 @@
+"""CPU tests of the host side: drop-in class surface, HF-compatible keys, flat-buffer layout, schedule, and the world_size-2
+data-parallel reduction over gloo."""
+import os
+import socket
+import sys
+
+import pytest
+import torch
+import torch.distributed as dist
+import torch.multiprocessing as mp
+
+from oracle import synth, vault_oracle as O
+from oracle.ref_loader import hf_configs
+
+ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+
+
+def tiny_model(**dkw):
+    from vault_b200 import VaultForTMSC
+
+    d = synth.Dims.tiny(**dkw)
+    vc, lc = hf_configs(d)
+    m = VaultForTMSC(vc, n_classes=d.n_classes, vilt_dropout_prob=0.1, bert_config=lc)
+    return d, m
+
+
+def test_state_dict_keys_are_hf_compatible():
+    d, m = tiny_model()
+    mine = {k: tuple(v.shape) for k, v in m.state_dict().items() if not k.endswith("position_ids") and not k.endswith("token_type_ids")}
+    assert mine == synth.param_shapes(d), set(mine) ^ set(synth.param_shapes(d))
+
+
+def test_reference_class_surface():
+    import vault_b200
+    from vault_b200.models.vault import VaultForMaskedLM, VaultForTMSC, VaultModel, VaultProcessor  # noqa: F401  reference import path
+
+    d, m = tiny_model()
+    assert isinstance(m, vault_b200.VaultModel) and m.bert is not None and m.freeze_lm is False
+    assert m.embeddings.text_embeddings.position_embedding_type == "NOT_absolute"  # ref:vault/models/vault/model.py:77-79
+    assert m.get_input_embeddings() is m.bert.get_input_embeddings()
+    # the reference's typo'd attributes leave ViLT's real dropout at the config value (0.0)
+    assert m.config.hidden_dropout_prob == 0.0 and m.config.t_prob == 0.1
+    m.resize_token_embeddings(600)
+    assert m.bert.get_input_embeddings().weight.shape[0] == 600
+    with pytest.raises(NotImplementedError):
+        VaultForMaskedLM()
+
+
+def test_frozen_lm_and_no_lm_variants():
+    from vault_b200 import VaultForTMSC, VaultModel
+
+    d = synth.Dims.tiny()
+    vc, lc = hf_configs(d)
+    m = VaultModel(vc, bert_config=lc, freeze_lm=True)
+    assert all(not p.requires_grad for p in m.bert.parameters()) and m.pooler is not None
+    d0 = synth.Dims.tiny(lm_layers=0)
+    vc0, _ = hf_configs(d0)
+    m0 = VaultForTMSC(vc0, n_classes=3)
+    assert m0.bert is None and m0.embeddings.text_embeddings.position_embedding_type == "absolute"
+
+
+def test_cpu_call_fails_loudly():
+    d, m = tiny_model()
+    inp = synth.make_inputs(d, batch=1, text_len=8)
+    with pytest.raises(RuntimeError, match="no CPU"):
+        m(input_ids=inp["input_ids"], attention_mask=inp["attention_mask"], token_type_ids=inp["token_type_ids"], pixel_values=inp["pixel_values"])
+
+
+def test_flat_layout_order_and_never_grad():
+    d, m = tiny_model()
+    eng = m.engine
+    train, static = eng._param_order()
+    assert set(static) == O.grads_never_set(d) == eng.never_grad_names()
+    # reverse-topological: head first, LM embeddings last; q,k,v adjacent so the fused [3H,H] slice is contiguous
+    assert train[0] == "classifier.1.weight" and train[-1].startswith("bert.embeddings.")
+    for pre in ("encoder.layer.1.attention.attention.", "bert.encoder.layer.0.attention.self."):
+        i = train.index(pre + "query.weight")
+        assert train[i:i + 6] == [pre + n for n in ("query.weight", "key.weight", "value.weight", "query.bias", "key.bias", "value.bias")]
+    m.freeze_lm = True
+    for p in m.bert.parameters():
+        p.requires_grad_(False)
+    train2, static2 = eng._param_order()
+    assert all(not n.startswith("bert.") for n in train2) and sum(n.startswith("bert.") for n in static2) > 0
+
+
+def test_schedule_matches_oracle():
+    from vault_b200.train import VaultTrainStep
+
+    ts = VaultTrainStep.__new__(VaultTrainStep)
+    ts.lr, ts.total_steps, ts.warmup_ratio = 2e-5, 1000, 0.1
+    for s in (0, 1, 50, 99, 100, 101, 555, 999, 1000):
+        assert abs(ts.lr_at(s) - O.linear_warmup_lr(s, 1000, 2e-5)) < 1e-15
+    assert ts.lr_at(0) == 0.0
+
+
+def _free_port():
+    s = socket.socket()
+    s.bind(("127.0.0.1", 0))
+    p = s.getsockname()[1]
+    s.close()
+    return p
+
+
+def _dp_worker(rank, world, port, out):
+    sys.path.insert(0, ROOT)
+    os.environ["MASTER_ADDR"], os.environ["MASTER_PORT"] = "127.0.0.1", str(port)
+    dist.init_process_group("gloo", rank=rank, world_size=world)
+    torch.set_num_threads(2)
+    from vault_b200.train import allreduce_flat_
+
+    d = synth.Dims.tiny()
+    sd = synth.make_state_dict(d, seed=0)
+    full = synth.make_inputs(d, batch=4, text_len=12, seed=5, var_text=True)
+    keys = ("input_ids", "attention_mask", "token_type_ids", "pixel_values", "pixel_mask")
+
+    def grads(batch):
+        params = {k: v.clone().requires_grad_(True) for k, v in sd.items()}
+        o = O.vault_forward(params, d, **{k: batch[k] for k in keys})
+        O.ce_loss(O.tmsc_logits(params, d, o["pooler_output"]), batch["labels"]).backward()
+        names = sorted(k for k, p in params.items() if p.grad is not None)
+        return names, torch.cat([params[k].grad.flatten() for k in names])
+
+    local = {k: v[rank * 2:(rank + 1) * 2] for k, v in full.items()}  # batch sharding: 2 rows per rank
+    names, flat = grads(local)
+    allreduce_flat_(flat, None, bucket_elems=100_000)  # several buckets
+    flat *= 1.0 / world                                # what AdamW's grad_scale applies
+    if rank == 0:
+        _, ref = grads(full)
+        torch.save(dict(err=(flat - ref).abs().max().item(), scale=ref.abs().max().item()), out)
+    dist.barrier()
+    dist.destroy_process_group()
+
+
+def test_data_parallel_gradient_average_world2_gloo(tmp_path):
+    """Sharding the batch over 2 ranks + sum-all-reduce + 1/world == the single-process full-batch gradient (CE mean, equal shards)."""
+    out = str(tmp_path / "dp.pt")
+    mp.spawn(_dp_worker, args=(2, _free_port(), out), nprocs=2, join=True)
+    r = torch.load(out)
+    assert r["err"] <= 2e-5 * max(r["scale"], 1.0), r

@@ -1,0 +1,268 @@
+"""GPU parity tests of the individual sm_100a kernels, called through the C ABI, against plain torch fp32 on the same
+(bf16-rounded) inputs.  Tolerances are stated per test."""
+import ctypes as C
+import math
+
+import pytest
+import torch
+
+pytestmark = pytest.mark.gpu
+
+from oracle import vault_oracle as O  # noqa: E402  (checker only)
+
+
+@pytest.fixture(scope="module")
+def dev():
+    return torch.device("cuda:0")
+
+
+@pytest.fixture(scope="module")
+def ops():
+    from vault_b200 import ops as o
+
+    return o
+
+
+def _rnd(dev, *shape, scale=1.0):
+    return (torch.randn(*shape, device=dev) * scale).to(torch.bfloat16)
+
+
+def _rel(got, ref):
+    return ((got.float() - ref).abs().max() / ref.abs().max().clamp_min(1e-6)).item()
+
+
+# ---------------------------------------------------------------- GEMM ----------------------------------------------------------------
+@pytest.mark.parametrize("M,N,K,a_mn,b_mn,bn", [
+    (128, 128, 64, False, False, 128), (128, 64, 64, False, False, 64), (128, 256, 768, False, False, 256),
+    (1000, 768, 768, False, False, 0), (5920, 2304, 768, False, False, 0), (185, 128, 128, False, False, 0),
+    (128, 256, 64, False, True, 256), (5920, 768, 2304, False, True, 0), (130, 3072, 768, False, True, 0),       # dgrad layout
+    (128, 128, 64, True, True, 128), (256, 256, 1000, True, True, 0), (2304, 768, 5920, True, True, 128),          # wgrad layout
+    (128, 128, 64, True, False, 128),
+])
+def test_gemm_layouts(dev, ops, M, N, K, a_mn, b_mn, bn):
+    """bit-level claim: bf16 x bf16 products accumulated in fp32 -> relative error <= 1e-4 of the fp32 torch result."""
+    torch.manual_seed(M + N + K)
+    a, b = _rnd(dev, M, K, scale=0.5), _rnd(dev, N, K, scale=0.5)
+    ref = a.float() @ b.float().t()
+    A = a.t().contiguous() if a_mn else a
+    Bm = b.t().contiguous() if b_mn else b
+    got = ops.gemm(A, Bm, ops.EPI_STORE_F32, a_mn=a_mn, b_mn=b_mn, block_n=bn)
+    assert _rel(got, ref) < 1e-4
+
+
+@pytest.mark.parametrize("split", [2, 4, 8])
+def test_gemm_split_k_atomic(dev, ops, split):
+    a, b = _rnd(dev, 768, 5920, scale=0.5), _rnd(dev, 768, 5920, scale=0.5)
+    ref = a.float() @ b.float().t()
+    out = torch.zeros(768, 768, device=dev)
+    ops.gemm(a.t().contiguous(), b.t().contiguous(), ops.EPI_ATOMIC_F32, a_mn=True, b_mn=True, split_k=split, out=out, block_n=128)
+    assert _rel(out, ref) < 1e-4
+
+
+def test_gemm_epilogues(dev, ops):
+    M, N, K = 777, 768, 768
+    a, b = _rnd(dev, M, K, scale=0.5), _rnd(dev, N, K, scale=0.5)
+    bias = torch.randn(N, device=dev)
+    acc = a.float() @ b.float().t()
+    tol = 1e-2  # outputs rounded to bf16 (2^-9 relative) on values up to ~max|acc|
+    assert _rel(ops.gemm(a, b, ops.EPI_BIAS_BF16, bias=bias), acc + bias) < tol
+    pre = torch.empty(M, N, device=dev, dtype=torch.bfloat16)
+    act = ops.gemm(a, b, ops.EPI_BIAS_GELU_BF16, bias=bias, out2=pre)
+    assert _rel(act, torch.nn.functional.gelu(acc + bias)) < tol and _rel(pre, acc + bias) < tol
+    resid = torch.randn(M, N, device=dev)
+    assert _rel(ops.gemm(a, b, ops.EPI_BIAS_RESID_F32, bias=bias, resid=resid), acc + bias + resid) < 1e-4
+    assert _rel(ops.gemm(a, b, ops.EPI_PLAIN_BF16), acc) < tol
+    aux = _rnd(dev, M, N)
+    x = aux.float()
+    gp = 0.5 * (1 + torch.erf(x / 2 ** 0.5)) + x * torch.exp(-0.5 * x * x) / (2 * math.pi) ** 0.5
+    assert _rel(ops.gemm(a, b, ops.EPI_DGELU_BF16, aux=aux), acc * gp) < tol
+    assert _rel(ops.gemm(a, b, ops.EPI_BIAS_F32, bias=bias), acc + bias) < 1e-4
+
+
+def test_gemm_dropout_epilogue_statistics(dev, ops):
+    M, N, K = 1024, 768, 128
+    a, b = _rnd(dev, M, K), _rnd(dev, N, K)
+    acc = a.float() @ b.float().t()
+    z = torch.zeros(M, N, device=dev)
+    y = ops.gemm(a, b, ops.EPI_BIAS_RESID_F32, resid=z, dropout_p=0.1, seed=11, site=3)
+    y2 = ops.gemm(a, b, ops.EPI_BIAS_RESID_F32, resid=z, dropout_p=0.1, seed=11, site=3)
+    y3 = ops.gemm(a, b, ops.EPI_BIAS_RESID_F32, resid=z, dropout_p=0.1, seed=12, site=3)
+    keep = (y != 0)
+    assert torch.equal(y, y2) and not torch.equal(y, y3)
+    assert abs(keep.float().mean().item() - 0.9) < 5e-3
+    assert torch.allclose(y[keep], acc[keep] / 0.9, rtol=1e-4, atol=1e-4)
+
+
+def test_gemm_rejects_bad_arguments(dev, ops):
+    a, b = _rnd(dev, 128, 64), _rnd(dev, 100, 64)  # N not a multiple of 8
+    with pytest.raises(RuntimeError, match="multiple of 8"):
+        ops.gemm(a, b, ops.EPI_STORE_F32)
+    with pytest.raises(RuntimeError, match="CUDA tensors only"):
+        ops.gemm(a.cpu(), b.cpu(), ops.EPI_STORE_F32)
+
+
+# ---------------------------------------------------------------- LayerNorm ----------------------------------------------------------------
+@pytest.mark.parametrize("rows,cols", [(5920, 768), (37, 128), (1, 768), (1280, 1024)])
+def test_layernorm_fwd_bwd(dev, ops, rows, cols):
+    torch.manual_seed(rows)
+    x = torch.randn(rows, cols, device=dev) * 2 + 0.5
+    g = 1 + 0.1 * torch.randn(cols, device=dev)
+    b = 0.1 * torch.randn(cols, device=dev)
+    y16, y32, mean, rstd = ops.layernorm_fwd(x, g, b, 1e-12, want_bf16=True, want_f32=True)
+    xr, gr, br = x.clone().requires_grad_(True), g.clone().requires_grad_(True), b.clone().requires_grad_(True)
+    ref = torch.nn.functional.layer_norm(xr, (cols,), gr, br, 1e-12)
+    assert (y32 - ref).abs().max() < 1e-4               # fp32 path
+    assert (y16.float() - ref).abs().max() < 4e-2       # bf16 rounding of O(4) values
+    dy16 = torch.randn(rows, cols, device=dev).to(torch.bfloat16)
+    dres = torch.randn(rows, cols, device=dev)
+    ref.backward(dy16.float())
+    dg, db = torch.zeros(cols, device=dev), torch.zeros(cols, device=dev)
+    dx32, dx16 = ops.layernorm_bwd(None, dy16, x, mean, rstd, g, dres, dg, db)
+    assert (dx32 - (xr.grad + dres)).abs().max() < 1e-3
+    assert _rel(dg, gr.grad) < 1e-3 and _rel(db, br.grad) < 1e-3
+    assert (dx16.float() - dx32).abs().max() < 4e-2
+
+
+def test_layernorm_dropout_roundtrip(dev, ops):
+    """Output dropout: the backward regenerates the forward's mask (same seed/site) -- checked through the kept pattern."""
+    rows, cols = 512, 768
+    x = torch.randn(rows, cols, device=dev)
+    g, b = torch.ones(cols, device=dev), torch.zeros(cols, device=dev)
+    _, y, mean, rstd = ops.layernorm_fwd(x, g, b, 1e-5, want_bf16=False, want_f32=True, dropout_p=0.1, seed=5, site=9)
+    _, y0, _, _ = ops.layernorm_fwd(x, g, b, 1e-5, want_bf16=False, want_f32=True)
+    keep = y != 0
+    assert abs(keep.float().mean().item() - 0.9) < 5e-3
+    assert torch.allclose(y[keep], y0[keep] / 0.9, rtol=1e-5, atol=1e-5)
+    dy = torch.randn(rows, cols, device=dev)
+    dx, _ = ops.layernorm_bwd(dy, None, x, mean, rstd, g, None, None, None, want_bf16=False, in_p=0.1, in_site=9, seed=5)
+    xr = x.clone().requires_grad_(True)
+    torch.nn.functional.layer_norm(xr, (cols,), g, b, 1e-5).backward(dy * keep / 0.9)
+    assert (dx - xr.grad).abs().max() < 1e-3
+
+
+# ---------------------------------------------------------------- attention ----------------------------------------------------------------
+def _attn_ref(qkv, mask, B, S, heads, drop_mask=None, p=0.0):
+    H = heads * 64
+    x = qkv.float().view(B, S, 3, heads, 64).permute(2, 0, 3, 1, 4).clone().requires_grad_(True)
+    sc = x[0] @ x[1].transpose(-1, -2) / 8.0
+    sc = sc.masked_fill(mask[:, None, None, :] == 0, float("-inf"))
+    pr = torch.softmax(sc, -1)
+    lse = torch.logsumexp(sc, -1)
+    if drop_mask is not None:
+        pr = pr * drop_mask / (1 - p)
+    return x, (pr @ x[2]).permute(0, 2, 1, 3).reshape(B * S, H), lse
+
+
+def _mid_mask(dev, B, S):
+    mask = torch.ones(B, S, dtype=torch.uint8, device=dev)
+    for b in range(B):
+        a = 3 + (b * 5) % max(1, S // 3)
+        z = min(S - 1, a + (b * 3) % max(1, S // 4))
+        mask[b, a:z] = 0  # padding in the MIDDLE of the sequence (text pad before the image tokens)
+        if b % 2:
+            mask[b, S - (b % 7) - 1:] = 0
+    return mask
+
+
+@pytest.mark.parametrize("B,S,heads", [(2, 64, 2), (3, 185, 12), (2, 369, 12), (2, 40, 12), (1, 17, 2), (2, 209, 12), (1, 512, 2)])
+def test_attention_fwd_bwd(dev, B, S, heads):
+    from vault_b200 import _abi
+
+    lib, st = _abi.lib(), torch.cuda.current_stream().cuda_stream
+    H = heads * 64
+    torch.manual_seed(S)
+    qkv = _rnd(dev, B * S, 3 * H, scale=0.7)
+    mask = _mid_mask(dev, B, S)
+    ctx = torch.empty(B * S, H, device=dev, dtype=torch.bfloat16)
+    lse = torch.empty(B, heads, S, device=dev)
+    _abi.check(lib.vault_attn_fwd(qkv.data_ptr(), mask.data_ptr(), ctx.data_ptr(), lse.data_ptr(), B, S, heads, 0.0, 0, None, 0, st))
+    x, ref, ref_lse = _attn_ref(qkv, mask, B, S, heads)
+    assert (ctx.float() - ref).abs().max() < 2e-2  # bf16 P and bf16 output on O(1) values
+    assert (lse - ref_lse).abs().max() < 1e-3
+    dctx = _rnd(dev, B * S, H, scale=0.5)
+    ref.backward(dctx.float())
+    dref = x.grad.permute(1, 3, 0, 2, 4).reshape(B * S, 3 * H)
+    dqkv = torch.empty_like(qkv)
+    delta = torch.empty(B, heads, S, device=dev)
+    _abi.check(lib.vault_attn_bwd(qkv.data_ptr(), mask.data_ptr(), ctx.data_ptr(), dctx.data_ptr(), lse.data_ptr(), delta.data_ptr(), dqkv.data_ptr(), B, S,
+                                  heads, 0.0, 0, None, 0, st))
+    assert _rel(dqkv, dref) < 2e-2
+
+
+@pytest.mark.parametrize("S", [40, 64])
+def test_attention_dropout_exact_mask(dev, S):
+    """With S <= 64 and V = identity the context IS the dropped probability matrix: recover the Philox mask, then check forward and
+    backward against torch with that exact mask."""
+    from vault_b200 import _abi
+
+    lib, st = _abi.lib(), torch.cuda.current_stream().cuda_stream
+    B, heads, p, seed, site = 2, 2, 0.1, 99, 4
+    H = heads * 64
+    torch.manual_seed(7)
+    qkv = _rnd(dev, B * S, 3 * H, scale=0.7)
+    mask = torch.ones(B, S, dtype=torch.uint8, device=dev)
+    probe = qkv.clone().view(B, S, 3, heads, 64)
+    probe[:, :, 2] = 0
+    for k in range(S):
+        probe[:, k, 2, :, k] = 1.0
+    probe = probe.view(B * S, 3 * H).contiguous()
+    ctx = torch.empty(B * S, H, device=dev, dtype=torch.bfloat16)
+    lse = torch.empty(B, heads, S, device=dev)
+    _abi.check(lib.vault_attn_fwd(probe.data_ptr(), mask.data_ptr(), ctx.data_ptr(), lse.data_ptr(), B, S, heads, p, seed, None, site, st))
+    pd = ctx.float().view(B, S, heads, 64)[..., :S].permute(0, 2, 1, 3)  # [B,h,q,k] dropped probabilities
+    drop_mask = (pd != 0).float()
+    assert abs(drop_mask.mean().item() - 0.9) < 0.02
+    _abi.check(lib.vault_attn_fwd(qkv.data_ptr(), mask.data_ptr(), ctx.data_ptr(), lse.data_ptr(), B, S, heads, p, seed, None, site, st))
+    x, ref, _ = _attn_ref(qkv, mask, B, S, heads, drop_mask, p)
+    assert (ctx.float() - ref).abs().max() < 2e-2
+    dctx = _rnd(dev, B * S, H, scale=0.5)
+    ref.backward(dctx.float())
+    dref = x.grad.permute(1, 3, 0, 2, 4).reshape(B * S, 3 * H)
+    dqkv = torch.empty_like(qkv)
+    delta = torch.empty(B, heads, S, device=dev)
+    _abi.check(lib.vault_attn_bwd(qkv.data_ptr(), mask.data_ptr(), ctx.data_ptr(), dctx.data_ptr(), lse.data_ptr(), delta.data_ptr(), dqkv.data_ptr(), B, S,
+                                  heads, p, seed, None, site, st))
+    assert _rel(dqkv, dref) < 2e-2
+
+
+# ---------------------------------------------------------------- optimizer / loss / reductions ----------------------------------------------------------------
+@pytest.mark.parametrize("correct_bias,wd", [(False, 0.0), (True, 0.01)])
+def test_adamw_matches_hf_rule(dev, correct_bias, wd):
+    """fp32 elementwise rule: bit-comparable up to fused-multiply-add rounding -> 1e-6 relative."""
+    from vault_b200 import _abi
+
+    n = 100003
+    torch.manual_seed(1)
+    p = torch.randn(n); g = torch.randn(n) * 1e-2
+    m, v = torch.zeros(n), torch.zeros(n)
+    pc, mc, vc = p.to(dev), m.to(dev), v.to(dev)
+    n_al = (n + 63) // 64 * 64
+    pd, md, vd, gd = (torch.zeros(n_al, device=dev) for _ in range(4))
+    pd[:n], gd[:n] = pc, g.to(dev)
+    sh = torch.zeros(n_al, device=dev, dtype=torch.bfloat16)
+    for step in (1, 2, 3):
+        O.hf_adamw_step(p, g, m, v, step, lr=1e-3, weight_decay=wd, correct_bias=correct_bias)
+        _abi.call("vault_adamw_step", pd.data_ptr(), gd.data_ptr(), md.data_ptr(), vd.data_ptr(), sh.data_ptr(), n, 1e-3, 0.9, 0.999, 1e-8, wd,
+                  int(correct_bias), step, 1.0, None, torch.cuda.current_stream().cuda_stream)
+    assert torch.allclose(pd[:n].cpu(), p, rtol=2e-6, atol=1e-7)
+    assert torch.allclose(md[:n].cpu(), m, rtol=2e-6, atol=1e-9) and torch.allclose(vd[:n].cpu(), v, rtol=2e-6, atol=1e-12)
+    assert torch.equal(sh[:n].cpu(), pd[:n].cpu().to(torch.bfloat16))
+
+
+def test_ce_loss_and_colsum(dev):
+    from vault_b200 import _abi
+
+    st = torch.cuda.current_stream().cuda_stream
+    logits = torch.randn(32, 3, device=dev)
+    labels = torch.randint(0, 3, (32,), device=dev)
+    loss = torch.zeros(1, device=dev)
+    dl = torch.empty_like(logits)
+    _abi.call("vault_ce_loss", logits.data_ptr(), labels.data_ptr(), loss.data_ptr(), dl.data_ptr(), 32, 3, 1.0, st)
+    lr = logits.clone().requires_grad_(True)
+    ref = torch.nn.functional.cross_entropy(lr, labels)
+    ref.backward()
+    assert abs(loss.item() - ref.item()) < 1e-6 and (dl - lr.grad).abs().max() < 1e-6
+    x = _rnd(dev, 5920, 2304)
+    out = torch.zeros(2304, device=dev)
+    _abi.call("vault_colsum_bf16", x.data_ptr(), 2304, out.data_ptr(), 5920, 2304, st)
+    assert _rel(out, x.float().sum(0)) < 1e-4

@@ -56,7 +56,7 @@ SIGNATURES = {
     "vault_dropout_f32": [c_p, c_p, c_i64, c_f32, c_u64, c_p, c_u32, c_p],
     "vault_ce_loss": [c_p, c_p, c_p, c_p, c_i32, c_i32, c_f32, c_p],
     "vault_colsum_bf16": [c_p, c_i64, c_p, c_i64, c_i32, c_p],
-    "vault_adamw_step": [c_p, c_p, c_p, c_p, c_p, c_i64, c_f32, c_f32, c_f32, c_f32, c_f32, c_i32, c_i32, c_f32, c_p],
+    "vault_adamw_step": [c_p, c_p, c_p, c_p, c_p, c_i64, c_f32, c_f32, c_f32, c_f32, c_f32, c_i32, c_i32, c_f32, c_p, c_p],
     "vault_cast_f32_bf16": [c_p, c_p, c_i64, c_p],
 }
 _RESTYPES = {"vault_last_error": C.c_size_t}
@@ -101,3 +101,48 @@ def check(rc: int, what: str = "") -> None:
 
 def call(name: str, *args) -> None:
     check(getattr(lib(), name)(*args), name)
+
+
+# kernels launched per ABI call (for launch accounting in bench.py; torch memsets / fills are not counted)
+KERNELS_PER_CALL = {"vault_attn_bwd": 2, "vault_vilt_assemble_bwd": 2, "vault_small_linear_bwd": 2}
+
+
+class CountingLib:
+    """Proxy around the loaded library that counts kernel launches and records GEMM problems (bench.py instrumentation)."""
+
+    def __init__(self, inner=None):
+        self._inner = inner or lib()
+        self.launches = 0
+        self.calls = {}
+        self.gemms = []  # (M, N, K, a_mn, b_mn, epilogue, split_k, block_n, args-copy)
+
+    def __getattr__(self, name):
+        fn = getattr(self._inner, name)
+        if not name.startswith("vault_") or name in ("vault_version", "vault_last_error", "vault_check_device"):
+            return fn
+
+        def wrapped(*args):
+            self.launches += KERNELS_PER_CALL.get(name, 1)
+            self.calls[name] = self.calls.get(name, 0) + 1
+            if name == "vault_gemm_bf16":
+                src = args[0]._obj
+                cp = GemmArgs()
+                C.memmove(C.byref(cp), C.byref(src), C.sizeof(GemmArgs))
+                self.gemms.append(cp)
+            return fn(*args)
+
+        return wrapped
+
+
+def install_counter():
+    """Route every subsequent ABI call through a CountingLib; returns it.  uninstall_counter() restores the plain library."""
+    global _lib
+    c = CountingLib(lib() if not isinstance(_lib, CountingLib) else _lib._inner)
+    _lib = c
+    return c
+
+
+def uninstall_counter():
+    global _lib
+    if isinstance(_lib, CountingLib):
+        _lib = _lib._inner

@@ -6,7 +6,11 @@ namespace vb {
 
 __global__ void __launch_bounds__(256)
 adamw_kernel(float* __restrict__ p, const float* __restrict__ g, float* __restrict__ m, float* __restrict__ v, bf16* __restrict__ shadow, long long n,
-             float step_size, float lr_wd, float beta1, float beta2, float eps, float grad_scale) {
+             float step_size, float lr_wd, float beta1, float beta2, float eps, float grad_scale, const float* __restrict__ sched_dev) {
+  if (sched_dev) {  // {step_size, lr*weight_decay} read from device memory: a captured CUDA graph can follow an lr schedule
+    step_size = sched_dev[0];
+    lr_wd = sched_dev[1];
+  }
   const long long n4 = n >> 2;
   const float ob1 = 1.f - beta1, ob2 = 1.f - beta2;
   for (long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x; i < n4; i += (long long)gridDim.x * blockDim.x) {
@@ -70,7 +74,8 @@ static unsigned flat_grid(long long n4) {
 using namespace vb;
 
 extern "C" int vault_adamw_step(float* p, const float* g, float* m, float* v, void* shadow_bf16, int64_t n, float lr, float beta1, float beta2,
-                                float eps, float weight_decay, int32_t correct_bias, int32_t step, float grad_scale, void* stream) {
+                                float eps, float weight_decay, int32_t correct_bias, int32_t step, float grad_scale, const float* sched_dev,
+                                void* stream) {
   VB_REQUIRE(p && g && m && v && n >= 0, "adamw_step: bad arguments");
   VB_REQUIRE((((uintptr_t)p | (uintptr_t)g | (uintptr_t)m | (uintptr_t)v) & 15) == 0, "adamw_step: buffers must be 16-byte aligned");
   VB_REQUIRE(shadow_bf16 == nullptr || ((uintptr_t)shadow_bf16 & 7) == 0, "adamw_step: shadow must be 8-byte aligned");
@@ -81,7 +86,7 @@ extern "C" int vault_adamw_step(float* p, const float* g, float* m, float* v, vo
     step_size = (double)lr * sqrt(1.0 - pow((double)beta2, step)) / (1.0 - pow((double)beta1, step));
   }
   adamw_kernel<<<flat_grid(n >> 2), 256, 0, (cudaStream_t)stream>>>(p, g, m, v, reinterpret_cast<bf16*>(shadow_bf16), n, (float)step_size,
-                                                                    weight_decay > 0.f ? lr * weight_decay : 0.f, beta1, beta2, eps, grad_scale);
+                                                                    weight_decay > 0.f ? lr * weight_decay : 0.f, beta1, beta2, eps, grad_scale, sched_dev);
   return check_launch("adamw_kernel");
 }
 

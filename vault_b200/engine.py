@@ -668,10 +668,17 @@ class VaultEngine:
     # ------------------------------------------------------------------------------------------------------------
     # fused optimizer (transformers==4.48.0 AdamW rule) over the flat trainable range
     # ------------------------------------------------------------------------------------------------------------
-    def adamw_step(self, lr: float, beta1=0.9, beta2=0.999, eps=1e-8, weight_decay=0.0, correct_bias=False, grad_scale=1.0):
+    def init_opt_state(self):
         if self.opt_state is None:
             self.opt_state = dict(step=0, m=torch.zeros(self.n_train, device=self.device), v=torch.zeros(self.n_train, device=self.device))
-        s = self.opt_state
+        return self.opt_state
+
+    def adamw_step(self, lr: float, beta1=0.9, beta2=0.999, eps=1e-8, weight_decay=0.0, correct_bias=False, grad_scale=1.0,
+                   sched_dev: Optional[torch.Tensor] = None):
+        """One fused launch over the whole trainable range.  With ``sched_dev`` (device float[2] = {step_size, lr*wd}) the
+        scalars are read on the device (CUDA-graph friendly); otherwise they are computed here from lr / step."""
+        s = self.init_opt_state()
         s["step"] += 1
         _abi.call("vault_adamw_step", self.master.data_ptr(), self.grad.data_ptr(), s["m"].data_ptr(), s["v"].data_ptr(), self.shadow.data_ptr(),
-                  self.n_train, lr, beta1, beta2, eps, weight_decay, int(correct_bias), s["step"], grad_scale, self._stream())
+                  self.n_train, lr, beta1, beta2, eps, weight_decay, int(correct_bias), max(1, s["step"]), grad_scale,
+                  sched_dev.data_ptr() if sched_dev is not None else None, self._stream())

@@ -67,15 +67,17 @@ def layernorm_fwd(x, gamma, beta, eps, *, want_bf16=True, want_f32=False, dropou
     mean = torch.empty(rows, device=x.device, dtype=torch.float32)
     rstd = torch.empty(rows, device=x.device, dtype=torch.float32)
     _abi.call("vault_layernorm_fwd_drop", x.data_ptr(), gamma.data_ptr(), beta.data_ptr(), _ptr(y16), _ptr(y32), mean.data_ptr(),
-              rstd.data_ptr(), rows, cols, eps, dropout_p, seed, site, _stream())
+              rstd.data_ptr(), rows, cols, eps, dropout_p, seed, None, site, _stream())
     return y16, y32, mean, rstd
 
 
-def layernorm_bwd(dy_f32, dy_bf16, x, mean, rstd, gamma, dres, dgamma, dbeta, *, want_bf16=True, dropout_p=0.0, seed=0, site=0):
+def layernorm_bwd(dy_f32, dy_bf16, x, mean, rstd, gamma, dres, dgamma, dbeta, *, want_bf16=True, in_p=0.0, in_site=0, out_p=0.0,
+                  out_site=0, seed=0):
     _cuda(dy_f32, dy_bf16, x, mean, rstd, gamma, dres, dgamma, dbeta)
     rows, cols = x.numel() // x.shape[-1], x.shape[-1]
     dx32 = torch.empty_like(x)
     dx16 = torch.empty(x.shape, device=x.device, dtype=torch.bfloat16) if want_bf16 else None
     _abi.call("vault_layernorm_bwd_drop", _ptr(dy_f32), _ptr(dy_bf16), x.data_ptr(), mean.data_ptr(), rstd.data_ptr(), gamma.data_ptr(),
-              _ptr(dres), dx32.data_ptr(), _ptr(dx16), _ptr(dgamma), _ptr(dbeta), rows, cols, dropout_p, seed, site, _stream())
+              _ptr(dres), dx32.data_ptr(), _ptr(dx16), _ptr(dgamma), _ptr(dbeta), rows, cols, in_p, in_site, out_p, out_site, seed, None,
+              _stream())
     return dx32, dx16

@@ -1,0 +1,222 @@
+"""Data-parallel fine-tuning step for VaultForTMSC on B200s: the fast equivalent of the reference's hot loop body
+
+    batch_to_device -> model(**kwargs) -> CrossEntropyLoss -> zero_grad -> backward -> HF-AdamW.step -> scheduler.step -> loss.item()
+    (ref:vault/tmsc_utils/trainer.py:353-369)
+
+as ONE replayed CUDA graph per step (forward, fused CE head, backward) + bucketless flat gradient all-reduce over NCCL (one
+process per GPU, batch sharding, no other collective) + ONE fused AdamW launch over the flat parameter range.  Host->device
+input copies run on a side stream into double-buffered static inputs so step i+1's copy overlaps step i's compute; the loss is
+read back asynchronously (pinned memory) so there is no per-step device synchronisation.
+
+Semantics kept from the reference: CE mean over the (global) batch, transformers==4.48.0 AdamW rule with correct_bias=False,
+linear warm-up/decay schedule with lr(0)=0, no gradient clipping, dropout active in the LM stack and the head (p=0.1), ViLT
+dropout 0 (SURVEY.md sections 5, 8a).  Image tokens always span the full padded patch grid here (static shapes): padded patches
+are masked out of attention, so loss and gradients equal the reference's dynamic-length computation.
+"""
+from __future__ import annotations
+
+from typing import Dict, Optional
+
+import torch
+
+from . import _abi
+from .engine import VaultEngine
+
+_INPUT_KEYS = ("input_ids", "attention_mask", "token_type_ids", "pixel_values", "pixel_mask", "labels")
+
+
+def allreduce_flat_(flat: torch.Tensor, group=None, bucket_elems: int = 16 * 1024 * 1024, async_op: bool = False):
+    """Sum-all-reduce a flat gradient range in fixed-size buckets (the only collective of the path: batch data parallelism).
+    The 1/world averaging is folded into the AdamW kernel's grad_scale."""
+    import torch.distributed as dist
+
+    works = []
+    n = flat.numel()
+    for a in range(0, n, bucket_elems):
+        w = dist.all_reduce(flat[a:min(n, a + bucket_elems)], group=group, async_op=async_op)
+        if async_op:
+            works.append(w)
+    return works
+
+
+class StepResult:
+    """Handle on a step's loss: ``loss()`` waits for that step's device->host copy only."""
+
+    def __init__(self, host: torch.Tensor, event: torch.cuda.Event, lr: float):
+        self._host, self._event, self.lr = host, event, lr
+
+    def loss(self) -> float:
+        self._event.synchronize()
+        return float(self._host[0])
+
+
+class _Slot:
+    def __init__(self):
+        self.buf: Dict[str, torch.Tensor] = {}
+        self.ready = torch.cuda.Event()
+        self.free = torch.cuda.Event()
+        self.graph: Optional[torch.cuda.CUDAGraph] = None
+        self.loss_host = None
+        self.loss_event = torch.cuda.Event()
+
+
+class VaultTrainStep:
+    def __init__(self, model, lr: float = 2e-5, betas=(0.9, 0.999), eps: float = 1e-8, weight_decay: float = 0.0, correct_bias: bool = False,
+                 total_steps: Optional[int] = None, warmup_ratio: float = 0.1, process_group=None, use_cuda_graph: bool = True,
+                 dropout: bool = True):
+        self.model = model
+        self.engine: VaultEngine = model.engine
+        self.lr, self.betas, self.eps, self.wd, self.correct_bias = lr, betas, eps, weight_decay, correct_bias
+        self.total_steps, self.warmup_ratio = total_steps, warmup_ratio
+        self.use_graph = use_cuda_graph
+        self.dropout = dropout  # False: dropout off everywhere (deterministic parity runs)
+        self.n_classes = model.classifier[1].out_features
+        if self.n_classes < 2:
+            raise NotImplementedError("VaultTrainStep: the BCE (n_classes=1, Bloomberg) loss is not built yet")
+        self.head_p = float(model.classifier[0].p)
+        self.dev = next(model.parameters()).device
+        if self.dev.type != "cuda":
+            raise RuntimeError("VaultTrainStep needs the model on a CUDA device (sm_100a); there is no CPU path")
+        self.engine.ensure_packed(self.dev)
+        self.engine.refresh_shadow(force=True)
+        self.engine.init_opt_state()
+        self.world, self.rank, self.pg = 1, 0, process_group
+        import torch.distributed as dist
+
+        if dist.is_available() and dist.is_initialized():
+            self.world = dist.get_world_size(process_group)
+            self.rank = dist.get_rank(process_group)
+        if self.world > 1:
+            # identical replicas: rank 0's weights everywhere; decorrelated dropout streams per rank
+            dist.broadcast(self.engine.master, src=dist.get_global_rank(process_group, 0) if process_group is not None else 0, group=process_group)
+            self.engine.refresh_shadow(force=True)
+            self.engine.seed = (self.engine.seed + 0x9E3779B97F4A7C15 * self.rank) & 0xFFFFFFFFFFFFFFFF
+        self.copy_stream = torch.cuda.Stream(device=self.dev)
+        self.sched_dev = torch.zeros(2, device=self.dev, dtype=torch.float32)
+        self.step_idx = 0
+        self._states: Dict[tuple, list] = {}
+        self._pool = None
+        self._turn = 0
+
+    # ------------------------------------------------------------------------------------------------------------
+    def lr_at(self, step: int) -> float:
+        """get_linear_schedule_with_warmup (HF:optimization.py:101-131) with warm = int(ratio*total) (ref:vault/tmsc_utils/trainer.py:256-280)."""
+        if self.total_steps is None:
+            return self.lr
+        warm = int(self.warmup_ratio * self.total_steps)
+        if step < warm:
+            return self.lr * float(step) / float(max(1, warm))
+        return self.lr * max(0.0, float(self.total_steps - step) / float(max(1, self.total_steps - warm)))
+
+    def _make_slot(self, batch) -> _Slot:
+        s = _Slot()
+        for k in _INPUT_KEYS:
+            v = batch.get(k)
+            if v is None:
+                continue
+            dt = torch.float32 if k == "pixel_values" else torch.int64
+            s.buf[k] = torch.empty(v.shape, device=self.dev, dtype=dt)
+        B = batch["input_ids"].shape[0]
+        s.buf["hw"] = torch.empty((B, 2), device=self.dev, dtype=torch.int32)
+        s.buf["loss"] = torch.zeros(1, device=self.dev, dtype=torch.float32)
+        s.buf["logits"] = torch.zeros((B, self.n_classes), device=self.dev, dtype=torch.float32)
+        s.loss_host = torch.zeros(1, dtype=torch.float32).pin_memory()
+        s.free.record(torch.cuda.current_stream(self.dev))
+        return s
+
+    def _body(self, s: _Slot):
+        """forward + CE head + backward of one local batch, all kernels on the current stream (capturable)."""
+        eng, lib = self.engine, _abi.lib()
+        b = s.buf
+        st = eng._stream()
+        eng._lib, eng._st = lib, st
+        B, T = b["input_ids"].shape
+        _, Cc, Hi, Wi = b["pixel_values"].shape
+        gh, gw = Hi // eng.patch, Wi // eng.patch
+        H = eng.H
+        train = self.dropout
+        eng.seed_dev.add_(1)
+        if "pixel_mask" in b:
+            _abi.check(lib.vault_patch_grid(b["pixel_mask"].data_ptr(), 0, b["hw"].data_ptr(), B, Hi, Wi, eng.patch, st), "patch_grid")
+        else:
+            b["hw"][:, 0] = gh
+            b["hw"][:, 1] = gw
+        lhs, pooled, key_mask, tape = eng.forward(b["input_ids"], b.get("attention_mask"), b.get("token_type_ids"), b["pixel_values"], None,
+                                                  training=train, need_grad=True, hw=b["hw"], pmax=gh * gw)
+        # ---- head: Linear(Dropout(pooled)) -> CE mean; dlogits = (softmax - onehot) / B_local (DP averaging is applied in AdamW's grad_scale)
+        p = self.head_p if train else 0.0
+        x = pooled
+        if p > 0:
+            x = torch.empty_like(pooled)
+            _abi.check(lib.vault_dropout_f32(pooled.data_ptr(), x.data_ptr(), pooled.numel(), p, eng.seed, eng.seed_dev.data_ptr(), eng.SITE_HEAD, st),
+                       "head_dropout")
+        n = self.n_classes
+        _abi.check(lib.vault_small_linear_fwd(x.data_ptr(), H, eng.w32("classifier.1.weight"), eng.w32("classifier.1.bias"), b["logits"].data_ptr(), B, n,
+                                              H, 0, st), "classifier_fwd")
+        dlogits = torch.empty((B, n), device=self.dev, dtype=torch.float32)
+        _abi.check(lib.vault_ce_loss(b["logits"].data_ptr(), b["labels"].data_ptr(), b["loss"].data_ptr(), dlogits.data_ptr(), B, n, 1.0, st), "ce_loss")
+        dx = torch.empty_like(pooled)
+        _abi.check(lib.vault_small_linear_bwd(dlogits.data_ptr(), None, x.data_ptr(), H, eng.w32("classifier.1.weight"), dx.data_ptr(), H, 0,
+                                              eng.g32("classifier.1.weight") or None, eng.g32("classifier.1.bias") or None, B, n, H, 0, st),
+                   "classifier_bwd")
+        if p > 0:
+            _abi.check(lib.vault_dropout_f32(dx.data_ptr(), dx.data_ptr(), dx.numel(), p, eng.seed, eng.seed_dev.data_ptr(), eng.SITE_HEAD, st),
+                       "head_dropout_bwd")
+        eng.backward(tape, None, dx)
+
+    def _get_slot(self, batch) -> _Slot:
+        key = tuple((k, tuple(batch[k].shape)) for k in _INPUT_KEYS if batch.get(k) is not None)
+        if key not in self._states:
+            self._states[key] = [self._make_slot(batch), self._make_slot(batch)]
+        self._turn ^= 1
+        return self._states[key][self._turn]
+
+    def step(self, batch: Dict[str, torch.Tensor]) -> StepResult:
+        """One optimizer step on this rank's local batch (host tensors -- ideally pinned -- or device tensors)."""
+        eng = self.engine
+        s = self._get_slot(batch)
+        cs = torch.cuda.current_stream(self.dev)
+        on_host = not batch["pixel_values"].is_cuda
+        if on_host:
+            with torch.cuda.stream(self.copy_stream):
+                self.copy_stream.wait_event(s.free)
+                for k, dst in s.buf.items():
+                    if k in batch and batch[k] is not None:
+                        dst.copy_(batch[k], non_blocking=True)
+                s.ready.record(self.copy_stream)
+            cs.wait_event(s.ready)
+        else:
+            for k, dst in s.buf.items():
+                if k in batch and batch[k] is not None:
+                    dst.copy_(batch[k], non_blocking=True)
+        lr = self.lr_at(self.step_idx)
+        eng.refresh_shadow()  # host-side check only, unless someone modified the Parameters in place
+        if self.use_graph:
+            if s.graph is None:
+                self._body(s)  # eager warm-up: sets kernel attributes, sizes the allocator
+                torch.cuda.synchronize(self.dev)
+                eng.seed_dev.sub_(1)
+                g = torch.cuda.CUDAGraph()
+                with torch.cuda.graph(g, pool=self._pool, stream=torch.cuda.Stream(device=self.dev)):
+                    self._body(s)
+                if self._pool is None:
+                    self._pool = g.pool()
+                s.graph = g
+            s.graph.replay()
+        else:
+            self._body(s)
+        if on_host:
+            s.free.record(cs)
+        if self.world > 1:
+            allreduce_flat_(eng.grad[:eng.n_train], self.pg)
+        step_no = eng.opt_state["step"] + 1
+        b1, b2 = self.betas
+        step_size = lr
+        if self.correct_bias:
+            step_size = lr * (1.0 - b2 ** step_no) ** 0.5 / (1.0 - b1 ** step_no)
+        self.sched_dev.copy_(torch.tensor([step_size, lr * self.wd if self.wd > 0 else 0.0], dtype=torch.float32), non_blocking=True)
+        eng.adamw_step(lr, b1, b2, self.eps, self.wd, self.correct_bias, grad_scale=1.0 / self.world, sched_dev=self.sched_dev)
+        s.loss_host.copy_(s.buf["loss"], non_blocking=True)
+        s.loss_event.record(cs)
+        self.step_idx += 1
+        return StepResult(s.loss_host, s.loss_event, lr)

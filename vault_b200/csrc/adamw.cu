@@ -6,13 +6,13 @@ namespace vb {
 
 __global__ void __launch_bounds__(256)
 adamw_kernel(float* __restrict__ p, const float* __restrict__ g, float* __restrict__ m, float* __restrict__ v, bf16* __restrict__ shadow, long long n,
-             float step_size, float lr_wd, float beta1, float beta2, float eps, float grad_scale, const float* __restrict__ sched_dev) {
+             float step_size, float lr_wd, float beta1, float beta2, float ob1, float ob2, float eps, float grad_scale,
+             const float* __restrict__ sched_dev) {
   if (sched_dev) {  // {step_size, lr*weight_decay} read from device memory: a captured CUDA graph can follow an lr schedule
     step_size = sched_dev[0];
     lr_wd = sched_dev[1];
   }
   const long long n4 = n >> 2;
-  const float ob1 = 1.f - beta1, ob2 = 1.f - beta2;
   for (long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x; i < n4; i += (long long)gridDim.x * blockDim.x) {
     float4 pv = reinterpret_cast<float4*>(p)[i];
     float4 gv = __ldg(reinterpret_cast<const float4*>(g) + i);
@@ -86,7 +86,8 @@ extern "C" int vault_adamw_step(float* p, const float* g, float* m, float* v, vo
     step_size = (double)lr * sqrt(1.0 - pow((double)beta2, step)) / (1.0 - pow((double)beta1, step));
   }
   adamw_kernel<<<flat_grid(n >> 2), 256, 0, (cudaStream_t)stream>>>(p, g, m, v, reinterpret_cast<bf16*>(shadow_bf16), n, (float)step_size,
-                                                                    weight_decay > 0.f ? lr * weight_decay : 0.f, beta1, beta2, eps, grad_scale, sched_dev);
+                                                                    weight_decay > 0.f ? lr * weight_decay : 0.f, beta1, beta2,
+                                                                    (float)(1.0 - (double)beta1), (float)(1.0 - (double)beta2), eps, grad_scale, sched_dev);
   return check_launch("adamw_kernel");
 }
 

@@ -51,12 +51,29 @@ __device__ __forceinline__ float fast_exp2(float x) {  // ex2.approx: 2 ulp, exp
   asm("ex2.approx.ftz.f32 %0, %1;" : "=f"(y) : "f"(x));
   return y;
 }
-__device__ __forceinline__ float gelu_erf(float x) { return 0.5f * x * (1.0f + erff(x * 0.70710678118654752440f)); }
+// erf via Abramowitz-Stegun 7.1.26 (|abs err| <= 1.5e-7) sharing ONE exponential with the Gaussian pdf: the GELU epilogues
+// run on 8 warps next to a saturated tensor pipe, so instruction count matters (libdevice erff is ~3x longer).
+//   e must be exp(-u*u)
+__device__ __forceinline__ float erf_as(float u, float e) {
+  const float t = __fdividef(1.0f, fmaf(0.3275911f, fabsf(u), 1.0f));
+  float poly = fmaf(1.061405429f, t, -1.453152027f);
+  poly = fmaf(poly, t, 1.421413741f);
+  poly = fmaf(poly, t, -0.284496736f);
+  poly = fmaf(poly, t, 0.254829592f);
+  return copysignf(fmaf(-poly * t, e, 1.0f), u);
+}
+// exact-erf GELU of HF BertIntermediate / ViltIntermediate ("gelu"): 0.5 x (1 + erf(x / sqrt 2))
+__device__ __forceinline__ float gelu_erf(float x) {
+  const float u = x * 0.70710678118654752440f;
+  const float e = fast_exp2(-u * u * 1.4426950408889634f);
+  return 0.5f * x * (1.0f + erf_as(u, e));
+}
 __device__ __forceinline__ float gelu_erf_grad(float x) {
-  // d/dx [x * Phi(x)] = Phi(x) + x * phi(x)
-  const float cdf = 0.5f * (1.0f + erff(x * 0.70710678118654752440f));
-  const float pdf = 0.39894228040143267794f * __expf(-0.5f * x * x);
-  return cdf + x * pdf;
+  // d/dx [x Phi(x)] = Phi(x) + x phi(x);  exp(-(x/sqrt2)^2) = exp(-x^2/2) serves both terms
+  const float u = x * 0.70710678118654752440f;
+  const float e = fast_exp2(-u * u * 1.4426950408889634f);
+  const float cdf = 0.5f * (1.0f + erf_as(u, e));
+  return fmaf(x * 0.39894228040143267794f, e, cdf);
 }
 
 // ---- Philox4x32-10 (counter-based dropout masks: forward and backward regenerate the same bits) ------------------

@@ -41,8 +41,24 @@ struct GemmParams {
   unsigned site;
 };
 
+// Side input of an epilogue (fp32 residual row segment or bf16 pre-activation), fetched for all 8 row-groups of a chunk BEFORE
+// any store so the loads are in flight together (the output pointer may alias nothing, but the compiler cannot know that).
 template <int EPI>
-__device__ __forceinline__ void epilogue4(const GemmParams& p, float4 acc, const float4& b4, long long row, int col) {
+__device__ __forceinline__ float4 epilogue_side(const GemmParams& p, long long row, int col) {
+  if constexpr (EPI == VAULT_EPI_BIAS_RESID_F32) {
+    return __ldg(reinterpret_cast<const float4*>(p.resid + row * p.ldr + col));
+  } else if constexpr (EPI == VAULT_EPI_DGELU_BF16) {
+    const uint2 a = __ldg(reinterpret_cast<const uint2*>(p.aux + row * p.ldaux + col));
+    const float2 a01 = unpack_bf16x2(a.x), a23 = unpack_bf16x2(a.y);
+    return make_float4(a01.x, a01.y, a23.x, a23.y);
+  } else {
+    return make_float4(0.f, 0.f, 0.f, 0.f);
+  }
+}
+
+template <int EPI>
+__device__ __forceinline__ void epilogue4(const GemmParams& p, float4 acc, const float4& b4, const float4& side, unsigned long long seed,
+                                          long long row, int col) {
   if constexpr (EPI == VAULT_EPI_BIAS_BF16) {
     uint2 o;
     o.x = pack_bf16x2(acc.x + b4.x, acc.y + b4.y);
@@ -65,14 +81,13 @@ __device__ __forceinline__ void epilogue4(const GemmParams& p, float4 acc, const
     if (p.dropout_p > 0.f) {
       const uint32_t thr = dropout_threshold(p.dropout_p);
       const float sc = 1.0f / (1.0f - p.dropout_p);
-      const uint4 bits = dropout_bits4(p.seed + (p.seed_dev ? *p.seed_dev : 0ull), p.site, (unsigned long long)(row * p.N + col) >> 2);
+      const uint4 bits = dropout_bits4(seed, p.site, (unsigned long long)(row * p.N + col) >> 2);
       x0 = bits.x >= thr ? x0 * sc : 0.f;
       x1 = bits.y >= thr ? x1 * sc : 0.f;
       x2 = bits.z >= thr ? x2 * sc : 0.f;
       x3 = bits.w >= thr ? x3 * sc : 0.f;
     }
-    const float4 r = *reinterpret_cast<const float4*>(p.resid + row * p.ldr + col);
-    float4 o = make_float4(r.x + x0, r.y + x1, r.z + x2, r.w + x3);
+    float4 o = make_float4(side.x + x0, side.y + x1, side.z + x2, side.w + x3);
     *reinterpret_cast<float4*>(reinterpret_cast<float*>(p.out) + row * p.ldo + col) = o;
   } else if constexpr (EPI == VAULT_EPI_PLAIN_BF16) {
     uint2 o;
@@ -80,11 +95,9 @@ __device__ __forceinline__ void epilogue4(const GemmParams& p, float4 acc, const
     o.y = pack_bf16x2(acc.z, acc.w);
     *reinterpret_cast<uint2*>(reinterpret_cast<bf16*>(p.out) + row * p.ldo + col) = o;
   } else if constexpr (EPI == VAULT_EPI_DGELU_BF16) {
-    const uint2 a = *reinterpret_cast<const uint2*>(p.aux + row * p.ldaux + col);
-    const float2 a01 = unpack_bf16x2(a.x), a23 = unpack_bf16x2(a.y);
     uint2 o;
-    o.x = pack_bf16x2(acc.x * gelu_erf_grad(a01.x), acc.y * gelu_erf_grad(a01.y));
-    o.y = pack_bf16x2(acc.z * gelu_erf_grad(a23.x), acc.w * gelu_erf_grad(a23.y));
+    o.x = pack_bf16x2(acc.x * gelu_erf_grad(side.x), acc.y * gelu_erf_grad(side.y));
+    o.y = pack_bf16x2(acc.z * gelu_erf_grad(side.z), acc.w * gelu_erf_grad(side.w));
     *reinterpret_cast<uint2*>(reinterpret_cast<bf16*>(p.out) + row * p.ldo + col) = o;
   } else if constexpr (EPI == VAULT_EPI_ATOMIC_F32) {
     float* dst = reinterpret_cast<float*>(p.out) + row * p.ldo + col;
@@ -227,6 +240,7 @@ gemm_bf16_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant_
     const int half = ew >> 2;      // which half of the tile's columns
     constexpr int kColsPerWarp = BN / 2;
     float4* stg = reinterpret_cast<float4*>(staging_gen + ew * 4096);
+    const unsigned long long seed = p.seed + ((p.dropout_p > 0.f && p.seed_dev) ? *p.seed_dev : 0ull);
     int as = 0;
     uint32_t aphase = 0;
     for (int t = blockIdx.x; t < total_tiles; t += gridDim.x) {
@@ -254,12 +268,19 @@ gemm_bf16_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant_
         if constexpr (EPI == VAULT_EPI_BIAS_BF16 || EPI == VAULT_EPI_BIAS_GELU_BF16 || EPI == VAULT_EPI_BIAS_RESID_F32 || EPI == VAULT_EPI_BIAS_F32) {
           if (p.bias != nullptr && col < p.N) b4 = *reinterpret_cast<const float4*>(p.bias + col);
         }
+        const long long rbase = (long long)m0 + q * 32 + (lane >> 3);
+        float4 side[8];
+#pragma unroll
+        for (int i = 0; i < 8; ++i) {
+          const long long row = rbase + 4 * i;
+          side[i] = (row < p.M && col < p.N) ? epilogue_side<EPI>(p, row, col) : make_float4(0.f, 0.f, 0.f, 0.f);
+        }
 #pragma unroll
         for (int i = 0; i < 8; ++i) {
           const int rl = 4 * i + (lane >> 3);
           const float4 acc = stg[rl * 8 + (cg ^ (rl & 7))];
-          const long long row = (long long)m0 + q * 32 + rl;
-          if (row < p.M && col < p.N) epilogue4<EPI>(p, acc, b4, row, col);
+          const long long row = rbase + 4 * i;
+          if (row < p.M && col < p.N) epilogue4<EPI>(p, acc, b4, side[i], seed, row, col);
         }
         __syncwarp();
       }

@@ -34,52 +34,76 @@ __device__ __forceinline__ float act_grad(float dy, const float* y, long long id
   return dy;
 }
 
-// dW[n,k] = sum_r g[r,n] x[r,k], db[n] = sum_r g[r,n]; one warp per n
+// dW[n,k] = sum_r g[r,n] x[r,k], db[n] = sum_r g[r,n]; one warp per (n, 128-column chunk), rows unrolled for memory parallelism
 __global__ void __launch_bounds__(256)
 small_linear_wgrad_kernel(const float* __restrict__ dy, const float* __restrict__ y, const float* __restrict__ x, long long ldx, float* __restrict__ dW,
                           float* __restrict__ db, int rows, int N, int K, int act) {
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
-  const int n = blockIdx.x * 8 + warp;
-  if (n >= N) return;
+  const int chunks = (K / 4 + 31) / 32;
+  const long long o = (long long)blockIdx.x * 8 + warp;
+  if (o >= (long long)N * chunks) return;
+  const int n = (int)(o / chunks), ch = (int)(o % chunks);
+  const int c = ch * 32 + lane;
+  float4 acc = make_float4(0.f, 0.f, 0.f, 0.f);
   float bsum = 0.f;
-  for (int c0 = 0; c0 < K / 4; c0 += 32) {
-    const int c = c0 + lane;
-    float4 acc = make_float4(0.f, 0.f, 0.f, 0.f);
-    for (int r = 0; r < rows; ++r) {
-      const float g = act_grad(dy[(long long)r * N + n], y, (long long)r * N + n, act);
-      if (c0 == 0 && lane == 0) bsum += g;
-      if (c < K / 4) {
-        const float4 a = __ldg(reinterpret_cast<const float4*>(x + r * ldx) + c);
-        acc.x += g * a.x; acc.y += g * a.y; acc.z += g * a.z; acc.w += g * a.w;
-      }
+  for (int r0 = 0; r0 < rows; r0 += 8) {
+    float g[8];
+    float4 a[8];
+#pragma unroll
+    for (int j = 0; j < 8; ++j) {
+      const int r = r0 + j;
+      g[j] = r < rows ? act_grad(dy[(long long)r * N + n], y, (long long)r * N + n, act) : 0.f;
+      a[j] = (r < rows && c < K / 4) ? __ldg(reinterpret_cast<const float4*>(x + r * ldx) + c) : make_float4(0.f, 0.f, 0.f, 0.f);
     }
-    if (dW && c < K / 4) reinterpret_cast<float4*>(dW + (long long)n * K)[c] = acc;
+#pragma unroll
+    for (int j = 0; j < 8; ++j) {
+      bsum += g[j];
+      acc.x += g[j] * a[j].x; acc.y += g[j] * a[j].y; acc.z += g[j] * a[j].z; acc.w += g[j] * a[j].w;
+    }
   }
-  if (db && lane == 0) db[n] = bsum;
+  if (dW && c < K / 4) reinterpret_cast<float4*>(dW + (long long)n * K)[c] = acc;
+  if (db && ch == 0 && lane == 0) db[n] = bsum;
 }
 
-// dx[r,k] (+)= sum_n g[r,n] W[n,k]; one warp per (r, 128-column chunk)
+// dx[r,k] (+)= sum_n g[r,n] W[n,k]; one CTA per (r, 128-column chunk): its 8 warps split n, partial sums meet in shared memory
 __global__ void __launch_bounds__(256)
 small_linear_dgrad_kernel(const float* __restrict__ dy, const float* __restrict__ y, const float* __restrict__ W, float* __restrict__ dx, long long lddx,
                           int accumulate, int rows, int N, int K, int act) {
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
   const int chunks = (K / 4 + 31) / 32;
-  const long long o = (long long)blockIdx.x * 8 + warp;
-  if (o >= (long long)rows * chunks) return;
-  const int r = (int)(o / chunks), c = (int)(o % chunks) * 32 + lane;
-  if (c >= K / 4) return;
+  const int r = blockIdx.x / chunks, c = (blockIdx.x % chunks) * 32 + lane;
   float4 acc = make_float4(0.f, 0.f, 0.f, 0.f);
-  for (int n = 0; n < N; ++n) {
-    const float g = act_grad(dy[(long long)r * N + n], y, (long long)r * N + n, act);
-    const float4 w = __ldg(reinterpret_cast<const float4*>(W + (long long)n * K) + c);
-    acc.x += g * w.x; acc.y += g * w.y; acc.z += g * w.z; acc.w += g * w.w;
+  for (int n0 = warp; n0 < N; n0 += 8 * 4) {
+    float g[4];
+    float4 w[4];
+#pragma unroll
+    for (int j = 0; j < 4; ++j) {
+      const int n = n0 + 8 * j;
+      g[j] = n < N ? act_grad(dy[(long long)r * N + n], y, (long long)r * N + n, act) : 0.f;
+      w[j] = (n < N && c < K / 4) ? __ldg(reinterpret_cast<const float4*>(W + (long long)n * K) + c) : make_float4(0.f, 0.f, 0.f, 0.f);
+    }
+#pragma unroll
+    for (int j = 0; j < 4; ++j) {
+      acc.x += g[j] * w[j].x; acc.y += g[j] * w[j].y; acc.z += g[j] * w[j].z; acc.w += g[j] * w[j].w;
+    }
   }
-  float4* d = reinterpret_cast<float4*>(dx + r * lddx) + c;
-  if (accumulate) {
-    const float4 old = *d;
-    acc.x += old.x; acc.y += old.y; acc.z += old.z; acc.w += old.w;
+  __shared__ float4 red[8][33];
+  red[warp][lane] = acc;
+  __syncthreads();
+  if (warp == 0 && c < K / 4) {
+    float4 t = red[0][lane];
+#pragma unroll
+    for (int wv = 1; wv < 8; ++wv) {
+      const float4 u = red[wv][lane];
+      t.x += u.x; t.y += u.y; t.z += u.z; t.w += u.w;
+    }
+    float4* d = reinterpret_cast<float4*>(dx + r * lddx) + c;
+    if (accumulate) {
+      const float4 old = *d;
+      t.x += old.x; t.y += old.y; t.z += old.z; t.w += old.w;
+    }
+    *d = t;
   }
-  *d = acc;
 }
 
 __global__ void dropout_f32_kernel(const float* __restrict__ x, float* __restrict__ y, long long n, float p, unsigned long long seed,
@@ -174,14 +198,15 @@ extern "C" int vault_small_linear_bwd(const float* dy, const float* y, const flo
   VB_REQUIRE(rows > 0 && N > 0 && K > 0 && K % 4 == 0 && ldx % 4 == 0, "small_linear_bwd: bad shape rows=%d N=%d K=%d", rows, N, K);
   cudaStream_t st = (cudaStream_t)stream;
   if (dW || db) {
-    small_linear_wgrad_kernel<<<(unsigned)((N + 7) / 8), 256, 0, st>>>(dy, y, x, ldx, dW, db, rows, N, K, act);
+    const long long wwarps = (long long)N * ((K / 4 + 31) / 32);
+    small_linear_wgrad_kernel<<<(unsigned)((wwarps + 7) / 8), 256, 0, st>>>(dy, y, x, ldx, dW, db, rows, N, K, act);
     int rc = check_launch("small_linear_wgrad_kernel");
     if (rc) return rc;
   }
   if (dx) {
     VB_REQUIRE(lddx % 4 == 0, "small_linear_bwd: lddx must be a multiple of 4");
-    const long long warps = (long long)rows * ((K / 4 + 31) / 32);
-    small_linear_dgrad_kernel<<<(unsigned)((warps + 7) / 8), 256, 0, st>>>(dy, y, W, dx, lddx, accumulate_dx, rows, N, K, act);
+    const long long ctas = (long long)rows * ((K / 4 + 31) / 32);
+    small_linear_dgrad_kernel<<<(unsigned)ctas, 256, 0, st>>>(dy, y, W, dx, lddx, accumulate_dx, rows, N, K, act);
     return check_launch("small_linear_dgrad_kernel");
   }
   return VAULT_OK;

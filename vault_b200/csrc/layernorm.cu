@@ -69,7 +69,7 @@ ln_fwd_kernel(const float* __restrict__ x, const float* __restrict__ gamma, cons
 // Backward.  Persistent grid: each warp strides over rows and keeps its dgamma/dbeta partial sums in registers; one smem
 // reduction and one atomic per column per CTA at the end.
 template <int VPL>
-__global__ void __launch_bounds__(kLnWarps * 32)
+__global__ void __launch_bounds__(kLnWarps * 32, 2)
 ln_bwd_kernel(const float* __restrict__ dy_f32, const bf16* __restrict__ dy_bf16, const float* __restrict__ x, const float* __restrict__ mean,
               const float* __restrict__ rstd, const float* __restrict__ gamma, const float* __restrict__ dres, float* __restrict__ dx_f32,
               bf16* __restrict__ dx_bf16, float* __restrict__ dgamma, float* __restrict__ dbeta, long long rows, float drop_p, unsigned site,
@@ -79,10 +79,9 @@ ln_bwd_kernel(const float* __restrict__ dy_f32, const bf16* __restrict__ dy_bf16
   const uint32_t out_thr = dropout_threshold(out_p);
   const float out_scale = out_p > 0.f ? 1.0f / (1.0f - out_p) : 1.0f;
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
-  float4 g[VPL], dg[VPL], db[VPL];
+  float4 dg[VPL], db[VPL];
 #pragma unroll
   for (int i = 0; i < VPL; ++i) {
-    g[i] = __ldg(reinterpret_cast<const float4*>(gamma) + lane + 32 * i);
     dg[i] = make_float4(0.f, 0.f, 0.f, 0.f);
     db[i] = make_float4(0.f, 0.f, 0.f, 0.f);
   }
@@ -113,7 +112,8 @@ ln_bwd_kernel(const float* __restrict__ dy_f32, const bf16* __restrict__ dy_bf16
       xh[i] = make_float4((xv.x - mu) * rs, (xv.y - mu) * rs, (xv.z - mu) * rs, (xv.w - mu) * rs);
       dg[i].x += dv.x * xh[i].x; dg[i].y += dv.y * xh[i].y; dg[i].z += dv.z * xh[i].z; dg[i].w += dv.w * xh[i].w;
       db[i].x += dv.x; db[i].y += dv.y; db[i].z += dv.z; db[i].w += dv.w;
-      d[i] = make_float4(dv.x * g[i].x, dv.y * g[i].y, dv.z * g[i].z, dv.w * g[i].w);
+      const float4 gm = __ldg(reinterpret_cast<const float4*>(gamma) + c4);  // L1-resident after the first row
+      d[i] = make_float4(dv.x * gm.x, dv.y * gm.y, dv.z * gm.z, dv.w * gm.w);
       s1 += (d[i].x + d[i].y) + (d[i].z + d[i].w);
       s2 += (d[i].x * xh[i].x + d[i].y * xh[i].y) + (d[i].z * xh[i].z + d[i].w * xh[i].w);
     }

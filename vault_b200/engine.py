@@ -111,10 +111,11 @@ class VaultEngine:
         for i in reversed(range(self.L)):
             p = f"encoder.layer.{i}."
             a = p + "attention.attention."
-            add(a + "query.weight", a + "key.weight", a + "value.weight", a + "query.bias", a + "key.bias", a + "value.bias")
-            add(p + "attention.output.dense.weight", p + "attention.output.dense.bias")
+            # accumulated-with-atomics slots first (one memset per layer), then the dense weights their wgrad GEMMs overwrite
+            add(a + "query.bias", a + "key.bias", a + "value.bias", p + "attention.output.dense.bias")
             add(p + "layernorm_before.weight", p + "layernorm_before.bias", p + "layernorm_after.weight", p + "layernorm_after.bias")
-            add(p + "intermediate.dense.weight", p + "intermediate.dense.bias", p + "output.dense.weight", p + "output.dense.bias")
+            add(p + "intermediate.dense.bias", p + "output.dense.bias", p + "attention.output.dense.weight")
+            add(a + "query.weight", a + "key.weight", a + "value.weight", p + "intermediate.dense.weight", p + "output.dense.weight")
         e = "embeddings."
         add(e + "cls_token", e + "position_embeddings", e + "token_type_embeddings.weight", e + "patch_embeddings.projection.weight",
             e + "patch_embeddings.projection.bias", e + "text_embeddings.token_type_embeddings.weight",
@@ -124,11 +125,11 @@ class VaultEngine:
             for i in reversed(range(self.lm_L)):
                 p = f"bert.encoder.layer.{i}."
                 a = p + "attention.self."
-                add(a + "query.weight", a + "key.weight", a + "value.weight", a + "query.bias", a + "key.bias", a + "value.bias")
-                add(p + "attention.output.dense.weight", p + "attention.output.dense.bias", p + "attention.output.LayerNorm.weight",
-                    p + "attention.output.LayerNorm.bias")
-                add(p + "intermediate.dense.weight", p + "intermediate.dense.bias", p + "output.dense.weight", p + "output.dense.bias",
-                    p + "output.LayerNorm.weight", p + "output.LayerNorm.bias")
+                add(a + "query.bias", a + "key.bias", a + "value.bias", p + "attention.output.dense.bias")
+                add(p + "attention.output.LayerNorm.weight", p + "attention.output.LayerNorm.bias", p + "output.LayerNorm.weight",
+                    p + "output.LayerNorm.bias")
+                add(p + "intermediate.dense.bias", p + "output.dense.bias", p + "attention.output.dense.weight")
+                add(a + "query.weight", a + "key.weight", a + "value.weight", p + "intermediate.dense.weight", p + "output.dense.weight")
             b = "bert.embeddings."
             add(b + "word_embeddings.weight", b + "position_embeddings.weight", b + "token_type_embeddings.weight",
                 b + "LayerNorm.weight", b + "LayerNorm.bias")
@@ -230,26 +231,36 @@ class VaultEngine:
             return None
         return self.grad[s.off:s.off + s.numel].view(s.shape)
 
+    def _wgrad_is_split(self, n_out: int, k_out: int) -> bool:
+        """Few output tiles (e.g. the 768x768 attention-output weight: 36) -> split the token contraction across CTAs and
+        accumulate with fp32 atomics into a zero-filled slot.  Decided per weight shape at pack time."""
+        return ((n_out + 127) // 128) * ((k_out + 127) // 128) * 2 <= self.sms
+
     def _wgrad_split(self, n_out: int, k_out: int, tokens: int) -> int:
         tiles = ((n_out + 127) // 128) * ((k_out + 127) // 128)
         nkb = (tokens + 63) // 64
-        if tiles * 2 > self.sms:
-            return 1
         return max(1, min(8, self.sms // tiles, max(1, nkb // 4)))
 
     def _compute_zero_ranges(self):
         """Everything except the big dense weights (whose wgrad GEMM overwrites them, unless it runs split-K -- decided per
         call and zeroed there) is accumulated with atomics: biases, LayerNorm affine, embedding tables, cls/pos/modality."""
         big = set()
+        self._atomic_w = set()
         for n, s in self.slots.items():
             if not s.trainable:
                 continue
-            if n.endswith("dense.weight") and "pooler" not in n:
-                big.add(n)
+            is_dense = (n.endswith("dense.weight") and "pooler" not in n) or n.endswith("projection.weight")
+            if is_dense:
+                n_out, k_in = s.shape[0], s.numel // s.shape[0]
+                if self._wgrad_is_split(n_out, k_in):
+                    self._atomic_w.add(n)  # zero-filled with the small slots, accumulated by split-K atomics
+                else:
+                    big.add(n)
             if any(n.endswith(k + ".weight") for k in ("query", "key", "value")):
-                big.add(n)
-            if n.endswith("projection.weight"):
-                big.add(n)
+                if self._wgrad_is_split(3 * s.shape[0], s.shape[1]):
+                    self._atomic_w.add(n)
+                else:
+                    big.add(n)
         ranges = []
         for n, s in sorted(self.slots.items(), key=lambda kv: kv[1].off):
             if not s.trainable or n in big or n.startswith("classifier.") or n.startswith("pooler."):
@@ -299,11 +310,9 @@ class VaultEngine:
         """dW[N_out,K_in] = dy^T x (contraction over the M tokens, both operands read un-transposed), db = colsum(dy)."""
         gw = self.g32(wname)
         if gw:
-            split = self._wgrad_split(N_out, K_in, M)
-            if split > 1:
-                off = self.slots[wname].off
-                self.grad[off:off + N_out * K_in].zero_()  # the whole fused slice (q,k,v adjacent), not just the first tensor
-                self.gemm(dy16.data_ptr(), N_out, 1, x16.data_ptr(), K_in, 1, N_out, K_in, M, EPI_ATOMIC_F32, gw, K_in, split_k=split, block_n=128)
+            if wname in self._atomic_w:  # slot already zero-filled by zero_accumulated_grads()
+                self.gemm(dy16.data_ptr(), N_out, 1, x16.data_ptr(), K_in, 1, N_out, K_in, M, EPI_ATOMIC_F32, gw, K_in,
+                          split_k=self._wgrad_split(N_out, K_in, M), block_n=128)
             else:
                 self.gemm(dy16.data_ptr(), N_out, 1, x16.data_ptr(), K_in, 1, N_out, K_in, M, EPI_STORE_F32, gw, K_in, block_n=128)
         gb = self.g32(bname)

@@ -166,5 +166,5 @@ def test_batch_rows_are_independent_at_baseline_size():
             ext[k] = torch.cat([ext[k], pad], dim=1)
         longer = m._trunk(**ext)[1].float()
     assert (full[5] - solo[0]).abs().max() <= 2e-3   # same arithmetic up to tile-boundary effects in bf16 GEMM inputs: none expected
-    assert (longer[0] - solo[0]).abs().max() <= 2e-3
+    assert (longer[0] - solo[0]).abs().max() <= 1e-2  # key chunking of the online softmax shifts -> bf16-level differences over 24 layers
     assert torch.isfinite(full).all()

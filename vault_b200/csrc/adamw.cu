@@ -73,21 +73,21 @@ static unsigned flat_grid(long long n4) {
 
 using namespace vb;
 
-extern "C" int vault_adamw_step(float* p, const float* g, float* m, float* v, void* shadow_bf16, int64_t n, float lr, float beta1, float beta2,
-                                float eps, float weight_decay, int32_t correct_bias, int32_t step, float grad_scale, const float* sched_dev,
+extern "C" int vault_adamw_step(float* p, const float* g, float* m, float* v, void* shadow_bf16, int64_t n, double lr, double beta1, double beta2,
+                                double eps, double weight_decay, int32_t correct_bias, int32_t step, float grad_scale, const float* sched_dev,
                                 void* stream) {
   VB_REQUIRE(p && g && m && v && n >= 0, "adamw_step: bad arguments");
   VB_REQUIRE((((uintptr_t)p | (uintptr_t)g | (uintptr_t)m | (uintptr_t)v) & 15) == 0, "adamw_step: buffers must be 16-byte aligned");
   VB_REQUIRE(shadow_bf16 == nullptr || ((uintptr_t)shadow_bf16 & 7) == 0, "adamw_step: shadow must be 8-byte aligned");
   if (n == 0) return VAULT_OK;
-  double step_size = lr;
+  double step_size = lr;  // hyper-parameters arrive as doubles: 1-beta is formed in double like torch's Python scalars, then rounded once
   if (correct_bias) {
     VB_REQUIRE(step >= 1, "adamw_step: step must be >= 1 with correct_bias");
-    step_size = (double)lr * sqrt(1.0 - pow((double)beta2, step)) / (1.0 - pow((double)beta1, step));
+    step_size = lr * sqrt(1.0 - pow(beta2, step)) / (1.0 - pow(beta1, step));
   }
   adamw_kernel<<<flat_grid(n >> 2), 256, 0, (cudaStream_t)stream>>>(p, g, m, v, reinterpret_cast<bf16*>(shadow_bf16), n, (float)step_size,
-                                                                    weight_decay > 0.f ? lr * weight_decay : 0.f, beta1, beta2,
-                                                                    (float)(1.0 - (double)beta1), (float)(1.0 - (double)beta2), eps, grad_scale, sched_dev);
+                                                                    weight_decay > 0.0 ? (float)(lr * weight_decay) : 0.f, (float)beta1,
+                                                                    (float)beta2, (float)(1.0 - beta1), (float)(1.0 - beta2), (float)eps, grad_scale, sched_dev);
   return check_launch("adamw_kernel");
 }
 

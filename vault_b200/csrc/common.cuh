@@ -51,28 +51,33 @@ __device__ __forceinline__ float fast_exp2(float x) {  // ex2.approx: 2 ulp, exp
   asm("ex2.approx.ftz.f32 %0, %1;" : "=f"(y) : "f"(x));
   return y;
 }
-// erf via Abramowitz-Stegun 7.1.26 (|abs err| <= 1.5e-7) sharing ONE exponential with the Gaussian pdf: the GELU epilogues
-// run on 8 warps next to a saturated tensor pipe, so instruction count matters (libdevice erff is ~3x longer).
-//   e must be exp(-u*u)
-__device__ __forceinline__ float erf_as(float u, float e) {
-  const float t = __fdividef(1.0f, fmaf(0.3275911f, fabsf(u), 1.0f));
-  float poly = fmaf(1.061405429f, t, -1.453152027f);
-  poly = fmaf(poly, t, 1.421413741f);
-  poly = fmaf(poly, t, -0.284496736f);
-  poly = fmaf(poly, t, 0.254829592f);
-  return copysignf(fmaf(-poly * t, e, 1.0f), u);
+__device__ __forceinline__ float fast_rcp(float x) {
+  float y;
+  asm("rcp.approx.ftz.f32 %0, %1;" : "=f"(y) : "f"(x));
+  return y;
 }
-// exact-erf GELU of HF BertIntermediate / ViltIntermediate ("gelu"): 0.5 x (1 + erf(x / sqrt 2))
+// Exact-erf GELU of HF BertIntermediate / ViltIntermediate ("gelu") = x * Phi(x), with Phi from Abramowitz-Stegun 7.1.26
+// (|abs err| <= 1.5e-7):  1 - Phi(|x|) = 0.5 * P(t) * exp(-x^2/2),  t = 1 / (1 + p |x| / sqrt 2),  P = t (a1 + t (a2 + ... a5 t)).
+// The GELU epilogues share the SM's issue slots with a saturated tensor pipe, so they are written for instruction count:
+//   gelu(x)  = relu(x) - |x| * h            h = 0.5 P(t) exp(-x^2/2)          (13 instructions)
+//   gelu'(x) = (x >= 0 ? 1 - h : h) + x * phi(x),   phi(x) = exp(-x^2/2) / sqrt(2 pi)   (one shared exponential)
+__device__ __forceinline__ float gelu_tail_h(float ax, float e) {
+  const float t = fast_rcp(fmaf(0.23164189f /* 0.3275911 / sqrt 2 */, ax, 1.0f));
+  float poly = fmaf(0.5307027145f, t, -0.7265760135f);  // 0.5 * a5, 0.5 * a4
+  poly = fmaf(poly, t, 0.7107068705f);                  // 0.5 * a3
+  poly = fmaf(poly, t, -0.142248368f);                  // 0.5 * a2
+  poly = fmaf(poly, t, 0.127414796f);                   // 0.5 * a1
+  return poly * t * e;
+}
 __device__ __forceinline__ float gelu_erf(float x) {
-  const float u = x * 0.70710678118654752440f;
-  const float e = fast_exp2(-u * u * 1.4426950408889634f);
-  return 0.5f * x * (1.0f + erf_as(u, e));
+  const float e = fast_exp2(x * x * -0.72134752044448170368f);  // exp(-x^2/2)
+  const float ax = fabsf(x);
+  return fmaf(-ax, gelu_tail_h(ax, e), fmaxf(x, 0.0f));
 }
 __device__ __forceinline__ float gelu_erf_grad(float x) {
-  // d/dx [x Phi(x)] = Phi(x) + x phi(x);  exp(-(x/sqrt2)^2) = exp(-x^2/2) serves both terms
-  const float u = x * 0.70710678118654752440f;
-  const float e = fast_exp2(-u * u * 1.4426950408889634f);
-  const float cdf = 0.5f * (1.0f + erf_as(u, e));
+  const float e = fast_exp2(x * x * -0.72134752044448170368f);
+  const float h = gelu_tail_h(fabsf(x), e);
+  const float cdf = x >= 0.0f ? 1.0f - h : h;
   return fmaf(x * 0.39894228040143267794f, e, cdf);
 }
 

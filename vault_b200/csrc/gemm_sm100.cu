@@ -41,14 +41,39 @@ struct GemmParams {
   unsigned site;
 };
 
-// Side input of an epilogue (fp32 residual row segment or bf16 pre-activation), fetched for all 8 row-groups of a chunk BEFORE
-// any store so the loads are in flight together (the output pointer may alias nothing, but the compiler cannot know that).
+// ---- fused epilogues -------------------------------------------------------------------------------------------------
+// After the smem transpose each lane owns 4 consecutive columns of 8 rows (row stride 4) of a 32x32 chunk.  Pointers are
+// formed once per chunk and advanced by a constant row stride; full tiles skip every bounds check (GUARD=false).
 template <int EPI>
-__device__ __forceinline__ float4 epilogue_side(const GemmParams& p, long long row, int col) {
+struct EpiPtrs {
+  char* out;          // bf16 or fp32
+  char* out2;         // bf16 (GELU pre-activation), may be null
+  const char* side;   // fp32 residual or bf16 pre-activation
+  long long out_step, out2_step, side_step;  // bytes per 4 rows
+};
+
+template <int EPI>
+__device__ __forceinline__ EpiPtrs<EPI> make_ptrs(const GemmParams& p, long long row, int col) {
+  constexpr bool kOutF32 = EPI == VAULT_EPI_BIAS_RESID_F32 || EPI == VAULT_EPI_ATOMIC_F32 || EPI == VAULT_EPI_BIAS_F32 || EPI == VAULT_EPI_STORE_F32;
+  constexpr int osz = kOutF32 ? 4 : 2;
+  EpiPtrs<EPI> e;
+  e.out = reinterpret_cast<char*>(p.out) + (row * p.ldo + col) * osz;
+  e.out_step = 4 * p.ldo * osz;
+  e.out2 = nullptr; e.out2_step = 0; e.side = nullptr; e.side_step = 0;
+  if constexpr (EPI == VAULT_EPI_BIAS_GELU_BF16) {
+    if (p.out2) { e.out2 = reinterpret_cast<char*>(p.out2) + (row * p.ldo2 + col) * 2; e.out2_step = 8 * p.ldo2; }
+  }
+  if constexpr (EPI == VAULT_EPI_BIAS_RESID_F32) { e.side = reinterpret_cast<const char*>(p.resid) + (row * p.ldr + col) * 4; e.side_step = 16 * p.ldr; }
+  if constexpr (EPI == VAULT_EPI_DGELU_BF16) { e.side = reinterpret_cast<const char*>(p.aux) + (row * p.ldaux + col) * 2; e.side_step = 8 * p.ldaux; }
+  return e;
+}
+
+template <int EPI>
+__device__ __forceinline__ float4 load_side(const char* ptr) {
   if constexpr (EPI == VAULT_EPI_BIAS_RESID_F32) {
-    return __ldg(reinterpret_cast<const float4*>(p.resid + row * p.ldr + col));
+    return __ldg(reinterpret_cast<const float4*>(ptr));
   } else if constexpr (EPI == VAULT_EPI_DGELU_BF16) {
-    const uint2 a = __ldg(reinterpret_cast<const uint2*>(p.aux + row * p.ldaux + col));
+    const uint2 a = __ldg(reinterpret_cast<const uint2*>(ptr));
     const float2 a01 = unpack_bf16x2(a.x), a23 = unpack_bf16x2(a.y);
     return make_float4(a01.x, a01.y, a23.x, a23.y);
   } else {
@@ -58,56 +83,62 @@ __device__ __forceinline__ float4 epilogue_side(const GemmParams& p, long long r
 
 template <int EPI>
 __device__ __forceinline__ void epilogue4(const GemmParams& p, float4 acc, const float4& b4, const float4& side, unsigned long long seed,
-                                          long long row, int col) {
+                                          unsigned long long drop_idx, char* out, char* out2) {
   if constexpr (EPI == VAULT_EPI_BIAS_BF16) {
-    uint2 o;
-    o.x = pack_bf16x2(acc.x + b4.x, acc.y + b4.y);
-    o.y = pack_bf16x2(acc.z + b4.z, acc.w + b4.w);
-    *reinterpret_cast<uint2*>(reinterpret_cast<bf16*>(p.out) + row * p.ldo + col) = o;
+    *reinterpret_cast<uint2*>(out) = make_uint2(pack_bf16x2(acc.x + b4.x, acc.y + b4.y), pack_bf16x2(acc.z + b4.z, acc.w + b4.w));
   } else if constexpr (EPI == VAULT_EPI_BIAS_GELU_BF16) {
     const float x0 = acc.x + b4.x, x1 = acc.y + b4.y, x2 = acc.z + b4.z, x3 = acc.w + b4.w;
-    if (p.out2) {
-      uint2 o2;
-      o2.x = pack_bf16x2(x0, x1);
-      o2.y = pack_bf16x2(x2, x3);
-      *reinterpret_cast<uint2*>(reinterpret_cast<bf16*>(p.out2) + row * p.ldo2 + col) = o2;
-    }
-    uint2 o;
-    o.x = pack_bf16x2(gelu_erf(x0), gelu_erf(x1));
-    o.y = pack_bf16x2(gelu_erf(x2), gelu_erf(x3));
-    *reinterpret_cast<uint2*>(reinterpret_cast<bf16*>(p.out) + row * p.ldo + col) = o;
+    if (out2) *reinterpret_cast<uint2*>(out2) = make_uint2(pack_bf16x2(x0, x1), pack_bf16x2(x2, x3));
+    *reinterpret_cast<uint2*>(out) = make_uint2(pack_bf16x2(gelu_erf(x0), gelu_erf(x1)), pack_bf16x2(gelu_erf(x2), gelu_erf(x3)));
   } else if constexpr (EPI == VAULT_EPI_BIAS_RESID_F32) {
     float x0 = acc.x + b4.x, x1 = acc.y + b4.y, x2 = acc.z + b4.z, x3 = acc.w + b4.w;
     if (p.dropout_p > 0.f) {
       const uint32_t thr = dropout_threshold(p.dropout_p);
       const float sc = 1.0f / (1.0f - p.dropout_p);
-      const uint4 bits = dropout_bits4(seed, p.site, (unsigned long long)(row * p.N + col) >> 2);
+      const uint4 bits = dropout_bits4(seed, p.site, drop_idx);
       x0 = bits.x >= thr ? x0 * sc : 0.f;
       x1 = bits.y >= thr ? x1 * sc : 0.f;
       x2 = bits.z >= thr ? x2 * sc : 0.f;
       x3 = bits.w >= thr ? x3 * sc : 0.f;
     }
-    float4 o = make_float4(side.x + x0, side.y + x1, side.z + x2, side.w + x3);
-    *reinterpret_cast<float4*>(reinterpret_cast<float*>(p.out) + row * p.ldo + col) = o;
+    *reinterpret_cast<float4*>(out) = make_float4(side.x + x0, side.y + x1, side.z + x2, side.w + x3);
   } else if constexpr (EPI == VAULT_EPI_PLAIN_BF16) {
-    uint2 o;
-    o.x = pack_bf16x2(acc.x, acc.y);
-    o.y = pack_bf16x2(acc.z, acc.w);
-    *reinterpret_cast<uint2*>(reinterpret_cast<bf16*>(p.out) + row * p.ldo + col) = o;
+    *reinterpret_cast<uint2*>(out) = make_uint2(pack_bf16x2(acc.x, acc.y), pack_bf16x2(acc.z, acc.w));
   } else if constexpr (EPI == VAULT_EPI_DGELU_BF16) {
-    uint2 o;
-    o.x = pack_bf16x2(acc.x * gelu_erf_grad(side.x), acc.y * gelu_erf_grad(side.y));
-    o.y = pack_bf16x2(acc.z * gelu_erf_grad(side.z), acc.w * gelu_erf_grad(side.w));
-    *reinterpret_cast<uint2*>(reinterpret_cast<bf16*>(p.out) + row * p.ldo + col) = o;
+    *reinterpret_cast<uint2*>(out) = make_uint2(pack_bf16x2(acc.x * gelu_erf_grad(side.x), acc.y * gelu_erf_grad(side.y)),
+                                                pack_bf16x2(acc.z * gelu_erf_grad(side.z), acc.w * gelu_erf_grad(side.w)));
   } else if constexpr (EPI == VAULT_EPI_ATOMIC_F32) {
-    float* dst = reinterpret_cast<float*>(p.out) + row * p.ldo + col;
-    asm volatile("red.global.add.v4.f32 [%0], {%1, %2, %3, %4};" ::"l"(dst), "f"(acc.x), "f"(acc.y), "f"(acc.z), "f"(acc.w)
-                 : "memory");
+    asm volatile("red.global.add.v4.f32 [%0], {%1, %2, %3, %4};" ::"l"(out), "f"(acc.x), "f"(acc.y), "f"(acc.z), "f"(acc.w) : "memory");
   } else if constexpr (EPI == VAULT_EPI_BIAS_F32) {
-    float4 o = make_float4(acc.x + b4.x, acc.y + b4.y, acc.z + b4.z, acc.w + b4.w);
-    *reinterpret_cast<float4*>(reinterpret_cast<float*>(p.out) + row * p.ldo + col) = o;
+    *reinterpret_cast<float4*>(out) = make_float4(acc.x + b4.x, acc.y + b4.y, acc.z + b4.z, acc.w + b4.w);
   } else {  // VAULT_EPI_STORE_F32
-    *reinterpret_cast<float4*>(reinterpret_cast<float*>(p.out) + row * p.ldo + col) = acc;
+    *reinterpret_cast<float4*>(out) = acc;
+  }
+}
+
+// one 32x32 chunk: side inputs of all 8 row groups are fetched before any store so the loads are in flight together
+template <int EPI, bool GUARD>
+__device__ __forceinline__ void epilogue_chunk(const GemmParams& p, const float4* stg, int lane, const float4& b4, unsigned long long seed,
+                                               long long row0, int col) {
+  const int cg = lane & 7, rsub = lane >> 3;
+  const long long rbase = row0 + rsub;
+  if (GUARD && col >= p.N) return;
+  EpiPtrs<EPI> e = make_ptrs<EPI>(p, rbase, col);
+  float4 side[8];
+  if constexpr (EPI == VAULT_EPI_BIAS_RESID_F32 || EPI == VAULT_EPI_DGELU_BF16) {
+#pragma unroll
+    for (int i = 0; i < 8; ++i) {
+      if (!GUARD || rbase + 4 * i < p.M) side[i] = load_side<EPI>(e.side + i * e.side_step);
+    }
+  }
+  const unsigned long long drop0 = (unsigned long long)(rbase * p.N + col) >> 2;
+  const unsigned long long drop_step = (unsigned long long)p.N;  // 4 rows * N / 4
+#pragma unroll
+  for (int i = 0; i < 8; ++i) {
+    const int rl = 4 * i + rsub;
+    const float4 acc = stg[rl * 8 + (cg ^ (rl & 7))];
+    if (!GUARD || rbase + 4 * i < p.M)
+      epilogue4<EPI>(p, acc, b4, side[i], seed, drop0 + i * drop_step, e.out + i * e.out_step, e.out2 ? e.out2 + i * e.out2_step : nullptr);
   }
 }
 
@@ -250,6 +281,7 @@ gemm_bf16_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant_
       const int n0 = (rem % p.num_n_blocks) * BN;
       mbar_wait(tfull_bar(as), aphase);
       tc_fence_after();
+      const bool full_tile = (m0 + BM <= p.M) && (n0 + BN <= p.N);
 #pragma unroll 1
       for (int c = half * kColsPerWarp; c < (half + 1) * kColsPerWarp; c += 32) {
         uint32_t r[32];
@@ -262,26 +294,14 @@ gemm_bf16_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant_
               make_float4(__uint_as_float(r[4 * j]), __uint_as_float(r[4 * j + 1]), __uint_as_float(r[4 * j + 2]), __uint_as_float(r[4 * j + 3]));
         }
         __syncwarp();
-        const int cg = lane & 7;
-        const int col = n0 + c + cg * 4;
+        const int col = n0 + c + (lane & 7) * 4;
         float4 b4 = make_float4(0.f, 0.f, 0.f, 0.f);
         if constexpr (EPI == VAULT_EPI_BIAS_BF16 || EPI == VAULT_EPI_BIAS_GELU_BF16 || EPI == VAULT_EPI_BIAS_RESID_F32 || EPI == VAULT_EPI_BIAS_F32) {
-          if (p.bias != nullptr && col < p.N) b4 = *reinterpret_cast<const float4*>(p.bias + col);
+          if (p.bias != nullptr && col < p.N) b4 = __ldg(reinterpret_cast<const float4*>(p.bias + col));
         }
-        const long long rbase = (long long)m0 + q * 32 + (lane >> 3);
-        float4 side[8];
-#pragma unroll
-        for (int i = 0; i < 8; ++i) {
-          const long long row = rbase + 4 * i;
-          side[i] = (row < p.M && col < p.N) ? epilogue_side<EPI>(p, row, col) : make_float4(0.f, 0.f, 0.f, 0.f);
-        }
-#pragma unroll
-        for (int i = 0; i < 8; ++i) {
-          const int rl = 4 * i + (lane >> 3);
-          const float4 acc = stg[rl * 8 + (cg ^ (rl & 7))];
-          const long long row = rbase + 4 * i;
-          if (row < p.M && col < p.N) epilogue4<EPI>(p, acc, b4, side[i], seed, row, col);
-        }
+        const long long row0 = (long long)m0 + q * 32;
+        if (full_tile) epilogue_chunk<EPI, false>(p, stg, lane, b4, seed, row0, col);
+        else epilogue_chunk<EPI, true>(p, stg, lane, b4, seed, row0, col);
         __syncwarp();
       }
       tc_fence_before();

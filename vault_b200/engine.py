@@ -90,6 +90,7 @@ class VaultEngine:
         self.seed = 0x5EED5EED
         self.seed_dev: Optional[torch.Tensor] = None  # device counter added to the seed (advanced once per training step)
         self.sms = 0
+        self.gemm_max_ctas = 0  # >0: leave SMs free for a concurrently running collective (data-parallel overlap)
 
     # ------------------------------------------------------------------------------------------------------------
     # parameter packing
@@ -293,7 +294,7 @@ class VaultEngine:
         g.out, g.ldo, g.out2, g.ldo2 = out, ldo, out2 or None, ldo2
         g.dropout_p, g.seed, g.site = p, self.seed, site
         g.seed_dev = self.seed_dev.data_ptr() if p > 0.0 else None
-        g.split_k, g.block_n, g.max_ctas = split_k, block_n, 0
+        g.split_k, g.block_n, g.max_ctas = split_k, block_n, self.gemm_max_ctas
         rc = self._lib.vault_gemm_bf16(C.byref(g), self._st)
         if rc:
             _abi.check(rc, "vault_gemm_bf16")
@@ -610,6 +611,17 @@ class VaultEngine:
 
     def backward(self, tape: Tape, dlhs: Optional[torch.Tensor], dpooled: Optional[torch.Tensor]):
         """Fills self.grad (fp32, flat) with dL/dparam for every trainable parameter; returns nothing."""
+        for _ in self.backward_iter(tape, dlhs, dpooled, segments=False):
+            pass
+
+    def _first_off(self, prefix: str) -> Optional[int]:
+        offs = [s.off for n, s in self.slots.items() if s.trainable and n.startswith(prefix)]
+        return min(offs) if offs else None
+
+    def backward_iter(self, tape: Tape, dlhs: Optional[torch.Tensor], dpooled: Optional[torch.Tensor], segments: bool = True):
+        """Generator form of backward: yields the flat-gradient offset up to which gradients are FINAL each time a segment of
+        the reverse-topological layout completes (upper ViLT half, all of ViLT, upper LM half), so a data-parallel caller
+        can all-reduce that range while the rest of backward runs.  Exhausting it completes the backward."""
         if tape.done:
             raise RuntimeError("vault_b200: backward called twice on the same forward (activations already released)")
         self._lib, self._st = _abi.lib(), self._stream()
@@ -630,6 +642,10 @@ class VaultEngine:
         g32, g16 = self.ln_bwd(g_lhs, None, sv["x_final"], sv["st_f"], M, "layernorm.weight", "layernorm.bias")
         for i in reversed(range(self.L)):
             g32, g16 = self.vilt_layer_bwd(i, g32, g16, M, B, S, sv["key_mask"], sv)
+            if segments and i == self.L // 2 and i > 0:
+                off = self._first_off(f"encoder.layer.{i - 1}.")
+                if off:
+                    yield off
         # ---- embeddings ----
         dtext_ln = self._new((Mt, H), torch.float32)
         dpatch = self._new((B * gh * gw, H), torch.bfloat16)
@@ -648,7 +664,11 @@ class VaultEngine:
             _abi.check(lib.vault_vilt_text_embed_bwd(tt_ptr, dv_sum.data_ptr(), self.g32("embeddings.text_embeddings.token_type_embeddings.weight") or None,
                                                      gpos or None, B, T, H, st), "vilt_text_embed_bwd")
             if mt["lm_trains"]:
-                self._lm_backward(dv_sum, sv, B, T, mt["training"])
+                if segments:
+                    off = self._first_off("bert.")
+                    if off:
+                        yield off
+                yield from self._lm_backward(dv_sum, sv, B, T, mt["training"], segments)
         else:
             _abi.check(lib.vault_lm_embed_bwd(sv["ids"].data_ptr(), tt_ptr, dv_sum.data_ptr(),
                                               self.g32("embeddings.text_embeddings.word_embeddings.weight") or None,
@@ -659,12 +679,16 @@ class VaultEngine:
         tape.done = True
         tape.t = {}
 
-    def _lm_backward(self, g32, sv, B, T, train):
+    def _lm_backward(self, g32, sv, B, T, train, segments=False):
         lib, st = self._lib, self._st
         Mt, H = B * T, self.H
         gx16 = None
         for i in reversed(range(self.lm_L)):
             g32, gx16 = self.lm_layer_bwd(i, g32, gx16, Mt, B, T, sv["lm.mask"], sv, train)
+            if segments and i == self.lm_L // 2 and i > 0:
+                off = self._first_off(f"bert.encoder.layer.{i - 1}.")
+                if off:
+                    yield off
         p_emb = self.lm_p if train else 0.0
         dx_sum, _ = self.ln_bwd(g32, gx16, sv["lm.x_sum"], sv["lm.st0"], Mt, "bert.embeddings.LayerNorm.weight", "bert.embeddings.LayerNorm.bias",
                                 want16=False, in_p=p_emb, in_site=self.SITE_LM_EMB)

@@ -55,7 +55,7 @@ class _Slot:
         self.buf: Dict[str, torch.Tensor] = {}
         self.ready = torch.cuda.Event()
         self.free = torch.cuda.Event()
-        self.graph: Optional[torch.cuda.CUDAGraph] = None
+        self.graphs = None   # list of (CUDAGraph, grad offset reached when it finishes)
         self.loss_host = None
         self.loss_event = torch.cuda.Event()
 
@@ -63,7 +63,7 @@ class _Slot:
 class VaultTrainStep:
     def __init__(self, model, lr: float = 2e-5, betas=(0.9, 0.999), eps: float = 1e-8, weight_decay: float = 0.0, correct_bias: bool = False,
                  total_steps: Optional[int] = None, warmup_ratio: float = 0.1, process_group=None, use_cuda_graph: bool = True,
-                 dropout: bool = True):
+                 dropout: bool = True, overlap_comm: bool = True, comm_reserve_sms: int = 8):
         self.model = model
         self.engine: VaultEngine = model.engine
         self.lr, self.betas, self.eps, self.wd, self.correct_bias = lr, betas, eps, weight_decay, correct_bias
@@ -91,6 +91,12 @@ class VaultTrainStep:
             dist.broadcast(self.engine.master, src=dist.get_global_rank(process_group, 0) if process_group is not None else 0, group=process_group)
             self.engine.refresh_shadow(force=True)
             self.engine.seed = (self.engine.seed + 0x9E3779B97F4A7C15 * self.rank) & 0xFFFFFFFFFFFFFFFF
+        # data-parallel overlap: backward is cut into segments of the reverse-topological gradient layout; each finished
+        # range is all-reduced (async, NCCL's stream) while the next segment computes.  The persistent GEMMs then leave a few
+        # SMs to the collective instead of queueing behind it.
+        self.overlap = bool(overlap_comm) and self.world > 1
+        if self.overlap and comm_reserve_sms > 0:
+            self.engine.gemm_max_ctas = max(1, self.engine.sms - comm_reserve_sms)
         self.copy_stream = torch.cuda.Stream(device=self.dev)
         self.sched_dev = torch.zeros(2, device=self.dev, dtype=torch.float32)
         self.step_idx = 0
@@ -125,7 +131,12 @@ class VaultTrainStep:
         return s
 
     def _body(self, s: _Slot):
-        """forward + CE head + backward of one local batch, all kernels on the current stream (capturable)."""
+        for _ in self._body_iter(s, segments=False):
+            pass
+
+    def _body_iter(self, s: _Slot, segments: bool):
+        """forward + CE head + backward of one local batch, all kernels on the current stream (capturable).  Generator: yields
+        the gradient offset that is final after each backward segment (see VaultEngine.backward_iter)."""
         eng, lib = self.engine, _abi.lib()
         b = s.buf
         st = eng._stream()
@@ -162,7 +173,11 @@ class VaultTrainStep:
         if p > 0:
             _abi.check(lib.vault_dropout_f32(dx.data_ptr(), dx.data_ptr(), dx.numel(), p, eng.seed, eng.seed_dev.data_ptr(), eng.SITE_HEAD, st),
                        "head_dropout_bwd")
-        eng.backward(tape, None, dx)
+        yield from eng.backward_iter(tape, None, dx, segments=segments)
+
+    def _reduce_range(self, lo: int, hi: int, works: list):
+        if self.world > 1 and hi > lo:
+            works.extend(allreduce_flat_(self.engine.grad[lo:hi], self.pg, async_op=True))
 
     def _get_slot(self, batch) -> _Slot:
         key = tuple((k, tuple(batch[k].shape)) for k in _INPUT_KEYS if batch.get(k) is not None)
@@ -191,24 +206,42 @@ class VaultTrainStep:
                     dst.copy_(batch[k], non_blocking=True)
         lr = self.lr_at(self.step_idx)
         eng.refresh_shadow()  # host-side check only, unless someone modified the Parameters in place
+        works: list = []
+        n_train = eng.n_train
         if self.use_graph:
-            if s.graph is None:
+            if s.graphs is None:
                 self._body(s)  # eager warm-up: sets kernel attributes, sizes the allocator
                 torch.cuda.synchronize(self.dev)
                 eng.seed_dev.sub_(1)
-                g = torch.cuda.CUDAGraph()
-                with torch.cuda.graph(g, pool=self._pool, stream=torch.cuda.Stream(device=self.dev)):
-                    self._body(s)
-                if self._pool is None:
-                    self._pool = g.pool()
-                s.graph = g
-            s.graph.replay()
+                s.graphs = []
+                it = self._body_iter(s, segments=self.overlap)
+                cap_stream = torch.cuda.Stream(device=self.dev)
+                done = False
+                while not done:
+                    g = torch.cuda.CUDAGraph()
+                    with torch.cuda.graph(g, pool=self._pool, stream=cap_stream):
+                        try:
+                            reached = next(it)
+                        except StopIteration:
+                            reached, done = n_train, True
+                    if self._pool is None:
+                        self._pool = g.pool()
+                    s.graphs.append((g, reached))
+            lo = 0
+            for g, reached in s.graphs:
+                g.replay()
+                self._reduce_range(lo, reached, works)
+                lo = reached
         else:
-            self._body(s)
+            lo = 0
+            for reached in self._body_iter(s, segments=self.overlap):
+                self._reduce_range(lo, reached, works)
+                lo = reached
+            self._reduce_range(lo, n_train, works)
         if on_host:
             s.free.record(cs)
-        if self.world > 1:
-            allreduce_flat_(eng.grad[:eng.n_train], self.pg)
+        for w in works:
+            w.wait()
         step_no = eng.opt_state["step"] + 1
         b1, b2 = self.betas
         step_size = lr

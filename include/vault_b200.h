@@ -86,6 +86,14 @@ typedef struct vault_gemm_args {
 
 int vault_gemm_bf16(const vault_gemm_args* args, void* stream);
 
+/* Patch embedding, im2col-free: Conv2d(C,N,k=32,s=32) as a TF32 tcgen05 GEMM whose A tiles are 5-D TMA boxes taken straight
+ * from the NCHW fp32 pixels (no patch matrix is materialised).  Replaces ViltPatchEmbeddings.forward,
+ * HF:models/vilt/modeling_vilt.py:293-303.
+ *   pixels [B,C,Hi,Wi] fp32, weight [N, C*32*32] fp32 (= projection.weight.view(N,-1)), bias [N] fp32 or NULL
+ *   out [B*(Hi/32)*(Wi/32), N] fp32, row = b*gh*gw + i*gw + j                                                     */
+int vault_patch_embed_fwd(const float* pixels, const float* weight, const float* bias, float* out, int32_t B, int32_t C,
+                          int32_t Hi, int32_t Wi, int32_t P, int32_t N, void* stream);
+
 /* ------------------------------------------------------------------------------------------------------------------
  * LayerNorm (HF nn.LayerNorm call sites: 25 in the LM, 26 in ViLT).  x fp32 [rows, cols].
  *   fwd: y = (x - mean) * rstd * gamma + beta -> y_bf16 and/or y_f32 (either may be NULL); saves mean, rstd [rows]

@@ -37,6 +37,7 @@ SIGNATURES = {
     "vault_last_error": [C.c_char_p, C.c_size_t],
     "vault_check_device": [c_i32],
     "vault_gemm_bf16": [C.POINTER(GemmArgs), c_p],
+    "vault_patch_embed_fwd": [c_p, c_p, c_p, c_p, c_i32, c_i32, c_i32, c_i32, c_i32, c_i32, c_p],
     "vault_layernorm_fwd": [c_p, c_p, c_p, c_p, c_p, c_p, c_p, c_i64, c_i32, c_f32, c_p],
     "vault_layernorm_bwd": [c_p, c_p, c_p, c_p, c_p, c_p, c_p, c_p, c_p, c_p, c_p, c_i64, c_i32, c_p],
     "vault_layernorm_fwd_drop": [c_p, c_p, c_p, c_p, c_p, c_p, c_p, c_i64, c_i32, c_f32, c_f32, c_u64, c_p, c_u32, c_p],

@@ -558,11 +558,22 @@ class VaultEngine:
         # ---------------- image: patch projection + assembly ----------------
         G = gh * gw
         Kp = self.C * self.patch * self.patch
-        patches = self._new((B * G, Kp), torch.bfloat16)
-        _abi.check(lib.vault_patchify_bf16(pixel_values.data_ptr(), patches.data_ptr(), B, self.C, Hi, Wi, self.patch, st), "patchify")
         patch_out = self._new((B * G, H), torch.float32)
-        self.gemm(patches.data_ptr(), Kp, 0, self.w16("embeddings.patch_embeddings.projection.weight"), Kp, 0, B * G, H, Kp, EPI_BIAS_F32,
-                  patch_out.data_ptr(), H, bias=self.w32("embeddings.patch_embeddings.projection.bias"))
+        if self.patch == 32:
+            # im2col-free: TF32 tcgen05 GEMM fed by 5-D TMA boxes over the raw NCHW pixels, fp32 master weight
+            _abi.check(lib.vault_patch_embed_fwd(pixel_values.data_ptr(), self.w32("embeddings.patch_embeddings.projection.weight"),
+                                                 self.w32("embeddings.patch_embeddings.projection.bias"), patch_out.data_ptr(), B, self.C, Hi, Wi,
+                                                 self.patch, H, st), "patch_embed_fwd")
+            patches = None
+        else:
+            patches = self._new((B * G, Kp), torch.bfloat16)
+            _abi.check(lib.vault_patchify_bf16(pixel_values.data_ptr(), patches.data_ptr(), B, self.C, Hi, Wi, self.patch, st), "patchify")
+            self.gemm(patches.data_ptr(), Kp, 0, self.w16("embeddings.patch_embeddings.projection.weight"), Kp, 0, B * G, H, Kp, EPI_BIAS_F32,
+                      patch_out.data_ptr(), H, bias=self.w32("embeddings.patch_embeddings.projection.bias"))
+        if sv is not None and patches is None and self.g32("embeddings.patch_embeddings.projection.weight"):
+            # the projection's wgrad (dW = dpatch^T * patches) reads the patch matrix as its MN-major B operand: bf16 im2col, training only
+            patches = self._new((B * G, Kp), torch.bfloat16)
+            _abi.check(lib.vault_patchify_bf16(pixel_values.data_ptr(), patches.data_ptr(), B, self.C, Hi, Wi, self.patch, st), "patchify")
         if hw is None:
             hw, pmax = self.patch_hw(pixel_mask, B, Hi, Wi)
         S = T + 1 + pmax
@@ -654,8 +665,9 @@ class VaultEngine:
                                                self.g32("embeddings.token_type_embeddings.weight") or None, B, T, pmax, gh, gw, self.grid, H,
                                                mt["img_type"], st), "vilt_assemble_bwd")
         Kp = self.C * self.patch * self.patch
-        self.linear_wgrad(dpatch, sv["patches"], B * gh * gw, "embeddings.patch_embeddings.projection.weight",
-                          "embeddings.patch_embeddings.projection.bias", H, Kp)
+        if sv["patches"] is not None:
+            self.linear_wgrad(dpatch, sv["patches"], B * gh * gw, "embeddings.patch_embeddings.projection.weight",
+                              "embeddings.patch_embeddings.projection.bias", H, Kp)
         dv_sum, _ = self.ln_bwd(dtext_ln, None, sv["v_sum"], sv["st_t"], Mt, "embeddings.text_embeddings.LayerNorm.weight",
                                 "embeddings.text_embeddings.LayerNorm.bias", want16=False)
         tt_ptr = sv["tt"].data_ptr() if sv["tt"] is not None else None

@@ -8,6 +8,7 @@ __global__ void __launch_bounds__(256)
 adamw_kernel(float* __restrict__ p, const float* __restrict__ g, float* __restrict__ m, float* __restrict__ v, bf16* __restrict__ shadow, long long n,
              float step_size, float lr_wd, float beta1, float beta2, float ob1, float ob2, float eps, float grad_scale,
              const float* __restrict__ sched_dev) {
+  pdl_enter();
   if (sched_dev) {  // {step_size, lr*weight_decay} read from device memory: a captured CUDA graph can follow an lr schedule
     step_size = sched_dev[0];
     lr_wd = sched_dev[1];
@@ -50,6 +51,7 @@ adamw_kernel(float* __restrict__ p, const float* __restrict__ g, float* __restri
 }
 
 __global__ void __launch_bounds__(256) cast_kernel(const float* __restrict__ src, bf16* __restrict__ dst, long long n) {
+  pdl_enter();
   const long long n4 = n >> 2;
   for (long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x; i < n4; i += (long long)gridDim.x * blockDim.x) {
     const float4 a = __ldg(reinterpret_cast<const float4*>(src) + i);
@@ -85,7 +87,7 @@ extern "C" int vault_adamw_step(float* p, const float* g, float* m, float* v, vo
     VB_REQUIRE(step >= 1, "adamw_step: step must be >= 1 with correct_bias");
     step_size = lr * sqrt(1.0 - pow(beta2, step)) / (1.0 - pow(beta1, step));
   }
-  adamw_kernel<<<flat_grid(n >> 2), 256, 0, (cudaStream_t)stream>>>(p, g, m, v, reinterpret_cast<bf16*>(shadow_bf16), n, (float)step_size,
+  launch(adamw_kernel, dim3(flat_grid(n >> 2)), dim3(256), 0, (cudaStream_t)stream, p, g, m, v, reinterpret_cast<bf16*>(shadow_bf16), n, (float)step_size,
                                                                     weight_decay > 0.0 ? (float)(lr * weight_decay) : 0.f, (float)beta1,
                                                                     (float)beta2, (float)(1.0 - beta1), (float)(1.0 - beta2), (float)eps, grad_scale, sched_dev);
   return check_launch("adamw_kernel");
@@ -95,6 +97,6 @@ extern "C" int vault_cast_f32_bf16(const float* src, void* dst_bf16, int64_t n, 
   VB_REQUIRE(src && dst_bf16 && n >= 0, "cast_f32_bf16: bad arguments");
   VB_REQUIRE(((uintptr_t)src & 15) == 0 && ((uintptr_t)dst_bf16 & 7) == 0, "cast_f32_bf16: misaligned buffers");
   if (n == 0) return VAULT_OK;
-  cast_kernel<<<flat_grid(n >> 2), 256, 0, (cudaStream_t)stream>>>(src, reinterpret_cast<bf16*>(dst_bf16), n);
+  launch(cast_kernel, dim3(flat_grid(n >> 2)), dim3(256), 0, (cudaStream_t)stream, src, reinterpret_cast<bf16*>(dst_bf16), n);
   return check_launch("cast_kernel");
 }

@@ -127,6 +127,7 @@ struct AttnParams {
 // ================================================== forward ==================================================
 template <bool DROP>
 __global__ void __launch_bounds__(kAttnThreads) attn_fwd_kernel(const AttnParams p) {
+  pdl_enter();
   extern __shared__ __align__(128) uint8_t smem[];
   const int S = p.S, S_pad = p.S_pad, H = p.heads * kHd;
   const int qt = blockIdx.x, h = blockIdx.y, b = blockIdx.z;
@@ -227,6 +228,7 @@ __global__ void __launch_bounds__(kAttnThreads) attn_fwd_kernel(const AttnParams
 // CTA = (b, h, 64 query rows).  delta[q] = sum_d dO[q,d] * O[q,d];  dQ = scale * sum_k dS[q,k] K[k,:]
 template <bool DROP>
 __global__ void __launch_bounds__(kAttnThreads) attn_bwd_dq_kernel(const AttnParams p) {
+  pdl_enter();
   extern __shared__ __align__(128) uint8_t smem[];
   const int S = p.S, S_pad = p.S_pad, H = p.heads * kHd;
   const int qt = blockIdx.x, h = blockIdx.y, b = blockIdx.z;
@@ -331,6 +333,7 @@ __global__ void __launch_bounds__(kAttnThreads) attn_bwd_dq_kernel(const AttnPar
 //   S^T = K Q^T ; P^T = exp2(S^T*c - lse[q]) ; dV += P_drop^T dO ; dP^T = V dO^T ; dS^T = P^T (dP^T_drop - delta[q]) ; dK += scale dS^T Q
 template <bool DROP>
 __global__ void __launch_bounds__(kAttnThreads) attn_bwd_dkv_kernel(const AttnParams p) {
+  pdl_enter();
   extern __shared__ __align__(128) uint8_t smem[];
   const int S = p.S, S_pad = p.S_pad, H = p.heads * kHd;
   const int kt = blockIdx.x, h = blockIdx.y, b = blockIdx.z;
@@ -468,10 +471,10 @@ extern "C" int vault_attn_fwd(const void* qkv, const uint8_t* key_mask, void* ct
   cudaStream_t st = reinterpret_cast<cudaStream_t>(stream);
   if (dropout_p > 0.f) {
     if ((rc = set_smem(attn_fwd_kernel<true>, smem))) return rc;
-    attn_fwd_kernel<true><<<grid, kAttnThreads, smem, st>>>(p);
+    launch(attn_fwd_kernel<true>, dim3(grid), dim3(kAttnThreads), smem, st, p);
   } else {
     if ((rc = set_smem(attn_fwd_kernel<false>, smem))) return rc;
-    attn_fwd_kernel<false><<<grid, kAttnThreads, smem, st>>>(p);
+    launch(attn_fwd_kernel<false>, dim3(grid), dim3(kAttnThreads), smem, st, p);
   }
   return check_launch("attn_fwd_kernel");
 }
@@ -493,15 +496,15 @@ extern "C" int vault_attn_bwd(const void* qkv, const uint8_t* key_mask, const vo
   if (dropout_p > 0.f) {
     if ((rc = set_smem(attn_bwd_dq_kernel<true>, smem_dq))) return rc;
     if ((rc = set_smem(attn_bwd_dkv_kernel<true>, smem_dkv))) return rc;
-    attn_bwd_dq_kernel<true><<<grid, kAttnThreads, smem_dq, st>>>(p);
+    launch(attn_bwd_dq_kernel<true>, dim3(grid), dim3(kAttnThreads), smem_dq, st, p);
     if ((rc = check_launch("attn_bwd_dq_kernel"))) return rc;
-    attn_bwd_dkv_kernel<true><<<grid, kAttnThreads, smem_dkv, st>>>(p);
+    launch(attn_bwd_dkv_kernel<true>, dim3(grid), dim3(kAttnThreads), smem_dkv, st, p);
   } else {
     if ((rc = set_smem(attn_bwd_dq_kernel<false>, smem_dq))) return rc;
     if ((rc = set_smem(attn_bwd_dkv_kernel<false>, smem_dkv))) return rc;
-    attn_bwd_dq_kernel<false><<<grid, kAttnThreads, smem_dq, st>>>(p);
+    launch(attn_bwd_dq_kernel<false>, dim3(grid), dim3(kAttnThreads), smem_dq, st, p);
     if ((rc = check_launch("attn_bwd_dq_kernel"))) return rc;
-    attn_bwd_dkv_kernel<false><<<grid, kAttnThreads, smem_dkv, st>>>(p);
+    launch(attn_bwd_dkv_kernel<false>, dim3(grid), dim3(kAttnThreads), smem_dkv, st, p);
   }
   return check_launch("attn_bwd_dkv_kernel");
 }

@@ -6,6 +6,8 @@
 #include <cuda_runtime.h>
 #include <stdint.h>
 #include <stdio.h>
+#include <stdlib.h>
+#include <utility>
 
 #include "../../include/vault_b200.h"
 
@@ -22,6 +24,40 @@ int device_sm_count();
   } while (0)
 
 typedef __nv_bfloat16 bf16;
+
+// ---- programmatic dependent launch (PDL) --------------------------------------------------------------------------
+// Every kernel of the library is launched with cudaLaunchAttributeProgrammaticStreamSerialization and begins with
+// griddepcontrol.wait (before its first global-memory access) + griddepcontrol.launch_dependents: the NEXT kernel's CTAs may be
+// scheduled and run their prologue (smem carve-up, barrier init, TMEM alloc, descriptor prefetch) while this one drains, and
+// block in their own griddepcontrol.wait until this grid has completed and flushed.  ~600 dependent launches per training step
+// make the launch/drain gap matter.  VAULT_B200_PDL=0 disables the attribute (the device instructions are then no-ops).
+__device__ __forceinline__ void pdl_wait() { asm volatile("griddepcontrol.wait;" ::: "memory"); }
+__device__ __forceinline__ void pdl_trigger() { asm volatile("griddepcontrol.launch_dependents;" ::: "memory"); }
+__device__ __forceinline__ void pdl_enter() { pdl_wait(); pdl_trigger(); }
+
+inline bool pdl_enabled() {
+  static int v = -1;
+  if (v < 0) {
+    const char* e = getenv("VAULT_B200_PDL");
+    v = (e != nullptr && e[0] == '0') ? 0 : 1;
+  }
+  return v != 0;
+}
+
+template <typename... KArgs, typename... Args>
+inline void launch(void (*kernel)(KArgs...), dim3 grid, dim3 block, size_t smem, cudaStream_t st, Args&&... args) {
+  cudaLaunchConfig_t cfg = {};
+  cfg.gridDim = grid;
+  cfg.blockDim = block;
+  cfg.dynamicSmemBytes = smem;
+  cfg.stream = st;
+  cudaLaunchAttribute attr[1];
+  attr[0].id = cudaLaunchAttributeProgrammaticStreamSerialization;
+  attr[0].val.programmaticStreamSerializationAllowed = 1;
+  cfg.attrs = attr;
+  cfg.numAttrs = pdl_enabled() ? 1 : 0;
+  (void)cudaLaunchKernelEx(&cfg, kernel, std::forward<Args>(args)...);  // errors surface through check_launch()
+}
 
 // ---- small device utilities -----------------------------------------------------------------------------------
 __device__ __forceinline__ uint32_t smem_u32(const void* p) { return (uint32_t)__cvta_generic_to_shared(p); }

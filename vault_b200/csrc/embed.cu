@@ -29,6 +29,7 @@ __global__ void __launch_bounds__(kEmbWarps * 32)
 lm_embed_fwd_kernel(const int64_t* __restrict__ ids, const int64_t* __restrict__ tt, const float* __restrict__ word, const float* __restrict__ type,
                     const float* __restrict__ pos, float* __restrict__ x, const int64_t* __restrict__ attn_mask, uint8_t* __restrict__ key_mask, int B,
                     int T, int H, int roberta_pad) {
+  pdl_enter();
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
   const long long row = (long long)blockIdx.x * kEmbWarps + warp;
   if (row >= (long long)B * T) return;
@@ -47,6 +48,7 @@ lm_embed_fwd_kernel(const int64_t* __restrict__ ids, const int64_t* __restrict__
 __global__ void __launch_bounds__(kEmbWarps * 32)
 lm_embed_bwd_kernel(const int64_t* __restrict__ ids, const int64_t* __restrict__ tt, const float* __restrict__ dx, float* __restrict__ dword,
                     float* __restrict__ dtype, float* __restrict__ dpos, int B, int T, int H, int roberta_pad, int word_pad) {
+  pdl_enter();
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
   const long long row = (long long)blockIdx.x * kEmbWarps + warp;
   if (row >= (long long)B * T) return;
@@ -69,6 +71,7 @@ lm_embed_bwd_kernel(const int64_t* __restrict__ ids, const int64_t* __restrict__
 __global__ void __launch_bounds__(kEmbWarps * 32)
 vilt_text_embed_fwd_kernel(const float* __restrict__ e, const int64_t* __restrict__ tt, const float* __restrict__ type, const float* __restrict__ pos,
                            float* __restrict__ x, int B, int T, int H) {
+  pdl_enter();
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
   const long long row = (long long)blockIdx.x * kEmbWarps + warp;
   if (row >= (long long)B * T) return;
@@ -87,6 +90,7 @@ vilt_text_embed_fwd_kernel(const float* __restrict__ e, const int64_t* __restric
 __global__ void __launch_bounds__(kEmbWarps * 32)
 vilt_text_embed_bwd_kernel(const int64_t* __restrict__ tt, const float* __restrict__ dx, float* __restrict__ dtype, float* __restrict__ dpos, int B,
                            int T, int H) {
+  pdl_enter();
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
   const long long row = (long long)blockIdx.x * kEmbWarps + warp;
   if (row >= (long long)B * T) return;
@@ -103,6 +107,7 @@ vilt_text_embed_bwd_kernel(const int64_t* __restrict__ tt, const float* __restri
 // h_b = #valid patch rows in patch column 0, w_b = #valid patch columns in patch row 0 (nearest down-sampling: pixel (P*i, P*j))
 template <typename MT>
 __global__ void patch_grid_kernel(const MT* __restrict__ mask, int* __restrict__ hw, int Hi, int Wi, int P) {
+  pdl_enter();
   const int b = blockIdx.x;
   const MT* m = mask + (long long)b * Hi * Wi;
   int h = 0, w = 0;
@@ -135,6 +140,7 @@ __global__ void __launch_bounds__(kEmbWarps * 32)
 vilt_assemble_fwd_kernel(const float* __restrict__ text_ln, const float* __restrict__ patch, const float* __restrict__ cls, const float* __restrict__ pos_table,
                          const float* __restrict__ modality, const int64_t* __restrict__ attn_mask, const int* __restrict__ hw, float* __restrict__ X,
                          uint8_t* __restrict__ key_mask, int B, int T, int Pmax, int gh, int gw, int grid, int H, int img_type) {
+  pdl_enter();
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
   const int S = T + 1 + Pmax;
   const long long row = (long long)blockIdx.x * kEmbWarps + warp;
@@ -186,6 +192,7 @@ vilt_assemble_fwd_kernel(const float* __restrict__ text_ln, const float* __restr
 __global__ void __launch_bounds__(kEmbWarps * 32)
 vilt_assemble_bwd_rows_kernel(const float* __restrict__ dX, const int* __restrict__ hw, float* __restrict__ dtext_ln, float* __restrict__ dcls,
                               float* __restrict__ dpos_table, float* __restrict__ dmodality, int B, int T, int Pmax, int grid, int H, int img_type) {
+  pdl_enter();
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
   const int S = T + 1 + Pmax;
   const int H4 = H / 4;
@@ -259,6 +266,7 @@ vilt_assemble_bwd_rows_kernel(const float* __restrict__ dX, const int* __restric
 __global__ void __launch_bounds__(kEmbWarps * 32)
 vilt_assemble_bwd_patch_kernel(const float* __restrict__ dX, const int* __restrict__ hw, bf16* __restrict__ dpatch, int B, int T, int Pmax, int gh, int gw,
                                int H) {
+  pdl_enter();
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
   const int S = T + 1 + Pmax;
   const long long cell = (long long)blockIdx.x * kEmbWarps + warp;
@@ -281,6 +289,7 @@ vilt_assemble_bwd_patch_kernel(const float* __restrict__ dX, const int* __restri
 // im2col: out[(b*gh+i)*gw+j, c*P*P + kh*P + kw] = bf16(pixels[b,c,i*P+kh,j*P+kw]); one thread = 8 consecutive kw
 __global__ void __launch_bounds__(256)
 patchify_kernel(const float* __restrict__ px, bf16* __restrict__ out, int B, int C, int Hi, int Wi, int P) {
+  pdl_enter();
   const int gh = Hi / P, gw = Wi / P;
   const int K = C * P * P;
   const long long total = (long long)B * gh * gw * (K / 8);
@@ -310,7 +319,7 @@ extern "C" int vault_lm_embed_fwd(const int64_t* ids, const int64_t* tt, const f
                                   void* stream) {
   VB_REQUIRE(ids && word && type && pos && x_sum, "lm_embed_fwd: null pointer");
   VB_REQUIRE(B > 0 && T > 0 && H % 4 == 0, "lm_embed_fwd: bad shape");
-  lm_embed_fwd_kernel<<<rows_grid((long long)B * T), kEmbWarps * 32, 0, (cudaStream_t)stream>>>(ids, tt, word, type, pos, x_sum, attention_mask, key_mask, B, T, H,
+  launch(lm_embed_fwd_kernel, dim3(rows_grid((long long)B * T)), dim3(kEmbWarps * 32), 0, (cudaStream_t)stream, ids, tt, word, type, pos, x_sum, attention_mask, key_mask, B, T, H,
                                                                                                 roberta_pad);
   return check_launch("lm_embed_fwd_kernel");
 }
@@ -319,7 +328,7 @@ extern "C" int vault_lm_embed_bwd(const int64_t* ids, const int64_t* tt, const f
                                   int32_t T, int32_t H, int32_t roberta_pad, int32_t word_pad, void* stream) {
   VB_REQUIRE(ids && dx, "lm_embed_bwd: null pointer");
   VB_REQUIRE(B > 0 && T > 0 && H % 4 == 0, "lm_embed_bwd: bad shape");
-  lm_embed_bwd_kernel<<<rows_grid((long long)B * T), kEmbWarps * 32, 0, (cudaStream_t)stream>>>(ids, tt, dx, dword, dtype, dpos, B, T, H, roberta_pad,
+  launch(lm_embed_bwd_kernel, dim3(rows_grid((long long)B * T)), dim3(kEmbWarps * 32), 0, (cudaStream_t)stream, ids, tt, dx, dword, dtype, dpos, B, T, H, roberta_pad,
                                                                                                 word_pad);
   return check_launch("lm_embed_bwd_kernel");
 }
@@ -328,7 +337,7 @@ extern "C" int vault_vilt_text_embed_fwd(const float* inputs_embeds, const int64
                                          int32_t B, int32_t T, int32_t H, void* stream) {
   VB_REQUIRE(inputs_embeds && type && x_sum, "vilt_text_embed_fwd: null pointer");
   VB_REQUIRE(B > 0 && T > 0 && H % 4 == 0, "vilt_text_embed_fwd: bad shape");
-  vilt_text_embed_fwd_kernel<<<rows_grid((long long)B * T), kEmbWarps * 32, 0, (cudaStream_t)stream>>>(inputs_embeds, tt, type, pos, x_sum, B, T, H);
+  launch(vilt_text_embed_fwd_kernel, dim3(rows_grid((long long)B * T)), dim3(kEmbWarps * 32), 0, (cudaStream_t)stream, inputs_embeds, tt, type, pos, x_sum, B, T, H);
   return check_launch("vilt_text_embed_fwd_kernel");
 }
 
@@ -336,15 +345,15 @@ extern "C" int vault_vilt_text_embed_bwd(const int64_t* tt, const float* dx, flo
                                          void* stream) {
   VB_REQUIRE(dx, "vilt_text_embed_bwd: null pointer");
   if (!dtype && !dpos) return VAULT_OK;
-  vilt_text_embed_bwd_kernel<<<rows_grid((long long)B * T), kEmbWarps * 32, 0, (cudaStream_t)stream>>>(tt, dx, dtype, dpos, B, T, H);
+  launch(vilt_text_embed_bwd_kernel, dim3(rows_grid((long long)B * T)), dim3(kEmbWarps * 32), 0, (cudaStream_t)stream, tt, dx, dtype, dpos, B, T, H);
   return check_launch("vilt_text_embed_bwd_kernel");
 }
 
 extern "C" int vault_patch_grid(const void* pixel_mask, int32_t mask_is_f32, int32_t* hw, int32_t B, int32_t Hi, int32_t Wi, int32_t P,
                                 void* stream) {
   VB_REQUIRE(pixel_mask && hw && B > 0 && Hi % P == 0 && Wi % P == 0, "patch_grid: bad arguments (Hi=%d Wi=%d P=%d)", Hi, Wi, P);
-  if (mask_is_f32) patch_grid_kernel<float><<<B, 32, 0, (cudaStream_t)stream>>>(reinterpret_cast<const float*>(pixel_mask), hw, Hi, Wi, P);
-  else patch_grid_kernel<int64_t><<<B, 32, 0, (cudaStream_t)stream>>>(reinterpret_cast<const int64_t*>(pixel_mask), hw, Hi, Wi, P);
+  if (mask_is_f32) launch(patch_grid_kernel<float>, dim3(B), dim3(32), 0, (cudaStream_t)stream, reinterpret_cast<const float*>(pixel_mask), hw, Hi, Wi, P);
+  else launch(patch_grid_kernel<int64_t>, dim3(B), dim3(32), 0, (cudaStream_t)stream, reinterpret_cast<const int64_t*>(pixel_mask), hw, Hi, Wi, P);
   return check_launch("patch_grid_kernel");
 }
 
@@ -354,7 +363,7 @@ extern "C" int vault_vilt_assemble_fwd(const float* text_ln, const float* patch,
   VB_REQUIRE(text_ln && patch && cls && pos_table && modality && hw && X && key_mask, "vilt_assemble_fwd: null pointer");
   VB_REQUIRE(H % 4 == 0 && Pmax <= gh * gw && Pmax >= 0, "vilt_assemble_fwd: bad shape");
   const long long rows = (long long)B * (T + 1 + Pmax);
-  vilt_assemble_fwd_kernel<<<rows_grid(rows), kEmbWarps * 32, 0, (cudaStream_t)stream>>>(text_ln, patch, cls, pos_table, modality, attention_mask, hw, X,
+  launch(vilt_assemble_fwd_kernel, dim3(rows_grid(rows)), dim3(kEmbWarps * 32), 0, (cudaStream_t)stream, text_ln, patch, cls, pos_table, modality, attention_mask, hw, X,
                                                                                          key_mask, B, T, Pmax, gh, gw, grid, H, img_type);
   return check_launch("vilt_assemble_fwd_kernel");
 }
@@ -368,12 +377,12 @@ extern "C" int vault_vilt_assemble_bwd(const float* dX, const int32_t* hw, float
   long long grid1 = rows_grid(rows);
   const long long cap = (long long)device_sm_count() * 2;
   if (grid1 > cap) grid1 = cap;
-  vilt_assemble_bwd_rows_kernel<<<(unsigned)grid1, kEmbWarps * 32, 0, (cudaStream_t)stream>>>(dX, hw, dtext_ln, dcls, dpos_table, dmodality, B, T, Pmax,
+  launch(vilt_assemble_bwd_rows_kernel, dim3((unsigned)grid1), dim3(kEmbWarps * 32), 0, (cudaStream_t)stream, dX, hw, dtext_ln, dcls, dpos_table, dmodality, B, T, Pmax,
                                                                                               grid, H, img_type);
   int rc = check_launch("vilt_assemble_bwd_rows_kernel");
   if (rc) return rc;
   if (dpatch_bf16) {
-    vilt_assemble_bwd_patch_kernel<<<rows_grid((long long)B * gh * gw), kEmbWarps * 32, 0, (cudaStream_t)stream>>>(
+    launch(vilt_assemble_bwd_patch_kernel, dim3(rows_grid((long long)B * gh * gw)), dim3(kEmbWarps * 32), 0, (cudaStream_t)stream, 
         dX, hw, reinterpret_cast<bf16*>(dpatch_bf16), B, T, Pmax, gh, gw, H);
     rc = check_launch("vilt_assemble_bwd_patch_kernel");
   }
@@ -387,6 +396,6 @@ extern "C" int vault_patchify_bf16(const float* pixels, void* out_bf16, int32_t 
   long long grid = (total + 255) / 256;
   const long long cap = (long long)device_sm_count() * 16;
   if (grid > cap) grid = cap;
-  patchify_kernel<<<(unsigned)grid, 256, 0, (cudaStream_t)stream>>>(pixels, reinterpret_cast<bf16*>(out_bf16), B, C, Hi, Wi, P);
+  launch(patchify_kernel, dim3((unsigned)grid), dim3(256), 0, (cudaStream_t)stream, pixels, reinterpret_cast<bf16*>(out_bf16), B, C, Hi, Wi, P);
   return check_launch("patchify_kernel");
 }

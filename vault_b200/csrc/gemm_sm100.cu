@@ -188,6 +188,7 @@ gemm_bf16_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant_
   __syncthreads();
   tc_fence_after();
   const uint32_t tmem_base = *tmem_slot_gen;
+  pdl_enter();  // everything above overlapped the previous kernel's tail; global memory is touched only below
 
   const int tiles_mn = p.num_m_blocks * p.num_n_blocks;
   const int total_tiles = tiles_mn * p.split_k;
@@ -365,7 +366,7 @@ int launch_gemm(const CUtensorMap& tmA, const CUtensorMap& tmB, const GemmParams
     if (e != cudaSuccess) return fail(VAULT_ERR_LAUNCH, "cudaFuncSetAttribute(smem=%d): %s", kSmemBytes, cudaGetErrorString(e));
     attr_set = true;
   }
-  gemm_bf16_kernel<BN, EPI><<<grid, kThreads, kSmemBytes, st>>>(tmA, tmB, p);
+  launch(gemm_bf16_kernel<BN, EPI>, dim3(grid), dim3(kThreads), kSmemBytes, st, tmA, tmB, p);
   return check_launch("gemm_bf16_kernel");
 }
 

@@ -8,6 +8,7 @@ namespace vb {
 __global__ void __launch_bounds__(256)
 small_linear_fwd_kernel(const float* __restrict__ x, long long ldx, const float* __restrict__ W, const float* __restrict__ b, float* __restrict__ y,
                         int rows, int N, int K, int act) {
+  pdl_enter();
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
   const long long o = (long long)blockIdx.x * 8 + warp;
   if (o >= (long long)rows * N) return;
@@ -38,6 +39,7 @@ __device__ __forceinline__ float act_grad(float dy, const float* y, long long id
 __global__ void __launch_bounds__(256)
 small_linear_wgrad_kernel(const float* __restrict__ dy, const float* __restrict__ y, const float* __restrict__ x, long long ldx, float* __restrict__ dW,
                           float* __restrict__ db, int rows, int N, int K, int act) {
+  pdl_enter();
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
   const int chunks = (K / 4 + 31) / 32;
   const long long o = (long long)blockIdx.x * 8 + warp;
@@ -69,6 +71,7 @@ small_linear_wgrad_kernel(const float* __restrict__ dy, const float* __restrict_
 __global__ void __launch_bounds__(256)
 small_linear_dgrad_kernel(const float* __restrict__ dy, const float* __restrict__ y, const float* __restrict__ W, float* __restrict__ dx, long long lddx,
                           int accumulate, int rows, int N, int K, int act) {
+  pdl_enter();
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
   const int chunks = (K / 4 + 31) / 32;
   const int r = blockIdx.x / chunks, c = (blockIdx.x % chunks) * 32 + lane;
@@ -108,6 +111,7 @@ small_linear_dgrad_kernel(const float* __restrict__ dy, const float* __restrict_
 
 __global__ void dropout_f32_kernel(const float* __restrict__ x, float* __restrict__ y, long long n, float p, unsigned long long seed,
                                    const unsigned long long* seed_dev, unsigned site) {
+  pdl_enter();
   if (seed_dev) seed += *seed_dev;
   const uint32_t thr = dropout_threshold(p);
   const float sc = 1.f / (1.f - p);
@@ -126,6 +130,7 @@ __global__ void dropout_f32_kernel(const float* __restrict__ x, float* __restric
 __global__ void __launch_bounds__(256)
 ce_loss_kernel(const float* __restrict__ logits, const int64_t* __restrict__ labels, float* __restrict__ loss, float* __restrict__ dlogits, int rows,
                int C, float grad_scale) {
+  pdl_enter();
   __shared__ float red[8];
   float local = 0.f;
   for (int r = threadIdx.x; r < rows; r += blockDim.x) {
@@ -154,6 +159,7 @@ ce_loss_kernel(const float* __restrict__ logits, const int64_t* __restrict__ lab
 // out[c] += sum_r x[r, c]  (bf16 in, fp32 atomics out); lane = 4 columns, warp = 128 columns, 8 warps stride rows
 __global__ void __launch_bounds__(256)
 colsum_bf16_kernel(const bf16* __restrict__ x, long long ldx, float* __restrict__ out, long long rows, int cols) {
+  pdl_enter();
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
   const int c = blockIdx.x * 128 + lane * 4;
   float4 acc = make_float4(0.f, 0.f, 0.f, 0.f);
@@ -187,7 +193,7 @@ extern "C" int vault_small_linear_fwd(const float* x, int64_t ldx, const float* 
   VB_REQUIRE(x && W && y, "small_linear_fwd: null pointer");
   VB_REQUIRE(rows > 0 && N > 0 && K > 0 && K % 4 == 0 && ldx % 4 == 0, "small_linear_fwd: bad shape rows=%d N=%d K=%d", rows, N, K);
   const long long outs = (long long)rows * N;
-  small_linear_fwd_kernel<<<(unsigned)((outs + 7) / 8), 256, 0, (cudaStream_t)stream>>>(x, ldx, W, b, y, rows, N, K, act);
+  launch(small_linear_fwd_kernel, dim3((unsigned)((outs + 7) / 8)), dim3(256), 0, (cudaStream_t)stream, x, ldx, W, b, y, rows, N, K, act);
   return check_launch("small_linear_fwd_kernel");
 }
 
@@ -199,14 +205,14 @@ extern "C" int vault_small_linear_bwd(const float* dy, const float* y, const flo
   cudaStream_t st = (cudaStream_t)stream;
   if (dW || db) {
     const long long wwarps = (long long)N * ((K / 4 + 31) / 32);
-    small_linear_wgrad_kernel<<<(unsigned)((wwarps + 7) / 8), 256, 0, st>>>(dy, y, x, ldx, dW, db, rows, N, K, act);
+    launch(small_linear_wgrad_kernel, dim3((unsigned)((wwarps + 7) / 8)), dim3(256), 0, st, dy, y, x, ldx, dW, db, rows, N, K, act);
     int rc = check_launch("small_linear_wgrad_kernel");
     if (rc) return rc;
   }
   if (dx) {
     VB_REQUIRE(lddx % 4 == 0, "small_linear_bwd: lddx must be a multiple of 4");
     const long long ctas = (long long)rows * ((K / 4 + 31) / 32);
-    small_linear_dgrad_kernel<<<(unsigned)ctas, 256, 0, st>>>(dy, y, W, dx, lddx, accumulate_dx, rows, N, K, act);
+    launch(small_linear_dgrad_kernel, dim3((unsigned)ctas), dim3(256), 0, st, dy, y, W, dx, lddx, accumulate_dx, rows, N, K, act);
     return check_launch("small_linear_dgrad_kernel");
   }
   return VAULT_OK;
@@ -217,14 +223,14 @@ extern "C" int vault_dropout_f32(const float* x, float* y, int64_t n, float p, u
   VB_REQUIRE(x && y && n >= 0 && p >= 0.f && p < 1.f, "dropout_f32: bad arguments");
   if (n == 0) return VAULT_OK;
   const long long q = (n + 3) / 4;
-  dropout_f32_kernel<<<(unsigned)((q + 255) / 256), 256, 0, (cudaStream_t)stream>>>(x, y, n, p, seed, reinterpret_cast<const unsigned long long*>(seed_dev), site);
+  launch(dropout_f32_kernel, dim3((unsigned)((q + 255) / 256)), dim3(256), 0, (cudaStream_t)stream, x, y, n, p, seed, reinterpret_cast<const unsigned long long*>(seed_dev), site);
   return check_launch("dropout_f32_kernel");
 }
 
 extern "C" int vault_ce_loss(const float* logits, const int64_t* labels, float* loss, float* dlogits, int32_t rows, int32_t n_classes,
                              float grad_scale, void* stream) {
   VB_REQUIRE(logits && labels && loss && rows > 0 && n_classes > 0, "ce_loss: bad arguments");
-  ce_loss_kernel<<<1, 256, 0, (cudaStream_t)stream>>>(logits, labels, loss, dlogits, rows, n_classes, grad_scale);
+  launch(ce_loss_kernel, dim3(1), dim3(256), 0, (cudaStream_t)stream, logits, labels, loss, dlogits, rows, n_classes, grad_scale);
   return check_launch("ce_loss_kernel");
 }
 
@@ -234,6 +240,6 @@ extern "C" int vault_colsum_bf16(const void* x, int64_t ldx, float* out, int64_t
   long long gy = (rows + 63) / 64;
   if (gy > 64) gy = 64;
   dim3 grid((cols + 127) / 128, (unsigned)gy);
-  colsum_bf16_kernel<<<grid, 256, 0, (cudaStream_t)stream>>>(reinterpret_cast<const bf16*>(x), ldx, out, rows, cols);
+  launch(colsum_bf16_kernel, dim3(grid), dim3(256), 0, (cudaStream_t)stream, reinterpret_cast<const bf16*>(x), ldx, out, rows, cols);
   return check_launch("colsum_bf16_kernel");
 }

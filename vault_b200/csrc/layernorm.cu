@@ -12,6 +12,7 @@ __global__ void __launch_bounds__(kLnWarps * 32)
 ln_fwd_kernel(const float* __restrict__ x, const float* __restrict__ gamma, const float* __restrict__ beta, bf16* __restrict__ y_bf16,
               float* __restrict__ y_f32, float* __restrict__ mean_out, float* __restrict__ rstd_out, long long rows, float eps,
               float drop_p, unsigned long long seed, const unsigned long long* seed_dev, unsigned site) {
+  pdl_enter();
   constexpr int cols = 128 * VPL;
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
   const long long row = (long long)blockIdx.x * kLnWarps + warp;
@@ -74,6 +75,7 @@ ln_bwd_kernel(const float* __restrict__ dy_f32, const bf16* __restrict__ dy_bf16
               const float* __restrict__ rstd, const float* __restrict__ gamma, const float* __restrict__ dres, float* __restrict__ dx_f32,
               bf16* __restrict__ dx_bf16, float* __restrict__ dgamma, float* __restrict__ dbeta, long long rows, float drop_p, unsigned site,
               float out_p, unsigned out_site, unsigned long long seed, const unsigned long long* seed_dev) {
+  pdl_enter();
   constexpr int cols = 128 * VPL;
   if ((drop_p > 0.f || out_p > 0.f) && seed_dev) seed += *seed_dev;
   const uint32_t out_thr = dropout_threshold(out_p);
@@ -175,7 +177,7 @@ template <int VPL>
 int ln_fwd_launch(const float* x, const float* gamma, const float* beta, void* y_bf16, float* y_f32, float* mean, float* rstd, long long rows,
                   float eps, float p, unsigned long long seed, const unsigned long long* seed_dev, unsigned site, cudaStream_t st) {
   const long long grid = (rows + kLnWarps - 1) / kLnWarps;
-  ln_fwd_kernel<VPL><<<(unsigned)grid, kLnWarps * 32, 0, st>>>(x, gamma, beta, reinterpret_cast<bf16*>(y_bf16), y_f32, mean, rstd, rows, eps, p,
+  launch(ln_fwd_kernel<VPL>, dim3((unsigned)grid), dim3(kLnWarps * 32), 0, st, x, gamma, beta, reinterpret_cast<bf16*>(y_bf16), y_f32, mean, rstd, rows, eps, p,
                                                                seed, seed_dev, site);
   return check_launch("ln_fwd_kernel");
 }
@@ -186,7 +188,7 @@ int ln_bwd_launch(const float* dy_f32, const void* dy_bf16, const float* x, cons
   long long grid = (rows + kLnWarps - 1) / kLnWarps;
   const long long cap = (long long)device_sm_count() * 4;
   if (grid > cap) grid = cap;
-  ln_bwd_kernel<VPL><<<(unsigned)grid, kLnWarps * 32, 0, st>>>(dy_f32, reinterpret_cast<const bf16*>(dy_bf16), x, mean, rstd, gamma, dres, dx_f32,
+  launch(ln_bwd_kernel<VPL>, dim3((unsigned)grid), dim3(kLnWarps * 32), 0, st, dy_f32, reinterpret_cast<const bf16*>(dy_bf16), x, mean, rstd, gamma, dres, dx_f32,
                                                                reinterpret_cast<bf16*>(dx_bf16), dgamma, dbeta, rows, p, site, out_p, out_site, seed, seed_dev);
   return check_launch("ln_bwd_kernel");
 }

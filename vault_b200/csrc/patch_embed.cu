@@ -63,6 +63,7 @@ patch_embed_tf32_kernel(const __grid_constant__ CUtensorMap tmX, const __grid_co
   __syncthreads();
   tc_fence_after();
   const uint32_t tmem_base = *tmem_slot_gen;
+  pdl_enter();  // everything above overlapped the previous kernel's tail; global memory is touched only below
 
   // tile -> (n block, image group, patch-row group)
   const int t = blockIdx.x;
@@ -199,6 +200,6 @@ extern "C" int vault_patch_embed_fwd(const float* pixels, const float* weight, c
     attr_set = true;
   }
   const int grid = p.tiles_ph * p.tiles_b * p.tiles_n;
-  patch_embed_tf32_kernel<<<grid, kPeThreads, kPeSmem, (cudaStream_t)stream>>>(tmX, tmW, p);
+  launch(patch_embed_tf32_kernel, dim3(grid), dim3(kPeThreads), kPeSmem, (cudaStream_t)stream, tmX, tmW, p);
   return check_launch("patch_embed_tf32_kernel");
 }

@@ -115,10 +115,11 @@ int vault_layernorm_bwd(const float* dy_f32, const void* dy_bf16, const float* x
 int vault_layernorm_fwd_drop(const float* x, const float* gamma, const float* beta, void* y_bf16, float* y_f32, float* mean,
                              float* rstd, int64_t rows, int32_t cols, float eps, float dropout_p, uint64_t seed,
                              const uint64_t* seed_dev, uint32_t site, void* stream);
+/*        dcolsum (optional, [cols], accumulated): column sums of the bf16 dx copy = bias gradient of the Linear whose dy it is */
 int vault_layernorm_bwd_drop(const float* dy_f32, const void* dy_bf16, const float* x, const float* mean, const float* rstd,
                              const float* gamma, const float* dres_f32, float* dx_f32, void* dx_bf16, float* dgamma,
-                             float* dbeta, int64_t rows, int32_t cols, float in_p, uint32_t in_site, float out_p,
-                             uint32_t out_site, uint64_t seed, const uint64_t* seed_dev, void* stream);
+                             float* dbeta, float* dcolsum, int64_t rows, int32_t cols, float in_p, uint32_t in_site,
+                             float out_p, uint32_t out_site, uint64_t seed, const uint64_t* seed_dev, void* stream);
 
 /* ------------------------------------------------------------------------------------------------------------------
  * Fused masked-softmax attention over the variable-length text+image sequence.

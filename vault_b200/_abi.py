@@ -41,7 +41,7 @@ SIGNATURES = {
     "vault_layernorm_fwd": [c_p, c_p, c_p, c_p, c_p, c_p, c_p, c_i64, c_i32, c_f32, c_p],
     "vault_layernorm_bwd": [c_p, c_p, c_p, c_p, c_p, c_p, c_p, c_p, c_p, c_p, c_p, c_i64, c_i32, c_p],
     "vault_layernorm_fwd_drop": [c_p, c_p, c_p, c_p, c_p, c_p, c_p, c_i64, c_i32, c_f32, c_f32, c_u64, c_p, c_u32, c_p],
-    "vault_layernorm_bwd_drop": [c_p, c_p, c_p, c_p, c_p, c_p, c_p, c_p, c_p, c_p, c_p, c_i64, c_i32, c_f32, c_u32, c_f32, c_u32, c_u64, c_p, c_p],
+    "vault_layernorm_bwd_drop": [c_p, c_p, c_p, c_p, c_p, c_p, c_p, c_p, c_p, c_p, c_p, c_p, c_i64, c_i32, c_f32, c_u32, c_f32, c_u32, c_u64, c_p, c_p],
     "vault_attn_fwd": [c_p, c_p, c_p, c_p, c_i32, c_i32, c_i32, c_f32, c_u64, c_p, c_u32, c_p],
     "vault_attn_bwd": [c_p, c_p, c_p, c_p, c_p, c_p, c_p, c_i32, c_i32, c_i32, c_f32, c_u64, c_p, c_u32, c_p],
     "vault_lm_embed_fwd": [c_p, c_p, c_p, c_p, c_p, c_p, c_p, c_p, c_i32, c_i32, c_i32, c_i32, c_p],
@@ -115,7 +115,8 @@ class CountingLib:
         self._inner = inner or lib()
         self.launches = 0
         self.calls = {}
-        self.gemms = []  # (M, N, K, a_mn, b_mn, epilogue, split_k, block_n, args-copy)
+        self.gemms = []  # GemmArgs copies, in launch order
+        self.trace = []  # (name, args) of every call, GemmArgs copied -- replayable with replay_trace()
 
     def __getattr__(self, name):
         fn = getattr(self._inner, name)
@@ -130,6 +131,9 @@ class CountingLib:
                 cp = GemmArgs()
                 C.memmove(C.byref(cp), C.byref(src), C.sizeof(GemmArgs))
                 self.gemms.append(cp)
+                self.trace.append((name, (cp,)))
+            else:
+                self.trace.append((name, args[:-1]))
             return fn(*args)
 
         return wrapped
@@ -147,3 +151,16 @@ def uninstall_counter():
     global _lib
     if isinstance(_lib, CountingLib):
         _lib = _lib._inner
+
+
+def replay_trace(trace, stream: int, only=None):
+    """Re-issue recorded ABI calls (same pointers) on `stream`; `only` filters by entry-point name."""
+    l = lib()
+    inner = l._inner if isinstance(l, CountingLib) else l
+    for name, args in trace:
+        if only is not None and not only(name):
+            continue
+        if name == "vault_gemm_bf16":
+            inner.vault_gemm_bf16(C.byref(args[0]), stream)
+        else:
+            getattr(inner, name)(*args, stream)

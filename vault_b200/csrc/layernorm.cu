@@ -67,31 +67,59 @@ ln_fwd_kernel(const float* __restrict__ x, const float* __restrict__ gamma, cons
   }
 }
 
-// Backward.  Persistent grid: each warp strides over rows and keeps its dgamma/dbeta partial sums in registers; one smem
-// reduction and one atomic per column per CTA at the end.
+constexpr int kLnBwdWarps = 16;
+
+// per-warp register partial sums [cols] -> one CTA sum -> fp32 atomics (red.v4); 16 warps fold to 8 first (48 KB static smem limit)
 template <int VPL>
-__global__ void __launch_bounds__(kLnWarps * 32, 2)
+__device__ __forceinline__ void cta_colsum_flush(float4 (&acc)[VPL], float4 (*red)[32 * VPL + 1], float* __restrict__ dst, int warp, int lane) {
+  __syncthreads();
+  if (warp >= kLnBwdWarps / 2) {
+#pragma unroll
+    for (int i = 0; i < VPL; ++i) red[warp - kLnBwdWarps / 2][lane + 32 * i] = acc[i];
+  }
+  __syncthreads();
+  if (warp < kLnBwdWarps / 2) {
+#pragma unroll
+    for (int i = 0; i < VPL; ++i) {
+      const float4 t = red[warp][lane + 32 * i];
+      red[warp][lane + 32 * i] = make_float4(acc[i].x + t.x, acc[i].y + t.y, acc[i].z + t.z, acc[i].w + t.w);
+    }
+  }
+  __syncthreads();
+  for (int c4 = threadIdx.x; c4 < 32 * VPL; c4 += kLnBwdWarps * 32) {
+    float4 a = red[0][c4];
+#pragma unroll
+    for (int w = 1; w < kLnBwdWarps / 2; ++w) {
+      const float4 t = red[w][c4];
+      a.x += t.x; a.y += t.y; a.z += t.z; a.w += t.w;
+    }
+    asm volatile("red.global.add.v4.f32 [%0], {%1, %2, %3, %4};" ::"l"(dst + 4 * c4), "f"(a.x), "f"(a.y), "f"(a.z), "f"(a.w) : "memory");
+  }
+}
+
+// Backward.  One 16-warp CTA per SM, each warp strides over rows; per-column sums (dgamma, dbeta and the column sum of the bf16
+// output = bias gradient of the GEMM that consumes it) stay in registers and meet in shared memory once per CTA, so the
+// fp32 atomics are O(SMs * cols), not O(rows * cols).  x is re-read (L1 hit) in the second phase instead of holding xhat.
+template <int VPL>
+__global__ void __launch_bounds__(kLnBwdWarps * 32, 1)
 ln_bwd_kernel(const float* __restrict__ dy_f32, const bf16* __restrict__ dy_bf16, const float* __restrict__ x, const float* __restrict__ mean,
               const float* __restrict__ rstd, const float* __restrict__ gamma, const float* __restrict__ dres, float* __restrict__ dx_f32,
-              bf16* __restrict__ dx_bf16, float* __restrict__ dgamma, float* __restrict__ dbeta, long long rows, float drop_p, unsigned site,
-              float out_p, unsigned out_site, unsigned long long seed, const unsigned long long* seed_dev) {
+              bf16* __restrict__ dx_bf16, float* __restrict__ dgamma, float* __restrict__ dbeta, float* __restrict__ dcolsum, long long rows,
+              float drop_p, unsigned site, float out_p, unsigned out_site, unsigned long long seed, const unsigned long long* seed_dev) {
   pdl_enter();
   constexpr int cols = 128 * VPL;
   if ((drop_p > 0.f || out_p > 0.f) && seed_dev) seed += *seed_dev;
   const uint32_t out_thr = dropout_threshold(out_p);
   const float out_scale = out_p > 0.f ? 1.0f / (1.0f - out_p) : 1.0f;
-  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
-  float4 dg[VPL], db[VPL];
-#pragma unroll
-  for (int i = 0; i < VPL; ++i) {
-    dg[i] = make_float4(0.f, 0.f, 0.f, 0.f);
-    db[i] = make_float4(0.f, 0.f, 0.f, 0.f);
-  }
   const uint32_t thr = dropout_threshold(drop_p);
   const float keep_scale = drop_p > 0.f ? 1.0f / (1.0f - drop_p) : 1.0f;
-  for (long long row = (long long)blockIdx.x * kLnWarps + warp; row < rows; row += (long long)gridDim.x * kLnWarps) {
+  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+  float4 dg[VPL], db[VPL], dcs[VPL];
+#pragma unroll
+  for (int i = 0; i < VPL; ++i) dg[i] = db[i] = dcs[i] = make_float4(0.f, 0.f, 0.f, 0.f);
+  for (long long row = (long long)blockIdx.x * kLnBwdWarps + warp; row < rows; row += (long long)gridDim.x * kLnBwdWarps) {
     const float mu = mean[row], rs = rstd[row];
-    float4 xh[VPL], d[VPL];
+    float4 d[VPL];
     float s1 = 0.f, s2 = 0.f;
 #pragma unroll
     for (int i = 0; i < VPL; ++i) {
@@ -111,24 +139,25 @@ ln_bwd_kernel(const float* __restrict__ dy_f32, const bf16* __restrict__ dy_bf16
         dv.z = bits.z >= thr ? dv.z * keep_scale : 0.f;
         dv.w = bits.w >= thr ? dv.w * keep_scale : 0.f;
       }
-      xh[i] = make_float4((xv.x - mu) * rs, (xv.y - mu) * rs, (xv.z - mu) * rs, (xv.w - mu) * rs);
-      dg[i].x += dv.x * xh[i].x; dg[i].y += dv.y * xh[i].y; dg[i].z += dv.z * xh[i].z; dg[i].w += dv.w * xh[i].w;
+      const float4 xh = make_float4((xv.x - mu) * rs, (xv.y - mu) * rs, (xv.z - mu) * rs, (xv.w - mu) * rs);
+      dg[i].x += dv.x * xh.x; dg[i].y += dv.y * xh.y; dg[i].z += dv.z * xh.z; dg[i].w += dv.w * xh.w;
       db[i].x += dv.x; db[i].y += dv.y; db[i].z += dv.z; db[i].w += dv.w;
       const float4 gm = __ldg(reinterpret_cast<const float4*>(gamma) + c4);  // L1-resident after the first row
       d[i] = make_float4(dv.x * gm.x, dv.y * gm.y, dv.z * gm.z, dv.w * gm.w);
       s1 += (d[i].x + d[i].y) + (d[i].z + d[i].w);
-      s2 += (d[i].x * xh[i].x + d[i].y * xh[i].y) + (d[i].z * xh[i].z + d[i].w * xh[i].w);
+      s2 += (d[i].x * xh.x + d[i].y * xh.y) + (d[i].z * xh.z + d[i].w * xh.w);
     }
     const float c1 = warp_sum(s1) * (1.0f / cols);
     const float c2 = warp_sum(s2) * (1.0f / cols);
 #pragma unroll
     for (int i = 0; i < VPL; ++i) {
       const int c4 = lane + 32 * i;
+      const float4 xv = __ldg(reinterpret_cast<const float4*>(x + row * cols) + c4);  // L1 hit
       float4 o;
-      o.x = rs * (d[i].x - c1 - xh[i].x * c2);
-      o.y = rs * (d[i].y - c1 - xh[i].y * c2);
-      o.z = rs * (d[i].z - c1 - xh[i].z * c2);
-      o.w = rs * (d[i].w - c1 - xh[i].w * c2);
+      o.x = rs * (d[i].x - c1 - (xv.x - mu) * rs * c2);
+      o.y = rs * (d[i].y - c1 - (xv.y - mu) * rs * c2);
+      o.z = rs * (d[i].z - c1 - (xv.z - mu) * rs * c2);
+      o.w = rs * (d[i].w - c1 - (xv.w - mu) * rs * c2);
       if (dres) {
         const float4 r = __ldg(reinterpret_cast<const float4*>(dres + row * cols) + c4);
         o.x += r.x; o.y += r.y; o.z += r.z; o.w += r.w;
@@ -146,31 +175,18 @@ ln_bwd_kernel(const float* __restrict__ dy_f32, const bf16* __restrict__ dy_bf16
         pk.x = pack_bf16x2(o.x, o.y);
         pk.y = pack_bf16x2(o.z, o.w);
         reinterpret_cast<uint2*>(dx_bf16 + row * cols)[c4] = pk;
+        if (dcolsum) {  // sum exactly what the consuming GEMMs will read (bf16-rounded, dropout applied)
+          const float2 a = unpack_bf16x2(pk.x), b = unpack_bf16x2(pk.y);
+          dcs[i].x += a.x; dcs[i].y += a.y; dcs[i].z += b.x; dcs[i].w += b.y;
+        }
       }
     }
   }
-  if (dgamma == nullptr && dbeta == nullptr) return;
-  __shared__ float4 red[kLnWarps][32 * VPL + 1];
-  for (int pass = 0; pass < 2; ++pass) {
-    float* dst = pass == 0 ? dgamma : dbeta;
-    if (dst == nullptr) continue;
-    __syncthreads();
-#pragma unroll
-    for (int i = 0; i < VPL; ++i) red[warp][lane + 32 * i] = pass == 0 ? dg[i] : db[i];
-    __syncthreads();
-    for (int c4 = threadIdx.x; c4 < 32 * VPL; c4 += kLnWarps * 32) {
-      float4 acc = red[0][c4];
-#pragma unroll
-      for (int w = 1; w < kLnWarps; ++w) {
-        const float4 t = red[w][c4];
-        acc.x += t.x; acc.y += t.y; acc.z += t.z; acc.w += t.w;
-      }
-      atomicAdd(dst + 4 * c4 + 0, acc.x);
-      atomicAdd(dst + 4 * c4 + 1, acc.y);
-      atomicAdd(dst + 4 * c4 + 2, acc.z);
-      atomicAdd(dst + 4 * c4 + 3, acc.w);
-    }
-  }
+  if (dgamma == nullptr && dbeta == nullptr && dcolsum == nullptr) return;
+  __shared__ float4 red[kLnBwdWarps / 2][32 * VPL + 1];
+  if (dgamma) cta_colsum_flush<VPL>(dg, red, dgamma, warp, lane);
+  if (dbeta) cta_colsum_flush<VPL>(db, red, dbeta, warp, lane);
+  if (dcolsum) cta_colsum_flush<VPL>(dcs, red, dcolsum, warp, lane);
 }
 
 template <int VPL>
@@ -183,13 +199,13 @@ int ln_fwd_launch(const float* x, const float* gamma, const float* beta, void* y
 }
 template <int VPL>
 int ln_bwd_launch(const float* dy_f32, const void* dy_bf16, const float* x, const float* mean, const float* rstd, const float* gamma,
-                  const float* dres, float* dx_f32, void* dx_bf16, float* dgamma, float* dbeta, long long rows, float p, unsigned site,
-                  float out_p, unsigned out_site, unsigned long long seed, const unsigned long long* seed_dev, cudaStream_t st) {
-  long long grid = (rows + kLnWarps - 1) / kLnWarps;
-  const long long cap = (long long)device_sm_count() * 4;
+                  const float* dres, float* dx_f32, void* dx_bf16, float* dgamma, float* dbeta, float* dcolsum, long long rows, float p,
+                  unsigned site, float out_p, unsigned out_site, unsigned long long seed, const unsigned long long* seed_dev, cudaStream_t st) {
+  long long grid = (rows + kLnBwdWarps - 1) / kLnBwdWarps;
+  const long long cap = (long long)device_sm_count();
   if (grid > cap) grid = cap;
-  launch(ln_bwd_kernel<VPL>, dim3((unsigned)grid), dim3(kLnWarps * 32), 0, st, dy_f32, reinterpret_cast<const bf16*>(dy_bf16), x, mean, rstd, gamma, dres, dx_f32,
-                                                               reinterpret_cast<bf16*>(dx_bf16), dgamma, dbeta, rows, p, site, out_p, out_site, seed, seed_dev);
+  launch(ln_bwd_kernel<VPL>, dim3((unsigned)grid), dim3(kLnBwdWarps * 32), 0, st, dy_f32, reinterpret_cast<const bf16*>(dy_bf16), x, mean, rstd, gamma, dres, dx_f32,
+                                                               reinterpret_cast<bf16*>(dx_bf16), dgamma, dbeta, dcolsum, rows, p, site, out_p, out_site, seed, seed_dev);
   return check_launch("ln_bwd_kernel");
 }
 
@@ -226,14 +242,14 @@ extern "C" int vault_layernorm_fwd(const float* x, const float* gamma, const flo
 
 extern "C" int vault_layernorm_bwd_drop(const float* dy_f32, const void* dy_bf16, const float* x, const float* mean, const float* rstd,
                                         const float* gamma, const float* dres_f32, float* dx_f32, void* dx_bf16, float* dgamma, float* dbeta,
-                                        int64_t rows, int32_t cols, float in_p, uint32_t in_site, float out_p, uint32_t out_site, uint64_t seed,
-                                        const uint64_t* seed_dev, void* stream) {
+                                        float* dcolsum, int64_t rows, int32_t cols, float in_p, uint32_t in_site, float out_p, uint32_t out_site,
+                                        uint64_t seed, const uint64_t* seed_dev, void* stream) {
   using namespace vb;
   VB_REQUIRE((dy_f32 || dy_bf16) && x && mean && rstd && gamma && dx_f32, "layernorm_bwd: null pointer");
   VB_REQUIRE(rows >= 0 && cols > 0 && cols % 128 == 0, "layernorm_bwd: bad shape rows=%lld cols=%d", (long long)rows, cols);
   if (rows == 0) return VAULT_OK;
   cudaStream_t st = reinterpret_cast<cudaStream_t>(stream);
-#define CALL(V) ln_bwd_launch<V>(dy_f32, dy_bf16, x, mean, rstd, gamma, dres_f32, dx_f32, dx_bf16, dgamma, dbeta, rows, in_p, in_site, out_p, out_site, seed, reinterpret_cast<const unsigned long long*>(seed_dev), st)
+#define CALL(V) ln_bwd_launch<V>(dy_f32, dy_bf16, x, mean, rstd, gamma, dres_f32, dx_f32, dx_bf16, dgamma, dbeta, dcolsum, rows, in_p, in_site, out_p, out_site, seed, reinterpret_cast<const unsigned long long*>(seed_dev), st)
   VB_LN_DISPATCH(cols, CALL)
 #undef CALL
 }
@@ -241,5 +257,6 @@ extern "C" int vault_layernorm_bwd_drop(const float* dy_f32, const void* dy_bf16
 extern "C" int vault_layernorm_bwd(const float* dy_f32, const void* dy_bf16, const float* x, const float* mean, const float* rstd,
                                    const float* gamma, const float* dres_f32, float* dx_f32, void* dx_bf16, float* dgamma, float* dbeta,
                                    int64_t rows, int32_t cols, void* stream) {
-  return vault_layernorm_bwd_drop(dy_f32, dy_bf16, x, mean, rstd, gamma, dres_f32, dx_f32, dx_bf16, dgamma, dbeta, rows, cols, 0.f, 0, 0.f, 0, 0, nullptr, stream);
+  return vault_layernorm_bwd_drop(dy_f32, dy_bf16, x, mean, rstd, gamma, dres_f32, dx_f32, dx_bf16, dgamma, dbeta, nullptr, rows, cols, 0.f, 0, 0.f, 0, 0,
+                                  nullptr, stream);
 }

@@ -307,8 +307,9 @@ class VaultEngine:
         """dx[M,K_in] = dy[M,N_out] W[N_out,K_in] : contraction over N_out, W read un-transposed as the MN-major operand."""
         self.gemm(dy16.data_ptr(), N_out, 0, self.w16(wname), K_in, 1, M, K_in, N_out, epi, out.data_ptr(), K_in, **kw)
 
-    def linear_wgrad(self, dy16, x16, M, wname, bname, N_out, K_in):
-        """dW[N_out,K_in] = dy^T x (contraction over the M tokens, both operands read un-transposed), db = colsum(dy)."""
+    def linear_wgrad(self, dy16, x16, M, wname, bname, N_out, K_in, bias=True):
+        """dW[N_out,K_in] = dy^T x (contraction over the M tokens, both operands read un-transposed), db = colsum(dy)
+        (bias=False when the kernel that produced dy already accumulated its column sums)."""
         gw = self.g32(wname)
         if gw:
             if wname in self._atomic_w:  # slot already zero-filled by zero_accumulated_grads()
@@ -316,7 +317,7 @@ class VaultEngine:
                           split_k=self._wgrad_split(N_out, K_in, M), block_n=128)
             else:
                 self.gemm(dy16.data_ptr(), N_out, 1, x16.data_ptr(), K_in, 1, N_out, K_in, M, EPI_STORE_F32, gw, K_in, block_n=128)
-        gb = self.g32(bname)
+        gb = self.g32(bname) if bias else 0
         if gb:
             rc = self._lib.vault_colsum_bf16(dy16.data_ptr(), N_out, gb, M, N_out, self._st)
             if rc:
@@ -333,14 +334,17 @@ class VaultEngine:
             _abi.check(rc, "vault_layernorm_fwd")
         return y16, y32, stats
 
-    def ln_bwd(self, dy32, dy16, x32, stats, rows, gname, bname, dres32=None, want16=True, in_p=0.0, in_site=0, out_p=0.0, out_site=0):
+    def ln_bwd(self, dy32, dy16, x32, stats, rows, gname, bname, dres32=None, want16=True, in_p=0.0, in_site=0, out_p=0.0, out_site=0,
+               colsum_to: Optional[str] = None):
+        """colsum_to: name of the bias whose gradient is the column sum of this call's bf16 output (fused, saves a pass)."""
         dx32 = self._new((rows, self.H), torch.float32)
         dx16 = self._new((rows, self.H), torch.bfloat16) if want16 else None
         use_seed = in_p > 0 or out_p > 0
         rc = self._lib.vault_layernorm_bwd_drop(dy32.data_ptr() if dy32 is not None else None, dy16.data_ptr() if dy16 is not None else None,
                                                 x32.data_ptr(), stats.data_ptr(), stats.data_ptr() + 4 * rows, self.w32(gname),
                                                 dres32.data_ptr() if dres32 is not None else None, dx32.data_ptr(),
-                                                dx16.data_ptr() if want16 else None, self.g32(gname) or None, self.g32(bname) or None, rows, self.H,
+                                                dx16.data_ptr() if want16 else None, self.g32(gname) or None, self.g32(bname) or None,
+                                                (self.g32(colsum_to) or None) if (colsum_to and want16) else None, rows, self.H,
                                                 in_p, in_site, out_p, out_site, self.seed, self.seed_dev.data_ptr() if use_seed else None, self._st)
         if rc:
             _abi.check(rc, "vault_layernorm_bwd")
@@ -417,19 +421,21 @@ class VaultEngine:
         H, I = self.H, self.I
         dpre = self._new((M, I), torch.bfloat16)
         self.linear_dgrad(g16, M, nm["w2"], H, I, EPI_DGELU_BF16, dpre, aux=sv[f"{li}.pre"].data_ptr(), ldaux=I)
-        self.linear_wgrad(g16, sv[f"{li}.act"], M, nm["w2"], nm["b2"], H, I)
+        self.linear_wgrad(g16, sv[f"{li}.act"], M, nm["w2"], nm["b2"], H, I, bias=False)  # db2: summed by the kernel that produced g16
         dn2 = self._new((M, H), torch.bfloat16)
         self.linear_dgrad(dpre, M, nm["w1"], I, H, EPI_PLAIN_BF16, dn2)
         self.linear_wgrad(dpre, sv[f"{li}.n2"], M, nm["w1"], nm["b1"], I, H)
-        g2_32, g2_16 = self.ln_bwd(None, dn2, sv[f"{li}.h"], sv[f"{li}.st2"], M, nm["ln2"] + ".weight", nm["ln2"] + ".bias", dres32=g32)
+        g2_32, g2_16 = self.ln_bwd(None, dn2, sv[f"{li}.h"], sv[f"{li}.st2"], M, nm["ln2"] + ".weight", nm["ln2"] + ".bias", dres32=g32,
+                                   colsum_to=nm["o_b"])
         dctx = self._new((M, H), torch.bfloat16)
         self.linear_dgrad(g2_16, M, nm["o_w"], H, H, EPI_PLAIN_BF16, dctx)
-        self.linear_wgrad(g2_16, sv[f"{li}.ctx"], M, nm["o_w"], nm["o_b"], H, H)
+        self.linear_wgrad(g2_16, sv[f"{li}.ctx"], M, nm["o_w"], nm["o_b"], H, H, bias=False)
         dqkv = self.attn_bwd(sv[f"{li}.qkv"], key_mask, sv[f"{li}.ctx"], dctx, sv[f"{li}.lse"], B, S)
         dn1 = self._new((M, H), torch.bfloat16)
         self.linear_dgrad(dqkv, M, nm["qkv_w"], 3 * H, H, EPI_PLAIN_BF16, dn1)
         self.linear_wgrad(dqkv, sv[f"{li}.n1"], M, nm["qkv_w"], nm["qkv_b"], 3 * H, H)
-        return self.ln_bwd(None, dn1, sv[f"{li}.x"], sv[f"{li}.st1"], M, nm["ln1"] + ".weight", nm["ln1"] + ".bias", dres32=g2_32)
+        below_b2 = self._names("", i - 1, True)["b2"] if i > 0 else None  # this output is the dy of the layer below's MLP-2
+        return self.ln_bwd(None, dn1, sv[f"{li}.x"], sv[f"{li}.st1"], M, nm["ln1"] + ".weight", nm["ln1"] + ".bias", dres32=g2_32, colsum_to=below_b2)
 
     # ---- LM (post-LN, dropout when training) ---------------------------------------------------------------------
     def lm_layer_fwd(self, i, r32, x16, M, B, T, key_mask, save, train):
@@ -455,18 +461,18 @@ class VaultEngine:
         H, I = self.H, self.I
         p, pa = (self.lm_p, self.lm_p_attn) if train else (0.0, 0.0)
         ds32, ds16 = self.ln_bwd(g32, gx16, sv[f"{li}.s"], sv[f"{li}.st2"], M, nm["ln2"] + ".weight", nm["ln2"] + ".bias", out_p=p,
-                                 out_site=self._site(i, 2))
+                                 out_site=self._site(i, 2), colsum_to=nm["b2"])
         dpre = self._new((M, I), torch.bfloat16)
         self.linear_dgrad(ds16, M, nm["w2"], H, I, EPI_DGELU_BF16, dpre, aux=sv[f"{li}.pre"].data_ptr(), ldaux=I)
-        self.linear_wgrad(ds16, sv[f"{li}.act"], M, nm["w2"], nm["b2"], H, I)
+        self.linear_wgrad(ds16, sv[f"{li}.act"], M, nm["w2"], nm["b2"], H, I, bias=False)
         da16 = self._new((M, H), torch.bfloat16)
         self.linear_dgrad(dpre, M, nm["w1"], I, H, EPI_PLAIN_BF16, da16)
         self.linear_wgrad(dpre, sv[f"{li}.a16"], M, nm["w1"], nm["b1"], I, H)
         dt32, dt16 = self.ln_bwd(ds32, da16, sv[f"{li}.t"], sv[f"{li}.st1"], M, nm["ln1"] + ".weight", nm["ln1"] + ".bias", out_p=p,
-                                 out_site=self._site(i, 1))
+                                 out_site=self._site(i, 1), colsum_to=nm["o_b"])
         dctx = self._new((M, H), torch.bfloat16)
         self.linear_dgrad(dt16, M, nm["o_w"], H, H, EPI_PLAIN_BF16, dctx)
-        self.linear_wgrad(dt16, sv[f"{li}.ctx"], M, nm["o_w"], nm["o_b"], H, H)
+        self.linear_wgrad(dt16, sv[f"{li}.ctx"], M, nm["o_w"], nm["o_b"], H, H, bias=False)
         dqkv = self.attn_bwd(sv[f"{li}.qkv"], key_mask, sv[f"{li}.ctx"], dctx, sv[f"{li}.lse"], B, T, p=pa, site=self._site(i, 0))
         gx = self._new((M, H), torch.bfloat16)
         self.linear_dgrad(dqkv, M, nm["qkv_w"], 3 * H, H, EPI_PLAIN_BF16, gx)
@@ -650,7 +656,8 @@ class VaultEngine:
             _abi.check(lib.vault_small_linear_bwd(dpooled.data_ptr(), sv["pooled"].data_ptr(), sv["lhs"].data_ptr(), S * H, self.w32("pooler.dense.weight"),
                                                   g_lhs.data_ptr(), S * H, 1, self.g32("pooler.dense.weight") or None,
                                                   self.g32("pooler.dense.bias") or None, B, H, H, 1, st), "pooler_bwd")
-        g32, g16 = self.ln_bwd(g_lhs, None, sv["x_final"], sv["st_f"], M, "layernorm.weight", "layernorm.bias")
+        g32, g16 = self.ln_bwd(g_lhs, None, sv["x_final"], sv["st_f"], M, "layernorm.weight", "layernorm.bias",
+                               colsum_to=self._names("", self.L - 1, True)["b2"])
         for i in reversed(range(self.L)):
             g32, g16 = self.vilt_layer_bwd(i, g32, g16, M, B, S, sv["key_mask"], sv)
             if segments and i == self.L // 2 and i > 0:

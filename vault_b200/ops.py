@@ -72,12 +72,12 @@ def layernorm_fwd(x, gamma, beta, eps, *, want_bf16=True, want_f32=False, dropou
 
 
 def layernorm_bwd(dy_f32, dy_bf16, x, mean, rstd, gamma, dres, dgamma, dbeta, *, want_bf16=True, in_p=0.0, in_site=0, out_p=0.0,
-                  out_site=0, seed=0):
+                  out_site=0, seed=0, dcolsum=None):
     _cuda(dy_f32, dy_bf16, x, mean, rstd, gamma, dres, dgamma, dbeta)
     rows, cols = x.numel() // x.shape[-1], x.shape[-1]
     dx32 = torch.empty_like(x)
     dx16 = torch.empty(x.shape, device=x.device, dtype=torch.bfloat16) if want_bf16 else None
     _abi.call("vault_layernorm_bwd_drop", _ptr(dy_f32), _ptr(dy_bf16), x.data_ptr(), mean.data_ptr(), rstd.data_ptr(), gamma.data_ptr(),
-              _ptr(dres), dx32.data_ptr(), _ptr(dx16), _ptr(dgamma), _ptr(dbeta), rows, cols, in_p, in_site, out_p, out_site, seed, None,
+              _ptr(dres), dx32.data_ptr(), _ptr(dx16), _ptr(dgamma), _ptr(dbeta), _ptr(dcolsum), rows, cols, in_p, in_site, out_p, out_site, seed, None,
               _stream())
     return dx32, dx16

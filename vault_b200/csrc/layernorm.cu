@@ -67,29 +67,25 @@ ln_fwd_kernel(const float* __restrict__ x, const float* __restrict__ gamma, cons
   }
 }
 
-constexpr int kLnBwdWarps = 16;
+// Backward.  HBM-bound (16-20 B per element) but each row needs two warp-wide reductions between its loads and its stores, so
+// a load-then-compute warp leaves the memory system idle most of the time.  Here one producer warp streams whole rows
+// (x, dy, residual gradient) into a 16-slot shared-memory ring with 1-D bulk TMA copies (cp.async.bulk + mbarrier
+// complete_tx), ~150 KB in flight per SM, and 8 consumer warps take rows from the ring: the memory pipe never waits for
+// arithmetic.  Per-column sums (dgamma, dbeta, bias-gradient column sum of the bf16 output) stay in the consumers' registers
+// and meet once per CTA: O(SMs * cols) fp32 atomics.
+constexpr int kLnBwdWarps = 8;    // consumer warps
+constexpr int kLnBwdSlots = 16;   // rows in flight per CTA
 
-// per-warp register partial sums [cols] -> one CTA sum -> fp32 atomics (red.v4); 16 warps fold to 8 first (48 KB static smem limit)
 template <int VPL>
 __device__ __forceinline__ void cta_colsum_flush(float4 (&acc)[VPL], float4 (*red)[32 * VPL + 1], float* __restrict__ dst, int warp, int lane) {
-  __syncthreads();
-  if (warp >= kLnBwdWarps / 2) {
+  asm volatile("bar.sync 1, %0;" ::"n"(kLnBwdWarps * 32));
 #pragma unroll
-    for (int i = 0; i < VPL; ++i) red[warp - kLnBwdWarps / 2][lane + 32 * i] = acc[i];
-  }
-  __syncthreads();
-  if (warp < kLnBwdWarps / 2) {
-#pragma unroll
-    for (int i = 0; i < VPL; ++i) {
-      const float4 t = red[warp][lane + 32 * i];
-      red[warp][lane + 32 * i] = make_float4(acc[i].x + t.x, acc[i].y + t.y, acc[i].z + t.z, acc[i].w + t.w);
-    }
-  }
-  __syncthreads();
-  for (int c4 = threadIdx.x; c4 < 32 * VPL; c4 += kLnBwdWarps * 32) {
+  for (int i = 0; i < VPL; ++i) red[warp][lane + 32 * i] = acc[i];
+  asm volatile("bar.sync 1, %0;" ::"n"(kLnBwdWarps * 32));
+  for (int c4 = warp * 32 + lane; c4 < 32 * VPL; c4 += kLnBwdWarps * 32) {
     float4 a = red[0][c4];
 #pragma unroll
-    for (int w = 1; w < kLnBwdWarps / 2; ++w) {
+    for (int w = 1; w < kLnBwdWarps; ++w) {
       const float4 t = red[w][c4];
       a.x += t.x; a.y += t.y; a.z += t.z; a.w += t.w;
     }
@@ -97,38 +93,80 @@ __device__ __forceinline__ void cta_colsum_flush(float4 (&acc)[VPL], float4 (*re
   }
 }
 
-// Backward.  One 16-warp CTA per SM, each warp strides over rows; per-column sums (dgamma, dbeta and the column sum of the bf16
-// output = bias gradient of the GEMM that consumes it) stay in registers and meet in shared memory once per CTA, so the
-// fp32 atomics are O(SMs * cols), not O(rows * cols).  x is re-read (L1 hit) in the second phase instead of holding xhat.
 template <int VPL>
-__global__ void __launch_bounds__(kLnBwdWarps * 32, 1)
+__global__ void __launch_bounds__((kLnBwdWarps + 1) * 32, 1)
 ln_bwd_kernel(const float* __restrict__ dy_f32, const bf16* __restrict__ dy_bf16, const float* __restrict__ x, const float* __restrict__ mean,
               const float* __restrict__ rstd, const float* __restrict__ gamma, const float* __restrict__ dres, float* __restrict__ dx_f32,
               bf16* __restrict__ dx_bf16, float* __restrict__ dgamma, float* __restrict__ dbeta, float* __restrict__ dcolsum, long long rows,
               float drop_p, unsigned site, float out_p, unsigned out_site, unsigned long long seed, const unsigned long long* seed_dev) {
-  pdl_enter();
   constexpr int cols = 128 * VPL;
+  constexpr uint32_t kRow32 = cols * 4, kRow16 = cols * 2;
+  extern __shared__ __align__(128) uint8_t ln_smem[];
+  // slot layout: [x f32][dres f32 (opt)][dy f32 (opt)][dy bf16 (opt)]
+  const uint32_t off_res = kRow32;
+  const uint32_t off_dy32 = off_res + (dres ? kRow32 : 0u);
+  const uint32_t off_dy16 = off_dy32 + (dy_f32 ? kRow32 : 0u);
+  const uint32_t slot_bytes = off_dy16 + (dy_bf16 ? kRow16 : 0u);
+  const uint32_t sbase = smem_u32(ln_smem);
+  const uint32_t bars = sbase + kLnBwdSlots * slot_bytes;  // full[16] | empty[16]
+  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+  if (threadIdx.x == 0) {
+    for (int s = 0; s < kLnBwdSlots; ++s) {
+      mbar_init(bars + 8u * s, 1);
+      mbar_init(bars + 8u * (kLnBwdSlots + s), 1);
+    }
+    mbar_fence_init();
+  }
+  __syncthreads();
+  pdl_enter();
+  const long long my_rows = rows > blockIdx.x ? (rows - blockIdx.x + gridDim.x - 1) / gridDim.x : 0;  // rows b, b+grid, ...
+
+  if (warp == kLnBwdWarps) {
+    // ===================== producer: bulk-copy rows into the ring =====================
+    if (lane == 0) {
+      for (long long k = 0; k < my_rows; ++k) {
+        const int slot = (int)(k % kLnBwdSlots);
+        const uint32_t ph = (uint32_t)((k / kLnBwdSlots) & 1);
+        mbar_wait(bars + 8u * (kLnBwdSlots + slot), ph ^ 1u);
+        const long long row = blockIdx.x + k * gridDim.x;
+        const uint32_t dst = sbase + slot * slot_bytes, fb = bars + 8u * slot;
+        mbar_expect_tx(fb, slot_bytes);
+        bulk_load(dst, x + row * cols, kRow32, fb);
+        if (dres) bulk_load(dst + off_res, dres + row * cols, kRow32, fb);
+        if (dy_f32) bulk_load(dst + off_dy32, dy_f32 + row * cols, kRow32, fb);
+        if (dy_bf16) bulk_load(dst + off_dy16, dy_bf16 + row * cols, kRow16, fb);
+      }
+    }
+    return;
+  }
+
+  // ===================== consumers =====================
   if ((drop_p > 0.f || out_p > 0.f) && seed_dev) seed += *seed_dev;
   const uint32_t out_thr = dropout_threshold(out_p);
   const float out_scale = out_p > 0.f ? 1.0f / (1.0f - out_p) : 1.0f;
   const uint32_t thr = dropout_threshold(drop_p);
   const float keep_scale = drop_p > 0.f ? 1.0f / (1.0f - drop_p) : 1.0f;
-  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
   float4 dg[VPL], db[VPL], dcs[VPL];
 #pragma unroll
   for (int i = 0; i < VPL; ++i) dg[i] = db[i] = dcs[i] = make_float4(0.f, 0.f, 0.f, 0.f);
-  for (long long row = (long long)blockIdx.x * kLnBwdWarps + warp; row < rows; row += (long long)gridDim.x * kLnBwdWarps) {
-    const float mu = mean[row], rs = rstd[row];
+  for (long long k = warp; k < my_rows; k += kLnBwdWarps) {
+    const int slot = (int)(k % kLnBwdSlots);
+    const uint32_t ph = (uint32_t)((k / kLnBwdSlots) & 1);
+    const long long row = blockIdx.x + k * gridDim.x;
+    const float mu = __ldg(mean + row), rs = __ldg(rstd + row);  // issued before the wait: off the critical path
+    mbar_wait(bars + 8u * slot, ph);
+    const uint8_t* sl = ln_smem + slot * slot_bytes;
+    const float4* sx = reinterpret_cast<const float4*>(sl);
     float4 d[VPL];
     float s1 = 0.f, s2 = 0.f;
 #pragma unroll
     for (int i = 0; i < VPL; ++i) {
       const int c4 = lane + 32 * i;
-      const float4 xv = __ldg(reinterpret_cast<const float4*>(x + row * cols) + c4);
+      const float4 xv = sx[c4];
       float4 dv = make_float4(0.f, 0.f, 0.f, 0.f);
-      if (dy_f32) dv = __ldg(reinterpret_cast<const float4*>(dy_f32 + row * cols) + c4);
+      if (dy_f32) dv = reinterpret_cast<const float4*>(sl + off_dy32)[c4];
       if (dy_bf16) {
-        const uint2 pk = __ldg(reinterpret_cast<const uint2*>(dy_bf16 + row * cols) + c4);
+        const uint2 pk = reinterpret_cast<const uint2*>(sl + off_dy16)[c4];
         const float2 a = unpack_bf16x2(pk.x), b = unpack_bf16x2(pk.y);
         dv.x += a.x; dv.y += a.y; dv.z += b.x; dv.w += b.y;
       }
@@ -142,7 +180,7 @@ ln_bwd_kernel(const float* __restrict__ dy_f32, const bf16* __restrict__ dy_bf16
       const float4 xh = make_float4((xv.x - mu) * rs, (xv.y - mu) * rs, (xv.z - mu) * rs, (xv.w - mu) * rs);
       dg[i].x += dv.x * xh.x; dg[i].y += dv.y * xh.y; dg[i].z += dv.z * xh.z; dg[i].w += dv.w * xh.w;
       db[i].x += dv.x; db[i].y += dv.y; db[i].z += dv.z; db[i].w += dv.w;
-      const float4 gm = __ldg(reinterpret_cast<const float4*>(gamma) + c4);  // L1-resident after the first row
+      const float4 gm = __ldg(reinterpret_cast<const float4*>(gamma) + c4);  // L1-resident
       d[i] = make_float4(dv.x * gm.x, dv.y * gm.y, dv.z * gm.z, dv.w * gm.w);
       s1 += (d[i].x + d[i].y) + (d[i].z + d[i].w);
       s2 += (d[i].x * xh.x + d[i].y * xh.y) + (d[i].z * xh.z + d[i].w * xh.w);
@@ -152,14 +190,14 @@ ln_bwd_kernel(const float* __restrict__ dy_f32, const bf16* __restrict__ dy_bf16
 #pragma unroll
     for (int i = 0; i < VPL; ++i) {
       const int c4 = lane + 32 * i;
-      const float4 xv = __ldg(reinterpret_cast<const float4*>(x + row * cols) + c4);  // L1 hit
+      const float4 xv = sx[c4];
       float4 o;
       o.x = rs * (d[i].x - c1 - (xv.x - mu) * rs * c2);
       o.y = rs * (d[i].y - c1 - (xv.y - mu) * rs * c2);
       o.z = rs * (d[i].z - c1 - (xv.z - mu) * rs * c2);
       o.w = rs * (d[i].w - c1 - (xv.w - mu) * rs * c2);
       if (dres) {
-        const float4 r = __ldg(reinterpret_cast<const float4*>(dres + row * cols) + c4);
+        const float4 r = reinterpret_cast<const float4*>(sl + off_res)[c4];
         o.x += r.x; o.y += r.y; o.z += r.z; o.w += r.w;
       }
       reinterpret_cast<float4*>(dx_f32 + row * cols)[c4] = o;
@@ -181,9 +219,12 @@ ln_bwd_kernel(const float* __restrict__ dy_f32, const bf16* __restrict__ dy_bf16
         }
       }
     }
+    __syncwarp();
+    if (lane == 0) mbar_arrive(bars + 8u * (kLnBwdSlots + slot));  // slot free for the producer
   }
   if (dgamma == nullptr && dbeta == nullptr && dcolsum == nullptr) return;
-  __shared__ float4 red[kLnBwdWarps / 2][32 * VPL + 1];
+  // the ring is idle now (every row of this CTA has been consumed by the time all consumers pass the first bar.sync)
+  float4(*red)[32 * VPL + 1] = reinterpret_cast<float4(*)[32 * VPL + 1]>(ln_smem);
   if (dgamma) cta_colsum_flush<VPL>(dg, red, dgamma, warp, lane);
   if (dbeta) cta_colsum_flush<VPL>(db, red, dbeta, warp, lane);
   if (dcolsum) cta_colsum_flush<VPL>(dcs, red, dcolsum, warp, lane);
@@ -201,11 +242,23 @@ template <int VPL>
 int ln_bwd_launch(const float* dy_f32, const void* dy_bf16, const float* x, const float* mean, const float* rstd, const float* gamma,
                   const float* dres, float* dx_f32, void* dx_bf16, float* dgamma, float* dbeta, float* dcolsum, long long rows, float p,
                   unsigned site, float out_p, unsigned out_site, unsigned long long seed, const unsigned long long* seed_dev, cudaStream_t st) {
-  long long grid = (rows + kLnBwdWarps - 1) / kLnBwdWarps;
+  constexpr int cols = 128 * VPL;
+  const int slot_bytes = cols * 4 + (dres ? cols * 4 : 0) + (dy_f32 ? cols * 4 : 0) + (dy_bf16 ? cols * 2 : 0);
+  int smem = kLnBwdSlots * slot_bytes + 2 * kLnBwdSlots * 8;
+  const int red_bytes = kLnBwdWarps * (32 * VPL + 1) * 16;
+  if (smem < red_bytes) smem = red_bytes;
+  static int smem_set = 0;
+  if (smem > smem_set) {
+    cudaError_t e = cudaFuncSetAttribute(ln_bwd_kernel<VPL>, cudaFuncAttributeMaxDynamicSharedMemorySize, 200 * 1024);
+    if (e != cudaSuccess) return fail(VAULT_ERR_LAUNCH, "ln_bwd: cudaFuncSetAttribute: %s", cudaGetErrorString(e));
+    smem_set = 200 * 1024;
+  }
+  if (smem > 200 * 1024) return fail(VAULT_ERR_INVALID, "ln_bwd: row too wide for the shared-memory ring (%d bytes)", smem);
+  long long grid = rows;
   const long long cap = (long long)device_sm_count();
   if (grid > cap) grid = cap;
-  launch(ln_bwd_kernel<VPL>, dim3((unsigned)grid), dim3(kLnBwdWarps * 32), 0, st, dy_f32, reinterpret_cast<const bf16*>(dy_bf16), x, mean, rstd, gamma, dres, dx_f32,
-                                                               reinterpret_cast<bf16*>(dx_bf16), dgamma, dbeta, dcolsum, rows, p, site, out_p, out_site, seed, seed_dev);
+  launch(ln_bwd_kernel<VPL>, dim3((unsigned)grid), dim3((kLnBwdWarps + 1) * 32), (size_t)smem, st, dy_f32, reinterpret_cast<const bf16*>(dy_bf16), x, mean,
+         rstd, gamma, dres, dx_f32, reinterpret_cast<bf16*>(dx_bf16), dgamma, dbeta, dcolsum, rows, p, site, out_p, out_site, seed, seed_dev);
   return check_launch("ln_bwd_kernel");
 }
 

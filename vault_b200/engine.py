@@ -15,6 +15,7 @@ from __future__ import annotations
 
 import ctypes as C
 import math
+import os
 from typing import Dict, List, Optional, Tuple
 
 import torch
@@ -91,6 +92,10 @@ class VaultEngine:
         self.seed_dev: Optional[torch.Tensor] = None  # device counter added to the seed (advanced once per training step)
         self.sms = 0
         self.gemm_max_ctas = 0  # >0: leave SMs free for a concurrently running collective (data-parallel overlap)
+        self.wgrad_side_stream = os.environ.get("VAULT_B200_WGRAD_SIDE", "1") != "0"
+        self._side = None
+        self._side_keep = []
+        self._side_dirty = False
 
     # ------------------------------------------------------------------------------------------------------------
     # parameter packing
@@ -198,6 +203,7 @@ class VaultEngine:
         # gradient ranges that are ACCUMULATED into (atomics): zero-filled at the start of every backward
         self._zero_ranges = self._compute_zero_ranges()
         self.opt_state = None
+        self._side = torch.cuda.Stream(device=device)
 
     def _params_in_place(self) -> bool:
         named = dict(self.model.named_parameters())
@@ -283,7 +289,7 @@ class VaultEngine:
         return torch.empty(shape, device=self.device, dtype=dtype)
 
     def gemm(self, A, lda, a_mn, B, ldb, b_mn, M, N, K, epi, out, ldo, bias=0, resid=0, ldr=0, aux=0, ldaux=0, out2=0, ldo2=0, p=0.0, site=0,
-             split_k=1, block_n=0):
+             split_k=1, block_n=0, stream=None):
         g = self._g
         g.M, g.N, g.K = M, N, K
         g.A, g.lda, g.a_mn = A, lda, a_mn
@@ -295,7 +301,7 @@ class VaultEngine:
         g.dropout_p, g.seed, g.site = p, self.seed, site
         g.seed_dev = self.seed_dev.data_ptr() if p > 0.0 else None
         g.split_k, g.block_n, g.max_ctas = split_k, block_n, self.gemm_max_ctas
-        rc = self._lib.vault_gemm_bf16(C.byref(g), self._st)
+        rc = self._lib.vault_gemm_bf16(C.byref(g), stream if stream is not None else self._st)
         if rc:
             _abi.check(rc, "vault_gemm_bf16")
 
@@ -311,17 +317,38 @@ class VaultEngine:
         """dW[N_out,K_in] = dy^T x (contraction over the M tokens, both operands read un-transposed), db = colsum(dy)
         (bias=False when the kernel that produced dy already accumulated its column sums)."""
         gw = self.g32(wname)
+        gb = self.g32(bname) if bias else 0
+        if not gw and not gb:
+            return
+        st = self._st
+        if self.wgrad_side_stream:
+            # weight gradients are off the critical path (nothing downstream in backward reads them): run them on a side stream
+            # so they fill the SMs the dgrad / LayerNorm / attention chain leaves idle in its tails.  Joined in _join_side().
+            ev = torch.cuda.Event()
+            ev.record(torch.cuda.current_stream(self.device))
+            self._side.wait_event(ev)
+            st = self._side.cuda_stream
+            self._side_keep.append((dy16, x16))  # keep the operands alive until the join
+            self._side_dirty = True
         if gw:
             if wname in self._atomic_w:  # slot already zero-filled by zero_accumulated_grads()
                 self.gemm(dy16.data_ptr(), N_out, 1, x16.data_ptr(), K_in, 1, N_out, K_in, M, EPI_ATOMIC_F32, gw, K_in,
-                          split_k=self._wgrad_split(N_out, K_in, M), block_n=128)
+                          split_k=self._wgrad_split(N_out, K_in, M), block_n=128, stream=st)
             else:
-                self.gemm(dy16.data_ptr(), N_out, 1, x16.data_ptr(), K_in, 1, N_out, K_in, M, EPI_STORE_F32, gw, K_in, block_n=128)
-        gb = self.g32(bname) if bias else 0
+                self.gemm(dy16.data_ptr(), N_out, 1, x16.data_ptr(), K_in, 1, N_out, K_in, M, EPI_STORE_F32, gw, K_in, block_n=128, stream=st)
         if gb:
-            rc = self._lib.vault_colsum_bf16(dy16.data_ptr(), N_out, gb, M, N_out, self._st)
+            rc = self._lib.vault_colsum_bf16(dy16.data_ptr(), N_out, gb, M, N_out, st)
             if rc:
                 _abi.check(rc, "vault_colsum_bf16")
+
+    def _join_side(self):
+        """Main stream waits for every weight-gradient kernel issued on the side stream so far."""
+        if self._side_dirty:
+            ev = torch.cuda.Event()
+            ev.record(self._side)
+            torch.cuda.current_stream(self.device).wait_event(ev)
+            self._side_dirty = False
+        self._side_keep = []
 
     def ln_fwd(self, x32, rows, gname, bname, eps, want16=True, want32=False, p=0.0, site=0):
         y16 = self._new((rows, self.H), torch.bfloat16) if want16 else None
@@ -663,6 +690,7 @@ class VaultEngine:
             if segments and i == self.L // 2 and i > 0:
                 off = self._first_off(f"encoder.layer.{i - 1}.")
                 if off:
+                    self._join_side()
                     yield off
         # ---- embeddings ----
         dtext_ln = self._new((Mt, H), torch.float32)
@@ -686,6 +714,7 @@ class VaultEngine:
                 if segments:
                     off = self._first_off("bert.")
                     if off:
+                        self._join_side()
                         yield off
                 yield from self._lm_backward(dv_sum, sv, B, T, mt["training"], segments)
         else:
@@ -695,6 +724,7 @@ class VaultEngine:
                                               self.g32("embeddings.text_embeddings.position_embeddings.weight") or None, B, T, H, -1,
                                               int(getattr(self.model.config, "pad_token_id", -1) if getattr(self.model.config, "pad_token_id", None) is not None else -1),
                                               st), "vilt_word_embed_bwd")
+        self._join_side()
         tape.done = True
         tape.t = {}
 
@@ -707,6 +737,7 @@ class VaultEngine:
             if segments and i == self.lm_L // 2 and i > 0:
                 off = self._first_off(f"bert.encoder.layer.{i - 1}.")
                 if off:
+                    self._join_side()
                     yield off
         p_emb = self.lm_p if train else 0.0
         dx_sum, _ = self.ln_bwd(g32, gx16, sv["lm.x_sum"], sv["lm.st0"], Mt, "bert.embeddings.LayerNorm.weight", "bert.embeddings.LayerNorm.bias",

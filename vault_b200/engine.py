@@ -554,6 +554,33 @@ class VaultEngine:
         tt_ptr = token_type_ids.data_ptr() if token_type_ids is not None else None
         lib, st = self._lib, self._st
 
+        # ---------------- image branch first, on the side stream: it is independent of the (latency-bound) LM forward ----------------
+        G = gh * gw
+        Kp = self.C * self.patch * self.patch
+        main_st = st
+        ev0 = torch.cuda.Event()
+        ev0.record(torch.cuda.current_stream(self.device))
+        self._side.wait_event(ev0)
+        st = self._st = self._side.cuda_stream
+        patch_out = self._new((B * G, H), torch.float32)
+        if self.patch == 32:
+            # im2col-free: TF32 tcgen05 GEMM fed by 5-D TMA boxes over the raw NCHW pixels, fp32 master weight
+            _abi.check(lib.vault_patch_embed_fwd(pixel_values.data_ptr(), self.w32("embeddings.patch_embeddings.projection.weight"),
+                                                 self.w32("embeddings.patch_embeddings.projection.bias"), patch_out.data_ptr(), B, self.C, Hi, Wi,
+                                                 self.patch, H, st), "patch_embed_fwd")
+            patches = None
+        else:
+            patches = self._new((B * G, Kp), torch.bfloat16)
+            _abi.check(lib.vault_patchify_bf16(pixel_values.data_ptr(), patches.data_ptr(), B, self.C, Hi, Wi, self.patch, st), "patchify")
+            self.gemm(patches.data_ptr(), Kp, 0, self.w16("embeddings.patch_embeddings.projection.weight"), Kp, 0, B * G, H, Kp, EPI_BIAS_F32,
+                      patch_out.data_ptr(), H, bias=self.w32("embeddings.patch_embeddings.projection.bias"))
+        if sv is not None and patches is None and self.g32("embeddings.patch_embeddings.projection.weight"):
+            # the projection's wgrad (dW = dpatch^T * patches) reads the patch matrix as its MN-major B operand: bf16 im2col, training only
+            patches = self._new((B * G, Kp), torch.bfloat16)
+            _abi.check(lib.vault_patchify_bf16(pixel_values.data_ptr(), patches.data_ptr(), B, self.C, Hi, Wi, self.patch, st), "patchify")
+        ev1 = torch.cuda.Event()
+        ev1.record(self._side)
+        st = self._st = main_st
         # ---------------- text: LM or ViLT word embeddings -> inputs_embeds fp32 [Mt,H] ----------------
         lm_trains = self.lm is not None and not getattr(self.model, "freeze_lm", False) and need_grad
         if self.lm is not None:
@@ -588,25 +615,8 @@ class VaultEngine:
         _, text_ln, st_t = self.ln_fwd(v_sum, Mt, "embeddings.text_embeddings.LayerNorm.weight", "embeddings.text_embeddings.LayerNorm.bias",
                                        self.vilt_eps, want16=False, want32=True)
 
-        # ---------------- image: patch projection + assembly ----------------
-        G = gh * gw
-        Kp = self.C * self.patch * self.patch
-        patch_out = self._new((B * G, H), torch.float32)
-        if self.patch == 32:
-            # im2col-free: TF32 tcgen05 GEMM fed by 5-D TMA boxes over the raw NCHW pixels, fp32 master weight
-            _abi.check(lib.vault_patch_embed_fwd(pixel_values.data_ptr(), self.w32("embeddings.patch_embeddings.projection.weight"),
-                                                 self.w32("embeddings.patch_embeddings.projection.bias"), patch_out.data_ptr(), B, self.C, Hi, Wi,
-                                                 self.patch, H, st), "patch_embed_fwd")
-            patches = None
-        else:
-            patches = self._new((B * G, Kp), torch.bfloat16)
-            _abi.check(lib.vault_patchify_bf16(pixel_values.data_ptr(), patches.data_ptr(), B, self.C, Hi, Wi, self.patch, st), "patchify")
-            self.gemm(patches.data_ptr(), Kp, 0, self.w16("embeddings.patch_embeddings.projection.weight"), Kp, 0, B * G, H, Kp, EPI_BIAS_F32,
-                      patch_out.data_ptr(), H, bias=self.w32("embeddings.patch_embeddings.projection.bias"))
-        if sv is not None and patches is None and self.g32("embeddings.patch_embeddings.projection.weight"):
-            # the projection's wgrad (dW = dpatch^T * patches) reads the patch matrix as its MN-major B operand: bf16 im2col, training only
-            patches = self._new((B * G, Kp), torch.bfloat16)
-            _abi.check(lib.vault_patchify_bf16(pixel_values.data_ptr(), patches.data_ptr(), B, self.C, Hi, Wi, self.patch, st), "patchify")
+        # ---------------- assembly (joins the image branch) ----------------
+        torch.cuda.current_stream(self.device).wait_event(ev1)
         if hw is None:
             hw, pmax = self.patch_hw(pixel_mask, B, Hi, Wi)
         S = T + 1 + pmax
@@ -687,7 +697,7 @@ class VaultEngine:
                                colsum_to=self._names("", self.L - 1, True)["b2"])
         for i in reversed(range(self.L)):
             g32, g16 = self.vilt_layer_bwd(i, g32, g16, M, B, S, sv["key_mask"], sv)
-            if segments and i == self.L // 2 and i > 0:
+            if segments and i > 0 and i in (self.L * 2 // 3, self.L // 3):
                 off = self._first_off(f"encoder.layer.{i - 1}.")
                 if off:
                     self._join_side()
@@ -734,11 +744,16 @@ class VaultEngine:
         gx16 = None
         for i in reversed(range(self.lm_L)):
             g32, gx16 = self.lm_layer_bwd(i, g32, gx16, Mt, B, T, sv["lm.mask"], sv, train)
-            if segments and i == self.lm_L // 2 and i > 0:
+            if segments and i > 0 and i in (self.lm_L * 2 // 3, self.lm_L // 3):
                 off = self._first_off(f"bert.encoder.layer.{i - 1}.")
                 if off:
                     self._join_side()
                     yield off
+        if segments:
+            off = self._first_off("bert.embeddings.")
+            if off:
+                self._join_side()
+                yield off
         p_emb = self.lm_p if train else 0.0
         dx_sum, _ = self.ln_bwd(g32, gx16, sv["lm.x_sum"], sv["lm.st0"], Mt, "bert.embeddings.LayerNorm.weight", "bert.embeddings.LayerNorm.bias",
                                 want16=False, in_p=p_emb, in_site=self.SITE_LM_EMB)
@@ -751,6 +766,13 @@ class VaultEngine:
     # ------------------------------------------------------------------------------------------------------------
     # fused optimizer (transformers==4.48.0 AdamW rule) over the flat trainable range
     # ------------------------------------------------------------------------------------------------------------
+    def adamw_range(self, lo: int, hi: int, step: int, lr: float, beta1, beta2, eps, weight_decay, correct_bias, grad_scale, sched_dev, stream: int):
+        """AdamW over the flat sub-range [lo, hi) on an explicit stream (per-segment updates overlapped with the rest of backward)."""
+        s = self.opt_state
+        _abi.call("vault_adamw_step", self.master.data_ptr() + 4 * lo, self.grad.data_ptr() + 4 * lo, s["m"].data_ptr() + 4 * lo,
+                  s["v"].data_ptr() + 4 * lo, self.shadow.data_ptr() + 2 * lo, hi - lo, lr, beta1, beta2, eps, weight_decay, int(correct_bias),
+                  max(1, step), grad_scale, sched_dev.data_ptr() if sched_dev is not None else None, stream)
+
     def init_opt_state(self):
         if self.opt_state is None:
             self.opt_state = dict(step=0, m=torch.zeros(self.n_train, device=self.device), v=torch.zeros(self.n_train, device=self.device))

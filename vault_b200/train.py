@@ -94,8 +94,10 @@ class VaultTrainStep:
         # data-parallel overlap: backward is cut into segments of the reverse-topological gradient layout; each finished
         # range is all-reduced (async, NCCL's stream) while the next segment computes.  The persistent GEMMs then leave a few
         # SMs to the collective instead of queueing behind it.
-        self.overlap = bool(overlap_comm) and self.world > 1
-        if self.overlap and comm_reserve_sms > 0:
+        # The same segmentation lets each range's AdamW update (HBM-bound) run on a side stream under the remaining
+        # (tensor-bound) backward, also on one GPU: a finished segment's weights are not read again in this step.
+        self.overlap = bool(overlap_comm)
+        if self.overlap and self.world > 1 and comm_reserve_sms > 0:
             self.engine.gemm_max_ctas = max(1, self.engine.sms - comm_reserve_sms)
         self.copy_stream = torch.cuda.Stream(device=self.dev)
         self.sched_dev = torch.zeros(2, device=self.dev, dtype=torch.float32)
@@ -175,9 +177,22 @@ class VaultTrainStep:
                        "head_dropout_bwd")
         yield from eng.backward_iter(tape, None, dx, segments=segments)
 
-    def _reduce_range(self, lo: int, hi: int, works: list):
-        if self.world > 1 and hi > lo:
-            works.extend(allreduce_flat_(self.engine.grad[lo:hi], self.pg, async_op=True))
+    def _finish_range(self, lo: int, hi: int, hp):
+        """Gradients in [lo, hi) are final on the main stream: all-reduce them (async) and apply AdamW to that range on the side
+        stream while the main stream carries on with the rest of backward."""
+        if hi <= lo:
+            return
+        eng = self.engine
+        works = allreduce_flat_(eng.grad[lo:hi], self.pg, async_op=True) if self.world > 1 else []
+        side = eng._side
+        ev = torch.cuda.Event()
+        ev.record(torch.cuda.current_stream(self.dev))
+        side.wait_event(ev)
+        with torch.cuda.stream(side):
+            for w in works:
+                w.wait()
+            eng.adamw_range(lo, hi, hp["step"], hp["lr"], hp["b1"], hp["b2"], self.eps, self.wd, self.correct_bias, 1.0 / self.world, self.sched_dev,
+                            side.cuda_stream)
 
     def _get_slot(self, batch) -> _Slot:
         key = tuple((k, tuple(batch[k].shape)) for k in _INPUT_KEYS if batch.get(k) is not None)
@@ -206,8 +221,15 @@ class VaultTrainStep:
                     dst.copy_(batch[k], non_blocking=True)
         lr = self.lr_at(self.step_idx)
         eng.refresh_shadow()  # host-side check only, unless someone modified the Parameters in place
-        works: list = []
         n_train = eng.n_train
+        eng.opt_state["step"] += 1
+        b1, b2 = self.betas
+        step_no = eng.opt_state["step"]
+        step_size = lr
+        if self.correct_bias:
+            step_size = lr * (1.0 - b2 ** step_no) ** 0.5 / (1.0 - b1 ** step_no)
+        self.sched_dev.copy_(torch.tensor([step_size, lr * self.wd if self.wd > 0 else 0.0], dtype=torch.float32), non_blocking=True)
+        hp = dict(step=step_no, lr=lr, b1=b1, b2=b2)
         if self.use_graph:
             if s.graphs is None:
                 self._body(s)  # eager warm-up: sets kernel attributes, sizes the allocator
@@ -230,25 +252,19 @@ class VaultTrainStep:
             lo = 0
             for g, reached in s.graphs:
                 g.replay()
-                self._reduce_range(lo, reached, works)
+                self._finish_range(lo, reached, hp)
                 lo = reached
         else:
             lo = 0
             for reached in self._body_iter(s, segments=self.overlap):
-                self._reduce_range(lo, reached, works)
+                self._finish_range(lo, reached, hp)
                 lo = reached
-            self._reduce_range(lo, n_train, works)
+            self._finish_range(lo, n_train, hp)
         if on_host:
             s.free.record(cs)
-        for w in works:
-            w.wait()
-        step_no = eng.opt_state["step"] + 1
-        b1, b2 = self.betas
-        step_size = lr
-        if self.correct_bias:
-            step_size = lr * (1.0 - b2 ** step_no) ** 0.5 / (1.0 - b1 ** step_no)
-        self.sched_dev.copy_(torch.tensor([step_size, lr * self.wd if self.wd > 0 else 0.0], dtype=torch.float32), non_blocking=True)
-        eng.adamw_step(lr, b1, b2, self.eps, self.wd, self.correct_bias, grad_scale=1.0 / self.world, sched_dev=self.sched_dev)
+        ev = torch.cuda.Event()
+        ev.record(eng._side)
+        cs.wait_event(ev)  # every range's AdamW (and all-reduce) is done before the next step touches weights or gradients
         s.loss_host.copy_(s.buf["loss"], non_blocking=True)
         s.loss_event.record(cs)
         self.step_idx += 1

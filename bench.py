@@ -243,7 +243,7 @@ def main():
     B, T, hw = args.batch, WORKLOAD["text_len"], tuple(WORKLOAD["image"])
     total_sched = 100000
     ts = VaultTrainStep(model, lr=2e-5, total_steps=total_sched, use_cuda_graph=not args.no_graph,
-                        overlap_comm=os.environ.get("VB_OVERLAP", "1") == "1", comm_reserve_sms=int(os.environ.get("VB_COMM_RESERVE", "8")))
+                        overlap_comm=os.environ.get("VB_OVERLAP", "1") == "1", comm_reserve_sms=int(os.environ.get("VB_COMM_RESERVE", "0")))
     ts.step_idx = total_sched // 5  # past warm-up: a non-zero learning rate so AdamW really moves the weights
     NB = 4
     host = [synth_batch(torch, B, T, hw, bc.vocab_size, 3, seed=1000 * rank + i, pin=True) for i in range(NB)]

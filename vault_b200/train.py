@@ -63,7 +63,7 @@ class _Slot:
 class VaultTrainStep:
     def __init__(self, model, lr: float = 2e-5, betas=(0.9, 0.999), eps: float = 1e-8, weight_decay: float = 0.0, correct_bias: bool = False,
                  total_steps: Optional[int] = None, warmup_ratio: float = 0.1, process_group=None, use_cuda_graph: bool = True,
-                 dropout: bool = True, overlap_comm: bool = True, comm_reserve_sms: int = 8):
+                 dropout: bool = True, overlap_comm: bool = True, comm_reserve_sms: int = 0):
         self.model = model
         self.engine: VaultEngine = model.engine
         self.lr, self.betas, self.eps, self.wd, self.correct_bias = lr, betas, eps, weight_decay, correct_bias
@@ -94,10 +94,12 @@ class VaultTrainStep:
         # data-parallel overlap: backward is cut into segments of the reverse-topological gradient layout; each finished
         # range is all-reduced (async, NCCL's stream) while the next segment computes.  The persistent GEMMs then leave a few
         # SMs to the collective instead of queueing behind it.
-        # The same segmentation lets each range's AdamW update (HBM-bound) run on a side stream under the remaining
-        # (tensor-bound) backward, also on one GPU: a finished segment's weights are not read again in this step.
-        self.overlap = bool(overlap_comm)
-        if self.overlap and self.world > 1 and comm_reserve_sms > 0:
+        # Each reduced range's AdamW update runs right behind its all-reduce on the side stream, under the remaining backward:
+        # a finished segment's weights are not read again in this step.
+        # (On one GPU the segmentation buys nothing measurable -- AdamW and the GEMMs contend for the same HBM/L2 -- so the step
+        # stays one graph there.)
+        self.overlap = bool(overlap_comm) and self.world > 1
+        if self.overlap and comm_reserve_sms > 0:
             self.engine.gemm_max_ctas = max(1, self.engine.sms - comm_reserve_sms)
         self.copy_stream = torch.cuda.Stream(device=self.dev)
         self.sched_dev = torch.zeros(2, device=self.dev, dtype=torch.float32)

@@ -26,6 +26,7 @@ struct GemmParams {
   int M, N, K;
   int a_mn, b_mn;
   int num_m_blocks, num_n_blocks, num_k_blocks, split_k, kb_per_split;
+  int cl;  // 0: no cluster; 1: CTA pair along M (B tile multicast); 2: CTA pair along N (A tile multicast)
   const float* bias;
   const float* resid;
   long long ldr;
@@ -175,7 +176,7 @@ gemm_bf16_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant_
   if (warp == 1 && lane == 0) {
     for (int s = 0; s < kStages; ++s) {
       mbar_init(full_bar(s), 1);
-      mbar_init(empty_bar(s), 1);
+      mbar_init(empty_bar(s), p.cl ? 2 : 1);  // a multicast-filled slot is released by BOTH consumers
     }
     for (int s = 0; s < 2; ++s) {
       mbar_init(tfull_bar(s), 1);
@@ -186,23 +187,35 @@ gemm_bf16_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant_
   if (warp == 2) tmem_alloc(tmem_slot, kTmemCols);
   tc_fence_before();
   __syncthreads();
+  if (p.cl) cluster_sync_all();  // the peer's barriers must exist before a multicast load or commit can reach them
   tc_fence_after();
   const uint32_t tmem_base = *tmem_slot_gen;
   pdl_enter();  // everything above overlapped the previous kernel's tail; global memory is touched only below
 
-  const int tiles_mn = p.num_m_blocks * p.num_n_blocks;
+  // Work units.  Without a cluster a unit is one 128 x BN tile.  With a CTA pair a unit is two tiles that share an operand:
+  // cl=1 -> (m_blk 2u+rank, same n_blk), the B tile is loaded half by each CTA and multicast to both;
+  // cl=2 -> (same m_blk, n_blk 2u+rank), the A tile is shared.  Odd tails give one CTA a phantom tile: it still takes part in
+  // the loads and commits, TMA zero-fills its out-of-range operand and the epilogue's bounds checks drop its stores.
+  const int rank = p.cl ? (int)cluster_ctarank() : 0;
+  const int unit0 = p.cl ? (int)(blockIdx.x >> 1) : (int)blockIdx.x;
+  const int unit_step = p.cl ? (int)(gridDim.x >> 1) : (int)gridDim.x;
+  const int m_units = p.cl == 1 ? (p.num_m_blocks + 1) / 2 : p.num_m_blocks;
+  const int n_units = p.cl == 2 ? (p.num_n_blocks + 1) / 2 : p.num_n_blocks;
+  const int tiles_mn = m_units * n_units;
   const int total_tiles = tiles_mn * p.split_k;
+  auto tile_m0 = [&](int rem) { return ((rem / n_units) * (p.cl == 1 ? 2 : 1) + (p.cl == 1 ? rank : 0)) * BM; };
+  auto tile_n0 = [&](int rem) { return ((rem % n_units) * (p.cl == 2 ? 2 : 1) + (p.cl == 2 ? rank : 0)) * BN; };
 
   if (warp == 0) {
     // ===================== TMA producer =====================
     if (lane == 0) {
       int stage = 0;
       uint32_t phase = 0;
-      for (int t = blockIdx.x; t < total_tiles; t += gridDim.x) {
+      for (int t = unit0; t < total_tiles; t += unit_step) {
         const int split = t / tiles_mn;
         const int rem = t - split * tiles_mn;
-        const int m0 = (rem / p.num_n_blocks) * BM;
-        const int n0 = (rem % p.num_n_blocks) * BN;
+        const int m0 = tile_m0(rem);
+        const int n0 = tile_n0(rem);
         const int kb0 = split * p.kb_per_split;
         const int kb1 = min(kb0 + p.kb_per_split, p.num_k_blocks);
         for (int kb = kb0; kb < kb1; ++kb) {
@@ -212,13 +225,28 @@ gemm_bf16_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant_
           const uint32_t fb = full_bar(stage);
           mbar_expect_tx(fb, kStage);
           const int k0 = kb * BK;
-          if (!p.a_mn) {
+          if (p.cl == 2) {
+            // A shared along N: this CTA fetches its half (64 rows / one 64-wide m box) and multicasts it to the pair
+            if (!p.a_mn) tma_load_2d_mc(sA + rank * 8192, &tmA, fb, k0, m0 + 64 * rank, (uint16_t)3);  // box {64 k, 64 rows}
+            else tma_load_2d_mc(sA + rank * 8192, &tmA, fb, m0 + 64 * rank, k0, (uint16_t)3);
+          } else if (!p.a_mn) {
             tma_load_2d(sA, &tmA, fb, k0, m0);  // box {64 k, 128 rows}
           } else {
 #pragma unroll
             for (int j = 0; j < BM / 64; ++j) tma_load_2d(sA + j * 8192, &tmA, fb, m0 + 64 * j, k0);  // box {64 m, 64 k-rows}
           }
-          if (!p.b_mn) {
+          if (p.cl == 1) {
+            // B shared along M: half of the tile's n range per CTA, multicast to both
+            if (!p.b_mn) {
+              tma_load_2d_mc(sB + rank * (BN / 2) * 128, &tmB, fb, k0, n0 + rank * (BN / 2), (uint16_t)3);  // box {64 k, BN/2 rows}
+            } else {
+#pragma unroll
+              for (int j = 0; j < BN / 128; ++j) {
+                const int jj = rank * (BN / 128) + j;
+                tma_load_2d_mc(sB + jj * 8192, &tmB, fb, n0 + 64 * jj, k0, (uint16_t)3);
+              }
+            }
+          } else if (!p.b_mn) {
             tma_load_2d(sB, &tmB, fb, k0, n0);  // box {64 k, BN rows}
           } else {
 #pragma unroll
@@ -239,7 +267,7 @@ gemm_bf16_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant_
       uint32_t phase = 0;
       int as = 0;
       uint32_t aphase = 0;
-      for (int t = blockIdx.x; t < total_tiles; t += gridDim.x) {
+      for (int t = unit0; t < total_tiles; t += unit_step) {
         const int split = t / tiles_mn;
         const int kb0 = split * p.kb_per_split;
         const int kb1 = min(kb0 + p.kb_per_split, p.num_k_blocks);
@@ -257,7 +285,8 @@ gemm_bf16_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant_
             const uint64_t bd = umma_desc_sw128(sB + k * b_kstep, b_lbo, 1024u);
             tc_mma_f16(d_tmem, ad, bd, idesc, (kb > kb0 || k > 0) ? 1u : 0u);
           }
-          tc_commit(empty_bar(stage));  // smem slot free once these MMAs have read it
+          if (p.cl) tc_commit_mc(empty_bar(stage), (uint16_t)3);  // both CTAs' producers write into this slot of both CTAs
+          else tc_commit(empty_bar(stage));               // smem slot free once these MMAs have read it
           if (++stage == kStages) { stage = 0; phase ^= 1u; }
         }
         tc_commit(tfull_bar(as));  // accumulator complete
@@ -275,11 +304,11 @@ gemm_bf16_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant_
     const unsigned long long seed = p.seed + ((p.dropout_p > 0.f && p.seed_dev) ? *p.seed_dev : 0ull);
     int as = 0;
     uint32_t aphase = 0;
-    for (int t = blockIdx.x; t < total_tiles; t += gridDim.x) {
+    for (int t = unit0; t < total_tiles; t += unit_step) {
       const int split = t / tiles_mn;
       const int rem = t - split * tiles_mn;
-      const int m0 = (rem / p.num_n_blocks) * BM;
-      const int n0 = (rem % p.num_n_blocks) * BN;
+      const int m0 = tile_m0(rem);
+      const int n0 = tile_n0(rem);
       mbar_wait(tfull_bar(as), aphase);
       tc_fence_after();
       const bool full_tile = (m0 + BM <= p.M) && (n0 + BN <= p.N);
@@ -315,6 +344,7 @@ gemm_bf16_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant_
 
   tc_fence_before();
   __syncthreads();
+  if (p.cl) cluster_sync_all();  // no CTA may leave while its peer can still multicast into it or arrive on its barriers
   if (warp == 2) {
     tc_fence_after();
     tmem_dealloc(tmem_base, kTmemCols);
@@ -366,7 +396,8 @@ int launch_gemm(const CUtensorMap& tmA, const CUtensorMap& tmB, const GemmParams
     if (e != cudaSuccess) return fail(VAULT_ERR_LAUNCH, "cudaFuncSetAttribute(smem=%d): %s", kSmemBytes, cudaGetErrorString(e));
     attr_set = true;
   }
-  launch(gemm_bf16_kernel<BN, EPI>, dim3(grid), dim3(kThreads), kSmemBytes, st, tmA, tmB, p);
+  if (p.cl) launch_cluster(gemm_bf16_kernel<BN, EPI>, dim3(grid), dim3(kThreads), kSmemBytes, st, 2u, tmA, tmB, p);
+  else launch(gemm_bf16_kernel<BN, EPI>, dim3(grid), dim3(kThreads), kSmemBytes, st, tmA, tmB, p);
   return check_launch("gemm_bf16_kernel");
 }
 
@@ -418,12 +449,16 @@ extern "C" int vault_gemm_bf16(const vault_gemm_args* a, void* stream) {
   const int sms = a->max_ctas > 0 ? a->max_ctas : device_sm_count();
   int bn = a->block_n > 0 ? a->block_n : pick_block_n(a->M, a->N, a->split_k, sms);
 
+  int cl = a->cluster > 0 ? a->cluster : 0;  // TODO(auto): 0 currently means "no cluster"
+  VB_REQUIRE(cl <= 2, "vault_gemm_bf16: cluster mode %d (0/-1 off, 1 pair along M, 2 pair along N)", a->cluster);
+  if (cl == 1 && a->b_mn && bn < 128) cl = 0;  // an MN-major B tile of one 64-wide box cannot be split across the pair
   CUtensorMap tmA, tmB;
   int rc;
-  if (!a->a_mn) rc = encode_tmap_2d(&tmA, CU_TENSOR_MAP_DATA_TYPE_BFLOAT16, 2, a->A, (uint64_t)a->K, (uint64_t)a->M, (uint64_t)a->lda, BK, BM);
+  if (!a->a_mn) rc = encode_tmap_2d(&tmA, CU_TENSOR_MAP_DATA_TYPE_BFLOAT16, 2, a->A, (uint64_t)a->K, (uint64_t)a->M, (uint64_t)a->lda, BK, cl == 2 ? 64 : BM);
   else rc = encode_tmap_2d(&tmA, CU_TENSOR_MAP_DATA_TYPE_BFLOAT16, 2, a->A, (uint64_t)a->M, (uint64_t)a->K, (uint64_t)a->lda, 64, BK);
   if (rc) return rc;
-  if (!a->b_mn) rc = encode_tmap_2d(&tmB, CU_TENSOR_MAP_DATA_TYPE_BFLOAT16, 2, a->B, (uint64_t)a->K, (uint64_t)a->N, (uint64_t)a->ldb, BK, (uint32_t)bn);
+  if (!a->b_mn) rc = encode_tmap_2d(&tmB, CU_TENSOR_MAP_DATA_TYPE_BFLOAT16, 2, a->B, (uint64_t)a->K, (uint64_t)a->N, (uint64_t)a->ldb, BK,
+                                    (uint32_t)(cl == 1 ? bn / 2 : bn));
   else rc = encode_tmap_2d(&tmB, CU_TENSOR_MAP_DATA_TYPE_BFLOAT16, 2, a->B, (uint64_t)a->N, (uint64_t)a->K, (uint64_t)a->ldb, 64, BK);
   if (rc) return rc;
 
@@ -440,8 +475,17 @@ extern "C" int vault_gemm_bf16(const vault_gemm_args* a, void* stream) {
   p.aux = reinterpret_cast<const bf16*>(a->aux); p.ldaux = a->ldaux;
   p.out = a->out; p.ldo = a->ldo; p.out2 = a->out2; p.ldo2 = a->ldo2;
   p.dropout_p = a->dropout_p; p.seed = a->seed; p.seed_dev = reinterpret_cast<const unsigned long long*>(a->seed_dev); p.site = a->site;
-  const long long total = (long long)p.num_m_blocks * p.num_n_blocks * p.split_k;
-  const int grid = (int)(total < sms ? total : sms);
+  p.cl = cl;
+  int grid;
+  if (cl) {
+    const long long mu = cl == 1 ? (p.num_m_blocks + 1) / 2 : p.num_m_blocks, nu = cl == 2 ? (p.num_n_blocks + 1) / 2 : p.num_n_blocks;
+    const long long units = mu * nu * p.split_k;
+    const long long pairs = sms / 2;
+    grid = 2 * (int)(units < pairs ? units : pairs);
+  } else {
+    const long long total = (long long)p.num_m_blocks * p.num_n_blocks * p.split_k;
+    grid = (int)(total < sms ? total : sms);
+  }
 
   switch (a->epilogue) {
     case VAULT_EPI_BIAS_BF16: return dispatch_bn<VAULT_EPI_BIAS_BF16>(bn, tmA, tmB, p, grid, st);

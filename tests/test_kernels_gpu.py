@@ -283,3 +283,19 @@ def test_patch_embed_tma_tf32(dev, B, Hi, Wi, N):
     ref = torch.nn.functional.conv2d(px, w, b, stride=32).flatten(2).transpose(1, 2).reshape(-1, N)
     assert torch.isfinite(out).all()  # every output row written exactly once
     assert _rel(out, ref) < 2e-3
+
+
+@pytest.mark.parametrize("cl,M,N,K,a_mn,b_mn,bn", [
+    (1, 5920, 2304, 768, False, False, 256), (1, 5920, 768, 2304, False, True, 256), (1, 300, 256, 192, False, False, 128),
+    (2, 1280, 768, 768, False, False, 64), (2, 2304, 768, 1280, True, True, 128), (2, 128, 192, 64, False, False, 64), (1, 128, 256, 64, True, True, 128),
+])
+def test_gemm_cta_pair_multicast(dev, ops, cl, M, N, K, a_mn, b_mn, bn):
+    """CTA-pair TMA multicast (incl. odd tile counts -> phantom tiles) must be bit-identical to the unclustered kernel."""
+    torch.manual_seed(cl * 1000 + M)
+    a, b = _rnd(dev, M, K, scale=0.5), _rnd(dev, N, K, scale=0.5)
+    A = a.t().contiguous() if a_mn else a
+    Bm = b.t().contiguous() if b_mn else b
+    ref = ops.gemm(A, Bm, ops.EPI_STORE_F32, a_mn=a_mn, b_mn=b_mn, block_n=bn)
+    got = ops.gemm(A, Bm, ops.EPI_STORE_F32, a_mn=a_mn, b_mn=b_mn, block_n=bn, cluster=cl)
+    assert torch.equal(got, ref)
+    assert _rel(got, a.float() @ b.float().t()) < 1e-4

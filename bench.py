@@ -243,7 +243,7 @@ def main():
     B, T, hw = args.batch, WORKLOAD["text_len"], tuple(WORKLOAD["image"])
     total_sched = 100000
     ts = VaultTrainStep(model, lr=2e-5, total_steps=total_sched, use_cuda_graph=not args.no_graph,
-                        overlap_comm=os.environ.get("VB_OVERLAP", "1") == "1", comm_reserve_sms=int(os.environ.get("VB_COMM_RESERVE", "0")))
+                        overlap_comm=os.environ.get("VB_OVERLAP", "1") == "1", comm_reserve_sms=int(os.environ.get("VB_COMM_RESERVE", "0")), grad_comm_dtype=os.environ.get("VB_COMM_DTYPE", "bf16"))
     ts.step_idx = total_sched // 5  # past warm-up: a non-zero learning rate so AdamW really moves the weights
     NB = 4
     host = [synth_batch(torch, B, T, hw, bc.vocab_size, 3, seed=1000 * rank + i, pin=True) for i in range(NB)]
@@ -307,7 +307,7 @@ def main():
             "metric": METRIC, "value": value, "unit": "samples/s", "n_gpus": world, "steps": args.steps, "warmup": args.warmup,
             "ms_per_step": ms_dev / args.steps, "higher_is_better": True, "scaling": "weak", "vs_baseline": None, "dtype": "bf16", "data": "synthetic",
             "config": dict(workload="VaultForTMSC fine-tune step (BASELINE config 3): fwd + CE + bwd + grad all-reduce + HF-AdamW", **WORKLOAD,
-                           global_batch=gb, parallelism=f"dp{world}", cuda_graph=not args.no_graph, comm_overlap=ts.overlap,
+                           global_batch=gb, parallelism=f"dp{world}", cuda_graph=not args.no_graph, comm_overlap=ts.overlap, grad_comm_dtype=("bf16" if ts.grad16 is not None else "fp32"),
                            gemm_ctas=ts.engine.gemm_max_ctas or ts.engine.sms,
                            l2="per-step working set (0.44 GB bf16 weights + 0.79 GB fp32 grads + ~2 GB activations) >> 126 MB L2; 4 rotating input batches"),
             "e2e": dict(value=e2e, unit="samples/s", h2d_bytes_per_step=h2d, d2h_bytes_per_step=4, ms_per_step=ms_e2e / args.steps,

@@ -217,9 +217,10 @@ int vault_colsum_bf16(const void* x, int64_t ldx, float* out, int64_t rows, int3
  * sched_dev (optional, DEVICE float[2] = {step_size, lr*weight_decay}) overrides the host-computed scalars at run time so a
  * captured CUDA graph can follow the linear-warmup schedule (HF:optimization.py:101-131) without re-capture.
  * ------------------------------------------------------------------------------------------------------------------ */
-int vault_adamw_step(float* p, const float* g, float* m, float* v, void* shadow_bf16, int64_t n, double lr, double beta1,
-                     double beta2, double eps, double weight_decay, int32_t correct_bias, int32_t step, float grad_scale,
-                     const float* sched_dev, void* stream);
+/* g: fp32 gradients, or bf16 if grad_is_bf16 (the data-parallel path all-reduces a bf16 copy of each gradient range) */
+int vault_adamw_step(float* p, const void* g, int32_t grad_is_bf16, float* m, float* v, void* shadow_bf16, int64_t n, double lr,
+                     double beta1, double beta2, double eps, double weight_decay, int32_t correct_bias, int32_t step,
+                     float grad_scale, const float* sched_dev, void* stream);
 /* fp32 -> bf16 cast of a flat range (shadow refresh after an external optimizer touched the masters) */
 int vault_cast_f32_bf16(const float* src, void* dst_bf16, int64_t n, void* stream);
 

@@ -242,7 +242,7 @@ def test_adamw_matches_hf_rule(dev, correct_bias, wd):
     sh = torch.zeros(n_al, device=dev, dtype=torch.bfloat16)
     for step in (1, 2, 3):
         O.hf_adamw_step(p, g, m, v, step, lr=1e-3, weight_decay=wd, correct_bias=correct_bias)
-        _abi.call("vault_adamw_step", pd.data_ptr(), gd.data_ptr(), md.data_ptr(), vd.data_ptr(), sh.data_ptr(), n, 1e-3, 0.9, 0.999, 1e-8, wd,
+        _abi.call("vault_adamw_step", pd.data_ptr(), gd.data_ptr(), 0, md.data_ptr(), vd.data_ptr(), sh.data_ptr(), n, 1e-3, 0.9, 0.999, 1e-8, wd,
                   int(correct_bias), step, 1.0, None, torch.cuda.current_stream().cuda_stream)
     assert torch.allclose(pd[:n].cpu(), p, rtol=2e-6, atol=1e-7)
     assert torch.allclose(md[:n].cpu(), m, rtol=2e-6, atol=1e-9) and torch.allclose(vd[:n].cpu(), v, rtol=2e-6, atol=1e-12)

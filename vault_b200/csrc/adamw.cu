@@ -4,8 +4,9 @@
 
 namespace vb {
 
+template <bool G16>
 __global__ void __launch_bounds__(256)
-adamw_kernel(float* __restrict__ p, const float* __restrict__ g, float* __restrict__ m, float* __restrict__ v, bf16* __restrict__ shadow, long long n,
+adamw_kernel(float* __restrict__ p, const void* __restrict__ gv, float* __restrict__ m, float* __restrict__ v, bf16* __restrict__ shadow, long long n,
              float step_size, float lr_wd, float beta1, float beta2, float ob1, float ob2, float eps, float grad_scale,
              const float* __restrict__ sched_dev) {
   pdl_enter();
@@ -14,9 +15,17 @@ adamw_kernel(float* __restrict__ p, const float* __restrict__ g, float* __restri
     lr_wd = sched_dev[1];
   }
   const long long n4 = n >> 2;
+  const void* gvp = gv;
   for (long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x; i < n4; i += (long long)gridDim.x * blockDim.x) {
     float4 pv = reinterpret_cast<float4*>(p)[i];
-    float4 gv = __ldg(reinterpret_cast<const float4*>(g) + i);
+    float4 gv;
+    if constexpr (G16) {  // gradients arrive as bf16 (data-parallel all-reduce ran on a bf16 copy)
+      const uint2 pk = __ldg(reinterpret_cast<const uint2*>(gvp) + i);
+      const float2 a = unpack_bf16x2(pk.x), b = unpack_bf16x2(pk.y);
+      gv = make_float4(a.x, a.y, b.x, b.y);
+    } else {
+      gv = __ldg(reinterpret_cast<const float4*>(gvp) + i);
+    }
     float4 mv = reinterpret_cast<float4*>(m)[i];
     float4 vv = reinterpret_cast<float4*>(v)[i];
     float* pp = reinterpret_cast<float*>(&pv);
@@ -40,7 +49,7 @@ adamw_kernel(float* __restrict__ p, const float* __restrict__ g, float* __restri
   // tail (n not a multiple of 4)
   if (blockIdx.x == 0 && threadIdx.x < (n & 3)) {
     const long long i = (n4 << 2) + threadIdx.x;
-    const float gg = g[i] * grad_scale;
+    const float gg = (G16 ? __bfloat162float(reinterpret_cast<const bf16*>(gvp)[i]) : reinterpret_cast<const float*>(gvp)[i]) * grad_scale;
     const float mm = beta1 * m[i] + ob1 * gg;
     const float vv = beta2 * v[i] + ob2 * gg * gg;
     float pp = p[i] - step_size * (mm / (sqrtf(vv) + eps));
@@ -75,11 +84,12 @@ static unsigned flat_grid(long long n4) {
 
 using namespace vb;
 
-extern "C" int vault_adamw_step(float* p, const float* g, float* m, float* v, void* shadow_bf16, int64_t n, double lr, double beta1, double beta2,
-                                double eps, double weight_decay, int32_t correct_bias, int32_t step, float grad_scale, const float* sched_dev,
-                                void* stream) {
+extern "C" int vault_adamw_step(float* p, const void* g, int32_t grad_is_bf16, float* m, float* v, void* shadow_bf16, int64_t n, double lr,
+                                double beta1, double beta2, double eps, double weight_decay, int32_t correct_bias, int32_t step, float grad_scale,
+                                const float* sched_dev, void* stream) {
   VB_REQUIRE(p && g && m && v && n >= 0, "adamw_step: bad arguments");
-  VB_REQUIRE((((uintptr_t)p | (uintptr_t)g | (uintptr_t)m | (uintptr_t)v) & 15) == 0, "adamw_step: buffers must be 16-byte aligned");
+  VB_REQUIRE((((uintptr_t)p | (uintptr_t)m | (uintptr_t)v) & 15) == 0 && ((uintptr_t)g & (grad_is_bf16 ? 7 : 15)) == 0,
+             "adamw_step: buffers must be 16-byte aligned (bf16 gradients: 8)");
   VB_REQUIRE(shadow_bf16 == nullptr || ((uintptr_t)shadow_bf16 & 7) == 0, "adamw_step: shadow must be 8-byte aligned");
   if (n == 0) return VAULT_OK;
   double step_size = lr;  // hyper-parameters arrive as doubles: 1-beta is formed in double like torch's Python scalars, then rounded once
@@ -87,9 +97,15 @@ extern "C" int vault_adamw_step(float* p, const float* g, float* m, float* v, vo
     VB_REQUIRE(step >= 1, "adamw_step: step must be >= 1 with correct_bias");
     step_size = lr * sqrt(1.0 - pow(beta2, step)) / (1.0 - pow(beta1, step));
   }
-  launch(adamw_kernel, dim3(flat_grid(n >> 2)), dim3(256), 0, (cudaStream_t)stream, p, g, m, v, reinterpret_cast<bf16*>(shadow_bf16), n, (float)step_size,
+  if (grad_is_bf16) {
+    launch(adamw_kernel<true>, dim3(flat_grid(n >> 2)), dim3(256), 0, (cudaStream_t)stream, p, g, m, v, reinterpret_cast<bf16*>(shadow_bf16), n, (float)step_size,
                                                                     weight_decay > 0.0 ? (float)(lr * weight_decay) : 0.f, (float)beta1,
                                                                     (float)beta2, (float)(1.0 - beta1), (float)(1.0 - beta2), (float)eps, grad_scale, sched_dev);
+    } else {
+    launch(adamw_kernel<false>, dim3(flat_grid(n >> 2)), dim3(256), 0, (cudaStream_t)stream, p, g, m, v, reinterpret_cast<bf16*>(shadow_bf16), n, (float)step_size,
+                                                                    weight_decay > 0.0 ? (float)(lr * weight_decay) : 0.f, (float)beta1,
+                                                                    (float)beta2, (float)(1.0 - beta1), (float)(1.0 - beta2), (float)eps, grad_scale, sched_dev);
+    }
   return check_launch("adamw_kernel");
 }
 

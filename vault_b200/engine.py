@@ -766,10 +766,13 @@ class VaultEngine:
     # ------------------------------------------------------------------------------------------------------------
     # fused optimizer (transformers==4.48.0 AdamW rule) over the flat trainable range
     # ------------------------------------------------------------------------------------------------------------
-    def adamw_range(self, lo: int, hi: int, step: int, lr: float, beta1, beta2, eps, weight_decay, correct_bias, grad_scale, sched_dev, stream: int):
-        """AdamW over the flat sub-range [lo, hi) on an explicit stream (per-segment updates overlapped with the rest of backward)."""
+    def adamw_range(self, lo: int, hi: int, step: int, lr: float, beta1, beta2, eps, weight_decay, correct_bias, grad_scale, sched_dev, stream: int,
+                    grad16: Optional[torch.Tensor] = None):
+        """AdamW over the flat sub-range [lo, hi) on an explicit stream (per-segment updates overlapped with the rest of backward).
+        grad16: bf16 copy of the flat gradient buffer to read instead of the fp32 one (data-parallel bf16 all-reduce)."""
         s = self.opt_state
-        _abi.call("vault_adamw_step", self.master.data_ptr() + 4 * lo, self.grad.data_ptr() + 4 * lo, s["m"].data_ptr() + 4 * lo,
+        gptr = (grad16.data_ptr() + 2 * lo) if grad16 is not None else (self.grad.data_ptr() + 4 * lo)
+        _abi.call("vault_adamw_step", self.master.data_ptr() + 4 * lo, gptr, int(grad16 is not None), s["m"].data_ptr() + 4 * lo,
                   s["v"].data_ptr() + 4 * lo, self.shadow.data_ptr() + 2 * lo, hi - lo, lr, beta1, beta2, eps, weight_decay, int(correct_bias),
                   max(1, step), grad_scale, sched_dev.data_ptr() if sched_dev is not None else None, stream)
 
@@ -784,6 +787,6 @@ class VaultEngine:
         scalars are read on the device (CUDA-graph friendly); otherwise they are computed here from lr / step."""
         s = self.init_opt_state()
         s["step"] += 1
-        _abi.call("vault_adamw_step", self.master.data_ptr(), self.grad.data_ptr(), s["m"].data_ptr(), s["v"].data_ptr(), self.shadow.data_ptr(),
+        _abi.call("vault_adamw_step", self.master.data_ptr(), self.grad.data_ptr(), 0, s["m"].data_ptr(), s["v"].data_ptr(), self.shadow.data_ptr(),
                   self.n_train, lr, beta1, beta2, eps, weight_decay, int(correct_bias), max(1, s["step"]), grad_scale,
                   sched_dev.data_ptr() if sched_dev is not None else None, self._stream())

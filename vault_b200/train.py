@@ -63,7 +63,7 @@ class _Slot:
 class VaultTrainStep:
     def __init__(self, model, lr: float = 2e-5, betas=(0.9, 0.999), eps: float = 1e-8, weight_decay: float = 0.0, correct_bias: bool = False,
                  total_steps: Optional[int] = None, warmup_ratio: float = 0.1, process_group=None, use_cuda_graph: bool = True,
-                 dropout: bool = True, overlap_comm: bool = True, comm_reserve_sms: int = 0):
+                 dropout: bool = True, overlap_comm: bool = True, comm_reserve_sms: int = 0, grad_comm_dtype: str = "bf16"):
         self.model = model
         self.engine: VaultEngine = model.engine
         self.lr, self.betas, self.eps, self.wd, self.correct_bias = lr, betas, eps, weight_decay, correct_bias
@@ -101,6 +101,11 @@ class VaultTrainStep:
         self.overlap = bool(overlap_comm) and self.world > 1
         if self.overlap and comm_reserve_sms > 0:
             self.engine.gemm_max_ctas = max(1, self.engine.sms - comm_reserve_sms)
+        # gradient all-reduce payload: "bf16" halves the NVLink bytes (each finished range is cast to a bf16 comm buffer, summed
+        # by NCCL, and AdamW reads the bf16 sums); "fp32" reduces the fp32 buffer in place (bit-faithful sum of the ranks' gradients)
+        if grad_comm_dtype not in ("bf16", "fp32"):
+            raise ValueError("grad_comm_dtype must be 'bf16' or 'fp32'")
+        self.grad16 = torch.empty(self.engine.n_train, device=self.dev, dtype=torch.bfloat16) if (self.world > 1 and grad_comm_dtype == "bf16") else None
         self.copy_stream = torch.cuda.Stream(device=self.dev)
         self.sched_dev = torch.zeros(2, device=self.dev, dtype=torch.float32)
         self.step_idx = 0
@@ -185,16 +190,22 @@ class VaultTrainStep:
         if hi <= lo:
             return
         eng = self.engine
-        works = allreduce_flat_(eng.grad[lo:hi], self.pg, async_op=True) if self.world > 1 else []
         side = eng._side
         ev = torch.cuda.Event()
         ev.record(torch.cuda.current_stream(self.dev))
         side.wait_event(ev)
         with torch.cuda.stream(side):
+            works = []
+            if self.world > 1:
+                if self.grad16 is not None:
+                    _abi.call("vault_cast_f32_bf16", eng.grad.data_ptr() + 4 * lo, self.grad16.data_ptr() + 2 * lo, hi - lo, side.cuda_stream)
+                    works = allreduce_flat_(self.grad16[lo:hi], self.pg, bucket_elems=1 << 30, async_op=True)
+                else:
+                    works = allreduce_flat_(eng.grad[lo:hi], self.pg, bucket_elems=1 << 30, async_op=True)
             for w in works:
                 w.wait()
             eng.adamw_range(lo, hi, hp["step"], hp["lr"], hp["b1"], hp["b2"], self.eps, self.wd, self.correct_bias, 1.0 / self.world, self.sched_dev,
-                            side.cuda_stream)
+                            side.cuda_stream, grad16=self.grad16)
 
     def _get_slot(self, batch) -> _Slot:
         key = tuple((k, tuple(batch[k].shape)) for k in _INPUT_KEYS if batch.get(k) is not None)

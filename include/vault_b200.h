@@ -82,6 +82,9 @@ typedef struct vault_gemm_args {
   int32_t split_k;        /* >=1; >1 only with EPI_ATOMIC_F32 */
   int32_t block_n;        /* 0 = choose; else 64 / 128 / 256 */
   int32_t max_ctas;       /* 0 = all SMs */
+  int32_t* sched;         /* optional DEVICE int32[2], zero-initialised, re-armed by the kernel: tiles are claimed dynamically (atomic
+                             counter) instead of round-robin, so SMs held by a concurrent kernel / collective do not stretch the launch.
+                             One pair per launch that may run concurrently with another. */
   int32_t cluster;        /* CTA-pair operand multicast: 0/-1 off, 1 pair along M (B tile shared), 2 pair along N (A tile shared) */
 } vault_gemm_args;
 

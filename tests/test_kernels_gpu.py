@@ -299,3 +299,21 @@ def test_gemm_cta_pair_multicast(dev, ops, cl, M, N, K, a_mn, b_mn, bn):
     got = ops.gemm(A, Bm, ops.EPI_STORE_F32, a_mn=a_mn, b_mn=b_mn, block_n=bn, cluster=cl)
     assert torch.equal(got, ref)
     assert _rel(got, a.float() @ b.float().t()) < 1e-4
+
+
+@pytest.mark.parametrize("M,N,K,a_mn,b_mn,bn,split", [(5920, 2304, 768, False, False, 0, 1), (130, 128, 64, False, False, 0, 1), (768, 768, 5920, True, True, 128, 4),
+                                                    (1280, 3072, 768, False, True, 0, 1)])
+def test_gemm_dynamic_tile_scheduler(dev, ops, M, N, K, a_mn, b_mn, bn, split):
+    """Dynamic (atomic-counter) tile claiming gives the same result as the static round-robin, and re-arms its counters."""
+    torch.manual_seed(M)
+    a, b = _rnd(dev, M, K, scale=0.5), _rnd(dev, N, K, scale=0.5)
+    A = a.t().contiguous() if a_mn else a
+    Bm = b.t().contiguous() if b_mn else b
+    epi = ops.EPI_ATOMIC_F32 if split > 1 else ops.EPI_STORE_F32
+    sched = torch.zeros(2, device=dev, dtype=torch.int32)
+    ref = a.float() @ b.float().t()
+    for _ in range(3):  # repeated launches reuse the same counters
+        out = torch.zeros(M, N, device=dev)
+        ops.gemm(A, Bm, epi, a_mn=a_mn, b_mn=b_mn, block_n=bn, split_k=split, out=out, sched=sched)
+        assert _rel(out, ref) < 1e-4
+        assert sched.tolist() == [0, 0]

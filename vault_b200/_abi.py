@@ -27,7 +27,7 @@ class GemmArgs(C.Structure):
         ("aux", c_p), ("ldaux", c_i64),
         ("out", c_p), ("ldo", c_i64), ("out2", c_p), ("ldo2", c_i64),
         ("dropout_p", c_f32), ("seed", c_u64), ("seed_dev", c_p), ("site", c_u32),
-        ("split_k", c_i32), ("block_n", c_i32), ("max_ctas", c_i32), ("cluster", c_i32),
+        ("split_k", c_i32), ("block_n", c_i32), ("max_ctas", c_i32), ("sched", c_p), ("cluster", c_i32),
     ]
 
 

@@ -20,12 +20,14 @@ constexpr int kEpiWarps = 8;
 constexpr int kThreads = 128 + kEpiWarps * 32;
 constexpr int kRingBytes = 196608;                 // smem ring for A/B stages
 constexpr int kStagingBytes = kEpiWarps * 4096;    // per-warp 32x32 fp32 transpose buffers
-constexpr int kSmemBytes = kRingBytes + kStagingBytes + 1024 /*align slack*/ + 256 /*barriers*/;
+constexpr int kSchedDepth = 4;
+constexpr int kSmemBytes = kRingBytes + kStagingBytes + 1024 /*align slack*/ + 384 /*barriers + tile ring*/;
 
 struct GemmParams {
   int M, N, K;
   int a_mn, b_mn;
   int num_m_blocks, num_n_blocks, num_k_blocks, split_k, kb_per_split;
+  int* sched;  // optional {next tile, finished CTAs} counters: dynamic tile scheduling (robust to SMs taken by other kernels)
   int cl;  // 0: no cluster; 1: CTA pair along M (B tile multicast); 2: CTA pair along N (A tile multicast)
   const float* bias;
   const float* resid;
@@ -165,6 +167,10 @@ gemm_bf16_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant_
   auto tempty_bar = [&](int s) { return bars + 8u * (2 * kStages + 2 + s); };
   const uint32_t tmem_slot = bars + 8u * (2 * kStages + 4);
   volatile uint32_t* tmem_slot_gen = reinterpret_cast<volatile uint32_t*>(smem_gen + kRingBytes + kStagingBytes + 8 * (2 * kStages + 4));
+  // dynamic scheduler ring: sfull[4] | sempty[4] | tile ids[4]
+  auto sfull_bar = [&](int s) { return bars + 8u * (2 * kStages + 5 + s); };
+  auto sempty_bar = [&](int s) { return bars + 8u * (2 * kStages + 5 + kSchedDepth + s); };
+  volatile int* tile_ring = reinterpret_cast<volatile int*>(smem_gen + kRingBytes + kStagingBytes + 8 * (2 * kStages + 5 + 2 * kSchedDepth));
 
   const int warp = threadIdx.x >> 5;
   const int lane = threadIdx.x & 31;
@@ -181,6 +187,10 @@ gemm_bf16_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant_
     for (int s = 0; s < 2; ++s) {
       mbar_init(tfull_bar(s), 1);
       mbar_init(tempty_bar(s), kEpiWarps);
+    }
+    for (int s = 0; s < kSchedDepth; ++s) {
+      mbar_init(sfull_bar(s), 1);
+      mbar_init(sempty_bar(s), 2 + kEpiWarps);  // TMA thread + MMA thread + 8 epilogue warps each take every tile id
     }
     mbar_fence_init();
   }
@@ -203,6 +213,27 @@ gemm_bf16_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant_
   const int n_units = p.cl == 2 ? (p.num_n_blocks + 1) / 2 : p.num_n_blocks;
   const int tiles_mn = m_units * n_units;
   const int total_tiles = tiles_mn * p.split_k;
+  // Tile sequence of this CTA: static round-robin, or (p.sched) claimed with an atomic counter by the scheduler warp and
+  // broadcast through a 4-deep smem ring, so a CTA that starts late (its SM was busy with another stream's kernel or a
+  // collective) simply takes fewer tiles instead of stretching the whole launch.
+  const bool dyn = p.sched != nullptr && p.cl == 0;
+  struct TileIter {
+    int t, step, total, slot;
+    uint32_t ph;
+  };
+  auto iter_begin = [&]() { return TileIter{unit0 - unit_step, unit_step, total_tiles, 0, 0u}; };
+  auto iter_next = [&](TileIter& it, bool arrive_lane, bool whole_warp) -> bool {
+    if (!dyn) {
+      it.t += it.step;
+      return it.t < it.total;
+    }
+    mbar_wait(sfull_bar(it.slot), it.ph);
+    it.t = tile_ring[it.slot];
+    if (whole_warp) __syncwarp();  // every lane has read the id before lane 0 hands the slot back
+    if (arrive_lane) mbar_arrive(sempty_bar(it.slot));
+    if (++it.slot == kSchedDepth) { it.slot = 0; it.ph ^= 1u; }
+    return it.t < it.total;
+  };
   auto tile_m0 = [&](int rem) { return ((rem / n_units) * (p.cl == 1 ? 2 : 1) + (p.cl == 1 ? rank : 0)) * BM; };
   auto tile_n0 = [&](int rem) { return ((rem % n_units) * (p.cl == 2 ? 2 : 1) + (p.cl == 2 ? rank : 0)) * BN; };
 
@@ -211,7 +242,9 @@ gemm_bf16_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant_
     if (lane == 0) {
       int stage = 0;
       uint32_t phase = 0;
-      for (int t = unit0; t < total_tiles; t += unit_step) {
+      TileIter it = iter_begin();
+      while (iter_next(it, true, false)) {
+        const int t = it.t;
         const int split = t / tiles_mn;
         const int rem = t - split * tiles_mn;
         const int m0 = tile_m0(rem);
@@ -267,7 +300,9 @@ gemm_bf16_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant_
       uint32_t phase = 0;
       int as = 0;
       uint32_t aphase = 0;
-      for (int t = unit0; t < total_tiles; t += unit_step) {
+      TileIter it = iter_begin();
+      while (iter_next(it, true, false)) {
+        const int t = it.t;
         const int split = t / tiles_mn;
         const int kb0 = split * p.kb_per_split;
         const int kb1 = min(kb0 + p.kb_per_split, p.num_k_blocks);
@@ -294,6 +329,22 @@ gemm_bf16_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant_
         if (as == 0) aphase ^= 1u;
       }
     }
+  } else if (warp == 3) {
+    // ===================== tile scheduler (dynamic mode only) =====================
+    if (dyn && lane == 0) {
+      int slot = 0;
+      uint32_t ph = 0;
+      bool first = true;
+      for (;;) {
+        mbar_wait(sempty_bar(slot), ph ^ 1u);
+        const int t = first ? (int)blockIdx.x : atomicAdd(p.sched, 1) + (int)gridDim.x;  // first tile needs no round trip
+        first = false;
+        tile_ring[slot] = t;
+        mbar_arrive(sfull_bar(slot));  // release: the tile id is visible to the waiters
+        if (t >= total_tiles) break;
+        if (++slot == kSchedDepth) { slot = 0; ph ^= 1u; }
+      }
+    }
   } else if (warp >= 4) {
     // ===================== epilogue warps =====================
     const int ew = warp - 4;
@@ -304,7 +355,9 @@ gemm_bf16_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant_
     const unsigned long long seed = p.seed + ((p.dropout_p > 0.f && p.seed_dev) ? *p.seed_dev : 0ull);
     int as = 0;
     uint32_t aphase = 0;
-    for (int t = unit0; t < total_tiles; t += unit_step) {
+    TileIter it = iter_begin();
+    while (iter_next(it, lane == 0, true)) {
+      const int t = it.t;
       const int split = t / tiles_mn;
       const int rem = t - split * tiles_mn;
       const int m0 = tile_m0(rem);
@@ -344,6 +397,14 @@ gemm_bf16_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant_
 
   tc_fence_before();
   __syncthreads();
+  if (dyn && threadIdx.x == 0) {  // the last CTA to finish re-arms the counters for the next launch that uses this slot
+    __threadfence();
+    if (atomicAdd(p.sched + 1, 1) == (int)gridDim.x - 1) {
+      p.sched[0] = 0;
+      p.sched[1] = 0;
+      __threadfence();
+    }
+  }
   if (p.cl) cluster_sync_all();  // no CTA may leave while its peer can still multicast into it or arrive on its barriers
   if (warp == 2) {
     tc_fence_after();
@@ -476,6 +537,7 @@ extern "C" int vault_gemm_bf16(const vault_gemm_args* a, void* stream) {
   p.out = a->out; p.ldo = a->ldo; p.out2 = a->out2; p.ldo2 = a->ldo2;
   p.dropout_p = a->dropout_p; p.seed = a->seed; p.seed_dev = reinterpret_cast<const unsigned long long*>(a->seed_dev); p.site = a->site;
   p.cl = cl;
+  p.sched = cl ? nullptr : a->sched;
   int grid;
   if (cl) {
     const long long mu = cl == 1 ? (p.num_m_blocks + 1) / 2 : p.num_m_blocks, nu = cl == 2 ? (p.num_n_blocks + 1) / 2 : p.num_n_blocks;

@@ -92,6 +92,7 @@ class VaultEngine:
         self.seed_dev: Optional[torch.Tensor] = None  # device counter added to the seed (advanced once per training step)
         self.sms = 0
         self.gemm_max_ctas = 0  # >0: leave SMs free for a concurrently running collective (data-parallel overlap)
+        self.dynamic_tiles = os.environ.get("VAULT_B200_DYNAMIC_TILES", "1") != "0"
         self.wgrad_side_stream = os.environ.get("VAULT_B200_WGRAD_SIDE", "1") != "0"
         self._side = None
         self._side_keep = []
@@ -204,6 +205,9 @@ class VaultEngine:
         self._zero_ranges = self._compute_zero_ranges()
         self.opt_state = None
         self._side = torch.cuda.Stream(device=device)
+        self._sched_slots = 512
+        self._sched = torch.zeros(2 * self._sched_slots, device=device, dtype=torch.int32)  # dynamic tile-scheduler counters
+        self._sched_i = 0
 
     def _params_in_place(self) -> bool:
         named = dict(self.model.named_parameters())
@@ -301,6 +305,11 @@ class VaultEngine:
         g.dropout_p, g.seed, g.site = p, self.seed, site
         g.seed_dev = self.seed_dev.data_ptr() if p > 0.0 else None
         g.split_k, g.block_n, g.max_ctas = split_k, block_n, self.gemm_max_ctas
+        if self.dynamic_tiles:
+            self._sched_i = (self._sched_i + 1) % self._sched_slots
+            g.sched = self._sched.data_ptr() + 8 * self._sched_i
+        else:
+            g.sched = None
         rc = self._lib.vault_gemm_bf16(C.byref(g), stream if stream is not None else self._st)
         if rc:
             _abi.check(rc, "vault_gemm_bf16")

@@ -190,7 +190,7 @@ gemm_bf16_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant_
     }
     for (int s = 0; s < kSchedDepth; ++s) {
       mbar_init(sfull_bar(s), 1);
-      mbar_init(sempty_bar(s), 2 + kEpiWarps);  // TMA thread + MMA thread + 8 epilogue warps each take every tile id
+      mbar_init(sempty_bar(s), 1 + kEpiWarps);  // MMA thread + 8 epilogue warps each take every tile id the producer publishes
     }
     mbar_fence_init();
   }
@@ -213,9 +213,10 @@ gemm_bf16_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant_
   const int n_units = p.cl == 2 ? (p.num_n_blocks + 1) / 2 : p.num_n_blocks;
   const int tiles_mn = m_units * n_units;
   const int total_tiles = tiles_mn * p.split_k;
-  // Tile sequence of this CTA: static round-robin, or (p.sched) claimed with an atomic counter by the scheduler warp and
-  // broadcast through a 4-deep smem ring, so a CTA that starts late (its SM was busy with another stream's kernel or a
-  // collective) simply takes fewer tiles instead of stretching the whole launch.
+  // Tile sequence of this CTA: static round-robin, or (p.sched) claimed just in time by the TMA producer with an atomic
+  // counter -- one tile of look-ahead, so the claim's round trip hides under the current tile's loads and no CTA hoards
+  // tiles -- and broadcast to the MMA / epilogue warps through a 4-deep smem ring.  A CTA that starts late (its SM was busy
+  // with another stream's kernel or a collective) then simply takes fewer tiles instead of stretching the whole launch.
   const bool dyn = p.sched != nullptr && p.cl == 0;
   struct TileIter {
     int t, step, total, slot;
@@ -242,9 +243,18 @@ gemm_bf16_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant_
     if (lane == 0) {
       int stage = 0;
       uint32_t phase = 0;
-      TileIter it = iter_begin();
-      while (iter_next(it, true, false)) {
-        const int t = it.t;
+      int t = unit0, pslot = 0;
+      uint32_t pph = 0;
+      for (;;) {
+        int t_next = t + unit_step;
+        if (dyn) {
+          t_next = atomicAdd(p.sched, 1) + (int)gridDim.x;  // result is first read after this tile's k-loop
+          mbar_wait(sempty_bar(pslot), pph ^ 1u);
+          tile_ring[pslot] = t;
+          mbar_arrive(sfull_bar(pslot));  // release: MMA and epilogue warps may read the id
+          if (++pslot == kSchedDepth) { pslot = 0; pph ^= 1u; }
+        }
+        if (t >= total_tiles) break;
         const int split = t / tiles_mn;
         const int rem = t - split * tiles_mn;
         const int m0 = tile_m0(rem);
@@ -287,6 +297,17 @@ gemm_bf16_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant_
           }
           if (++stage == kStages) { stage = 0; phase ^= 1u; }
         }
+        t = t_next;
+      }
+      if (dyn) {
+        // This CTA will not touch the counter again.  The last CTA to get here re-arms both counters for the next launch
+        // that uses this slot -- off the critical path, while the MMA / epilogue warps are still working.
+        __threadfence();
+        if (atomicAdd(p.sched + 1, 1) == (int)gridDim.x - 1) {
+          p.sched[0] = 0;
+          p.sched[1] = 0;
+          __threadfence();
+        }
       }
     }
   } else if (warp == 1) {
@@ -327,22 +348,6 @@ gemm_bf16_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant_
         tc_commit(tfull_bar(as));  // accumulator complete
         as ^= 1;
         if (as == 0) aphase ^= 1u;
-      }
-    }
-  } else if (warp == 3) {
-    // ===================== tile scheduler (dynamic mode only) =====================
-    if (dyn && lane == 0) {
-      int slot = 0;
-      uint32_t ph = 0;
-      bool first = true;
-      for (;;) {
-        mbar_wait(sempty_bar(slot), ph ^ 1u);
-        const int t = first ? (int)blockIdx.x : atomicAdd(p.sched, 1) + (int)gridDim.x;  // first tile needs no round trip
-        first = false;
-        tile_ring[slot] = t;
-        mbar_arrive(sfull_bar(slot));  // release: the tile id is visible to the waiters
-        if (t >= total_tiles) break;
-        if (++slot == kSchedDepth) { slot = 0; ph ^= 1u; }
       }
     }
   } else if (warp >= 4) {
@@ -397,14 +402,6 @@ gemm_bf16_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant_
 
   tc_fence_before();
   __syncthreads();
-  if (dyn && threadIdx.x == 0) {  // the last CTA to finish re-arms the counters for the next launch that uses this slot
-    __threadfence();
-    if (atomicAdd(p.sched + 1, 1) == (int)gridDim.x - 1) {
-      p.sched[0] = 0;
-      p.sched[1] = 0;
-      __threadfence();
-    }
-  }
   if (p.cl) cluster_sync_all();  // no CTA may leave while its peer can still multicast into it or arrive on its barriers
   if (warp == 2) {
     tc_fence_after();

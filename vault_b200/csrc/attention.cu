@@ -31,28 +31,14 @@ __device__ __forceinline__ void cp_async16(uint32_t dst, const void* src) {
 __device__ __forceinline__ void cp_async_wait_all() {
   asm volatile("cp.async.commit_group;\ncp.async.wait_group 0;" ::: "memory");
 }
-__device__ __forceinline__ void cp_async_commit() { asm volatile("cp.async.commit_group;" ::: "memory"); }
-// wait until at most `pending` of this thread's most recent commit groups are still in flight (pending <= 7)
-__device__ __forceinline__ void cp_async_wait_pending(int pending) {
-  switch (pending) {
-    case 0: asm volatile("cp.async.wait_group 0;" ::: "memory"); break;
-    case 1: asm volatile("cp.async.wait_group 1;" ::: "memory"); break;
-    case 2: asm volatile("cp.async.wait_group 2;" ::: "memory"); break;
-    case 3: asm volatile("cp.async.wait_group 3;" ::: "memory"); break;
-    case 4: asm volatile("cp.async.wait_group 4;" ::: "memory"); break;
-    case 5: asm volatile("cp.async.wait_group 5;" ::: "memory"); break;
-    case 6: asm volatile("cp.async.wait_group 6;" ::: "memory"); break;
-    default: asm volatile("cp.async.wait_group 7;" ::: "memory"); break;
-  }
-}
 
 // 64-wide bf16 tiles: row r lives at r*128 bytes, its eight 16-byte chunks XOR-swizzled by (r & 7)
 __device__ __forceinline__ uint32_t sw_addr(uint32_t base, int row, int col) {
   return base + (uint32_t)row * 128u + (uint32_t)((((col >> 3) ^ (row & 7)) << 4) + ((col & 7) << 1));
 }
 // rows [0, n_total) of a tile; rows >= n_valid are zero-filled.  src row stride in elements.
-__device__ __forceinline__ void load_tile(uint32_t sbase, uint8_t* sgen, const bf16* src, long long stride, int n_valid, int n_total, int row0 = 0) {
-  for (int idx = threadIdx.x + row0 * 8; idx < n_total * 8; idx += kAttnThreads) {
+__device__ __forceinline__ void load_tile(uint32_t sbase, uint8_t* sgen, const bf16* src, long long stride, int n_valid, int n_total) {
+  for (int idx = threadIdx.x; idx < n_total * 8; idx += kAttnThreads) {
     const int r = idx >> 3, ch = idx & 7;
     const uint32_t off = (uint32_t)r * 128u + (uint32_t)((ch ^ (r & 7)) << 4);
     if (r < n_valid) cp_async16(sbase + off, src + (long long)r * stride + ch * 8);
@@ -154,16 +140,11 @@ __global__ void __launch_bounds__(kAttnThreads) attn_fwd_kernel(const AttnParams
   const long long ld = 3LL * H;
   const bf16* base = p.qkv + (long long)b * S * ld + h * kHd;
   const int q0 = qt * kTile;
-  // K/V arrive in 64-key chunks, one cp.async group each: chunk c is consumed while chunks c+1.. are still in flight
-  const int nchunks = S_pad / kTile;
   load_tile(sQ, sQg, base + (long long)q0 * ld, ld, min(kTile, S - q0), kTile);
-  for (int c = 0; c < nchunks; ++c) {
-    load_tile(sK, sKg, base + H, ld, S, (c + 1) * kTile, c * kTile);
-    load_tile(sV, sVg, base + 2 * H, ld, S, (c + 1) * kTile, c * kTile);
-    cp_async_commit();
-  }
+  load_tile(sK, sKg, base + H, ld, S, S_pad);
+  load_tile(sV, sVg, base + 2 * H, ld, S, S_pad);
   for (int i = threadIdx.x; i < S_pad; i += kAttnThreads) sMg[i] = i < S ? p.key_mask[(long long)b * S + i] : (uint8_t)0;
-  cp_async_wait_pending(nchunks - 1);
+  cp_async_wait_all();
   __syncthreads();
 
   uint32_t aQ[4][4];
@@ -175,10 +156,6 @@ __global__ void __launch_bounds__(kAttnThreads) attn_fwd_kernel(const AttnParams
   const long long bh = (long long)b * p.heads + h;
 
   for (int kc = 0; kc < S_pad; kc += kTile) {
-    if (kc > 0) {
-      cp_async_wait_pending(nchunks - 1 - kc / kTile);
-      __syncthreads();
-    }
     float s[8][4];
     zero_acc(s);
     mma_a_tn(s, aQ, sK, kc, lane);
@@ -267,17 +244,13 @@ __global__ void __launch_bounds__(kAttnThreads) attn_bwd_dq_kernel(const AttnPar
   const bf16* base = p.qkv + (long long)b * S * ld + h * kHd;
   const int q0 = qt * kTile;
   const int nq = min(kTile, S - q0);
-  const int nchunks = S_pad / kTile;
   load_tile(sQ, sQg, base + (long long)q0 * ld, ld, nq, kTile);
   load_tile(sdO, sdOg, p.dctx + ((long long)b * S + q0) * H + h * kHd, H, nq, kTile);
   load_tile(sO, sOg, p.ctx + ((long long)b * S + q0) * H + h * kHd, H, nq, kTile);
-  for (int c = 0; c < nchunks; ++c) {
-    load_tile(sK, sKg, base + H, ld, S, (c + 1) * kTile, c * kTile);
-    load_tile(sV, sVg, base + 2 * H, ld, S, (c + 1) * kTile, c * kTile);
-    cp_async_commit();
-  }
+  load_tile(sK, sKg, base + H, ld, S, S_pad);
+  load_tile(sV, sVg, base + 2 * H, ld, S, S_pad);
   for (int i = threadIdx.x; i < S_pad; i += kAttnThreads) sMg[i] = i < S ? p.key_mask[(long long)b * S + i] : (uint8_t)0;
-  cp_async_wait_pending(nchunks - 1);
+  cp_async_wait_all();
   __syncthreads();
 
   const int r0 = warp * 16 + g, r1 = r0 + 8;
@@ -315,10 +288,6 @@ __global__ void __launch_bounds__(kAttnThreads) attn_bwd_dq_kernel(const AttnPar
   float dq[8][4];
   zero_acc(dq);
   for (int kc = 0; kc < S_pad; kc += kTile) {
-    if (kc > 0) {
-      cp_async_wait_pending(nchunks - 1 - kc / kTile);
-      __syncthreads();
-    }
     float s[8][4], dp[8][4];
     zero_acc(s);
     zero_acc(dp);
@@ -381,19 +350,15 @@ __global__ void __launch_bounds__(kAttnThreads) attn_bwd_dkv_kernel(const AttnPa
   const int k0 = kt * kTile;
   const int nk = min(kTile, S - k0);
   const long long bh = (long long)b * p.heads + h;
-  const int nchunks = S_pad / kTile;
   load_tile(sK, sKg, base + H + (long long)k0 * ld, ld, nk, kTile);
   load_tile(sV, sVg, base + 2 * H + (long long)k0 * ld, ld, nk, kTile);
-  for (int c = 0; c < nchunks; ++c) {
-    load_tile(sQ, sQg, base, ld, S, (c + 1) * kTile, c * kTile);
-    load_tile(sdO, sdOg, p.dctx + (long long)b * S * H + h * kHd, H, S, (c + 1) * kTile, c * kTile);
-    cp_async_commit();
-  }
+  load_tile(sQ, sQg, base, ld, S, S_pad);
+  load_tile(sdO, sdOg, p.dctx + (long long)b * S * H + h * kHd, H, S, S_pad);
   for (int i = threadIdx.x; i < S_pad; i += kAttnThreads) {
     sLse[i] = i < S ? p.lse[bh * S + i] * kLog2e : 0.f;
     sDelta[i] = i < S ? p.delta[bh * S + i] : 0.f;
   }
-  cp_async_wait_pending(nchunks - 1);
+  cp_async_wait_all();
   __syncthreads();
 
   const int kr0 = k0 + warp * 16 + g, kr1 = kr0 + 8;  // this thread's two keys (rows of the transposed problem)
@@ -406,10 +371,6 @@ __global__ void __launch_bounds__(kAttnThreads) attn_bwd_dkv_kernel(const AttnPa
   zero_acc(dk);
   zero_acc(dv);
   for (int qc = 0; qc < S_pad; qc += kTile) {
-    if (qc > 0) {
-      cp_async_wait_pending(nchunks - 1 - qc / kTile);
-      __syncthreads();
-    }
     float s[8][4], dp[8][4];
     zero_acc(s);
     zero_acc(dp);

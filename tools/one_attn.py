@@ -1,0 +1,13 @@
+import os, sys, torch
+sys.path.insert(0, os.path.dirname(os.path.dirname(os.path.abspath(__file__))))
+from vault_b200 import _abi
+dev = torch.device("cuda:0"); lib = _abi.lib(); st = torch.cuda.current_stream().cuda_stream
+B, S, heads = 32, int(sys.argv[1]) if len(sys.argv) > 1 else 185, 12
+H = heads * 64
+qkv = torch.randn(B * S, 3 * H, device=dev).to(torch.bfloat16); mask = torch.ones(B, S, dtype=torch.uint8, device=dev)
+ctx = torch.empty(B * S, H, device=dev, dtype=torch.bfloat16); lse = torch.empty(B, heads, S, device=dev)
+dctx = torch.randn(B * S, H, device=dev).to(torch.bfloat16); dqkv = torch.empty_like(qkv); delta = torch.empty(B, heads, S, device=dev)
+for _ in range(3):
+    lib.vault_attn_fwd(qkv.data_ptr(), mask.data_ptr(), ctx.data_ptr(), lse.data_ptr(), B, S, heads, 0.0, 0, None, 0, st)
+    lib.vault_attn_bwd(qkv.data_ptr(), mask.data_ptr(), ctx.data_ptr(), dctx.data_ptr(), lse.data_ptr(), delta.data_ptr(), dqkv.data_ptr(), B, S, heads, 0.0, 0, None, 0, st)
+torch.cuda.synchronize()

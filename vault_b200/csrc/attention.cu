@@ -45,33 +45,54 @@ __device__ __forceinline__ void load_tile(uint32_t sbase, uint8_t* sgen, const b
     else *reinterpret_cast<uint4*>(sgen + off) = make_uint4(0, 0, 0, 0);
   }
 }
-// A fragments (16 rows x 64 cols) of a warp from a swizzled tile starting at row0
-__device__ __forceinline__ void load_a_frags(uint32_t sbase, int row0, int lane, uint32_t (&a)[4][4]) {
+// Per-lane pieces of the swizzled ldmatrix addresses, computed once: every fragment load below is then ONE integer add
+// (tile base + 2 KB * block + lane row + pre-XORed 16-byte chunk), which matters because these kernels are issue-bound.
+struct LaneOff {
+  uint32_t row_n;   // (lane&7) + (lane>>4)*8   rows of a non-transposed B fragment pair, * 128 B
+  uint32_t row_t;   // (lane&7) + ((lane>>3)&1)*8   rows of a transposed B fragment pair, * 128 B
+  uint32_t row_a;   // lane & 15   rows of an A fragment, * 128 B
+  uint32_t xn[4];   // ((2*ks + ((lane>>3)&1)) ^ (lane&7)) << 4
+  uint32_t xt[4];   // ((2*j  + (lane>>4))     ^ (lane&7)) << 4   (transposed B fragments and A fragments)
+  __device__ __forceinline__ explicit LaneOff(int lane) {
+    row_n = (uint32_t)(((lane & 7) + (lane >> 4) * 8) * 128);
+    row_t = (uint32_t)(((lane & 7) + ((lane >> 3) & 1) * 8) * 128);
+    row_a = (uint32_t)((lane & 15) * 128);
 #pragma unroll
-  for (int ks = 0; ks < 4; ++ks)
-    ldsm_x4(sw_addr(sbase, row0 + (lane & 15), ks * 16 + (lane >> 4) * 8), a[ks][0], a[ks][1], a[ks][2], a[ks][3]);
+    for (int k = 0; k < 4; ++k) {
+      xn[k] = (uint32_t)(((2 * k + ((lane >> 3) & 1)) ^ (lane & 7)) << 4);
+      xt[k] = (uint32_t)(((2 * k + (lane >> 4)) ^ (lane & 7)) << 4);
+    }
+  }
+};
+// A fragments (16 rows x 64 cols) of a warp from a swizzled tile starting at row0 (multiple of 16)
+__device__ __forceinline__ void load_a_frags(uint32_t sbase, int row0, const LaneOff& lo, uint32_t (&a)[4][4]) {
+  const uint32_t base = sbase + (uint32_t)row0 * 128u + lo.row_a;
+#pragma unroll
+  for (int ks = 0; ks < 4; ++ks) ldsm_x4(base + lo.xt[ks], a[ks][0], a[ks][1], a[ks][2], a[ks][3]);
 }
 // C[16 x 64] += A[16 x 64(d)] * T[64 rows x 64(d)]^T  where T rows are the n index (non-transposed ldmatrix): S = Q K^T
-__device__ __forceinline__ void mma_a_tn(float (&c)[8][4], const uint32_t (&a)[4][4], uint32_t sbase, int trow0, int lane) {
+__device__ __forceinline__ void mma_a_tn(float (&c)[8][4], const uint32_t (&a)[4][4], uint32_t sbase, int trow0, const LaneOff& lo) {
+  const uint32_t base = sbase + (uint32_t)trow0 * 128u + lo.row_n;
 #pragma unroll
   for (int ks = 0; ks < 4; ++ks) {
 #pragma unroll
     for (int nb2 = 0; nb2 < 4; ++nb2) {
       uint32_t b0, b1, b2, b3;
-      ldsm_x4(sw_addr(sbase, trow0 + nb2 * 16 + (lane & 7) + (lane >> 4) * 8, ks * 16 + ((lane >> 3) & 1) * 8), b0, b1, b2, b3);
+      ldsm_x4(base + nb2 * 2048 + lo.xn[ks], b0, b1, b2, b3);
       mma16816(c[2 * nb2], a[ks], b0, b1);
       mma16816(c[2 * nb2 + 1], a[ks], b2, b3);
     }
   }
 }
 // C[16 x 64(d)] += P[16 x 64(k)] * T[64 rows(k) x 64(d)]  (transposed ldmatrix): O = P V, dQ = dS K, dV = P^T dO, dK = dS^T Q
-__device__ __forceinline__ void mma_p_t(float (&c)[8][4], const uint32_t (&p)[4][4], uint32_t sbase, int trow0, int lane) {
+__device__ __forceinline__ void mma_p_t(float (&c)[8][4], const uint32_t (&p)[4][4], uint32_t sbase, int trow0, const LaneOff& lo) {
+  const uint32_t base = sbase + (uint32_t)trow0 * 128u + lo.row_t;
 #pragma unroll
   for (int kk = 0; kk < 4; ++kk) {
 #pragma unroll
     for (int db2 = 0; db2 < 4; ++db2) {
       uint32_t b0, b1, b2, b3;
-      ldsm_x4_t(sw_addr(sbase, trow0 + kk * 16 + (lane & 7) + ((lane >> 3) & 1) * 8, db2 * 16 + (lane >> 4) * 8), b0, b1, b2, b3);
+      ldsm_x4_t(base + kk * 2048 + lo.xt[db2], b0, b1, b2, b3);
       mma16816(c[2 * db2], p[kk], b0, b1);
       mma16816(c[2 * db2 + 1], p[kk], b2, b3);
     }
@@ -132,6 +153,7 @@ __global__ void __launch_bounds__(kAttnThreads) attn_fwd_kernel(const AttnParams
   const int S = p.S, S_pad = p.S_pad, H = p.heads * kHd;
   const int qt = blockIdx.x, h = blockIdx.y, b = blockIdx.z;
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31, g = lane >> 2, t = lane & 3;
+  const LaneOff lo(lane);
   uint8_t* sQg = smem;
   uint8_t* sKg = sQg + kTile * 128;
   uint8_t* sVg = sKg + S_pad * 128;
@@ -148,7 +170,7 @@ __global__ void __launch_bounds__(kAttnThreads) attn_fwd_kernel(const AttnParams
   __syncthreads();
 
   uint32_t aQ[4][4];
-  load_a_frags(sQ, warp * 16, lane, aQ);
+  load_a_frags(sQ, warp * 16, lo, aQ);
   float o[8][4];
   zero_acc(o);
   float m0 = -INFINITY, m1 = -INFINITY, l0 = 0.f, l1 = 0.f;
@@ -158,7 +180,7 @@ __global__ void __launch_bounds__(kAttnThreads) attn_fwd_kernel(const AttnParams
   for (int kc = 0; kc < S_pad; kc += kTile) {
     float s[8][4];
     zero_acc(s);
-    mma_a_tn(s, aQ, sK, kc, lane);
+    mma_a_tn(s, aQ, sK, kc, lo);
     float mx0 = -INFINITY, mx1 = -INFINITY;
 #pragma unroll
     for (int j = 0; j < 8; ++j) {
@@ -204,7 +226,7 @@ __global__ void __launch_bounds__(kAttnThreads) attn_fwd_kernel(const AttnParams
     }
     uint32_t aP[4][4];
     c_to_a(s, aP);
-    mma_p_t(o, aP, sV, kc, lane);
+    mma_p_t(o, aP, sV, kc, lo);
   }
   l0 += __shfl_xor_sync(0xffffffffu, l0, 1);
   l0 += __shfl_xor_sync(0xffffffffu, l0, 2);
@@ -233,6 +255,7 @@ __global__ void __launch_bounds__(kAttnThreads) attn_bwd_dq_kernel(const AttnPar
   const int S = p.S, S_pad = p.S_pad, H = p.heads * kHd;
   const int qt = blockIdx.x, h = blockIdx.y, b = blockIdx.z;
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31, g = lane >> 2, t = lane & 3;
+  const LaneOff lo(lane);
   uint8_t* sQg = smem;
   uint8_t* sdOg = sQg + kTile * 128;
   uint8_t* sOg = sdOg + kTile * 128;
@@ -283,16 +306,16 @@ __global__ void __launch_bounds__(kAttnThreads) attn_bwd_dq_kernel(const AttnPar
   const float lse1 = qr1 < S ? p.lse[bh * S + qr1] * kLog2e : 0.f;
 
   uint32_t aQ[4][4], adO[4][4];
-  load_a_frags(sQ, warp * 16, lane, aQ);
-  load_a_frags(sdO, warp * 16, lane, adO);
+  load_a_frags(sQ, warp * 16, lo, aQ);
+  load_a_frags(sdO, warp * 16, lo, adO);
   float dq[8][4];
   zero_acc(dq);
   for (int kc = 0; kc < S_pad; kc += kTile) {
     float s[8][4], dp[8][4];
     zero_acc(s);
     zero_acc(dp);
-    mma_a_tn(s, aQ, sK, kc, lane);
-    mma_a_tn(dp, adO, sV, kc, lane);
+    mma_a_tn(s, aQ, sK, kc, lo);
+    mma_a_tn(dp, adO, sV, kc, lo);
 #pragma unroll
     for (int j = 0; j < 8; ++j) {
       const int key = kc + 8 * j + 2 * t;
@@ -317,7 +340,7 @@ __global__ void __launch_bounds__(kAttnThreads) attn_bwd_dq_kernel(const AttnPar
     }
     uint32_t aS[4][4];
     c_to_a(s, aS);
-    mma_p_t(dq, aS, sK, kc, lane);
+    mma_p_t(dq, aS, sK, kc, lo);
   }
   bf16* drow0 = p.dqkv + ((long long)b * S + qr0) * ld + h * kHd;
   bf16* drow1 = p.dqkv + ((long long)b * S + qr1) * ld + h * kHd;
@@ -338,6 +361,7 @@ __global__ void __launch_bounds__(kAttnThreads) attn_bwd_dkv_kernel(const AttnPa
   const int S = p.S, S_pad = p.S_pad, H = p.heads * kHd;
   const int kt = blockIdx.x, h = blockIdx.y, b = blockIdx.z;
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31, g = lane >> 2, t = lane & 3;
+  const LaneOff lo(lane);
   uint8_t* sKg = smem;
   uint8_t* sVg = sKg + kTile * 128;
   uint8_t* sQg = sVg + kTile * 128;
@@ -365,8 +389,8 @@ __global__ void __launch_bounds__(kAttnThreads) attn_bwd_dkv_kernel(const AttnPa
   const bool kv0 = kr0 < S && p.key_mask[(long long)b * S + kr0] != 0;
   const bool kv1 = kr1 < S && p.key_mask[(long long)b * S + kr1] != 0;
   uint32_t aK[4][4], aV[4][4];
-  load_a_frags(sK, warp * 16, lane, aK);
-  load_a_frags(sV, warp * 16, lane, aV);
+  load_a_frags(sK, warp * 16, lo, aK);
+  load_a_frags(sV, warp * 16, lo, aV);
   float dk[8][4], dv[8][4];
   zero_acc(dk);
   zero_acc(dv);
@@ -374,8 +398,8 @@ __global__ void __launch_bounds__(kAttnThreads) attn_bwd_dkv_kernel(const AttnPa
     float s[8][4], dp[8][4];
     zero_acc(s);
     zero_acc(dp);
-    mma_a_tn(s, aK, sQ, qc, lane);    // [16 keys x 64 queries]
-    mma_a_tn(dp, aV, sdO, qc, lane);  // dP^T
+    mma_a_tn(s, aK, sQ, qc, lo);    // [16 keys x 64 queries]
+    mma_a_tn(dp, aV, sdO, qc, lo);  // dP^T
     float pt[8][4];
 #pragma unroll
     for (int j = 0; j < 8; ++j) {
@@ -413,9 +437,9 @@ __global__ void __launch_bounds__(kAttnThreads) attn_bwd_dkv_kernel(const AttnPa
     }
     uint32_t aP[4][4];
     c_to_a(pt, aP);
-    mma_p_t(dv, aP, sdO, qc, lane);
+    mma_p_t(dv, aP, sdO, qc, lo);
     c_to_a(s, aP);
-    mma_p_t(dk, aP, sQ, qc, lane);
+    mma_p_t(dk, aP, sQ, qc, lo);
   }
   bf16* krow0 = p.dqkv + ((long long)b * S + kr0) * ld + H + h * kHd;
   bf16* krow1 = p.dqkv + ((long long)b * S + kr1) * ld + H + h * kHd;

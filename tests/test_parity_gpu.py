@@ -168,3 +168,23 @@ def test_batch_rows_are_independent_at_baseline_size():
     assert (full[5] - solo[0]).abs().max() <= 2e-3   # same arithmetic up to tile-boundary effects in bf16 GEMM inputs: none expected
     assert (longer[0] - solo[0]).abs().max() <= 1e-2  # key chunking of the online softmax shifts -> bf16-level differences over 24 layers
     assert torch.isfinite(full).all()
+
+
+def test_inference_config2_batch64_matches_oracle_rows():
+    """BASELINE config 2: VaultModel inference, batch 64, T=64, 384x384 (S=209), bf16 operands vs the fp32 oracle.  The oracle runs
+    on a subset of rows (batch rows are independent -- checked separately), the CUDA path on the full batch."""
+    d = synth.Dims.base()
+    sd = synth.make_state_dict(d, seed=0)
+    inp = synth.make_inputs(d, batch=64, text_len=64, seed=11)
+    m = build(d, sd)
+    cu = {k: inp[k].to(DEV) for k in FWD}
+    with torch.no_grad():
+        lhs, pooled, _ = m._trunk(**cu)
+    assert tuple(lhs.shape) == (64, 209, 768) and torch.isfinite(pooled).all()
+    rows = [0, 31, 63]
+    sub = {k: inp[k][rows] for k in FWD}
+    with torch.no_grad():
+        o = O.vault_forward(sd, d, **sub)
+    got, ref = pooled[rows].float().cpu(), o["pooler_output"]
+    assert ((got - ref).norm(dim=1) / ref.norm(dim=1)).max() <= 1e-2
+    assert (got - ref).abs().max() / ref.abs().max() <= 2e-2

@@ -92,7 +92,7 @@ class VaultEngine:
         self.seed_dev: Optional[torch.Tensor] = None  # device counter added to the seed (advanced once per training step)
         self.sms = 0
         self.gemm_max_ctas = 0  # >0: leave SMs free for a concurrently running collective (data-parallel overlap)
-        self.dynamic_tiles = os.environ.get("VAULT_B200_DYNAMIC_TILES", "1") != "0"
+        self.dynamic_tiles = os.environ.get("VAULT_B200_DYNAMIC_TILES", "0") == "1"  # measured neutral on B200: opt-in
         self.wgrad_side_stream = os.environ.get("VAULT_B200_WGRAD_SIDE", "1") != "0"
         self._side = None
         self._side_keep = []

@@ -535,12 +535,26 @@ class VaultEngine:
         pmax = int((hw[:, 0] * hw[:, 1]).max().item())
         return hw, pmax
 
-    def forward(self, input_ids, attention_mask, token_type_ids, pixel_values, pixel_mask, image_token_type_idx=1, training=False,
-                need_grad=False, hw: Optional[torch.Tensor] = None, pmax: Optional[int] = None):
+    def forward(self, *args, **kwargs):
         """Returns (last_hidden_state fp32 [B,S,H], pooler_output fp32 [B,H] or None, key_mask uint8 [B,S], tape or None)."""
+        it = self.forward_iter(*args, **kwargs)
+        try:
+            while True:
+                next(it)
+        except StopIteration as e:
+            return e.value
+
+    def forward_iter(self, input_ids, attention_mask, token_type_ids, pixel_values, pixel_mask, image_token_type_idx=1, training=False,
+                     need_grad=False, hw: Optional[torch.Tensor] = None, pmax: Optional[int] = None, split_lm: bool = False):
+        """Generator form of forward.  With split_lm it yields "lm_done" once the language model's forward is enqueued and before
+        anything reads a ViLT parameter, so a caller can start the LM while the previous step's AdamW is still updating the
+        ViLT range (VaultTrainStep); the return value (StopIteration.value) is forward()'s tuple."""
         dev = pixel_values.device
         self.ensure_packed(dev)
         self._lib, self._st = _abi.lib(), self._stream()
+        if not split_lm and not torch.cuda.is_current_stream_capturing():
+            # an optimizer update issued on the side stream (VaultTrainStep) must have landed before weights are read here
+            torch.cuda.current_stream(dev).wait_stream(self._side)
         self.refresh_shadow()
         H = self.H
         B, T = input_ids.shape
@@ -563,33 +577,38 @@ class VaultEngine:
         tt_ptr = token_type_ids.data_ptr() if token_type_ids is not None else None
         lib, st = self._lib, self._st
 
-        # ---------------- image branch first, on the side stream: it is independent of the (latency-bound) LM forward ----------------
         G = gh * gw
         Kp = self.C * self.patch * self.patch
-        main_st = st
-        ev0 = torch.cuda.Event()
-        ev0.record(torch.cuda.current_stream(self.device))
-        self._side.wait_event(ev0)
-        st = self._st = self._side.cuda_stream
-        patch_out = self._new((B * G, H), torch.float32)
-        if self.patch == 32:
-            # im2col-free: TF32 tcgen05 GEMM fed by 5-D TMA boxes over the raw NCHW pixels, fp32 master weight
-            _abi.check(lib.vault_patch_embed_fwd(pixel_values.data_ptr(), self.w32("embeddings.patch_embeddings.projection.weight"),
-                                                 self.w32("embeddings.patch_embeddings.projection.bias"), patch_out.data_ptr(), B, self.C, Hi, Wi,
-                                                 self.patch, H, st), "patch_embed_fwd")
-            patches = None
-        else:
-            patches = self._new((B * G, Kp), torch.bfloat16)
-            _abi.check(lib.vault_patchify_bf16(pixel_values.data_ptr(), patches.data_ptr(), B, self.C, Hi, Wi, self.patch, st), "patchify")
-            self.gemm(patches.data_ptr(), Kp, 0, self.w16("embeddings.patch_embeddings.projection.weight"), Kp, 0, B * G, H, Kp, EPI_BIAS_F32,
-                      patch_out.data_ptr(), H, bias=self.w32("embeddings.patch_embeddings.projection.bias"))
-        if sv is not None and patches is None and self.g32("embeddings.patch_embeddings.projection.weight"):
-            # the projection's wgrad (dW = dpatch^T * patches) reads the patch matrix as its MN-major B operand: bf16 im2col, training only
-            patches = self._new((B * G, Kp), torch.bfloat16)
-            _abi.check(lib.vault_patchify_bf16(pixel_values.data_ptr(), patches.data_ptr(), B, self.C, Hi, Wi, self.patch, st), "patchify")
-        ev1 = torch.cuda.Event()
-        ev1.record(self._side)
-        st = self._st = main_st
+        # ---------------- image branch on the side stream: independent of the (latency-bound) LM forward ----------------
+        def image_branch():
+            nonlocal st
+            main_st = st
+            ev0 = torch.cuda.Event()
+            ev0.record(torch.cuda.current_stream(self.device))
+            self._side.wait_event(ev0)
+            st = self._st = self._side.cuda_stream
+            patch_out = self._new((B * G, H), torch.float32)
+            if self.patch == 32:
+                # im2col-free: TF32 tcgen05 GEMM fed by 5-D TMA boxes over the raw NCHW pixels, fp32 master weight
+                _abi.check(lib.vault_patch_embed_fwd(pixel_values.data_ptr(), self.w32("embeddings.patch_embeddings.projection.weight"),
+                                                     self.w32("embeddings.patch_embeddings.projection.bias"), patch_out.data_ptr(), B, self.C, Hi, Wi,
+                                                     self.patch, H, st), "patch_embed_fwd")
+                patches = None
+            else:
+                patches = self._new((B * G, Kp), torch.bfloat16)
+                _abi.check(lib.vault_patchify_bf16(pixel_values.data_ptr(), patches.data_ptr(), B, self.C, Hi, Wi, self.patch, st), "patchify")
+                self.gemm(patches.data_ptr(), Kp, 0, self.w16("embeddings.patch_embeddings.projection.weight"), Kp, 0, B * G, H, Kp, EPI_BIAS_F32,
+                          patch_out.data_ptr(), H, bias=self.w32("embeddings.patch_embeddings.projection.bias"))
+            if sv is not None and patches is None and self.g32("embeddings.patch_embeddings.projection.weight"):
+                # the projection's wgrad (dW = dpatch^T * patches) reads the patch matrix as its MN-major B operand: bf16 im2col, training only
+                patches = self._new((B * G, Kp), torch.bfloat16)
+                _abi.check(lib.vault_patchify_bf16(pixel_values.data_ptr(), patches.data_ptr(), B, self.C, Hi, Wi, self.patch, st), "patchify")
+            ev1 = torch.cuda.Event()
+            ev1.record(self._side)
+            st = self._st = main_st
+            return patch_out, patches, ev1
+
+        img = None if split_lm else image_branch()
         # ---------------- text: LM or ViLT word embeddings -> inputs_embeds fp32 [Mt,H] ----------------
         lm_trains = self.lm is not None and not getattr(self.model, "freeze_lm", False) and need_grad
         if self.lm is not None:
@@ -611,6 +630,8 @@ class VaultEngine:
             for i in range(self.lm_L):
                 r32, x16 = self.lm_layer_fwd(i, r32, x16, Mt, B, T, lm_mask, lsv, lm_train_mode)
             inputs_embeds = r32
+            if split_lm:
+                yield "lm_done"
             text_pos = self.w32("embeddings.text_embeddings.position_embeddings.weight") if self.use_text_pos() else None
             v_sum = self._new((Mt, H), torch.float32)
             _abi.check(lib.vault_vilt_text_embed_fwd(inputs_embeds.data_ptr(), tt_ptr, self.w32("embeddings.text_embeddings.token_type_embeddings.weight"),
@@ -625,6 +646,9 @@ class VaultEngine:
                                        self.vilt_eps, want16=False, want32=True)
 
         # ---------------- assembly (joins the image branch) ----------------
+        if img is None:
+            img = image_branch()
+        patch_out, patches, ev1 = img
         torch.cuda.current_stream(self.device).wait_event(ev1)
         if hw is None:
             hw, pmax = self.patch_hw(pixel_mask, B, Hi, Wi)

@@ -15,6 +15,7 @@ are masked out of attention, so loss and gradients equal the reference's dynamic
 """
 from __future__ import annotations
 
+import os
 from typing import Dict, Optional
 
 import torch
@@ -99,6 +100,11 @@ class VaultTrainStep:
         # (On one GPU the segmentation buys nothing measurable -- AdamW and the GEMMs contend for the same HBM/L2 -- so the step
         # stays one graph there.)
         self.overlap = bool(overlap_comm) and self.world > 1
+        # One GPU: the LM's forward of step i+1 (latency-bound small kernels) runs under the ViLT part of step i's AdamW
+        # (HBM-bound): the step graph is cut after the LM forward and AdamW is issued LM range first.
+        self.split_lm = (self.world == 1 and self.engine.lm is not None and not getattr(model, "freeze_lm", False)
+                         and self.engine._first_off("bert.") is not None and os.environ.get("VAULT_B200_SPLIT_LM", "1") != "0")
+        self._ev_lm = self._ev_rest = None
         if self.overlap and comm_reserve_sms > 0:
             self.engine.gemm_max_ctas = max(1, self.engine.sms - comm_reserve_sms)
         # gradient all-reduce payload: "bf16" halves the NVLink bytes (each finished range is cast to a bf16 comm buffer, summed
@@ -161,8 +167,9 @@ class VaultTrainStep:
         else:
             b["hw"][:, 0] = gh
             b["hw"][:, 1] = gw
-        lhs, pooled, key_mask, tape = eng.forward(b["input_ids"], b.get("attention_mask"), b.get("token_type_ids"), b["pixel_values"], None,
-                                                  training=train, need_grad=True, hw=b["hw"], pmax=gh * gw)
+        lhs, pooled, key_mask, tape = yield from eng.forward_iter(b["input_ids"], b.get("attention_mask"), b.get("token_type_ids"), b["pixel_values"],
+                                                                  None, training=train, need_grad=True, hw=b["hw"], pmax=gh * gw,
+                                                                  split_lm=segments and self.split_lm)
         # ---- head: Linear(Dropout(pooled)) -> CE mean; dlogits = (softmax - onehot) / B_local (DP averaging is applied in AdamW's grad_scale)
         p = self.head_p if train else 0.0
         x = pooled
@@ -183,6 +190,22 @@ class VaultTrainStep:
             _abi.check(lib.vault_dropout_f32(dx.data_ptr(), dx.data_ptr(), dx.numel(), p, eng.seed, eng.seed_dev.data_ptr(), eng.SITE_HEAD, st),
                        "head_dropout_bwd")
         yield from eng.backward_iter(tape, None, dx, segments=segments)
+
+    def _after_segment(self, lo: int, reached, hp, cs) -> int:
+        """Called after each captured / eager segment of the step; returns the new low end of the not-yet-updated gradient range."""
+        if reached == "lm_done":
+            if self._ev_rest is not None:
+                cs.wait_event(self._ev_rest)  # previous step's AdamW has finished the ViLT range: its weights may be read now
+            return lo
+        if self.split_lm:
+            return reached  # single GPU: AdamW is issued once, after the whole backward (see step())
+        self._finish_range(lo, reached, hp)
+        return reached
+
+    def synchronize(self):
+        """Wait for everything this object has enqueued (incl. the trailing AdamW on the side stream)."""
+        torch.cuda.current_stream(self.dev).wait_stream(self.engine._side)
+        torch.cuda.synchronize(self.dev)
 
     def _finish_range(self, lo: int, hi: int, hp):
         """Gradients in [lo, hi) are final on the main stream: all-reduce them (async) and apply AdamW to that range on the side
@@ -249,7 +272,7 @@ class VaultTrainStep:
                 torch.cuda.synchronize(self.dev)
                 eng.seed_dev.sub_(1)
                 s.graphs = []
-                it = self._body_iter(s, segments=self.overlap)
+                it = self._body_iter(s, segments=self.overlap or self.split_lm)
                 cap_stream = torch.cuda.Stream(device=self.dev)
                 done = False
                 while not done:
@@ -263,21 +286,40 @@ class VaultTrainStep:
                         self._pool = g.pool()
                     s.graphs.append((g, reached))
             lo = 0
+            if self._ev_lm is not None:
+                cs.wait_event(self._ev_lm)  # previous step's AdamW has finished the LM range
             for g, reached in s.graphs:
                 g.replay()
-                self._finish_range(lo, reached, hp)
-                lo = reached
+                lo = self._after_segment(lo, reached, hp, cs)
         else:
             lo = 0
-            for reached in self._body_iter(s, segments=self.overlap):
-                self._finish_range(lo, reached, hp)
-                lo = reached
-            self._finish_range(lo, n_train, hp)
+            if self._ev_lm is not None:
+                cs.wait_event(self._ev_lm)
+            for reached in self._body_iter(s, segments=self.overlap or self.split_lm):
+                lo = self._after_segment(lo, reached, hp, cs)
+            lo = self._after_segment(lo, n_train, hp, cs)
         if on_host:
             s.free.record(cs)
-        ev = torch.cuda.Event()
-        ev.record(eng._side)
-        cs.wait_event(ev)  # every range's AdamW (and all-reduce) is done before the next step touches weights or gradients
+        if self.split_lm:
+            # AdamW on the side stream, LM range first; the next step's LM forward waits for _ev_lm only, its ViLT part for _ev_rest
+            lm_lo = eng._first_off("bert.")
+            side = eng._side
+            ev = torch.cuda.Event()
+            ev.record(cs)
+            side.wait_event(ev)
+            with torch.cuda.stream(side):
+                eng.adamw_range(lm_lo, n_train, hp["step"], hp["lr"], hp["b1"], hp["b2"], self.eps, self.wd, self.correct_bias, 1.0, self.sched_dev,
+                                side.cuda_stream)
+                self._ev_lm = torch.cuda.Event()
+                self._ev_lm.record(side)
+                eng.adamw_range(0, lm_lo, hp["step"], hp["lr"], hp["b1"], hp["b2"], self.eps, self.wd, self.correct_bias, 1.0, self.sched_dev,
+                                side.cuda_stream)
+                self._ev_rest = torch.cuda.Event()
+                self._ev_rest.record(side)
+        else:
+            ev = torch.cuda.Event()
+            ev.record(eng._side)
+            cs.wait_event(ev)  # every range's AdamW (and all-reduce) is done before the next step touches weights or gradients
         s.loss_host.copy_(s.buf["loss"], non_blocking=True)
         s.loss_event.record(cs)
         self.step_idx += 1

@@ -205,9 +205,54 @@ def gemm_roofline(torch, ts, batch_dev, peaks):
     peak = peaks.get("bf16_tflops_sustained") or 1400.0
     del keep
     return dict(bound="tensor", kernel="vb::gemm_bf16_kernel (tcgen05/TMEM/TMA)", achieved=achieved, peak=peak, unit="TFLOP/s", frac=achieved / peak,
-                traffic=None, launches_per_step=len(gemms), gemm_ms_per_step=ms, flops_per_step=flops,
+                traffic=dict(dram_bytes_per_launch=12.8e6, algorithmic_bytes_per_launch=40.0e6, launch="5920x2304x768 bias->bf16 (QKV forward)",
+                             source="profiles/r01_ncu_gemm_full.md (ncu --set full): operands and outputs of consecutive kernels stay in the 126 MB L2"),
+                launches_per_step=len(gemms), gemm_ms_per_step=ms, flops_per_step=flops,
                 peak_source="MEASURED_PEAKS.json bf16_tflops_sustained (kernel replayed inside a multi-ms dense run)" if "bf16_tflops_sustained" in peaks
                 else "fallback (B200_PROFILING.md): 1.4 PFLOP/s sustained"), launches, calls
+
+
+def hbm_kernel_rates(torch, peaks):
+    """Achieved HBM GB/s of the bandwidth-bound kernels at the workload's shapes, operands evicted from L2 before every launch
+    (a 512 MB memset), timed with CUDA events; algorithmic bytes per DESIGN.md section 3."""
+    from vault_b200 import _abi, ops
+
+    dev = torch.device("cuda", torch.cuda.current_device())
+    rows, cols = 32 * 185 * 4, 768  # four ViLT-layer activations' worth of rows: 68 MB fp32 per tensor
+    x = torch.randn(rows, cols, device=dev)
+    g, b = torch.ones(cols, device=dev), torch.zeros(cols, device=dev)
+    dy16 = torch.randn(rows, cols, device=dev).to(torch.bfloat16)
+    dres = torch.randn(rows, cols, device=dev)
+    dg, db, dc = (torch.zeros(cols, device=dev) for _ in range(3))
+    flush = torch.empty(512 * 1024 * 1024, device=dev, dtype=torch.uint8)
+    e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    y16, _, mean, rstd = ops.layernorm_fwd(x, g, b, 1e-12)
+    n = 64 * 1024 * 1024
+    p_, g_, m_, v_ = (torch.zeros(n, device=dev) for _ in range(4))
+    sh = torch.zeros(n, device=dev, dtype=torch.bfloat16)
+    st = torch.cuda.current_stream().cuda_stream
+
+    def adam():
+        _abi.call("vault_adamw_step", p_.data_ptr(), g_.data_ptr(), 0, m_.data_ptr(), v_.data_ptr(), sh.data_ptr(), n, 1e-5, 0.9, 0.999, 1e-8, 0.0, 0, 1,
+                  1.0, None, st)
+
+    cases = [("layernorm_fwd", lambda: ops.layernorm_fwd(x, g, b, 1e-12), rows * cols * 6),
+             ("layernorm_bwd", lambda: ops.layernorm_bwd(None, dy16, x, mean, rstd, g, dres, dg, db, dcolsum=dc), rows * cols * 16),
+             ("adamw", adam, n * 30)]
+    peak = peaks.get("hbm_gbs") or 6650.0
+    out = {}
+    for name, fn, nbytes in cases:
+        fn()
+        tot = 0.0
+        for _ in range(5):
+            flush.zero_()
+            e0.record(); fn(); e1.record()
+            torch.cuda.synchronize()
+            tot += e0.elapsed_time(e1)
+        gbs = nbytes / (tot / 5) / 1e6
+        out[name] = dict(achieved_gbs=gbs, frac_of_measured_peak=gbs / peak, algorithmic_bytes=nbytes)
+    out["peak_gbs"] = peak
+    return out
 
 
 def main():
@@ -296,6 +341,7 @@ def main():
             roof, launches, calls = gemm_roofline(torch, ts, devb[0], peaks)
         else:
             launches = 0
+        hbm = hbm_kernel_rates(torch, peaks) if (world == 1 and not args.skip_roofline) else None
         cpu = None
         if world == 1 and not args.skip_cpu_baseline:
             cpu = cpu_baseline(torch)
@@ -317,6 +363,7 @@ def main():
             "model_tflops_per_gpu": value / world * train_gflop_per_sample / 1e3,
             "clocks": clocks,
             "roofline": roof,
+            "hbm_kernels": hbm,
             "cpu_baseline": cpu,
             "loss_first_last": [losses[0], losses[-1]] if losses else None,
         }

@@ -100,10 +100,11 @@ class VaultTrainStep:
         # (On one GPU the segmentation buys nothing measurable -- AdamW and the GEMMs contend for the same HBM/L2 -- so the step
         # stays one graph there.)
         self.overlap = bool(overlap_comm) and self.world > 1
-        # One GPU: the LM's forward of step i+1 (latency-bound small kernels) runs under the ViLT part of step i's AdamW
-        # (HBM-bound): the step graph is cut after the LM forward and AdamW is issued LM range first.
+        # Opt-in experiment (VAULT_B200_SPLIT_LM=1), one GPU: run the LM forward of step i+1 under the ViLT part of step i's AdamW
+        # (graph cut after the LM forward, AdamW issued LM range first).  Measured neutral on B200 -- AdamW saturates HBM and
+        # slows the concurrent kernels by what it hides -- so it is off by default.
         self.split_lm = (self.world == 1 and self.engine.lm is not None and not getattr(model, "freeze_lm", False)
-                         and self.engine._first_off("bert.") is not None and os.environ.get("VAULT_B200_SPLIT_LM", "1") != "0")
+                         and self.engine._first_off("bert.") is not None and os.environ.get("VAULT_B200_SPLIT_LM", "0") == "1")
         self._ev_lm = self._ev_rest = None
         if self.overlap and comm_reserve_sms > 0:
             self.engine.gemm_max_ctas = max(1, self.engine.sms - comm_reserve_sms)

@@ -227,18 +227,25 @@ def hbm_kernel_rates(torch, peaks):
     flush = torch.empty(512 * 1024 * 1024, device=dev, dtype=torch.uint8)
     e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
     y16, _, mean, rstd = ops.layernorm_fwd(x, g, b, 1e-12)
+    dx32, dx16 = torch.empty_like(x), torch.empty_like(y16)
     n = 64 * 1024 * 1024
     p_, g_, m_, v_ = (torch.zeros(n, device=dev) for _ in range(4))
     sh = torch.zeros(n, device=dev, dtype=torch.bfloat16)
     st = torch.cuda.current_stream().cuda_stream
+    lib = _abi.lib()
+
+    # outputs are preallocated and the C ABI is called directly: nothing but the kernel sits between the two events
+    def ln_fwd():
+        lib.vault_layernorm_fwd(x.data_ptr(), g.data_ptr(), b.data_ptr(), y16.data_ptr(), None, mean.data_ptr(), rstd.data_ptr(), rows, cols, 1e-12, st)
+
+    def ln_bwd():
+        lib.vault_layernorm_bwd_drop(None, dy16.data_ptr(), x.data_ptr(), mean.data_ptr(), rstd.data_ptr(), g.data_ptr(), dres.data_ptr(), dx32.data_ptr(),
+                                     dx16.data_ptr(), dg.data_ptr(), db.data_ptr(), dc.data_ptr(), rows, cols, 0.0, 0, 0.0, 0, 0, None, st)
 
     def adam():
-        _abi.call("vault_adamw_step", p_.data_ptr(), g_.data_ptr(), 0, m_.data_ptr(), v_.data_ptr(), sh.data_ptr(), n, 1e-5, 0.9, 0.999, 1e-8, 0.0, 0, 1,
-                  1.0, None, st)
+        lib.vault_adamw_step(p_.data_ptr(), g_.data_ptr(), 0, m_.data_ptr(), v_.data_ptr(), sh.data_ptr(), n, 1e-5, 0.9, 0.999, 1e-8, 0.0, 0, 1, 1.0, None, st)
 
-    cases = [("layernorm_fwd", lambda: ops.layernorm_fwd(x, g, b, 1e-12), rows * cols * 6),
-             ("layernorm_bwd", lambda: ops.layernorm_bwd(None, dy16, x, mean, rstd, g, dres, dg, db, dcolsum=dc), rows * cols * 16),
-             ("adamw", adam, n * 30)]
+    cases = [("layernorm_fwd", ln_fwd, rows * cols * 6), ("layernorm_bwd", ln_bwd, rows * cols * 16), ("adamw", adam, n * 30)]
     peak = peaks.get("hbm_gbs") or 6650.0
     out = {}
     for name, fn, nbytes in cases:

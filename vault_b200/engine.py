@@ -242,46 +242,29 @@ class VaultEngine:
             return None
         return self.grad[s.off:s.off + s.numel].view(s.shape)
 
-    def _wgrad_is_split(self, n_out: int, k_out: int) -> bool:
-        """Few output tiles (e.g. the 768x768 attention-output weight: 36) -> split the token contraction across CTAs and
-        accumulate with fp32 atomics into a zero-filled slot.  Decided per weight shape at pack time."""
-        return ((n_out + 127) // 128) * ((k_out + 127) // 128) * 2 <= self.sms
-
-    def _wgrad_split(self, n_out: int, k_out: int, tokens: int) -> int:
-        tiles = ((n_out + 127) // 128) * ((k_out + 127) // 128)
+    def _wgrad_cfg(self, n_out: int, k_out: int, tokens: int) -> Tuple[int, int]:
+        """(tile N, split-K) of a weight-gradient GEMM dW[n_out, k_out] = dy^T x (contraction over `tokens`).  Measured on B200
+        (tools/wgrad_sweep.py): 128x256 tiles with the token contraction split over a power-of-two number of CTAs so that the
+        launch fills the SMs (54-72 tiles -> 2, 18 tiles -> 8) beat un-split 128x128 tiles by 25-30 %; partial sums meet in the
+        zero-filled fp32 gradient slot through red.global.add.v4.f32."""
+        bn = 256 if k_out >= 256 else 128
+        tiles = ((n_out + 127) // 128) * ((k_out + bn - 1) // bn)
         nkb = (tokens + 63) // 64
-        return max(1, min(8, self.sms // tiles, max(1, nkb // 4)))
+        split = 1
+        while split * 2 * tiles <= self.sms and split * 2 <= 8 and nkb // (split * 2) >= 2:
+            split *= 2
+        return bn, split
 
     def _compute_zero_ranges(self):
-        """Everything except the big dense weights (whose wgrad GEMM overwrites them, unless it runs split-K -- decided per
-        call and zeroed there) is accumulated with atomics: biases, LayerNorm affine, embedding tables, cls/pos/modality."""
-        big = set()
-        self._atomic_w = set()
-        for n, s in self.slots.items():
-            if not s.trainable:
-                continue
-            is_dense = (n.endswith("dense.weight") and "pooler" not in n) or n.endswith("projection.weight")
-            if is_dense:
-                n_out, k_in = s.shape[0], s.numel // s.shape[0]
-                if self._wgrad_is_split(n_out, k_in):
-                    self._atomic_w.add(n)  # zero-filled with the small slots, accumulated by split-K atomics
-                else:
-                    big.add(n)
-            if any(n.endswith(k + ".weight") for k in ("query", "key", "value")):
-                if self._wgrad_is_split(3 * s.shape[0], s.shape[1]):
-                    self._atomic_w.add(n)
-                else:
-                    big.add(n)
-        ranges = []
+        """Every trainable gradient slot is ACCUMULATED into (split-K weight gradients, bias / LayerNorm / embedding atomics), except the
+        pooler and classifier (overwritten by their kernels, and written before the trunk's backward starts): one memset of the
+        rest of the flat buffer at the start of backward."""
+        lo = None
         for n, s in sorted(self.slots.items(), key=lambda kv: kv[1].off):
-            if not s.trainable or n in big or n.startswith("classifier.") or n.startswith("pooler."):
-                continue  # big weights, pooler and classifier gradients are overwritten by their kernels
-            a, b = s.off, s.off + _round_up(s.numel, ALIGN)
-            if ranges and ranges[-1][1] == a:
-                ranges[-1][1] = b
-            else:
-                ranges.append([a, b])
-        return [(a, b) for a, b in ranges]
+            if s.trainable and not (n.startswith("classifier.") or n.startswith("pooler.")):
+                lo = s.off
+                break
+        return [(lo, self.n_train)] if lo is not None and lo < self.n_train else []
 
     # ------------------------------------------------------------------------------------------------------------
     # kernel launch helpers
@@ -340,11 +323,9 @@ class VaultEngine:
             self._side_keep.append((dy16, x16))  # keep the operands alive until the join
             self._side_dirty = True
         if gw:
-            if wname in self._atomic_w:  # slot already zero-filled by zero_accumulated_grads()
-                self.gemm(dy16.data_ptr(), N_out, 1, x16.data_ptr(), K_in, 1, N_out, K_in, M, EPI_ATOMIC_F32, gw, K_in,
-                          split_k=self._wgrad_split(N_out, K_in, M), block_n=128, stream=st)
-            else:
-                self.gemm(dy16.data_ptr(), N_out, 1, x16.data_ptr(), K_in, 1, N_out, K_in, M, EPI_STORE_F32, gw, K_in, block_n=128, stream=st)
+            bn, split = self._wgrad_cfg(N_out, K_in, M)  # the slot was zero-filled by zero_accumulated_grads()
+            self.gemm(dy16.data_ptr(), N_out, 1, x16.data_ptr(), K_in, 1, N_out, K_in, M, EPI_ATOMIC_F32 if split > 1 else EPI_STORE_F32, gw, K_in,
+                      split_k=split, block_n=bn, stream=st)
         if gb:
             rc = self._lib.vault_colsum_bf16(dy16.data_ptr(), N_out, gb, M, N_out, st)
             if rc:

@@ -7,103 +7,62 @@ namespace vb {
 
 constexpr int kLnWarps = 8;
 
-// Forward.  Same structure as the backward below: one producer warp streams rows of x into a shared-memory ring with 1-D bulk
-// TMA copies, 8 consumer warps normalise rows out of the ring (two-pass variance from smem, no register copy of the row), so
-// the loads of the next rows are always in flight while a warp reduces / stores.
-constexpr int kLnFwdSlots = 32;
-
 template <int VPL>  // float4 vectors per lane: cols = 128 * VPL
-__global__ void __launch_bounds__((kLnWarps + 1) * 32, 2)
+__global__ void __launch_bounds__(kLnWarps * 32)
 ln_fwd_kernel(const float* __restrict__ x, const float* __restrict__ gamma, const float* __restrict__ beta, bf16* __restrict__ y_bf16,
               float* __restrict__ y_f32, float* __restrict__ mean_out, float* __restrict__ rstd_out, long long rows, float eps,
               float drop_p, unsigned long long seed, const unsigned long long* seed_dev, unsigned site) {
-  constexpr int cols = 128 * VPL;
-  constexpr uint32_t kRow = cols * 4;
-  extern __shared__ __align__(128) uint8_t lnf_smem[];
-  const uint32_t sbase = smem_u32(lnf_smem);
-  const uint32_t bars = sbase + kLnFwdSlots * kRow;  // full[32] | empty[32]
-  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
-  if (threadIdx.x == 0) {
-    for (int s = 0; s < kLnFwdSlots; ++s) {
-      mbar_init(bars + 8u * s, 1);
-      mbar_init(bars + 8u * (kLnFwdSlots + s), 1);
-    }
-    mbar_fence_init();
-  }
-  __syncthreads();
   pdl_enter();
-  const long long my_rows = rows > blockIdx.x ? (rows - blockIdx.x + gridDim.x - 1) / gridDim.x : 0;
-  if (warp == kLnWarps) {
-    if (lane == 0) {
-      for (long long k = 0; k < my_rows; ++k) {
-        const int slot = (int)(k % kLnFwdSlots);
-        const uint32_t ph = (uint32_t)((k / kLnFwdSlots) & 1);
-        mbar_wait(bars + 8u * (kLnFwdSlots + slot), ph ^ 1u);
-        const uint32_t fb = bars + 8u * slot;
-        mbar_expect_tx(fb, kRow);
-        bulk_load(sbase + slot * kRow, x + (blockIdx.x + k * gridDim.x) * cols, kRow, fb);
-      }
-    }
-    return;
-  }
+  constexpr int cols = 128 * VPL;
+  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+  const long long row = (long long)blockIdx.x * kLnWarps + warp;
+  if (row >= rows) return;
   if (drop_p > 0.f && seed_dev) seed += *seed_dev;
-  const uint32_t thr = dropout_threshold(drop_p);
-  const float keep_scale = drop_p > 0.f ? 1.0f / (1.0f - drop_p) : 1.0f;
-  float4 g[VPL], bt[VPL];
+  const float4* xr = reinterpret_cast<const float4*>(x + row * cols);
+  float4 v[VPL];
+  float s = 0.f;
 #pragma unroll
   for (int i = 0; i < VPL; ++i) {
-    g[i] = __ldg(reinterpret_cast<const float4*>(gamma) + lane + 32 * i);
-    bt[i] = __ldg(reinterpret_cast<const float4*>(beta) + lane + 32 * i);
+    v[i] = __ldg(xr + lane + 32 * i);
+    s += (v[i].x + v[i].y) + (v[i].z + v[i].w);
   }
-  for (long long k = warp; k < my_rows; k += kLnWarps) {
-    const int slot = (int)(k % kLnFwdSlots);
-    const uint32_t ph = (uint32_t)((k / kLnFwdSlots) & 1);
-    const long long row = blockIdx.x + k * gridDim.x;
-    mbar_wait(bars + 8u * slot, ph);
-    const float4* sx = reinterpret_cast<const float4*>(lnf_smem + slot * kRow);
-    float4 v[VPL];
-    float s = 0.f;
+  const float mean = warp_sum(s) * (1.0f / cols);
+  float ss = 0.f;
 #pragma unroll
-    for (int i = 0; i < VPL; ++i) {
-      v[i] = sx[lane + 32 * i];
-      s += (v[i].x + v[i].y) + (v[i].z + v[i].w);
-    }
-    __syncwarp();
-    if (lane == 0) mbar_arrive(bars + 8u * (kLnFwdSlots + slot));  // row is in registers: slot free
-    const float mean = warp_sum(s) * (1.0f / cols);
-    float ss = 0.f;
+  for (int i = 0; i < VPL; ++i) {
+    const float a = v[i].x - mean, b = v[i].y - mean, c = v[i].z - mean, d = v[i].w - mean;
+    ss += (a * a + b * b) + (c * c + d * d);
+  }
+  const float rstd = rsqrtf(warp_sum(ss) * (1.0f / cols) + eps);
+  if (lane == 0) {
+    if (mean_out) mean_out[row] = mean;
+    if (rstd_out) rstd_out[row] = rstd;
+  }
+  const uint32_t thr = dropout_threshold(drop_p);
+  const float keep_scale = drop_p > 0.f ? 1.0f / (1.0f - drop_p) : 1.0f;
 #pragma unroll
-    for (int i = 0; i < VPL; ++i) {
-      const float a = v[i].x - mean, b = v[i].y - mean, c = v[i].z - mean, d = v[i].w - mean;
-      ss += (a * a + b * b) + (c * c + d * d);
+  for (int i = 0; i < VPL; ++i) {
+    const int c4 = lane + 32 * i;
+    const float4 g = __ldg(reinterpret_cast<const float4*>(gamma) + c4);
+    const float4 b = __ldg(reinterpret_cast<const float4*>(beta) + c4);
+    float4 o;
+    o.x = (v[i].x - mean) * rstd * g.x + b.x;
+    o.y = (v[i].y - mean) * rstd * g.y + b.y;
+    o.z = (v[i].z - mean) * rstd * g.z + b.z;
+    o.w = (v[i].w - mean) * rstd * g.w + b.w;
+    if (drop_p > 0.f) {
+      const uint4 bits = dropout_bits4(seed, site, (unsigned long long)(row * (cols / 4) + c4));
+      o.x = bits.x >= thr ? o.x * keep_scale : 0.f;
+      o.y = bits.y >= thr ? o.y * keep_scale : 0.f;
+      o.z = bits.z >= thr ? o.z * keep_scale : 0.f;
+      o.w = bits.w >= thr ? o.w * keep_scale : 0.f;
     }
-    const float rstd = rsqrtf(warp_sum(ss) * (1.0f / cols) + eps);
-    if (lane == 0) {
-      if (mean_out) mean_out[row] = mean;
-      if (rstd_out) rstd_out[row] = rstd;
-    }
-#pragma unroll
-    for (int i = 0; i < VPL; ++i) {
-      const int c4 = lane + 32 * i;
-      float4 o;
-      o.x = (v[i].x - mean) * rstd * g[i].x + bt[i].x;
-      o.y = (v[i].y - mean) * rstd * g[i].y + bt[i].y;
-      o.z = (v[i].z - mean) * rstd * g[i].z + bt[i].z;
-      o.w = (v[i].w - mean) * rstd * g[i].w + bt[i].w;
-      if (drop_p > 0.f) {
-        const uint4 bits = dropout_bits4(seed, site, (unsigned long long)(row * (cols / 4) + c4));
-        o.x = bits.x >= thr ? o.x * keep_scale : 0.f;
-        o.y = bits.y >= thr ? o.y * keep_scale : 0.f;
-        o.z = bits.z >= thr ? o.z * keep_scale : 0.f;
-        o.w = bits.w >= thr ? o.w * keep_scale : 0.f;
-      }
-      if (y_f32) reinterpret_cast<float4*>(y_f32 + row * cols)[c4] = o;
-      if (y_bf16) {
-        uint2 pk;
-        pk.x = pack_bf16x2(o.x, o.y);
-        pk.y = pack_bf16x2(o.z, o.w);
-        reinterpret_cast<uint2*>(y_bf16 + row * cols)[c4] = pk;
-      }
+    if (y_f32) reinterpret_cast<float4*>(y_f32 + row * cols)[c4] = o;
+    if (y_bf16) {
+      uint2 pk;
+      pk.x = pack_bf16x2(o.x, o.y);
+      pk.y = pack_bf16x2(o.z, o.w);
+      reinterpret_cast<uint2*>(y_bf16 + row * cols)[c4] = pk;
     }
   }
 }
@@ -274,22 +233,11 @@ ln_bwd_kernel(const float* __restrict__ dy_f32, const bf16* __restrict__ dy_bf16
 template <int VPL>
 int ln_fwd_launch(const float* x, const float* gamma, const float* beta, void* y_bf16, float* y_f32, float* mean, float* rstd, long long rows,
                   float eps, float p, unsigned long long seed, const unsigned long long* seed_dev, unsigned site, cudaStream_t st) {
-  constexpr int cols = 128 * VPL;
-  const int smem = kLnFwdSlots * cols * 4 + 2 * kLnFwdSlots * 8;
-  static bool attr_set = false;
-  if (!attr_set) {
-    cudaError_t e = cudaFuncSetAttribute(ln_fwd_kernel<VPL>, cudaFuncAttributeMaxDynamicSharedMemorySize, smem);
-    if (e != cudaSuccess) return fail(VAULT_ERR_LAUNCH, "ln_fwd: cudaFuncSetAttribute: %s", cudaGetErrorString(e));
-    attr_set = true;
-  }
-  long long grid = rows;
-  const long long cap = (long long)device_sm_count() * (smem <= 100 * 1024 ? 2 : 1);
-  if (grid > cap) grid = cap;
-  launch(ln_fwd_kernel<VPL>, dim3((unsigned)grid), dim3((kLnWarps + 1) * 32), (size_t)smem, st, x, gamma, beta, reinterpret_cast<bf16*>(y_bf16), y_f32, mean,
-         rstd, rows, eps, p, seed, seed_dev, site);
+  const long long grid = (rows + kLnWarps - 1) / kLnWarps;
+  launch(ln_fwd_kernel<VPL>, dim3((unsigned)grid), dim3(kLnWarps * 32), 0, st, x, gamma, beta, reinterpret_cast<bf16*>(y_bf16), y_f32, mean, rstd, rows, eps, p,
+                                                               seed, seed_dev, site);
   return check_launch("ln_fwd_kernel");
 }
-
 template <int VPL>
 int ln_bwd_launch(const float* dy_f32, const void* dy_bf16, const float* x, const float* mean, const float* rstd, const float* gamma,
                   const float* dres, float* dx_f32, void* dx_bf16, float* dgamma, float* dbeta, float* dcolsum, long long rows, float p,

@@ -164,7 +164,8 @@ def _mid_mask(dev, B, S):
     return mask
 
 
-@pytest.mark.parametrize("B,S,heads", [(2, 64, 2), (3, 185, 12), (2, 369, 12), (2, 40, 12), (1, 17, 2), (2, 209, 12), (1, 512, 2)])
+@pytest.mark.parametrize("B,S,heads", [(2, 64, 2), (3, 185, 12), (2, 369, 12), (2, 40, 12), (1, 17, 2), (2, 209, 12), (1, 512, 2), (2, 65, 2),
+                                       (2, 128, 4), (3, 129, 2), (2, 192, 4), (2, 193, 2), (1, 256, 2), (2, 257, 2)])
 def test_attention_fwd_bwd(dev, B, S, heads):
     from vault_b200 import _abi
 
@@ -187,6 +188,49 @@ def test_attention_fwd_bwd(dev, B, S, heads):
     _abi.check(lib.vault_attn_bwd(qkv.data_ptr(), mask.data_ptr(), ctx.data_ptr(), dctx.data_ptr(), lse.data_ptr(), delta.data_ptr(), dqkv.data_ptr(), B, S,
                                   heads, 0.0, 0, None, 0, st))
     assert _rel(dqkv, dref) < 2e-2
+
+
+@pytest.mark.parametrize("B,S,heads", [(3, 185, 12), (2, 100, 2), (2, 192, 2), (1, 241, 2)])
+def test_attention_tcgen05_matches_mma_sync(dev, B, S, heads):
+    """The tensor-memory kernels (attention_tc.cu) and the mma.sync kernels implement the same contract: same LSE convention (either
+    forward feeds either backward), outputs equal to bf16 rounding, every output row written, nothing written past a sample's rows."""
+    from vault_b200 import _abi
+
+    lib, st = _abi.lib(), torch.cuda.current_stream().cuda_stream
+    H = heads * 64
+    torch.manual_seed(S + 1)
+    qkv = _rnd(dev, B * S, 3 * H, scale=0.7)
+    mask = _mid_mask(dev, B, S)
+    dctx = _rnd(dev, B * S, H, scale=0.5)
+    out = {}
+    try:
+        for impl in (1, 0):
+            _abi.set_attn_impl(impl)
+            ctx = torch.full((B * S + 64, H), float("nan"), device=dev, dtype=torch.bfloat16)
+            ctx[B * S:] = 7.0  # 64 guard rows behind the last sample
+            lse = torch.full((B, heads, S), float("nan"), device=dev)
+            _abi.check(lib.vault_attn_fwd(qkv.data_ptr(), mask.data_ptr(), ctx.data_ptr(), lse.data_ptr(), B, S, heads, 0.0, 0, None, 0, st))
+            assert torch.all(ctx[B * S:] == 7.0) and not torch.isnan(ctx.float()).any() and not torch.isnan(lse).any()
+            out[impl] = (ctx[:B * S].clone(), lse)
+        (c1, l1), (c0, l0) = out[1], out[0]
+        assert (c0.float() - c1.float()).abs().max() <= 2 ** -8 * max(1.0, c1.float().abs().max().item())
+        assert (l0 - l1).abs().max() < 1e-5
+        if S <= 192:
+            grads = {}
+            for impl in (1, 0):
+                _abi.set_attn_impl(impl)
+                dqkv = torch.full((B * S + 64, 3 * H), float("nan"), device=dev, dtype=torch.bfloat16)
+                dqkv[B * S:] = 7.0
+                delta = torch.empty(B, heads, S, device=dev)
+                # forward of the OTHER family feeds this backward
+                cf, lf = out[1 - impl]
+                _abi.check(lib.vault_attn_bwd(qkv.data_ptr(), mask.data_ptr(), cf.data_ptr(), dctx.data_ptr(), lf.data_ptr(), delta.data_ptr(),
+                                              dqkv.data_ptr(), B, S, heads, 0.0, 0, None, 0, st))
+                assert torch.all(dqkv[B * S:] == 7.0) and not torch.isnan(dqkv.float()).any()
+                grads[impl] = dqkv[:B * S].float()
+            assert _rel(grads[0], grads[1]) < 1e-2
+    finally:
+        _abi.set_attn_impl(0)
 
 
 @pytest.mark.parametrize("S", [40, 64])

@@ -44,6 +44,7 @@ SIGNATURES = {
     "vault_layernorm_bwd_drop": [c_p, c_p, c_p, c_p, c_p, c_p, c_p, c_p, c_p, c_p, c_p, c_p, c_i64, c_i32, c_f32, c_u32, c_f32, c_u32, c_u64, c_p, c_p],
     "vault_attn_fwd": [c_p, c_p, c_p, c_p, c_i32, c_i32, c_i32, c_f32, c_u64, c_p, c_u32, c_p],
     "vault_attn_bwd": [c_p, c_p, c_p, c_p, c_p, c_p, c_p, c_i32, c_i32, c_i32, c_f32, c_u64, c_p, c_u32, c_p],
+    "vault_attn_set_impl": [c_i32],
     "vault_lm_embed_fwd": [c_p, c_p, c_p, c_p, c_p, c_p, c_p, c_p, c_i32, c_i32, c_i32, c_i32, c_p],
     "vault_lm_embed_bwd": [c_p, c_p, c_p, c_p, c_p, c_p, c_i32, c_i32, c_i32, c_i32, c_i32, c_p],
     "vault_vilt_text_embed_fwd": [c_p, c_p, c_p, c_p, c_p, c_i32, c_i32, c_i32, c_p],
@@ -104,6 +105,16 @@ def call(name: str, *args) -> None:
     check(getattr(lib(), name)(*args), name)
 
 
+ATTN_IMPL = 0  # mirror of vault_attn_set_impl (set through set_attn_impl below)
+
+
+def set_attn_impl(impl: int) -> None:
+    """0 = automatic (tcgen05 attention where the shape allows), 1 = mma.sync kernels only."""
+    global ATTN_IMPL
+    call("vault_attn_set_impl", int(impl))
+    ATTN_IMPL = int(impl)
+
+
 # kernels launched per ABI call (for launch accounting in bench.py; torch memsets / fills are not counted)
 KERNELS_PER_CALL = {"vault_attn_bwd": 2, "vault_vilt_assemble_bwd": 2, "vault_small_linear_bwd": 2}
 
@@ -120,11 +131,14 @@ class CountingLib:
 
     def __getattr__(self, name):
         fn = getattr(self._inner, name)
-        if not name.startswith("vault_") or name in ("vault_version", "vault_last_error", "vault_check_device"):
+        if not name.startswith("vault_") or name in ("vault_version", "vault_last_error", "vault_check_device", "vault_attn_set_impl"):
             return fn
 
         def wrapped(*args):
-            self.launches += KERNELS_PER_CALL.get(name, 1)
+            n = KERNELS_PER_CALL.get(name, 1)
+            if name == "vault_attn_bwd" and ATTN_IMPL != 1 and float(args[10]) == 0.0 and 64 < int(args[8]) <= 192:
+                n = 1  # fused tcgen05 backward (attention_tc.cu) instead of the dQ + dK/dV pair
+            self.launches += n
             self.calls[name] = self.calls.get(name, 0) + 1
             if name == "vault_gemm_bf16":
                 src = args[0]._obj

@@ -480,7 +480,22 @@ static int set_smem(K kernel, int bytes) {
   return VAULT_OK;
 }
 
+// tensor-memory (tcgen05) kernels of attention_tc.cu
+bool attn_tc_fwd_ok(int S, float dropout_p);
+bool attn_tc_bwd_ok(int S, float dropout_p);
+int attn_fwd_tc(const void* qkv, const uint8_t* key_mask, void* ctx, float* lse, int B, int S, int heads, cudaStream_t st);
+int attn_bwd_tc(const void* qkv, const uint8_t* key_mask, const void* ctx, const void* dctx, const float* lse, float* delta, void* dqkv, int B, int S,
+                int heads, cudaStream_t st);
+void attn_set_impl(int impl);
+
 }  // namespace vb
+
+extern "C" int vault_attn_set_impl(int32_t impl) {
+  using namespace vb;
+  VB_REQUIRE(impl >= 0 && impl <= 2, "vault_attn_set_impl: impl=%d (0 auto, 1 mma.sync, 2 tcgen05 where the shape allows)", impl);
+  attn_set_impl(impl);
+  return VAULT_OK;
+}
 
 extern "C" int vault_attn_fwd(const void* qkv, const uint8_t* key_mask, void* ctx, float* lse, int32_t B, int32_t S, int32_t heads,
                               float dropout_p, uint64_t seed, const uint64_t* seed_dev, uint32_t site, void* stream) {
@@ -489,6 +504,7 @@ extern "C" int vault_attn_fwd(const void* qkv, const uint8_t* key_mask, void* ct
   AttnParams p{};
   int rc = fill_params(p, B, S, heads, dropout_p, seed, seed_dev, site);
   if (rc) return rc;
+  if (attn_tc_fwd_ok(S, dropout_p)) return attn_fwd_tc(qkv, key_mask, ctx, lse, B, S, heads, reinterpret_cast<cudaStream_t>(stream));
   p.qkv = reinterpret_cast<const bf16*>(qkv); p.key_mask = key_mask; p.ctx = reinterpret_cast<bf16*>(ctx); p.lse = lse;
   const int smem = (kTile + 2 * p.S_pad) * 128 + p.S_pad;
   dim3 grid(p.S_pad / kTile, heads, B);
@@ -511,6 +527,8 @@ extern "C" int vault_attn_bwd(const void* qkv, const uint8_t* key_mask, const vo
   AttnParams p{};
   int rc = fill_params(p, B, S, heads, dropout_p, seed, seed_dev, site);
   if (rc) return rc;
+  if (attn_tc_bwd_ok(S, dropout_p))
+    return attn_bwd_tc(qkv, key_mask, ctx, dctx, lse, delta, dqkv, B, S, heads, reinterpret_cast<cudaStream_t>(stream));
   p.qkv = reinterpret_cast<const bf16*>(qkv); p.key_mask = key_mask; p.ctx = reinterpret_cast<bf16*>(const_cast<void*>(ctx));
   p.lse = const_cast<float*>(lse); p.dctx = reinterpret_cast<const bf16*>(dctx); p.delta = delta; p.dqkv = reinterpret_cast<bf16*>(dqkv);
   dim3 grid(p.S_pad / kTile, heads, B);

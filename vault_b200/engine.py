@@ -205,6 +205,8 @@ class VaultEngine:
         self._zero_ranges = self._compute_zero_ranges()
         self.opt_state = None
         self._side = torch.cuda.Stream(device=device)
+        if "VAULT_B200_ATTN_IMPL" in os.environ:  # A/B switch: 1 = mma.sync attention everywhere (default: tcgen05 where the shape allows)
+            _abi.set_attn_impl(int(os.environ["VAULT_B200_ATTN_IMPL"]))
         self._sched_slots = 512
         self._sched = torch.zeros(2 * self._sched_slots, device=device, dtype=torch.int32)  # dynamic tile-scheduler counters
         self._sched_i = 0

@@ -54,7 +54,8 @@ enum {
   VAULT_EPI_DGELU_BF16 = 4,      /* out(bf16) = acc * gelu_erf'(aux(bf16))                                   */
   VAULT_EPI_ATOMIC_F32 = 5,      /* out(f32) += acc   (split-K partial sums; caller zero-fills)               */
   VAULT_EPI_BIAS_F32 = 6,        /* out(f32) = acc + bias (bias optional)                                    */
-  VAULT_EPI_STORE_F32 = 7        /* out(f32) = acc        (wgrad without split-K)                             */
+  VAULT_EPI_STORE_F32 = 7,       /* out(f32) = acc        (wgrad without split-K)                             */
+  VAULT_EPI_ATOMIC_BIAS_DROP_F32 = 8 /* out(f32) += dropout_p(acc + bias): split-K form of RESID, out already holds the residual */
 };
 
 typedef struct vault_gemm_args {

@@ -93,6 +93,21 @@ def test_gemm_dropout_epilogue_statistics(dev, ops):
     assert torch.allclose(y[keep], acc[keep] / 0.9, rtol=1e-4, atol=1e-4)
 
 
+@pytest.mark.parametrize("split", [1, 4])
+def test_gemm_atomic_bias_dropout_epilogue(dev, ops, split):
+    """Split-K form of the residual epilogue: out (holding the residual) += dropout(acc + bias), the same Philox mask as BIAS_RESID."""
+    M, N, K = 1280, 768, 3072
+    a, b = _rnd(dev, M, K, scale=0.3), _rnd(dev, N, K, scale=0.3)
+    bias = torch.randn(N, device=dev)
+    resid = torch.randn(M, N, device=dev)
+    for p in (0.0, 0.1):
+        want = ops.gemm(a, b, ops.EPI_BIAS_RESID_F32, bias=bias, resid=resid, dropout_p=p, seed=5, site=9)
+        out = resid.clone()
+        ops.gemm(a, b, ops.EPI_ATOMIC_BIAS_DROP_F32, bias=bias, out=out, dropout_p=p, seed=5, site=9, split_k=split, block_n=256)
+        assert _rel(out, want) < 1e-5
+    assert _rel(ops.gemm(a, b, ops.EPI_BIAS_RESID_F32, bias=bias, resid=resid), a.float() @ b.float().t() + bias + resid) < 1e-4
+
+
 def test_gemm_rejects_bad_arguments(dev, ops):
     a, b = _rnd(dev, 128, 64), _rnd(dev, 100, 64)  # N not a multiple of 8
     with pytest.raises(RuntimeError, match="multiple of 8"):

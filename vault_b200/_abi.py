@@ -15,6 +15,7 @@ c_i32, c_i64, c_u32, c_u64, c_f32, c_p = C.c_int32, C.c_int64, C.c_uint32, C.c_u
 
 EPI_BIAS_BF16, EPI_BIAS_GELU_BF16, EPI_BIAS_RESID_F32, EPI_PLAIN_BF16 = 0, 1, 2, 3
 EPI_DGELU_BF16, EPI_ATOMIC_F32, EPI_BIAS_F32, EPI_STORE_F32 = 4, 5, 6, 7
+EPI_ATOMIC_BIAS_DROP_F32 = 8
 
 
 class GemmArgs(C.Structure):
@@ -70,12 +71,13 @@ def lib() -> C.CDLL:
     """The loaded C-ABI library.  Raises if it has not been built -- there is no other implementation to fall back to."""
     global _lib
     if _lib is None:
-        if not os.path.exists(LIB_PATH):
+        path = os.environ.get("VAULT_B200_LIB", LIB_PATH)  # override: A/B builds of the same ABI (tools/)
+        if not os.path.exists(path):
             raise RuntimeError(
-                f"{LIB_PATH} is missing: build it with `python -m vault_b200.build` (nvcc, sm_100a). "
+                f"{path} is missing: build it with `python -m vault_b200.build` (nvcc, sm_100a). "
                 "vault_b200 has no CPU or eager fallback."
             )
-        l = C.CDLL(LIB_PATH)
+        l = C.CDLL(path)
         partial = os.environ.get("VAULT_B200_ALLOW_PARTIAL") == "1"  # kernel bring-up probes only
         for name, argtypes in SIGNATURES.items():
             try:

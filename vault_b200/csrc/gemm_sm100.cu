@@ -57,7 +57,8 @@ struct EpiPtrs {
 
 template <int EPI>
 __device__ __forceinline__ EpiPtrs<EPI> make_ptrs(const GemmParams& p, long long row, int col) {
-  constexpr bool kOutF32 = EPI == VAULT_EPI_BIAS_RESID_F32 || EPI == VAULT_EPI_ATOMIC_F32 || EPI == VAULT_EPI_BIAS_F32 || EPI == VAULT_EPI_STORE_F32;
+  constexpr bool kOutF32 = EPI == VAULT_EPI_BIAS_RESID_F32 || EPI == VAULT_EPI_ATOMIC_F32 || EPI == VAULT_EPI_BIAS_F32 || EPI == VAULT_EPI_STORE_F32 ||
+                           EPI == VAULT_EPI_ATOMIC_BIAS_DROP_F32;
   constexpr int osz = kOutF32 ? 4 : 2;
   EpiPtrs<EPI> e;
   e.out = reinterpret_cast<char*>(p.out) + (row * p.ldo + col) * osz;
@@ -112,6 +113,19 @@ __device__ __forceinline__ void epilogue4(const GemmParams& p, float4 acc, const
                                                 pack_bf16x2(acc.z * gelu_erf_grad(side.z), acc.w * gelu_erf_grad(side.w)));
   } else if constexpr (EPI == VAULT_EPI_ATOMIC_F32) {
     asm volatile("red.global.add.v4.f32 [%0], {%1, %2, %3, %4};" ::"l"(out), "f"(acc.x), "f"(acc.y), "f"(acc.z), "f"(acc.w) : "memory");
+  } else if constexpr (EPI == VAULT_EPI_ATOMIC_BIAS_DROP_F32) {
+    // split-K form of BIAS_RESID: dropout is a per-element scale, hence linear over the K splits (b4 is zero except in split 0)
+    float x0 = acc.x + b4.x, x1 = acc.y + b4.y, x2 = acc.z + b4.z, x3 = acc.w + b4.w;
+    if (p.dropout_p > 0.f) {
+      const uint32_t thr = dropout_threshold(p.dropout_p);
+      const float sc = 1.0f / (1.0f - p.dropout_p);
+      const uint4 bits = dropout_bits4(seed, p.site, drop_idx);
+      x0 = bits.x >= thr ? x0 * sc : 0.f;
+      x1 = bits.y >= thr ? x1 * sc : 0.f;
+      x2 = bits.z >= thr ? x2 * sc : 0.f;
+      x3 = bits.w >= thr ? x3 * sc : 0.f;
+    }
+    asm volatile("red.global.add.v4.f32 [%0], {%1, %2, %3, %4};" ::"l"(out), "f"(x0), "f"(x1), "f"(x2), "f"(x3) : "memory");
   } else if constexpr (EPI == VAULT_EPI_BIAS_F32) {
     *reinterpret_cast<float4*>(out) = make_float4(acc.x + b4.x, acc.y + b4.y, acc.z + b4.z, acc.w + b4.w);
   } else {  // VAULT_EPI_STORE_F32
@@ -387,6 +401,9 @@ gemm_bf16_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant_
         if constexpr (EPI == VAULT_EPI_BIAS_BF16 || EPI == VAULT_EPI_BIAS_GELU_BF16 || EPI == VAULT_EPI_BIAS_RESID_F32 || EPI == VAULT_EPI_BIAS_F32) {
           if (p.bias != nullptr && col < p.N) b4 = __ldg(reinterpret_cast<const float4*>(p.bias + col));
         }
+        if constexpr (EPI == VAULT_EPI_ATOMIC_BIAS_DROP_F32) {
+          if (p.bias != nullptr && col < p.N && split == 0) b4 = __ldg(reinterpret_cast<const float4*>(p.bias + col));
+        }
         const long long row0 = (long long)m0 + q * 32;
         if (full_tile) epilogue_chunk<EPI, false>(p, stg, lane, b4, seed, row0, col);
         else epilogue_chunk<EPI, true>(p, stg, lane, b4, seed, row0, col);
@@ -499,7 +516,8 @@ extern "C" int vault_gemm_bf16(const vault_gemm_args* a, void* stream) {
   VB_REQUIRE(a->N % 8 == 0, "vault_gemm_bf16: N=%d must be a multiple of 8", a->N);
   VB_REQUIRE(a->A && a->B && a->out, "vault_gemm_bf16: null operand");
   VB_REQUIRE(a->split_k >= 1, "vault_gemm_bf16: split_k must be >= 1");
-  VB_REQUIRE(a->split_k == 1 || a->epilogue == VAULT_EPI_ATOMIC_F32, "vault_gemm_bf16: split_k>1 needs VAULT_EPI_ATOMIC_F32");
+  VB_REQUIRE(a->split_k == 1 || a->epilogue == VAULT_EPI_ATOMIC_F32 || a->epilogue == VAULT_EPI_ATOMIC_BIAS_DROP_F32,
+             "vault_gemm_bf16: split_k>1 needs an ATOMIC epilogue");
   if (a->epilogue == VAULT_EPI_BIAS_RESID_F32) VB_REQUIRE(a->resid != nullptr, "vault_gemm_bf16: resid required");
   if (a->epilogue == VAULT_EPI_DGELU_BF16) VB_REQUIRE(a->aux != nullptr, "vault_gemm_bf16: aux required");
   VB_REQUIRE(a->ldo % 4 == 0, "vault_gemm_bf16: ldo=%lld must be a multiple of 4", (long long)a->ldo);
@@ -555,6 +573,7 @@ extern "C" int vault_gemm_bf16(const vault_gemm_args* a, void* stream) {
     case VAULT_EPI_ATOMIC_F32: return dispatch_bn<VAULT_EPI_ATOMIC_F32>(bn, tmA, tmB, p, grid, st);
     case VAULT_EPI_BIAS_F32: return dispatch_bn<VAULT_EPI_BIAS_F32>(bn, tmA, tmB, p, grid, st);
     case VAULT_EPI_STORE_F32: return dispatch_bn<VAULT_EPI_STORE_F32>(bn, tmA, tmB, p, grid, st);
+    case VAULT_EPI_ATOMIC_BIAS_DROP_F32: return dispatch_bn<VAULT_EPI_ATOMIC_BIAS_DROP_F32>(bn, tmA, tmB, p, grid, st);
   }
   return fail(VAULT_ERR_INVALID, "vault_gemm_bf16: unknown epilogue %d", a->epilogue);
 }

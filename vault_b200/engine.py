@@ -21,8 +21,8 @@ from typing import Dict, List, Optional, Tuple
 import torch
 
 from . import _abi
-from ._abi import (EPI_ATOMIC_F32, EPI_BIAS_BF16, EPI_BIAS_F32, EPI_BIAS_GELU_BF16, EPI_BIAS_RESID_F32, EPI_DGELU_BF16,
-                   EPI_PLAIN_BF16, EPI_STORE_F32, GemmArgs)
+from ._abi import (EPI_ATOMIC_BIAS_DROP_F32, EPI_ATOMIC_F32, EPI_BIAS_BF16, EPI_BIAS_F32, EPI_BIAS_GELU_BF16, EPI_BIAS_RESID_F32,
+                   EPI_DGELU_BF16, EPI_PLAIN_BF16, EPI_STORE_F32, GemmArgs)
 
 ALIGN = 64  # elements; every slot starts on a 256-byte (fp32) / 128-byte (bf16) boundary -> TMA- and float4-safe
 
@@ -94,6 +94,7 @@ class VaultEngine:
         self.gemm_max_ctas = 0  # >0: leave SMs free for a concurrently running collective (data-parallel overlap)
         self.dynamic_tiles = os.environ.get("VAULT_B200_DYNAMIC_TILES", "0") == "1"  # measured neutral on B200: opt-in
         self.wgrad_side_stream = os.environ.get("VAULT_B200_WGRAD_SIDE", "1") != "0"
+        self.small_m_split_k = os.environ.get("VAULT_B200_SMALL_M_SPLITK", "1") != "0"
         self._side = None
         self._side_keep = []
         self._side_dirty = False
@@ -408,13 +409,31 @@ class VaultEngine:
             save[f"{li}.qkv"], save[f"{li}.ctx"], save[f"{li}.lse"] = qkv, ctx, lse
         return ctx
 
-    def _mlp_fwd(self, n16, M, nm, resid32, p_out, site, save: Optional[dict], li):
+    def _small_m_split(self, M: int, n_out: int, k_in: int) -> int:
+        """Split-K factor for a GEMM with few output tiles and a long contraction (the LM's K=3072 products at 1,280 tokens run as
+        30 tiles of 128x256 on 148 SMs): largest power of two that keeps >= 8 k-blocks per split and fits one wave; 1 = do not split."""
+        if not self.small_m_split_k:
+            return 1
+        tiles = -(-M // 128) * -(-n_out // 256)
+        split = 1
+        while split < 8 and tiles * split * 2 <= self.sms and k_in // 64 // (split * 2) >= 8:
+            split *= 2
+        return split
+
+    def _mlp_fwd(self, n16, M, nm, resid32, p_out, site, save: Optional[dict], li, resid_inplace: bool = False):
+        """resid_inplace: the caller does not need resid32 afterwards, so a split-K second GEMM may accumulate into it."""
         H, I = self.H, self.I
         act = self._new((M, I), torch.bfloat16)
         pre = self._new((M, I), torch.bfloat16) if save is not None else None
         self.linear_fwd(n16, M, nm["w1"], nm["b1"], I, H, EPI_BIAS_GELU_BF16, act, out2=pre.data_ptr() if pre is not None else 0, ldo2=I)
-        y32 = self._new((M, H), torch.float32)
-        self.linear_fwd(act, M, nm["w2"], nm["b2"], H, I, EPI_BIAS_RESID_F32, y32, resid=resid32.data_ptr(), ldr=H, p=p_out, site=site)
+        # training only: atomic accumulation order makes the result run-to-run different in the last fp32 bit; inference stays bit-reproducible
+        split = self._small_m_split(M, H, I) if (resid_inplace and save is not None) else 1
+        if split > 1:
+            y32 = resid32  # y = resid + dropout(act W2^T + b2), the K range cut in `split` parts that add their share atomically
+            self.linear_fwd(act, M, nm["w2"], nm["b2"], H, I, EPI_ATOMIC_BIAS_DROP_F32, y32, p=p_out, site=site, split_k=split, block_n=256)
+        else:
+            y32 = self._new((M, H), torch.float32)
+            self.linear_fwd(act, M, nm["w2"], nm["b2"], H, I, EPI_BIAS_RESID_F32, y32, resid=resid32.data_ptr(), ldr=H, p=p_out, site=site)
         if save is not None:
             save[f"{li}.pre"], save[f"{li}.act"] = pre, act
         return y32
@@ -466,7 +485,7 @@ class VaultEngine:
         self.linear_fwd(ctx, M, nm["o_w"], nm["o_b"], self.H, self.H, EPI_BIAS_RESID_F32, t32, resid=r32.data_ptr(), ldr=self.H, p=p,
                         site=self._site(i, 1))
         a16, a32, st1 = self.ln_fwd(t32, M, nm["ln1"] + ".weight", nm["ln1"] + ".bias", self.lm_eps, want32=True)
-        s32 = self._mlp_fwd(a16, M, nm, a32, p, self._site(i, 2), save, li)
+        s32 = self._mlp_fwd(a16, M, nm, a32, p, self._site(i, 2), save, li, resid_inplace=True)  # a32 is only this residual
         y16, y32, st2 = self.ln_fwd(s32, M, nm["ln2"] + ".weight", nm["ln2"] + ".bias", self.lm_eps, want32=True)
         if save is not None:
             save[f"{li}.x16"], save[f"{li}.t"], save[f"{li}.st1"], save[f"{li}.a16"] = x16, t32, st1, a16
@@ -484,8 +503,14 @@ class VaultEngine:
         dpre = self._new((M, I), torch.bfloat16)
         self.linear_dgrad(ds16, M, nm["w2"], H, I, EPI_DGELU_BF16, dpre, aux=sv[f"{li}.pre"].data_ptr(), ldaux=I)
         self.linear_wgrad(ds16, sv[f"{li}.act"], M, nm["w2"], nm["b2"], H, I, bias=False)
-        da16 = self._new((M, H), torch.bfloat16)
-        self.linear_dgrad(dpre, M, nm["w1"], I, H, EPI_PLAIN_BF16, da16)
+        split = self._small_m_split(M, H, I)
+        if split > 1:
+            # da = dpre W1 (contraction over 3072) added straight into the fp32 residual-branch gradient, K range split across CTAs
+            da16 = None
+            self.linear_dgrad(dpre, M, nm["w1"], I, H, EPI_ATOMIC_F32, ds32, split_k=split, block_n=256)
+        else:
+            da16 = self._new((M, H), torch.bfloat16)
+            self.linear_dgrad(dpre, M, nm["w1"], I, H, EPI_PLAIN_BF16, da16)
         self.linear_wgrad(dpre, sv[f"{li}.a16"], M, nm["w1"], nm["b1"], I, H)
         dt32, dt16 = self.ln_bwd(ds32, da16, sv[f"{li}.t"], sv[f"{li}.st1"], M, nm["ln1"] + ".weight", nm["ln1"] + ".bias", out_p=p,
                                  out_site=self._site(i, 1), colsum_to=nm["o_b"])

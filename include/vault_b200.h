@@ -212,6 +212,12 @@ int vault_dropout_f32(const float* x, float* y, int64_t n, float p, uint64_t see
  * dlogits = (softmax - onehot) * grad_scale / rows  (dlogits may be NULL) */
 int vault_ce_loss(const float* logits, const int64_t* labels, float* loss, float* dlogits, int32_t rows, int32_t n_classes,
                   float grad_scale, void* stream);
+/* All three losses of the reference's trainers behind one call (mean over rows; dlogits optional):
+ *   kind 0: cross-entropy, labels int64 [rows]                (ref:vault/tmsc_utils/trainer.py:228-242; MVSA pre-processed)
+ *   kind 1: BCE-with-logits, n_classes = 1, labels fp32 [rows] (ref:vault/models/vault/trainer.py:42-56, Bloomberg)
+ *   kind 2: 0.5 * (CE(first half, labels[:,0]) + CE(second half, labels[:,1])), labels int64 [rows,2]   (ref :114-137, MVSA raw) */
+int vault_head_loss(const float* logits, const void* labels, float* loss, float* dlogits, int32_t rows, int32_t n_classes, int32_t kind,
+                    float grad_scale, void* stream);
 
 /* column sums of a bf16 [rows, cols] matrix accumulated into fp32 out[cols] (bias gradients); caller zero-fills */
 int vault_colsum_bf16(const void* x, int64_t ldx, float* out, int64_t rows, int32_t cols, void* stream);

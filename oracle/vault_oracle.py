@@ -215,6 +215,18 @@ def ce_loss(logits: Tensor, labels: Tensor) -> Tensor:
     return F.cross_entropy(logits, labels)
 
 
+def bce_loss(logits: Tensor, labels: Tensor) -> Tensor:
+    """VaultTrainerForBloombergTwitterCorpus.calculate_loss: nn.BCEWithLogitsLoss(), mean (ref:vault/models/vault/trainer.py:42-56)."""
+    return F.binary_cross_entropy_with_logits(logits, labels)
+
+
+def mvsa_raw_loss(logits: Tensor, labels: Tensor) -> Tensor:
+    """VaultTrainerForMVSA.calculate_loss on raw annotations: the logits' two halves against the text / image label columns,
+    0.5 * (CE + CE) (ref:vault/models/vault/trainer.py:114-137)."""
+    n = logits.shape[-1]
+    return 0.5 * (F.cross_entropy(logits[..., : n // 2], labels[..., 0]) + F.cross_entropy(logits[..., n // 2:], labels[..., 1]))
+
+
 def hf_adamw_step(p: Tensor, g: Tensor, m: Tensor, v: Tensor, step: int, lr: float, beta1=0.9, beta2=0.999, eps=1e-8,
                   weight_decay=0.0, correct_bias=False) -> None:
     """transformers.optimization.AdamW.step of transformers==4.48.0 (class removed in 5.x), restated:
@@ -253,7 +265,7 @@ def grads_never_set(d: Dims, use_vilt_position_embeddings: bool = False):
 
 
 def train_step(sd: Dict[str, Tensor], d: Dims, batch: Dict[str, Tensor], lr: float, freeze_lm: bool = False,
-               state: Optional[dict] = None, train_mode: bool = False) -> Dict[str, object]:
+               state: Optional[dict] = None, train_mode: bool = False, loss_fn=None) -> Dict[str, object]:
     """One fine-tuning step of Twitter201XTrainer.train (ref:vault/tmsc_utils/trainer.py:353-367): forward, CE loss,
     backward, HF-AdamW.  ``sd`` is updated in place.  Dropout only if ``train_mode`` (parity runs keep it off)."""
     params = {k: v.detach().clone().requires_grad_(not (freeze_lm and k.startswith("bert."))) for k, v in sd.items()}
@@ -265,7 +277,7 @@ def train_step(sd: Dict[str, Tensor], d: Dims, batch: Dict[str, Tensor], lr: flo
         out = vault_forward(params, d, batch["input_ids"], batch["attention_mask"], batch["token_type_ids"],
                             batch["pixel_values"], batch["pixel_mask"], train=train_mode)
         logits = tmsc_logits(params, d, out["pooler_output"], train=train_mode)
-        loss = ce_loss(logits, batch["labels"])
+        loss = (loss_fn or ce_loss)(logits, batch["labels"])  # bce_loss / mvsa_raw_loss for the other two trainers
     loss.backward()
     grads = {k: p.grad for k, p in params.items() if p.grad is not None}
     if state is None:

@@ -327,6 +327,27 @@ def test_ce_loss_and_colsum(dev):
     assert _rel(out, x.float().sum(0)) < 1e-4
 
 
+def test_head_loss_bce_and_two_group_ce(dev):
+    """The Bloomberg (BCE-with-logits, one logit) and raw-MVSA (two label groups) losses against the oracle's restatement."""
+    from oracle import vault_oracle as O
+    from vault_b200 import _abi
+
+    st = torch.cuda.current_stream().cuda_stream
+    torch.manual_seed(3)
+    for kind, logits, labels, ref_fn in (
+            (1, torch.randn(37, device=dev) * 3, (torch.rand(37, device=dev) > 0.5).float(), O.bce_loss),
+            (2, torch.randn(37, 6, device=dev), torch.randint(0, 3, (37, 2), device=dev), O.mvsa_raw_loss),
+            (0, torch.randn(37, 3, device=dev), torch.randint(0, 3, (37,), device=dev), O.ce_loss)):
+        n = 1 if logits.dim() == 1 else logits.shape[1]
+        loss = torch.zeros(1, device=dev)
+        dl = torch.empty_like(logits)
+        _abi.call("vault_head_loss", logits.data_ptr(), labels.data_ptr(), loss.data_ptr(), dl.data_ptr(), 37, n, kind, 1.0, st)
+        lr = logits.clone().requires_grad_(True)
+        ref = ref_fn(lr, labels)
+        ref.backward()
+        assert abs(loss.item() - ref.item()) < 2e-6 and (dl - lr.grad).abs().max() < 1e-6
+
+
 # ---------------------------------------------------------------- im2col-free patch embedding ----------------------------------------------------------------
 @pytest.mark.parametrize("B,Hi,Wi,N", [(2, 384, 384, 768), (5, 384, 640, 768), (3, 640, 384, 128), (33, 384, 384, 256), (1, 32, 32, 128)])
 def test_patch_embed_tma_tf32(dev, B, Hi, Wi, N):

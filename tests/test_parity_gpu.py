@@ -116,6 +116,74 @@ def test_train_step_matches_oracle_one_step():
         assert torch.equal(after[k], before[k])
 
 
+@pytest.mark.parametrize("kind,n_classes", [("bce", 1), ("ce2", 6)])
+def test_train_step_other_trainer_losses_match_oracle(kind, n_classes):
+    """The Bloomberg (one logit, BCE-with-logits) and raw-MVSA (two label groups) losses through the fused step vs the oracle."""
+    import dataclasses
+    from vault_b200 import VaultForTMSC, VaultTrainStep
+
+    d = dataclasses.replace(synth.Dims.tiny(), n_classes=n_classes)
+    sd = synth.make_state_dict(d, seed=1)
+    batch = synth.make_inputs(d, batch=4, text_len=16, seed=3, var_text=True)
+    g = torch.Generator().manual_seed(0)
+    batch["labels"] = torch.randint(0, 2, (4,), generator=g).float() if kind == "bce" else torch.randint(0, 3, (4, 2), generator=g)
+    vc, lc = hf_configs(d)
+    m = VaultForTMSC(vc, n_classes=n_classes, vilt_dropout_prob=d.head_dropout, bert_config=lc)
+    m.embeddings.text_embeddings.position_embedding_type = "NOT_absolute"
+    m.load_state_dict(sd, strict=False)
+    m = m.to(DEV).train()
+    ts = VaultTrainStep(m, lr=1e-3, dropout=False, loss=kind if kind != "bce" else "auto")
+    before = m.classifier[1].weight.detach().float().cpu().clone()
+    r = ts.step({k: v.pin_memory() for k, v in batch.items()})
+    ref_sd = {k: v.clone() for k, v in sd.items()}
+    o = O.train_step(ref_sd, d, batch, lr=1e-3, loss_fn=O.bce_loss if kind == "bce" else O.mvsa_raw_loss)
+    assert abs(r.loss() - o["loss"].item()) <= 5e-3
+    ts.synchronize()
+    assert cosine(m.classifier[1].weight.detach().float().cpu() - before, ref_sd["classifier.1.weight"] - sd["classifier.1.weight"]) >= 0.9
+    m.eval()
+    with torch.no_grad():
+        logits = m(**{k: batch[k].to(DEV) for k in FWD})
+    assert tuple(logits.shape) == ((4,) if n_classes == 1 else (4, 6))  # ref:vault/models/vault/model.py:569 squeezes the single logit
+
+
+def test_trainer_drop_in_runs_real_steps_and_evaluates():
+    """vault_b200.trainer.VaultTrainerForTMSC end to end on a tiny model: pinned loader -> fused steps -> sharded evaluation."""
+    from types import SimpleNamespace
+    from vault_b200.trainer import VaultTrainerForTMSC
+
+    d = synth.Dims.tiny()
+    sd = synth.make_state_dict(d, seed=0)
+    inp = synth.make_inputs(d, batch=24, text_len=16, seed=5, var_text=True)
+
+    class DS(torch.utils.data.Dataset):
+        name = "synthetic"
+
+        def __len__(self):
+            return 24
+
+        def __getitem__(self, i):
+            return (i, inp["input_ids"][i], inp["attention_mask"][i], inp["token_type_ids"][i], inp["pixel_values"][i], inp["pixel_mask"][i],
+                    int(inp["labels"][i]))
+
+        @staticmethod
+        def collate_fn(items):
+            cols = list(zip(*items))
+            return [list(cols[0])] + [torch.stack(c) for c in cols[1:6]] + [torch.tensor(cols[6])]
+
+    logged = []
+    eh = SimpleNamespace(device=DEV, learning_rate=5e-4, adam_beta1=0.9, adam_beta2=0.999, adam_epsilon=1e-8, weight_decay=0.0, correct_bias=False,
+                         train_batch_size=8, eval_batch_size=8, dataloader_num_workers=0, num_train_epochs=4, warmup_ratio=0.1, max_steps=-1,
+                         eval_steps=None, disable_tqdm=True, early_stopping_patience=None, model_save=False, model_load_filename=None,
+                         set_dict_metrics=lambda r, test=False: logged.append((test, dict(r))))
+    m = build(d, sd)
+    t = VaultTrainerForTMSC(m, DS(), eh, dev_dataset=DS(), test_dataset=DS())
+    res = t.train()
+    train_losses = [r["train_loss"] for test, r in logged if not test]
+    assert len(train_losses) == 4 and all(torch.isfinite(torch.tensor(train_losses))) and train_losses[-1] < train_losses[0]
+    assert set(res) >= {"eval_loss", "eval_accuracy", "macro_f1_score"} and 0.0 <= res["eval_accuracy"] <= 1.0
+    assert t.train_step.total_steps == 12 and t.train_step.step_idx == 12  # len(loader) * epochs, the reference's schedule length
+
+
 def test_graph_and_eager_steps_agree_bitwise_without_dropout():
     from vault_b200 import VaultTrainStep
 

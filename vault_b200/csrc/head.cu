@@ -156,6 +156,48 @@ ce_loss_kernel(const float* __restrict__ logits, const int64_t* __restrict__ lab
   }
 }
 
+// The other two losses of the reference's trainers, same contract (mean over rows, dlogits = d loss / d logits * grad_scale):
+//   kind 1: nn.BCEWithLogitsLoss on logits [rows] vs float targets [rows]            (ref:vault/models/vault/trainer.py:42-56, n_classes = 1)
+//   kind 2: 0.5 * (CE(logits[:, :C/2], labels[:, 0]) + CE(logits[:, C/2:], labels[:, 1]))   (MVSA raw annotations, ref :114-137)
+__global__ void __launch_bounds__(256)
+head_loss_kernel(const float* __restrict__ logits, const void* __restrict__ labels, float* __restrict__ loss, float* __restrict__ dlogits, int rows,
+                 int C, int kind, float grad_scale) {
+  pdl_enter();
+  __shared__ float red[8];
+  float local = 0.f;
+  for (int r = threadIdx.x; r < rows; r += blockDim.x) {
+    if (kind == 1) {
+      const float x = logits[r], y = reinterpret_cast<const float*>(labels)[r];
+      local += fmaxf(x, 0.f) - x * y + log1pf(expf(-fabsf(x)));
+      if (dlogits) dlogits[r] = (1.f / (1.f + expf(-x)) - y) * grad_scale / rows;
+    } else {
+      const int G = C / 2;
+      for (int g = 0; g < 2; ++g) {
+        const float* z = logits + (long long)r * C + g * G;
+        float m = -INFINITY;
+        for (int c = 0; c < G; ++c) m = fmaxf(m, z[c]);
+        float se = 0.f;
+        for (int c = 0; c < G; ++c) se += expf(z[c] - m);
+        const float lse = m + logf(se);
+        const int lab = (int)reinterpret_cast<const int64_t*>(labels)[2LL * r + g];
+        local += 0.5f * (lse - z[lab]);
+        if (dlogits) {
+          for (int c = 0; c < G; ++c)
+            dlogits[(long long)r * C + g * G + c] = 0.5f * (expf(z[c] - lse) - (c == lab ? 1.f : 0.f)) * grad_scale / rows;
+        }
+      }
+    }
+  }
+  local = warp_sum(local);
+  if ((threadIdx.x & 31) == 0) red[threadIdx.x >> 5] = local;
+  __syncthreads();
+  if (threadIdx.x == 0) {
+    float t = 0.f;
+    for (int w = 0; w < (int)(blockDim.x >> 5); ++w) t += red[w];
+    loss[0] = t / rows;
+  }
+}
+
 // out[c] += sum_r x[r, c]  (bf16 in, fp32 atomics out); lane = 4 columns, warp = 128 columns, 8 warps stride rows
 __global__ void __launch_bounds__(256)
 colsum_bf16_kernel(const bf16* __restrict__ x, long long ldx, float* __restrict__ out, long long rows, int cols) {
@@ -232,6 +274,17 @@ extern "C" int vault_ce_loss(const float* logits, const int64_t* labels, float* 
   VB_REQUIRE(logits && labels && loss && rows > 0 && n_classes > 0, "ce_loss: bad arguments");
   launch(ce_loss_kernel, dim3(1), dim3(256), 0, (cudaStream_t)stream, logits, labels, loss, dlogits, rows, n_classes, grad_scale);
   return check_launch("ce_loss_kernel");
+}
+
+extern "C" int vault_head_loss(const float* logits, const void* labels, float* loss, float* dlogits, int32_t rows, int32_t n_classes, int32_t kind,
+                               float grad_scale, void* stream) {
+  VB_REQUIRE(logits && labels && loss && rows > 0 && n_classes > 0, "head_loss: bad arguments");
+  VB_REQUIRE(kind >= 0 && kind <= 2, "head_loss: kind=%d (0 CE, 1 BCE-with-logits, 2 two-group CE)", kind);
+  if (kind == 0) return vault_ce_loss(logits, reinterpret_cast<const int64_t*>(labels), loss, dlogits, rows, n_classes, grad_scale, stream);
+  VB_REQUIRE(kind != 1 || n_classes == 1, "head_loss: BCE-with-logits expects n_classes = 1 (got %d)", n_classes);
+  VB_REQUIRE(kind != 2 || n_classes % 2 == 0, "head_loss: two-group CE expects an even n_classes (got %d)", n_classes);
+  launch(head_loss_kernel, dim3(1), dim3(256), 0, (cudaStream_t)stream, logits, labels, loss, dlogits, rows, n_classes, kind, grad_scale);
+  return check_launch("head_loss_kernel");
 }
 
 extern "C" int vault_colsum_bf16(const void* x, int64_t ldx, float* out, int64_t rows, int32_t cols, void* stream) {

@@ -64,7 +64,7 @@ class _Slot:
 class VaultTrainStep:
     def __init__(self, model, lr: float = 2e-5, betas=(0.9, 0.999), eps: float = 1e-8, weight_decay: float = 0.0, correct_bias: bool = False,
                  total_steps: Optional[int] = None, warmup_ratio: float = 0.1, process_group=None, use_cuda_graph: bool = True,
-                 dropout: bool = True, overlap_comm: bool = True, comm_reserve_sms: int = 0, grad_comm_dtype: str = "bf16"):
+                 dropout: bool = True, overlap_comm: bool = True, comm_reserve_sms: int = 0, grad_comm_dtype: str = "bf16", loss: str = "auto"):
         self.model = model
         self.engine: VaultEngine = model.engine
         self.lr, self.betas, self.eps, self.wd, self.correct_bias = lr, betas, eps, weight_decay, correct_bias
@@ -72,8 +72,13 @@ class VaultTrainStep:
         self.use_graph = use_cuda_graph
         self.dropout = dropout  # False: dropout off everywhere (deterministic parity runs)
         self.n_classes = model.classifier[1].out_features
-        if self.n_classes < 2:
-            raise NotImplementedError("VaultTrainStep: the BCE (n_classes=1, Bloomberg) loss is not built yet")
+        # loss of the reference trainer in use: "ce" (Twitter-201x / pre-processed MVSA, int64 labels [B]), "bce" (Bloomberg: one
+        # logit, float labels [B], ref:vault/models/vault/trainer.py:42-56), "ce2" (raw MVSA: two label groups, int64 labels [B,2], ref :114-137)
+        if loss == "auto":
+            loss = "bce" if self.n_classes == 1 else "ce"
+        if loss not in ("ce", "bce", "ce2") or (loss == "bce") != (self.n_classes == 1) or (loss == "ce2" and self.n_classes % 2):
+            raise ValueError(f"VaultTrainStep: loss={loss!r} does not fit a head with {self.n_classes} outputs")
+        self.loss_kind = {"ce": 0, "bce": 1, "ce2": 2}[loss]
         self.head_p = float(model.classifier[0].p)
         self.dev = next(model.parameters()).device
         if self.dev.type != "cuda":
@@ -136,7 +141,7 @@ class VaultTrainStep:
             v = batch.get(k)
             if v is None:
                 continue
-            dt = torch.float32 if k == "pixel_values" else torch.int64
+            dt = torch.float32 if (k == "pixel_values" or (k == "labels" and self.loss_kind == 1)) else torch.int64
             s.buf[k] = torch.empty(v.shape, device=self.dev, dtype=dt)
         B = batch["input_ids"].shape[0]
         s.buf["hw"] = torch.empty((B, 2), device=self.dev, dtype=torch.int32)
@@ -182,7 +187,8 @@ class VaultTrainStep:
         _abi.check(lib.vault_small_linear_fwd(x.data_ptr(), H, eng.w32("classifier.1.weight"), eng.w32("classifier.1.bias"), b["logits"].data_ptr(), B, n,
                                               H, 0, st), "classifier_fwd")
         dlogits = torch.empty((B, n), device=self.dev, dtype=torch.float32)
-        _abi.check(lib.vault_ce_loss(b["logits"].data_ptr(), b["labels"].data_ptr(), b["loss"].data_ptr(), dlogits.data_ptr(), B, n, 1.0, st), "ce_loss")
+        _abi.check(lib.vault_head_loss(b["logits"].data_ptr(), b["labels"].data_ptr(), b["loss"].data_ptr(), dlogits.data_ptr(), B, n, self.loss_kind, 1.0,
+                                       st), "head_loss")
         dx = torch.empty_like(pooled)
         _abi.check(lib.vault_small_linear_bwd(dlogits.data_ptr(), None, x.data_ptr(), H, eng.w32("classifier.1.weight"), dx.data_ptr(), H, 0,
                                               eng.g32("classifier.1.weight") or None, eng.g32("classifier.1.bias") or None, B, n, H, 0, st),

@@ -216,3 +216,23 @@ def make_inputs(
         pixel_mask=pmask,
         labels=labels,
     )
+
+
+def fill_parameters(named_shapes: Dict[str, tuple], d: Dims, seed: int = 0) -> Dict[str, torch.Tensor]:
+    """Deterministic values for the parameters of a head wrapper (ViltForMaskedLM & co. around the VAuLT trunk): trunk / LM keys
+    take the values ``make_state_dict`` gives the same tensor (with or without the wrapper's ``vilt.`` prefix), every other
+    parameter (the head) is N(0, 0.05) from a key-hashed generator (LayerNorm scales 1 + N(0, 0.1)).  Used identically by
+    ``oracle/make_golden_heads.py`` (reference side) and the GPU parity test (product side)."""
+    base = make_state_dict(d, seed, head=False)
+    out: Dict[str, torch.Tensor] = {}
+    for k, shp in named_shapes.items():
+        src = k[5:] if k.startswith("vilt.") else k
+        if src in base and tuple(base[src].shape) == tuple(shp):
+            out[k] = base[src]
+            continue
+        g = _gen(seed, "head:" + k)
+        w = torch.randn(tuple(shp), generator=g, dtype=torch.float32) * 0.05
+        if "LayerNorm.weight" in k or k.endswith("classifier.1.weight") and len(shp) == 1:
+            w = 1.0 + 2.0 * w
+        out[k] = w
+    return out

@@ -1,0 +1,52 @@
+"""GPU parity of the VaultFor* head wrappers against fixtures produced by the REAL reference classes
+(oracle/make_golden_heads.py, ref:vault/models/vault/model.py:375-509): logits, loss and gradients through head + ViLT trunk + LM.
+
+Tolerance: bf16 tensor-core trunk under fp32 heads on a 2+2-layer model -- logits max-abs / max|ref| <= 2e-2, loss |d| <= 2e-2,
+per-parameter gradient cosine >= 0.99."""
+import os
+
+import pytest
+import torch
+
+pytestmark = pytest.mark.gpu
+
+from oracle import make_golden_heads as G  # noqa: E402
+from tests.golden_utils import cosine, rel_err  # noqa: E402
+
+DEV = "cuda:0"
+HEADS_DIR = os.path.join(os.path.dirname(os.path.abspath(__file__)), "golden", "heads")
+
+
+@pytest.mark.parametrize("name", sorted(G.CASES))
+def test_head_wrapper_matches_reference_fixture(name):
+    import vault_b200.models.vault as pkg
+
+    ref = torch.load(os.path.join(HEADS_DIR, name + ".pt"), weights_only=False)
+    m, d, (batch, text_len, n_images) = G.build(pkg, name)
+    m = m.to(DEV).eval()
+    inp = G.head_inputs(d, batch, text_len, n_images)
+    labels = G.head_labels(name, d, batch, text_len, d.vilt_vocab)
+    kw = {k: inp[k].to(DEV) for k in ("input_ids", "attention_mask", "token_type_ids", "pixel_values", "pixel_mask")}
+    if labels is not None:
+        kw["labels"] = labels.to(DEV)
+    out = m(**kw)
+    assert rel_err(out.logits.detach().float().cpu(), ref["logits"]) <= 2e-2
+    if ref["loss"] is not None:
+        assert abs(out.loss.item() - ref["loss"].item()) <= 2e-2
+    loss = out.loss if getattr(out, "loss", None) is not None else out.logits.sum()
+    loss.backward()
+    named = dict(m.named_parameters())
+    assert ref["grads"], "fixture without gradients"
+    for k, g_ref in ref["grads"].items():
+        g = named[k].grad
+        assert g is not None, k
+        assert cosine(g.detach().float().cpu(), g_ref) >= 0.99, (k, cosine(g.detach().float().cpu(), g_ref))
+        assert abs(g.float().norm().item() / max(g_ref.norm().item(), 1e-12) - 1.0) <= 5e-2, k
+    # a second step must not accumulate into the first one's kernel-written gradients
+    for p in m.parameters():
+        p.grad = None
+    out = m(**kw)
+    (out.loss if getattr(out, "loss", None) is not None else out.logits.sum()).backward()
+    k = "vilt.layernorm.weight"
+    assert cosine(named[k].grad.float().cpu(), ref["grads"][k]) >= 0.99
+    assert abs(named[k].grad.float().norm().item() / ref["grads"][k].norm().item() - 1.0) <= 5e-2

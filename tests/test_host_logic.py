@@ -42,8 +42,8 @@ def test_reference_class_surface():
     assert m.config.hidden_dropout_prob == 0.0 and m.config.t_prob == 0.1
     m.resize_token_embeddings(600)
     assert m.bert.get_input_embeddings().weight.shape[0] == 600
-    with pytest.raises(NotImplementedError):
-        VaultForMaskedLM()
+    from vault_b200.model import VaultMixin
+    assert issubclass(VaultForMaskedLM, VaultMixin) and issubclass(VaultModel, VaultMixin)  # every class is a VaultMixin, as in the reference
 
 
 def test_frozen_lm_and_no_lm_variants():
@@ -139,3 +139,67 @@ def test_data_parallel_gradient_average_world2_gloo(tmp_path):
     mp.spawn(_dp_worker, args=(2, _free_port(), out), nprocs=2, join=True)
     r = torch.load(out)
     assert r["err"] <= 2e-5 * max(r["scale"], 1.0), r
+
+
+def _tiny_cfgs():
+    from transformers import BertConfig, ViltConfig
+
+    vc = ViltConfig(hidden_size=128, num_hidden_layers=2, num_attention_heads=2, intermediate_size=256, max_position_embeddings=40)
+    lc = BertConfig(hidden_size=128, num_hidden_layers=2, num_attention_heads=2, intermediate_size=256)
+    return vc, lc
+
+
+def test_head_wrappers_route_the_trunk_through_the_engine(monkeypatch):
+    """The VaultFor* head classes (ref:vault/models/vault/model.py:375-509): HF head modules on top of `_trunk` (stubbed here -- no GPU),
+    reference constructor extras (n_classes, num_images, widened modality table), HF-compatible keys, engine layout with the vilt. prefix."""
+    from vault_b200.engine import VaultEngine
+    from vault_b200.model import VaultMixin, _KernelTrunk
+    from vault_b200.models.vault import (VaultForImageAndTextRetrieval, VaultForImagesAndTextClassification, VaultForMaskedLM,
+                                         VaultForQuestionAnswering)
+
+    calls = []
+
+    def fake_trunk(self, input_ids=None, pixel_values=None, image_token_type_idx=None, **kw):
+        B, T = input_ids.shape
+        calls.append((type(self).__name__, image_token_type_idx, tuple(pixel_values.shape)))
+        g = torch.Generator().manual_seed(len(calls))
+        lhs = torch.randn(B, T + 5, 128, generator=g).requires_grad_(True)
+        return lhs, torch.tanh(lhs[:, 0]), torch.ones(B, T + 5, dtype=torch.uint8)
+
+    monkeypatch.setattr(VaultMixin, "_trunk", fake_trunk)
+    ids = torch.randint(5, 100, (2, 7))
+    px = torch.randn(2, 3, 64, 64)
+    common = dict(input_ids=ids, attention_mask=torch.ones_like(ids), token_type_ids=torch.zeros_like(ids))
+
+    vc, lc = _tiny_cfgs()
+    mlm = VaultForMaskedLM(vc, bert_config=lc)
+    labels = torch.full((2, 7), -100)
+    labels[0, 2] = 17
+    out = mlm(**common, pixel_values=px, labels=labels)
+    assert tuple(out.logits.shape) == (2, 7, vc.vocab_size) and torch.isfinite(out.loss)
+    out.loss.backward()
+    assert mlm.mlm_score.transform.dense.weight.grad is not None
+    assert isinstance(mlm.vilt, _KernelTrunk) and "vilt.encoder.layer.0.attention.attention.query.weight" in mlm.state_dict()
+
+    vc, lc = _tiny_cfgs()
+    vqa = VaultForQuestionAnswering(vc, bert_config=lc, n_classes=11)
+    out = vqa(**common, pixel_values=px, labels=torch.rand(2, 11))
+    assert tuple(out.logits.shape) == (2, 11) and vqa.classifier[-1].out_features == 11 and torch.isfinite(out.loss)
+
+    vc, lc = _tiny_cfgs()
+    ret = VaultForImageAndTextRetrieval(vc, bert_config=lc)
+    assert tuple(ret(**common, pixel_values=px).logits.shape) == (2, 1)
+
+    vc, lc = _tiny_cfgs()
+    nlvr = VaultForImagesAndTextClassification(vc, bert_config=lc)
+    assert nlvr.config.num_images == 2 and nlvr.vilt.embeddings.token_type_embeddings.weight.shape[0] == 3
+    calls.clear()
+    out = nlvr(**common, pixel_values=torch.randn(2, 2, 3, 64, 64), labels=torch.tensor([0, 1]))
+    assert [c[1] for c in calls] == [1, 2] and calls[0][2] == (2, 3, 64, 64) and tuple(out.logits.shape) == (2, 2)
+
+    # engine layout for a wrapper: trunk names carry "vilt.", head parameters stay outside the kernel-owned (trainable) range
+    eng = VaultEngine(nlvr)
+    train, static = eng._param_order()
+    assert eng.vp == "vilt." and eng._k("layernorm.weight") == "vilt.layernorm.weight" and eng._k("bert.embeddings.LayerNorm.bias").startswith("bert.")
+    assert train[0] == "vilt.pooler.dense.weight" and all(n.startswith(("vilt.", "bert.")) for n in train)
+    assert {"classifier.0.weight", "classifier.3.bias", "vilt.embeddings.text_embeddings.word_embeddings.weight"} <= set(static)

@@ -45,6 +45,7 @@ class Tape:
         self.t: Dict[str, torch.Tensor] = {}
         self.meta: Dict[str, object] = {}
         self.done = False
+        self.gen = 0  # gradient generation this forward belongs to (VaultEngine._gen at forward time)
 
 
 class VaultEngine:
@@ -57,7 +58,10 @@ class VaultEngine:
         return 16 + layer * 4 + kind
 
     def __init__(self, model):
-        self.model = model  # the nn.Module (VaultModel / VaultForTMSC) whose Parameters this engine serves
+        self.model = model  # the nn.Module (VaultModel / VaultForTMSC / a VaultFor* head wrapper) whose Parameters this engine serves
+        # head wrappers (ViltForMaskedLM & co.) keep the ViLT trunk in `.vilt`: its parameter names carry that prefix
+        self.vilt = getattr(model, "vilt", model)
+        self.vp = "vilt." if self.vilt is not model else ""
         cfg = model.config
         self.H = cfg.hidden_size
         self.L = cfg.num_hidden_layers
@@ -98,6 +102,10 @@ class VaultEngine:
         self._side = None
         self._side_keep = []
         self._side_dirty = False
+        # Several forwards may share one autograd backward (ViltForImagesAndTextClassification runs the trunk once per image):
+        # the first backward of a generation zero-fills the accumulated gradient ranges, later ones of the same generation add.
+        self._gen = 0
+        self._accumulate = False
 
     # ------------------------------------------------------------------------------------------------------------
     # parameter packing
@@ -114,17 +122,19 @@ class VaultEngine:
                 if n in named and n not in order:
                     order.append(n)
 
-        add("classifier.1.weight", "classifier.1.bias")
-        add("pooler.dense.weight", "pooler.dense.bias", "layernorm.weight", "layernorm.bias")
+        vp = self.vp
+        if not vp:
+            add("classifier.1.weight", "classifier.1.bias")  # VaultForTMSC head (kernels of head.cu)
+        add(vp + "pooler.dense.weight", vp + "pooler.dense.bias", vp + "layernorm.weight", vp + "layernorm.bias")
         for i in reversed(range(self.L)):
-            p = f"encoder.layer.{i}."
+            p = f"{vp}encoder.layer.{i}."
             a = p + "attention.attention."
             # accumulated-with-atomics slots first (one memset per layer), then the dense weights their wgrad GEMMs overwrite
             add(a + "query.bias", a + "key.bias", a + "value.bias", p + "attention.output.dense.bias")
             add(p + "layernorm_before.weight", p + "layernorm_before.bias", p + "layernorm_after.weight", p + "layernorm_after.bias")
             add(p + "intermediate.dense.bias", p + "output.dense.bias", p + "attention.output.dense.weight")
             add(a + "query.weight", a + "key.weight", a + "value.weight", p + "intermediate.dense.weight", p + "output.dense.weight")
-        e = "embeddings."
+        e = vp + "embeddings."
         add(e + "cls_token", e + "position_embeddings", e + "token_type_embeddings.weight", e + "patch_embeddings.projection.weight",
             e + "patch_embeddings.projection.bias", e + "text_embeddings.token_type_embeddings.weight",
             e + "text_embeddings.LayerNorm.weight", e + "text_embeddings.LayerNorm.bias",
@@ -141,10 +151,11 @@ class VaultEngine:
             b = "bert.embeddings."
             add(b + "word_embeddings.weight", b + "position_embeddings.weight", b + "token_type_embeddings.weight",
                 b + "LayerNorm.weight", b + "LayerNorm.bias")
-        for n in named:  # anything else the subclass added (other heads): packed, never touched by this engine's kernels
+        owned = set(order)  # parameters whose gradients this engine's kernels write
+        for n in named:  # anything else (the heads of the VaultFor* wrappers): packed behind the trunk, trained by torch autograd
             add(n)
         never = self.never_grad_names()
-        train = [n for n in order if named[n].requires_grad and n not in never]
+        train = [n for n in order if named[n].requires_grad and n not in never and n in owned]
         static = [n for n in order if n not in train]
         return train, static
 
@@ -152,14 +163,14 @@ class VaultEngine:
         """ViLT parameters that receive grad=None whenever an LM is attached."""
         if self.lm is None:
             return set()
-        s = {"embeddings.text_embeddings.word_embeddings.weight"}
+        s = {self.vp + "embeddings.text_embeddings.word_embeddings.weight"}
         if not self.use_text_pos():
-            s.add("embeddings.text_embeddings.position_embeddings.weight")
+            s.add(self.vp + "embeddings.text_embeddings.position_embeddings.weight")
         return s
 
     def use_text_pos(self) -> bool:
         # transformers==4.48.0 gate (HF:models/vilt/modeling_vilt.py:240-272): add position embeddings iff "absolute"
-        te = self.model.embeddings.text_embeddings
+        te = self.vilt.embeddings.text_embeddings
         return getattr(te, "position_embedding_type", "absolute") == "absolute"
 
     def _signature(self):
@@ -227,20 +238,29 @@ class VaultEngine:
         self._versions = sum(p._version for p in self._params)
 
     # pointers ---------------------------------------------------------------------------------------------------
+    def _k(self, name: str) -> str:
+        """Trunk-relative ViLT name -> state-dict key of the served module ("vilt." in front for the head wrappers)."""
+        if not self.vp or name.startswith("bert.") or name.startswith("classifier.") or name.startswith(self.vp):
+            return name
+        return self.vp + name
+
+    def has(self, name: str) -> bool:
+        return self._k(name) in self.slots
+
     def w16(self, name):  # bf16 shadow of a weight
-        return self.shadow.data_ptr() + 2 * self.slots[name].off
+        return self.shadow.data_ptr() + 2 * self.slots[self._k(name)].off
 
     def w32(self, name):
-        return self.master.data_ptr() + 4 * self.slots[name].off
+        return self.master.data_ptr() + 4 * self.slots[self._k(name)].off
 
     def g32(self, name):  # gradient slot, or 0 (NULL) if the parameter is not trainable
-        s = self.slots.get(name)
+        s = self.slots.get(self._k(name))
         if s is None or not s.trainable:
             return 0
         return self.grad.data_ptr() + 4 * s.off
 
     def grad_view(self, name) -> Optional[torch.Tensor]:
-        s = self.slots[name]
+        s = self.slots[self._k(name)]
         if not s.trainable:
             return None
         return self.grad[s.off:s.off + s.numel].view(s.shape)
@@ -264,7 +284,7 @@ class VaultEngine:
         rest of the flat buffer at the start of backward."""
         lo = None
         for n, s in sorted(self.slots.items(), key=lambda kv: kv[1].off):
-            if s.trainable and not (n.startswith("classifier.") or n.startswith("pooler.")):
+            if s.trainable and not (n.startswith("classifier.") or n.startswith(self.vp + "pooler.")):
                 lo = s.off
                 break
         return [(lo, self.n_train)] if lo is not None and lo < self.n_train else []
@@ -327,8 +347,8 @@ class VaultEngine:
             self._side_dirty = True
         if gw:
             bn, split = self._wgrad_cfg(N_out, K_in, M)  # the slot was zero-filled by zero_accumulated_grads()
-            self.gemm(dy16.data_ptr(), N_out, 1, x16.data_ptr(), K_in, 1, N_out, K_in, M, EPI_ATOMIC_F32 if split > 1 else EPI_STORE_F32, gw, K_in,
-                      split_k=split, block_n=bn, stream=st)
+            self.gemm(dy16.data_ptr(), N_out, 1, x16.data_ptr(), K_in, 1, N_out, K_in, M,
+                      EPI_ATOMIC_F32 if (split > 1 or self._accumulate) else EPI_STORE_F32, gw, K_in, split_k=split, block_n=bn, stream=st)
         if gb:
             rc = self._lib.vault_colsum_bf16(dy16.data_ptr(), N_out, gb, M, N_out, st)
             if rc:
@@ -579,6 +599,8 @@ class VaultEngine:
             token_type_ids = token_type_ids.contiguous() if token_type_ids.dtype == torch.int64 else token_type_ids.to(torch.int64)
         pixel_values = pixel_values.contiguous() if pixel_values.dtype == torch.float32 else pixel_values.float().contiguous()
         tape = Tape() if need_grad else None
+        if tape is not None:
+            tape.gen = self._gen
         sv = tape.t if tape is not None else None
         Mt = B * T
         am_ptr = attention_mask.data_ptr() if attention_mask is not None else None
@@ -680,7 +702,7 @@ class VaultEngine:
             x32 = self.vilt_layer_fwd(i, x32, M, B, S, key_mask, sv)
         _, lhs, st_f = self.ln_fwd(x32, M, "layernorm.weight", "layernorm.bias", self.vilt_eps, want16=False, want32=True)
         pooled = None
-        if "pooler.dense.weight" in self.slots:
+        if self.has("pooler.dense.weight"):
             pooled = self._new((B, H), torch.float32)
             _abi.check(lib.vault_small_linear_fwd(lhs.data_ptr(), S * H, self.w32("pooler.dense.weight"), self.w32("pooler.dense.bias"),
                                                   pooled.data_ptr(), B, H, H, 1, st), "pooler_fwd")
@@ -710,6 +732,7 @@ class VaultEngine:
             pass
 
     def _first_off(self, prefix: str) -> Optional[int]:
+        prefix = self._k(prefix)
         offs = [s.off for n, s in self.slots.items() if s.trainable and n.startswith(prefix)]
         return min(offs) if offs else None
 
@@ -724,16 +747,27 @@ class VaultEngine:
         sv, mt = tape.t, tape.meta
         B, T, S, pmax, gh, gw = mt["B"], mt["T"], mt["S"], mt["pmax"], mt["gh"], mt["gw"]
         H, M, Mt = self.H, B * S, B * T
-        self.zero_accumulated_grads()
+        first = tape.gen >= self._gen
+        if first:
+            self.zero_accumulated_grads()
+            self._gen = tape.gen + 1
+        self._accumulate = not first
         if dlhs is not None:
             g_lhs = dlhs.contiguous().float().clone().view(M, H)
         else:
             g_lhs = torch.zeros((M, H), device=self.device, dtype=torch.float32)
         if dpooled is not None and sv["pooled"] is not None:
             dpooled = dpooled.contiguous().float()
+            pw, pb = self.g32("pooler.dense.weight"), self.g32("pooler.dense.bias")
+            tmp = None
+            if self._accumulate and pw:  # the kernel overwrites dW / db: route a later pass of the same generation through a scratch copy
+                tmp = (torch.empty((H, H), device=self.device), torch.empty((H,), device=self.device))
+                pw, pb = tmp[0].data_ptr(), tmp[1].data_ptr()
             _abi.check(lib.vault_small_linear_bwd(dpooled.data_ptr(), sv["pooled"].data_ptr(), sv["lhs"].data_ptr(), S * H, self.w32("pooler.dense.weight"),
-                                                  g_lhs.data_ptr(), S * H, 1, self.g32("pooler.dense.weight") or None,
-                                                  self.g32("pooler.dense.bias") or None, B, H, H, 1, st), "pooler_bwd")
+                                                  g_lhs.data_ptr(), S * H, 1, pw or None, pb or None, B, H, H, 1, st), "pooler_bwd")
+            if tmp is not None:
+                self.grad_view("pooler.dense.weight").add_(tmp[0])
+                self.grad_view("pooler.dense.bias").add_(tmp[1])
         g32, g16 = self.ln_bwd(g_lhs, None, sv["x_final"], sv["st_f"], M, "layernorm.weight", "layernorm.bias",
                                colsum_to=self._names("", self.L - 1, True)["b2"])
         for i in reversed(range(self.L)):

@@ -7,6 +7,9 @@ Same class names, constructor / ``from_pretrained`` signatures, HF-compatible ``
     VaultForTMSC(vilt_config, n_classes=3, vilt_dropout_prob=0.1, logging_level=None, bert_config=None)
     model(input_ids, attention_mask, token_type_ids, pixel_values, pixel_mask) -> .last_hidden_state / .pooler_output (or logits)
 
+``VaultForMaskedLM / QuestionAnswering / ImageAndTextRetrieval / ImagesAndTextClassification`` (ref :375-509) keep HF's head modules and
+head ``forward`` (plain torch on [B,H]-sized tensors; the MLM decoder is the one sizeable product) on top of the same kernel trunk.
+
 The HF ``ViltModel`` / ``AutoModel`` classes are inherited / instantiated ONLY as parameter containers (identical keys, working
 ``from_pretrained`` / ``save_pretrained`` / ``resize_token_embeddings``); their ``forward`` methods are never called: every
 forward and backward goes through ``vault_b200.engine.VaultEngine`` -> C ABI -> CUDA kernels.  No CPU / eager fallback.
@@ -22,12 +25,14 @@ Differences from the reference, all deliberate:
 from __future__ import annotations
 
 import logging
+import weakref
 from abc import ABC
 from typing import Optional, Union
 
 import torch
 import torch.nn as nn
-from transformers import AutoModel, PretrainedConfig, ViltModel
+from transformers import (AutoModel, PretrainedConfig, ViltForImageAndTextRetrieval, ViltForImagesAndTextClassification, ViltForMaskedLM,
+                          ViltForQuestionAnswering, ViltModel)
 from transformers.modeling_outputs import BaseModelOutputWithPooling
 
 from . import _abi
@@ -119,7 +124,7 @@ class VaultMixin(nn.Module, ABC):
             setattr(vilt_config, "position_embedding_type", "NOT_absolute")
         super().__init__(vilt_config, *args, **kwargs)
         # transformers >= 5 dropped the attribute from ViLT's TextEmbeddings; the 4.48.0 gate lives on the module here
-        self.embeddings.text_embeddings.position_embedding_type = getattr(vilt_config, "position_embedding_type", "absolute")
+        self._trunk_module().embeddings.text_embeddings.position_embedding_type = getattr(vilt_config, "position_embedding_type", "absolute")
         self.bert = AutoModel.from_config(config=bert_config, add_pooling_layer=False) if bert_config is not None else None
         self.freeze_lm = freeze_lm
         if self.bert is not None and freeze_lm:
@@ -127,6 +132,10 @@ class VaultMixin(nn.Module, ABC):
         self._check_supported(vilt_config)
         self._engine: Optional[VaultEngine] = None
         self._anchor = None
+
+    def _trunk_module(self):
+        """The ViltModel holding the trunk parameters: the module itself, or ``.vilt`` of a head wrapper (ViltForMaskedLM & co.)."""
+        return self.vilt if "vilt" in self._modules else self
 
     @staticmethod
     def _check_supported(cfg):
@@ -140,10 +149,8 @@ class VaultMixin(nn.Module, ABC):
                         use_vilt_position_embeddings: bool = False, *args, **kwargs):
         """ref:vault/models/vault/model.py:92-128"""
         model = super().from_pretrained(pretrained_vilt, *args, **kwargs)
-        if pretrained_bert is not None and not use_vilt_position_embeddings:
-            model.embeddings.text_embeddings.position_embedding_type = "NOT_absolute"
-        else:
-            model.embeddings.text_embeddings.position_embedding_type = "absolute"
+        te = model._trunk_module().embeddings.text_embeddings  # (the reference reads model.embeddings and so fails for the head wrappers)
+        te.position_embedding_type = "NOT_absolute" if (pretrained_bert is not None and not use_vilt_position_embeddings) else "absolute"
         model.bert = AutoModel.from_pretrained(pretrained_bert, add_pooling_layer=False) if pretrained_bert is not None else None
         model.freeze_lm = freeze_lm
         if model.bert is not None and freeze_lm:
@@ -198,22 +205,54 @@ class VaultMixin(nn.Module, ABC):
         kw.update({k: v for k, v in extra.items() if k in ("hw", "pmax")})
         if need_grad:
             eng.ensure_packed(pixel_values.device)
-            if self.training:
+            if self.training and not self.__dict__.get("_seed_held", False):
                 eng.seed_dev.add_(1)  # fresh dropout masks per training forward; the backward regenerates them from the same value
+                if "vilt" in self._modules:
+                    # a head wrapper may run the trunk several times per forward (one pass per image): the reference runs the LM ONCE
+                    # (ref:vault/models/vault/model.py:207-218), so every pass of this forward must see the same LM dropout masks
+                    self.__dict__["_seed_held"] = True
             if self._anchor is None or self._anchor.device != pixel_values.device:
                 self._anchor = torch.zeros(1, device=pixel_values.device, requires_grad=True)
             lhs, pooled, key_mask = _TrunkFn.apply(self._anchor, eng, kw)
         else:
             lhs, pooled, key_mask, _ = eng.forward(need_grad=False, **kw)
-        if self.pooler is None:
+        if self._trunk_module().pooler is None:
             pooled = None
         return lhs, pooled, key_mask
 
     def forward(self, *args, **kwargs):
         """ref:vault/models/vault/model.py:207-218 (lm_preprocess + vilt_forward, fused).  Positional order follows ViltModel.forward of
         transformers==4.48.0: input_ids, attention_mask, token_type_ids, pixel_values, pixel_mask, head_mask, inputs_embeds, ..."""
+        if "vilt" in self._modules:
+            # head wrapper: the HF head's own forward runs on top of the trunk; its `self.vilt(...)` call is served by the kernels
+            # (LM included), so the reference's lm_preprocess step has nothing left to do here
+            trunk = self.vilt
+            if not isinstance(trunk, _KernelTrunk):
+                trunk.__class__ = _KernelTrunk
+            object.__setattr__(trunk, "_owner", weakref.ref(self))
+            self.__dict__["_seed_held"] = False
+            try:
+                return super().forward(*args, **kwargs)
+            finally:
+                self.__dict__["_seed_held"] = False
         lhs, pooled, _ = self._trunk(*args, **kwargs)
         if kwargs.get("return_dict") is False:
+            return (lhs, pooled)
+        return BaseModelOutputWithPooling(last_hidden_state=lhs, pooler_output=pooled)
+
+
+class _KernelTrunk(ViltModel):
+    """``.vilt`` of a head wrapper: same parameters and state-dict keys as ViltModel, forward served by the wrapper's engine."""
+
+    def forward(self, input_ids=None, attention_mask=None, token_type_ids=None, pixel_values=None, pixel_mask=None, head_mask=None,
+                inputs_embeds=None, image_embeds=None, image_token_type_idx=None, output_attentions=None, output_hidden_states=None,
+                return_dict=None, **kwargs):
+        owner = self._owner()
+        lhs, pooled, _ = owner._trunk(input_ids=input_ids, attention_mask=attention_mask, token_type_ids=token_type_ids, pixel_values=pixel_values,
+                                      pixel_mask=pixel_mask, head_mask=head_mask, inputs_embeds=inputs_embeds, image_embeds=image_embeds,
+                                      image_token_type_idx=image_token_type_idx, output_attentions=output_attentions,
+                                      output_hidden_states=output_hidden_states)
+        if return_dict is False:
             return (lhs, pooled)
         return BaseModelOutputWithPooling(last_hidden_state=lhs, pooler_output=pooled)
 
@@ -245,16 +284,89 @@ class VaultForTMSC(VaultModel):
         return logits.squeeze(-1)
 
 
-def _not_built(name):
-    class _Stub:  # keeps `from vault_b200.models.vault import <name>` importable (ref:vault/models/vault/__init__.py)
-        def __init__(self, *a, **k):
-            raise NotImplementedError(f"{name}: head not built yet in vault_b200 (SURVEY.md section 8f, rank 3); the trunk is VaultModel")
+class VaultForImageAndTextRetrieval(VaultMixin, ViltForImageAndTextRetrieval):
+    """ref:vault/models/vault/model.py:375-405 -- rank_output on the pooler; ITM checkpoints initialise it from itm_score.fc[1:]."""
 
-    _Stub.__name__ = name
-    return _Stub
+    def __init__(self, *args, **kwargs):
+        from_pretrained = kwargs.pop("__from_pretrained__", False)
+        super().__init__(*args, **kwargs)
+        if from_pretrained:
+            self.itm_score = nn.Sequential()
+            self.itm_score.add_module("fc", nn.Linear(self.config.hidden_size, 2))
+
+    @classmethod
+    def from_pretrained(cls, pretrained_vilt: str, *args, **kwargs):
+        from_pretrained = "itm" in pretrained_vilt
+        kwargs["__from_pretrained__"] = from_pretrained
+        model = super().from_pretrained(pretrained_vilt, *args, **kwargs)
+        if from_pretrained:
+            model.rank_output.weight.data = model.itm_score.fc.weight.data[1:]
+            model.rank_output.bias.data = model.itm_score.fc.bias.data[1:]
+            del model.itm_score
+            model._engine = None
+        return model
 
 
-VaultForImageAndTextRetrieval = _not_built("VaultForImageAndTextRetrieval")
-VaultForImagesAndTextClassification = _not_built("VaultForImagesAndTextClassification")
-VaultForMaskedLM = _not_built("VaultForMaskedLM")
-VaultForQuestionAnswering = _not_built("VaultForQuestionAnswering")
+class VaultForImagesAndTextClassification(VaultMixin, ViltForImagesAndTextClassification):
+    """ref:vault/models/vault/model.py:408-452 -- NLVR2: one trunk pass per image (image_token_type_idx = 1, 2, ...), pooled outputs
+    concatenated into the classifier; loadable from base ViLT checkpoints (the modality table is widened to num_images + 1 rows)."""
+
+    def __init__(self, config, *args, **kwargs):
+        from_pretrained = kwargs.pop("__from_pretrained__", False)
+        num_images = kwargs.pop("num_images", None)
+        if num_images is not None:
+            config.num_images = num_images
+        elif config.num_images == -1:
+            config.num_images = 2  # nlvr2
+        super().__init__(config, *args, **kwargs)
+        if not from_pretrained:
+            self.resize_token_type_embeddings()
+
+    def resize_token_type_embeddings(self):
+        if self.config.modality_type_vocab_size != self.config.num_images + 1:
+            self.config.modality_type_vocab_size = self.config.num_images + 1
+            old = self.vilt.embeddings.token_type_embeddings.weight.data
+            assert len(old) == 2
+            new = nn.Embedding(self.config.modality_type_vocab_size, self.vilt.config.hidden_size).to(old.device)
+            new.weight.data[0] = old[0]
+            new.weight.data[1:] = old[1]
+            self.vilt.embeddings.token_type_embeddings = new
+            self._engine = None
+
+    @classmethod
+    def from_pretrained(cls, *args, **kwargs):
+        kwargs["__from_pretrained__"] = True
+        model = super().from_pretrained(*args, **kwargs)
+        VaultForImagesAndTextClassification.resize_token_type_embeddings(model)
+        return model
+
+
+class VaultForMaskedLM(VaultMixin, ViltForMaskedLM):
+    """ref:vault/models/vault/model.py:455-456 -- MLM head on the text rows of the trunk output."""
+
+
+class VaultForQuestionAnswering(VaultMixin, ViltForQuestionAnswering):
+    """ref:vault/models/vault/model.py:460-509 -- VQA head; ``n_classes`` swaps in a freshly initialised output layer."""
+
+    def __init__(self, config, *args, **kwargs):
+        num_labels = kwargs.pop("n_classes", None)
+        super().__init__(config, *args, **kwargs)
+        if num_labels is not None and num_labels != self.config.num_labels:
+            self.renew_classifier(num_labels)
+
+    @classmethod
+    def from_pretrained(cls, *args, **kwargs):
+        num_labels = kwargs.pop("n_classes", None)
+        model = super().from_pretrained(*args, **kwargs)
+        if num_labels is not None and num_labels != model.config.num_labels:
+            VaultForQuestionAnswering.renew_classifier(model, num_labels)
+        return model
+
+    def renew_classifier(self, num_labels):
+        cur = self.classifier[-1]
+        new = nn.Linear(cur.in_features, num_labels, cur.bias is not None).to(cur.weight.device)
+        new.weight.data.normal_(mean=0, std=0.02)
+        if new.bias is not None:
+            new.bias.data.zero_()
+        self.classifier[-1] = new
+        self._engine = None

@@ -190,6 +190,16 @@ int vault_vilt_assemble_bwd(const float* dX, const int32_t* hw, float* dtext_ln,
 
 /* im2col of NCHW fp32 pixels into bf16 patch rows [B*gh*gw, C*P*P] (k = c*P*P + kh*P + kw): the B operand of the
  * patch-projection wgrad (dW = dpatch^T * patches). */
+/* Pre-embedded image tokens (ViltEmbeddings.forward with image_embeds=..., HF:models/vilt/modeling_vilt.py:196-201; the TomViLT
+ * path ref:vault/models/tomvilt/model.py:281-287): X [B,T+P,H] = [text_ln + modality[0] | image_embeds + modality[img_type]] (no CLS, no
+ * position table), key_mask = [attention_mask | image_mask (uint8 [B,P], NULL = all valid)].  Backward: dtext_ln / dimage_embeds are
+ * overwritten (either may be NULL), dmodality rows 0 and img_type are accumulated. */
+int vault_vilt_assemble_embeds_fwd(const float* text_ln, const float* image_embeds, const float* modality, const int64_t* attention_mask,
+                                   const uint8_t* image_mask, float* X, uint8_t* key_mask, int32_t B, int32_t T, int32_t P, int32_t H,
+                                   int32_t img_type, void* stream);
+int vault_vilt_assemble_embeds_bwd(const float* dX, float* dtext_ln, float* dimage_embeds, float* dmodality, int32_t B, int32_t T, int32_t P,
+                                   int32_t H, int32_t img_type, void* stream);
+
 int vault_patchify_bf16(const float* pixels, void* out_bf16, int32_t B, int32_t C, int32_t Hi, int32_t Wi, int32_t P,
                         void* stream);
 

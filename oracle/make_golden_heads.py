@@ -73,9 +73,45 @@ def build(mod_or_pkg, name):
     return m, d, (batch, text_len, n_images)
 
 
+def embeds_case(pkg):
+    """VaultModel fed pre-embedded image tokens (image_embeds + flat pixel_mask): the TomViLT-style call, ref:vault/models/tomvilt/model.py:281-287."""
+    d = synth.Dims.tiny()
+    vc, lc = hf_configs(d)
+    m = pkg.VaultModel(vc, bert_config=lc)
+    m.embeddings.text_embeddings.position_embedding_type = "NOT_absolute"
+    shapes = {k: tuple(p.shape) for k, p in m.named_parameters()}
+    missing, unexpected = m.load_state_dict(synth.fill_parameters(shapes, d, seed=0), strict=False)
+    assert not unexpected
+    inp = synth.make_inputs(d, batch=3, text_len=16, seed=21, var_text=True)
+    g = torch.Generator().manual_seed(9)
+    P = 10
+    image_embeds = torch.randn(3, P, d.hidden, generator=g) * 0.5
+    image_mask = torch.ones(3, P, dtype=torch.long)
+    image_mask[1, 7:] = 0
+    image_mask[2, 4] = 0
+    w_pool = torch.randn(3, d.hidden, generator=g)
+    w_lhs = torch.randn(3, 16 + P, d.hidden, generator=g) * 0.1
+    return m, d, inp, image_embeds, image_mask, w_pool, w_lhs
+
+
+EMBEDS_GRAD_KEYS = ("pooler.dense.bias", "layernorm.weight", "embeddings.token_type_embeddings.weight", "encoder.layer.0.attention.attention.value.bias",
+                    "bert.encoder.layer.1.output.dense.bias")
+
+
 def main():
     os.makedirs(OUT, exist_ok=True)
     mod = load_reference_module()
+    m, d, inp, image_embeds, image_mask, w_pool, w_lhs = embeds_case(mod)
+    m.eval()
+    ie = image_embeds.clone().requires_grad_(True)
+    out = m(input_ids=inp["input_ids"], attention_mask=inp["attention_mask"], token_type_ids=inp["token_type_ids"], image_embeds=ie, pixel_mask=image_mask)
+    loss = (out.pooler_output * w_pool).sum() + (out.last_hidden_state * w_lhs).sum()
+    loss.backward()
+    named = dict(m.named_parameters())
+    torch.save(dict(case="image_embeds", pooler_output=out.pooler_output.detach().clone(), last_hidden_state=out.last_hidden_state.detach().clone(),
+                    d_image_embeds=ie.grad.clone(), grads={k: named[k].grad.detach().clone() for k in EMBEDS_GRAD_KEYS}),
+               os.path.join(OUT, "image_embeds.pt"))
+    print("image_embeds", tuple(out.last_hidden_state.shape), float(loss))
     for name in CASES:
         torch.manual_seed(0)
         m, d, (batch, text_len, n_images) = build(mod, name)

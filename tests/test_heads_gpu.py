@@ -50,3 +50,29 @@ def test_head_wrapper_matches_reference_fixture(name):
     k = "vilt.layernorm.weight"
     assert cosine(named[k].grad.float().cpu(), ref["grads"][k]) >= 0.99
     assert abs(named[k].grad.float().norm().item() / ref["grads"][k].norm().item() - 1.0) <= 5e-2
+
+
+def test_image_embeds_path_matches_reference_fixture():
+    """VaultModel(image_embeds=..., pixel_mask=flat mask) -- SURVEY.md section 8f rank 4 -- against the real reference: outputs on valid rows,
+    gradient w.r.t. the caller's image_embeds and a few parameters."""
+    import vault_b200.models.vault as pkg
+
+    ref = torch.load(os.path.join(HEADS_DIR, "image_embeds.pt"), weights_only=False)
+    m, d, inp, image_embeds, image_mask, w_pool, w_lhs = G.embeds_case(pkg)
+    m = m.to(DEV).eval()
+    ie = image_embeds.to(DEV).requires_grad_(True)
+    out = m(input_ids=inp["input_ids"].to(DEV), attention_mask=inp["attention_mask"].to(DEV), token_type_ids=inp["token_type_ids"].to(DEV),
+            image_embeds=ie, pixel_mask=image_mask.to(DEV))
+    assert rel_err(out.pooler_output.detach().cpu(), ref["pooler_output"]) <= 2e-2
+    valid = torch.cat([inp["attention_mask"], image_mask], dim=1).bool()
+    assert rel_err(out.last_hidden_state.detach().cpu()[valid], ref["last_hidden_state"][valid]) <= 2e-2
+    loss = (out.pooler_output * w_pool.to(DEV)).sum() + (out.last_hidden_state * w_lhs.to(DEV)).sum()
+    loss.backward()
+    assert cosine(ie.grad.cpu(), ref["d_image_embeds"]) >= 0.99
+    named = dict(m.named_parameters())
+    for k, g_ref in ref["grads"].items():
+        assert cosine(named[k].grad.float().cpu(), g_ref) >= 0.99, k
+    with torch.no_grad():
+        again = m(input_ids=inp["input_ids"].to(DEV), attention_mask=inp["attention_mask"].to(DEV), token_type_ids=inp["token_type_ids"].to(DEV),
+                  image_embeds=image_embeds.to(DEV), pixel_mask=image_mask.to(DEV))
+    assert torch.equal(again.pooler_output, out.pooler_output.detach())

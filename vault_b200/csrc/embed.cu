@@ -286,6 +286,73 @@ vilt_assemble_bwd_patch_kernel(const float* __restrict__ dX, const int* __restri
   }
 }
 
+// ---- pre-embedded image tokens (HF ViltEmbeddings.forward with image_embeds=..., HF:models/vilt/modeling_vilt.py:196-201; the TomViLT
+// path ref:vault/models/tomvilt/model.py:281-287): X = [text_ln + modality[0] | image_embeds + modality[img_type]], no CLS, no position
+// table, key validity = [attention_mask | image_mask].
+__global__ void __launch_bounds__(kEmbWarps * 32)
+vilt_assemble_embeds_fwd_kernel(const float* __restrict__ text_ln, const float* __restrict__ img, const float* __restrict__ modality,
+                                const int64_t* __restrict__ attn_mask, const uint8_t* __restrict__ img_mask, float* __restrict__ X,
+                                uint8_t* __restrict__ key_mask, int B, int T, int P, int H, int img_type) {
+  pdl_enter();
+  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+  const int S = T + P;
+  const long long row = (long long)blockIdx.x * kEmbWarps + warp;
+  if (row >= (long long)B * S) return;
+  const int b = (int)(row / S), s = (int)(row % S);
+  float4* o = reinterpret_cast<float4*>(X + row * H);
+  const bool text = s < T;
+  const float4* src = reinterpret_cast<const float4*>(text ? text_ln + ((long long)b * T + s) * H : img + ((long long)b * P + (s - T)) * H);
+  const float4* m4 = reinterpret_cast<const float4*>(modality + (long long)(text ? 0 : img_type) * H);
+  for (int c = lane; c < H / 4; c += 32) o[c] = f4add(__ldg(src + c), __ldg(m4 + c));
+  if (lane == 0) {
+    if (text) key_mask[row] = attn_mask ? (attn_mask[(long long)b * T + s] != 0) : 1;
+    else key_mask[row] = img_mask ? (img_mask[(long long)b * P + (s - T)] != 0) : 1;
+  }
+}
+
+__global__ void __launch_bounds__(kEmbWarps * 32)
+vilt_assemble_embeds_bwd_kernel(const float* __restrict__ dX, float* __restrict__ dtext_ln, float* __restrict__ dimg, float* __restrict__ dmodality, int B,
+                                int T, int P, int H, int img_type) {
+  pdl_enter();
+  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+  const int S = T + P, H4 = H / 4;
+  float4 acc_t[8], acc_i[8];
+#pragma unroll
+  for (int k = 0; k < 8; ++k) acc_t[k] = acc_i[k] = make_float4(0.f, 0.f, 0.f, 0.f);
+  for (long long row = (long long)blockIdx.x * kEmbWarps + warp; row < (long long)B * S; row += (long long)gridDim.x * kEmbWarps) {
+    const int b = (int)(row / S), s = (int)(row % S);
+    const float4* g = reinterpret_cast<const float4*>(dX + row * H);
+    const bool text = s < T;
+    float* dst = text ? dtext_ln : dimg;
+    float4* o = dst ? reinterpret_cast<float4*>(dst + (text ? (long long)b * T + s : (long long)b * P + (s - T)) * H) : nullptr;
+#pragma unroll
+    for (int k = 0; k < 8; ++k) {
+      const int c = lane + 32 * k;
+      if (c < H4) {
+        const float4 v = __ldg(g + c);
+        if (o) o[c] = v;
+        if (text) acc_t[k] = f4add(acc_t[k], v);
+        else acc_i[k] = f4add(acc_i[k], v);
+      }
+    }
+  }
+  if (dmodality == nullptr) return;
+  __shared__ float4 red[kEmbWarps][256 + 1];
+  for (int pass = 0; pass < 2; ++pass) {
+    __syncthreads();
+#pragma unroll
+    for (int k = 0; k < 8; ++k) red[warp][lane + 32 * k] = pass == 0 ? acc_t[k] : acc_i[k];
+    __syncthreads();
+    float* dst = dmodality + (long long)(pass == 0 ? 0 : img_type) * H;
+    for (int c = threadIdx.x; c < H4; c += kEmbWarps * 32) {
+      float4 a = red[0][c];
+#pragma unroll
+      for (int wv = 1; wv < kEmbWarps; ++wv) a = f4add(a, red[wv][c]);
+      atomic_add4(dst + 4 * c, a);
+    }
+  }
+}
+
 // im2col: out[(b*gh+i)*gw+j, c*P*P + kh*P + kw] = bf16(pixels[b,c,i*P+kh,j*P+kw]); one thread = 8 consecutive kw
 __global__ void __launch_bounds__(256)
 patchify_kernel(const float* __restrict__ px, bf16* __restrict__ out, int B, int C, int Hi, int Wi, int P) {
@@ -387,6 +454,28 @@ extern "C" int vault_vilt_assemble_bwd(const float* dX, const int32_t* hw, float
     rc = check_launch("vilt_assemble_bwd_patch_kernel");
   }
   return rc;
+}
+
+extern "C" int vault_vilt_assemble_embeds_fwd(const float* text_ln, const float* image_embeds, const float* modality, const int64_t* attention_mask,
+                                              const uint8_t* image_mask, float* X, uint8_t* key_mask, int32_t B, int32_t T, int32_t P, int32_t H,
+                                              int32_t img_type, void* stream) {
+  VB_REQUIRE(text_ln && image_embeds && modality && X && key_mask, "vilt_assemble_embeds_fwd: null pointer");
+  VB_REQUIRE(H % 4 == 0 && P > 0 && T > 0, "vilt_assemble_embeds_fwd: bad shape");
+  launch(vilt_assemble_embeds_fwd_kernel, dim3(rows_grid((long long)B * (T + P))), dim3(kEmbWarps * 32), 0, (cudaStream_t)stream, text_ln, image_embeds,
+         modality, attention_mask, image_mask, X, key_mask, B, T, P, H, img_type);
+  return check_launch("vilt_assemble_embeds_fwd_kernel");
+}
+
+extern "C" int vault_vilt_assemble_embeds_bwd(const float* dX, float* dtext_ln, float* dimage_embeds, float* dmodality, int32_t B, int32_t T, int32_t P,
+                                              int32_t H, int32_t img_type, void* stream) {
+  VB_REQUIRE(dX, "vilt_assemble_embeds_bwd: null pointer");
+  VB_REQUIRE(H % 4 == 0 && H <= 1024, "vilt_assemble_embeds_bwd: H=%d must be a multiple of 4 and <= 1024", H);
+  long long grid1 = rows_grid((long long)B * (T + P));
+  const long long cap = (long long)device_sm_count() * 2;
+  if (grid1 > cap) grid1 = cap;
+  launch(vilt_assemble_embeds_bwd_kernel, dim3((unsigned)grid1), dim3(kEmbWarps * 32), 0, (cudaStream_t)stream, dX, dtext_ln, dimage_embeds, dmodality, B, T,
+         P, H, img_type);
+  return check_launch("vilt_assemble_embeds_bwd_kernel");
 }
 
 extern "C" int vault_patchify_bf16(const float* pixels, void* out_bf16, int32_t B, int32_t C, int32_t Hi, int32_t Wi, int32_t P, void* stream) {

@@ -573,11 +573,13 @@ class VaultEngine:
             return e.value
 
     def forward_iter(self, input_ids, attention_mask, token_type_ids, pixel_values, pixel_mask, image_token_type_idx=1, training=False,
-                     need_grad=False, hw: Optional[torch.Tensor] = None, pmax: Optional[int] = None, split_lm: bool = False):
+                     need_grad=False, hw: Optional[torch.Tensor] = None, pmax: Optional[int] = None, split_lm: bool = False,
+                     image_embeds: Optional[torch.Tensor] = None):
         """Generator form of forward.  With split_lm it yields "lm_done" once the language model's forward is enqueued and before
         anything reads a ViLT parameter, so a caller can start the LM while the previous step's AdamW is still updating the
         ViLT range (VaultTrainStep); the return value (StopIteration.value) is forward()'s tuple."""
-        dev = pixel_values.device
+        embeds_mode = image_embeds is not None  # pre-embedded image tokens [B,P,H] (+ pixel_mask flattened to [B,P]) instead of pixels
+        dev = image_embeds.device if embeds_mode else pixel_values.device
         self.ensure_packed(dev)
         self._lib, self._st = _abi.lib(), self._stream()
         if not split_lm and not torch.cuda.is_current_stream_capturing():
@@ -586,10 +588,22 @@ class VaultEngine:
         self.refresh_shadow()
         H = self.H
         B, T = input_ids.shape
-        Cc, Hi, Wi = pixel_values.shape[1:]
-        if Cc != self.C or Hi % self.patch or Wi % self.patch:
-            raise ValueError(f"pixel_values {tuple(pixel_values.shape)}: need {self.C} channels and sides divisible by {self.patch}")
-        gh, gw = Hi // self.patch, Wi // self.patch
+        if embeds_mode:
+            if image_embeds.dim() != 3 or image_embeds.shape[0] != B or image_embeds.shape[2] != self.H:
+                raise ValueError(f"image_embeds {tuple(image_embeds.shape)}: need [B={B}, P, {self.H}]")
+            image_embeds = image_embeds.contiguous().float()
+            P_img = image_embeds.shape[1]
+            img_mask = None
+            if pixel_mask is not None:
+                img_mask = (pixel_mask.reshape(B, -1) != 0).to(torch.uint8).contiguous()  # HF: image_masks = pixel_mask.flatten(1)
+                if img_mask.shape[1] != P_img:
+                    raise ValueError(f"pixel_mask flattens to {img_mask.shape[1]} positions, image_embeds has {P_img}")
+            Cc = Hi = Wi = gh = gw = 0
+        else:
+            Cc, Hi, Wi = pixel_values.shape[1:]
+            if Cc != self.C or Hi % self.patch or Wi % self.patch:
+                raise ValueError(f"pixel_values {tuple(pixel_values.shape)}: need {self.C} channels and sides divisible by {self.patch}")
+            gh, gw = Hi // self.patch, Wi // self.patch
         input_ids = input_ids.contiguous()
         if input_ids.dtype != torch.int64:
             input_ids = input_ids.to(torch.int64)
@@ -597,7 +611,8 @@ class VaultEngine:
             attention_mask = attention_mask.contiguous() if attention_mask.dtype == torch.int64 else attention_mask.to(torch.int64)
         if token_type_ids is not None:
             token_type_ids = token_type_ids.contiguous() if token_type_ids.dtype == torch.int64 else token_type_ids.to(torch.int64)
-        pixel_values = pixel_values.contiguous() if pixel_values.dtype == torch.float32 else pixel_values.float().contiguous()
+        if not embeds_mode:
+            pixel_values = pixel_values.contiguous() if pixel_values.dtype == torch.float32 else pixel_values.float().contiguous()
         tape = Tape() if need_grad else None
         if tape is not None:
             tape.gen = self._gen
@@ -638,7 +653,7 @@ class VaultEngine:
             st = self._st = main_st
             return patch_out, patches, ev1
 
-        img = None if split_lm else image_branch()
+        img = None if (split_lm or embeds_mode) else image_branch()
         # ---------------- text: LM or ViLT word embeddings -> inputs_embeds fp32 [Mt,H] ----------------
         lm_trains = self.lm is not None and not getattr(self.model, "freeze_lm", False) and need_grad
         if self.lm is not None:
@@ -676,25 +691,35 @@ class VaultEngine:
                                        self.vilt_eps, want16=False, want32=True)
 
         # ---------------- assembly (joins the image branch) ----------------
-        if img is None:
-            img = image_branch()
-        patch_out, patches, ev1 = img
-        torch.cuda.current_stream(self.device).wait_event(ev1)
-        if hw is None:
-            hw, pmax = self.patch_hw(pixel_mask, B, Hi, Wi)
-        S = T + 1 + pmax
-        M = B * S
-        X = self._new((B, S, H), torch.float32)
-        key_mask = self._new((B, S), torch.uint8)
-        _abi.check(lib.vault_vilt_assemble_fwd(text_ln.data_ptr(), patch_out.data_ptr(), self.w32("embeddings.cls_token"),
-                                               self.w32("embeddings.position_embeddings"), self.w32("embeddings.token_type_embeddings.weight"), am_ptr,
-                                               hw.data_ptr(), X.data_ptr(), key_mask.data_ptr(), B, T, pmax, gh, gw, self.grid, H,
-                                               int(image_token_type_idx), st), "vilt_assemble_fwd")
+        if embeds_mode:
+            S = T + P_img
+            M = B * S
+            X = self._new((B, S, H), torch.float32)
+            key_mask = self._new((B, S), torch.uint8)
+            _abi.check(lib.vault_vilt_assemble_embeds_fwd(text_ln.data_ptr(), image_embeds.data_ptr(), self.w32("embeddings.token_type_embeddings.weight"),
+                                                          am_ptr, img_mask.data_ptr() if img_mask is not None else None, X.data_ptr(), key_mask.data_ptr(),
+                                                          B, T, P_img, H, int(image_token_type_idx), st), "vilt_assemble_embeds_fwd")
+            pmax, patches = P_img, None
+        else:
+            if img is None:
+                img = image_branch()
+            patch_out, patches, ev1 = img
+            torch.cuda.current_stream(self.device).wait_event(ev1)
+            if hw is None:
+                hw, pmax = self.patch_hw(pixel_mask, B, Hi, Wi)
+            S = T + 1 + pmax
+            M = B * S
+            X = self._new((B, S, H), torch.float32)
+            key_mask = self._new((B, S), torch.uint8)
+            _abi.check(lib.vault_vilt_assemble_fwd(text_ln.data_ptr(), patch_out.data_ptr(), self.w32("embeddings.cls_token"),
+                                                   self.w32("embeddings.position_embeddings"), self.w32("embeddings.token_type_embeddings.weight"), am_ptr,
+                                                   hw.data_ptr(), X.data_ptr(), key_mask.data_ptr(), B, T, pmax, gh, gw, self.grid, H,
+                                                   int(image_token_type_idx), st), "vilt_assemble_fwd")
         if sv is not None:
             sv["v_sum"], sv["st_t"], sv["patches"], sv["hw"], sv["key_mask"] = v_sum, st_t, patches, hw, key_mask
             sv["ids"], sv["tt"], sv["am"] = input_ids, token_type_ids, attention_mask
             tape.meta.update(B=B, T=T, S=S, pmax=pmax, gh=gh, gw=gw, Hi=Hi, Wi=Wi, img_type=int(image_token_type_idx), training=training,
-                             lm_trains=lm_trains)
+                             lm_trains=lm_trains, embeds_mode=embeds_mode)
 
         # ---------------- ViLT encoder, final LN, pooler ----------------
         x32 = X.view(M, H)
@@ -779,15 +804,22 @@ class VaultEngine:
                     yield off
         # ---- embeddings ----
         dtext_ln = self._new((Mt, H), torch.float32)
-        dpatch = self._new((B * gh * gw, H), torch.bfloat16)
-        _abi.check(lib.vault_vilt_assemble_bwd(g32.data_ptr(), sv["hw"].data_ptr(), dtext_ln.data_ptr(), dpatch.data_ptr(),
-                                               self.g32("embeddings.cls_token") or None, self.g32("embeddings.position_embeddings") or None,
-                                               self.g32("embeddings.token_type_embeddings.weight") or None, B, T, pmax, gh, gw, self.grid, H,
-                                               mt["img_type"], st), "vilt_assemble_bwd")
-        Kp = self.C * self.patch * self.patch
-        if sv["patches"] is not None:
-            self.linear_wgrad(dpatch, sv["patches"], B * gh * gw, "embeddings.patch_embeddings.projection.weight",
-                              "embeddings.patch_embeddings.projection.bias", H, Kp)
+        if mt.get("embeds_mode"):
+            d_img = self._new((B, pmax, H), torch.float32)  # gradient w.r.t. the caller's image_embeds (returned through autograd)
+            _abi.check(lib.vault_vilt_assemble_embeds_bwd(g32.data_ptr(), dtext_ln.data_ptr(), d_img.data_ptr(),
+                                                          self.g32("embeddings.token_type_embeddings.weight") or None, B, T, pmax, H, mt["img_type"], st),
+                       "vilt_assemble_embeds_bwd")
+            tape.meta["d_image_embeds"] = d_img
+        else:
+            dpatch = self._new((B * gh * gw, H), torch.bfloat16)
+            _abi.check(lib.vault_vilt_assemble_bwd(g32.data_ptr(), sv["hw"].data_ptr(), dtext_ln.data_ptr(), dpatch.data_ptr(),
+                                                   self.g32("embeddings.cls_token") or None, self.g32("embeddings.position_embeddings") or None,
+                                                   self.g32("embeddings.token_type_embeddings.weight") or None, B, T, pmax, gh, gw, self.grid, H,
+                                                   mt["img_type"], st), "vilt_assemble_bwd")
+            Kp = self.C * self.patch * self.patch
+            if sv["patches"] is not None:
+                self.linear_wgrad(dpatch, sv["patches"], B * gh * gw, "embeddings.patch_embeddings.projection.weight",
+                                  "embeddings.patch_embeddings.projection.bias", H, Kp)
         dv_sum, _ = self.ln_bwd(dtext_ln, None, sv["v_sum"], sv["st_t"], Mt, "embeddings.text_embeddings.LayerNorm.weight",
                                 "embeddings.text_embeddings.LayerNorm.bias", want16=False)
         tt_ptr = sv["tt"].data_ptr() if sv["tt"] is not None else None

@@ -50,9 +50,10 @@ class _TrunkFn(torch.autograd.Function):
     into the engine's flat buffer and attached as ``p.grad`` views in ``backward``."""
 
     @staticmethod
-    def forward(ctx, anchor, engine: VaultEngine, kw: dict):
-        lhs, pooled, key_mask, tape = engine.forward(need_grad=True, **kw)
+    def forward(ctx, anchor, engine: VaultEngine, kw: dict, image_embeds=None):
+        lhs, pooled, key_mask, tape = engine.forward(need_grad=True, image_embeds=image_embeds, **kw)
         ctx.engine, ctx.tape = engine, tape
+        ctx.embeds_grad = image_embeds is not None and image_embeds.requires_grad
         ctx.has_pooled = pooled is not None
         ctx.mark_non_differentiable(key_mask)
         if pooled is None:
@@ -62,9 +63,10 @@ class _TrunkFn(torch.autograd.Function):
     @staticmethod
     def backward(ctx, dlhs, dpooled, _dmask):
         engine: VaultEngine = ctx.engine
-        engine.backward(ctx.tape, dlhs, dpooled if ctx.has_pooled else None)
+        tape = ctx.tape
+        engine.backward(tape, dlhs, dpooled if ctx.has_pooled else None)
         engine.attach_grads(exclude_prefix="classifier.")
-        return None, None, None
+        return None, None, None, (tape.meta.get("d_image_embeds") if ctx.embeds_grad else None)
 
 
 class _HeadFn(torch.autograd.Function):
@@ -187,11 +189,13 @@ class VaultMixin(nn.Module, ABC):
                return_dict=None, **extra):
         if head_mask is not None or output_attentions or output_hidden_states:
             raise NotImplementedError("vault_b200: head_mask / output_attentions / output_hidden_states are not on the hot path")
-        if image_embeds is not None or inputs_embeds is not None:
-            raise NotImplementedError("vault_b200: image_embeds / inputs_embeds inputs are not built yet (SURVEY.md section 8f)")
-        if input_ids is None or pixel_values is None:
-            raise ValueError("You have to specify input_ids and pixel_values")
-        if not pixel_values.is_cuda:
+        if inputs_embeds is not None:
+            raise NotImplementedError("vault_b200: text inputs_embeds are not on the hot path (pass input_ids; the LM runs inside the engine)")
+        if input_ids is None or (pixel_values is None and image_embeds is None):
+            raise ValueError("You have to specify input_ids and pixel_values (or image_embeds)")
+        if image_embeds is not None and pixel_values is not None:
+            raise ValueError("You cannot specify both pixel_values and image_embeds at the same time")
+        if not (pixel_values if pixel_values is not None else image_embeds).is_cuda:
             raise RuntimeError("vault_b200 runs on CUDA (sm_100a) only: move the model and the batch to the GPU -- there is no CPU fallback")
         for p in self.parameters():
             if p.dtype != torch.float32:
@@ -203,19 +207,21 @@ class VaultMixin(nn.Module, ABC):
                   pixel_mask=pixel_mask, image_token_type_idx=1 if image_token_type_idx is None else image_token_type_idx,
                   training=self.training)
         kw.update({k: v for k, v in extra.items() if k in ("hw", "pmax")})
+        dev = (pixel_values if pixel_values is not None else image_embeds).device
+        need_grad = need_grad or (torch.is_grad_enabled() and image_embeds is not None and image_embeds.requires_grad)
         if need_grad:
-            eng.ensure_packed(pixel_values.device)
+            eng.ensure_packed(dev)
             if self.training and not self.__dict__.get("_seed_held", False):
                 eng.seed_dev.add_(1)  # fresh dropout masks per training forward; the backward regenerates them from the same value
                 if "vilt" in self._modules:
                     # a head wrapper may run the trunk several times per forward (one pass per image): the reference runs the LM ONCE
                     # (ref:vault/models/vault/model.py:207-218), so every pass of this forward must see the same LM dropout masks
                     self.__dict__["_seed_held"] = True
-            if self._anchor is None or self._anchor.device != pixel_values.device:
-                self._anchor = torch.zeros(1, device=pixel_values.device, requires_grad=True)
-            lhs, pooled, key_mask = _TrunkFn.apply(self._anchor, eng, kw)
+            if self._anchor is None or self._anchor.device != dev:
+                self._anchor = torch.zeros(1, device=dev, requires_grad=True)
+            lhs, pooled, key_mask = _TrunkFn.apply(self._anchor, eng, kw, image_embeds)
         else:
-            lhs, pooled, key_mask, _ = eng.forward(need_grad=False, **kw)
+            lhs, pooled, key_mask, _ = eng.forward(need_grad=False, image_embeds=image_embeds, **kw)
         if self._trunk_module().pooler is None:
             pooled = None
         return lhs, pooled, key_mask

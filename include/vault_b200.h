@@ -190,6 +190,25 @@ int vault_vilt_assemble_bwd(const float* dX, const int32_t* hw, float* dtext_ln,
 
 /* im2col of NCHW fp32 pixels into bf16 patch rows [B*gh*gw, C*P*P] (k = c*P*P + kh*P + kw): the B operand of the
  * patch-projection wgrad (dW = dpatch^T * patches). */
+/* ------------------------------------------------------------------------------------------------------------------
+ * Image pre-processing of the ViLT processor: per-image bicubic resize in uint8 -- bit-identical to
+ * Pillow's ImagingResample as called by transformers==4.48.0 image_transforms.resize(resample=BICUBIC) from
+ * HF:models/vilt/image_processing_vilt.py -- then rescale 1/255 + normalise through lut256 (fp32 [3,256], one row per channel), zero padding to [Hmax, Wmax] and the
+ * pixel mask.  The host computes the output sizes and the fixed-point filter taps (vault_b200/image_processing.py).
+ *   src: packed uint8 HWC RGB images; descs[B] (device); coefs / bounds: int32 tap tables (Pillow precompute_coeffs +
+ *   normalize_coeffs_8bpc, 22 fractional bits; bounds = {first source index, tap count} per output index); tmp: uint8 scratch for
+ *   the horizontal pass; pixel_values [B,3,Hmax,Wmax] fp32 and pixel_mask [B,Hmax,Wmax] int64 are fully overwritten.
+ * ------------------------------------------------------------------------------------------------------------------ */
+typedef struct {
+  int64_t src_off, tmp_off;             /* byte offsets of this image in src / tmp */
+  int32_t h_in, w_in, h_out, w_out;
+  int32_t ksize_h, ksize_v;             /* taps per output column / row (row stride of the coefficient tables) */
+  int32_t coef_h, bound_h, coef_v, bound_v; /* element offsets into coefs / bounds */
+} vault_image_desc;
+int vault_image_preprocess(const uint8_t* src, const vault_image_desc* descs, const int32_t* coefs, const int32_t* bounds, uint8_t* tmp,
+                           const float* lut256, float* pixel_values, int64_t* pixel_mask, int32_t B, int32_t Hmax, int32_t Wmax,
+                           int32_t max_h_in, int32_t max_w_out, void* stream);
+
 /* Pre-embedded image tokens (ViltEmbeddings.forward with image_embeds=..., HF:models/vilt/modeling_vilt.py:196-201; the TomViLT
  * path ref:vault/models/tomvilt/model.py:281-287): X [B,T+P,H] = [text_ln + modality[0] | image_embeds + modality[img_type]] (no CLS, no
  * position table), key_mask = [attention_mask | image_mask (uint8 [B,P], NULL = all valid)].  Backward: dtext_ln / dimage_embeds are

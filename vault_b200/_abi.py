@@ -55,6 +55,7 @@ SIGNATURES = {
     "vault_vilt_assemble_bwd": [c_p, c_p, c_p, c_p, c_p, c_p, c_p, c_i32, c_i32, c_i32, c_i32, c_i32, c_i32, c_i32, c_i32, c_p],
     "vault_vilt_assemble_embeds_fwd": [c_p, c_p, c_p, c_p, c_p, c_p, c_p, c_i32, c_i32, c_i32, c_i32, c_i32, c_p],
     "vault_vilt_assemble_embeds_bwd": [c_p, c_p, c_p, c_p, c_i32, c_i32, c_i32, c_i32, c_i32, c_p],
+    "vault_image_preprocess": [c_p, c_p, c_p, c_p, c_p, c_p, c_p, c_p, c_i32, c_i32, c_i32, c_i32, c_i32, c_p],
     "vault_patchify_bf16": [c_p, c_p, c_i32, c_i32, c_i32, c_i32, c_i32, c_p],
     "vault_small_linear_fwd": [c_p, c_i64, c_p, c_p, c_p, c_i32, c_i32, c_i32, c_i32, c_p],
     "vault_small_linear_bwd": [c_p, c_p, c_p, c_i64, c_p, c_p, c_i64, c_i32, c_p, c_p, c_i32, c_i32, c_i32, c_i32, c_p],

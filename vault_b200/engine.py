@@ -216,7 +216,7 @@ class VaultEngine:
         # gradient ranges that are ACCUMULATED into (atomics): zero-filled at the start of every backward
         self._zero_ranges = self._compute_zero_ranges()
         self.opt_state = None
-        self._side = torch.cuda.Stream(device=device)
+        self._side = torch.cuda.Stream(device=device, priority=-1 if os.environ.get("VAULT_B200_SIDE_PRIORITY", "0") != "0" else 0)
         if "VAULT_B200_ATTN_IMPL" in os.environ:  # A/B switch: 1 = mma.sync attention everywhere (default: tcgen05 where the shape allows)
             _abi.set_attn_impl(int(os.environ["VAULT_B200_ATTN_IMPL"]))
         self._sched_slots = 512

@@ -280,7 +280,9 @@ class VaultTrainStep:
                 eng.seed_dev.sub_(1)
                 s.graphs = []
                 it = self._body_iter(s, segments=self.overlap or self.split_lm)
-                cap_stream = torch.cuda.Stream(device=self.dev)
+                # the dependency chain (forward; dgrad -> LayerNorm -> attention) is captured on a HIGH-priority stream, the engine's side
+                # stream (weight gradients, bias sums) keeps the default priority: pending chain CTAs are placed first, the rest fills in
+                cap_stream = torch.cuda.Stream(device=self.dev, priority=-1 if os.environ.get("VAULT_B200_CHAIN_PRIORITY", "0") != "0" else 0)
                 done = False
                 while not done:
                     g = torch.cuda.CUDAGraph()

@@ -248,10 +248,11 @@ def test_attention_tcgen05_matches_mma_sync(dev, B, S, heads):
         _abi.set_attn_impl(0)
 
 
-@pytest.mark.parametrize("S", [40, 64])
+@pytest.mark.parametrize("S", [40, 64, 100, 128, 185])
 def test_attention_dropout_exact_mask(dev, S):
-    """With S <= 64 and V = identity the context IS the dropped probability matrix: recover the Philox mask, then check forward and
-    backward against torch with that exact mask."""
+    """With V = identity over one 64-key chunk the context IS that chunk of the dropped probability matrix: recover the Philox mask chunk
+    by chunk (the mask depends only on seed / site / (b, h, q, k), never on the data), then check forward and backward against torch
+    with that exact mask -- several key chunks, ragged tails and mid-sequence padding included."""
     from vault_b200 import _abi
 
     lib, st = _abi.lib(), torch.cuda.current_stream().cuda_stream
@@ -259,17 +260,21 @@ def test_attention_dropout_exact_mask(dev, S):
     H = heads * 64
     torch.manual_seed(7)
     qkv = _rnd(dev, B * S, 3 * H, scale=0.7)
-    mask = torch.ones(B, S, dtype=torch.uint8, device=dev)
-    probe = qkv.clone().view(B, S, 3, heads, 64)
-    probe[:, :, 2] = 0
-    for k in range(S):
-        probe[:, k, 2, :, k] = 1.0
-    probe = probe.view(B * S, 3 * H).contiguous()
+    mask = _mid_mask(dev, B, S) if S > 64 else torch.ones(B, S, dtype=torch.uint8, device=dev)
+    ones = torch.ones(B, S, dtype=torch.uint8, device=dev)
     ctx = torch.empty(B * S, H, device=dev, dtype=torch.bfloat16)
     lse = torch.empty(B, heads, S, device=dev)
-    _abi.check(lib.vault_attn_fwd(probe.data_ptr(), mask.data_ptr(), ctx.data_ptr(), lse.data_ptr(), B, S, heads, p, seed, None, site, st))
-    pd = ctx.float().view(B, S, heads, 64)[..., :S].permute(0, 2, 1, 3)  # [B,h,q,k] dropped probabilities
-    drop_mask = (pd != 0).float()
+    drop_mask = torch.zeros(B, heads, S, S, device=dev)
+    for c0 in range(0, S, 64):
+        probe = qkv.clone().view(B, S, 3, heads, 64)
+        probe[:, :, 2] = 0
+        for k in range(c0, min(S, c0 + 64)):
+            probe[:, k, 2, :, k - c0] = 1.0
+        probe = probe.view(B * S, 3 * H).contiguous()
+        _abi.check(lib.vault_attn_fwd(probe.data_ptr(), ones.data_ptr(), ctx.data_ptr(), lse.data_ptr(), B, S, heads, p, seed, None, site, st))
+        n = min(S, c0 + 64) - c0
+        pd = ctx.float().view(B, S, heads, 64)[..., :n].permute(0, 2, 1, 3)  # [B,h,q,k in chunk] dropped probabilities
+        drop_mask[..., c0:c0 + n] = (pd != 0).float()
     assert abs(drop_mask.mean().item() - 0.9) < 0.02
     _abi.check(lib.vault_attn_fwd(qkv.data_ptr(), mask.data_ptr(), ctx.data_ptr(), lse.data_ptr(), B, S, heads, p, seed, None, site, st))
     x, ref, _ = _attn_ref(qkv, mask, B, S, heads, drop_mask, p)

@@ -58,11 +58,13 @@ def run(B, S, heads, p=0.0, seed=0, mask_mode="mid"):
         _abi.check(lib.vault_attn_bwd(qkv.data_ptr(), mask.data_ptr(), c1.data_ptr(), dctx.data_ptr(), lse.data_ptr(), delta.data_ptr(), dqkv.data_ptr(),
                                       B, S, heads, p, 77, None, 5, st()), "bwd")
         lhs = (dqkv[:, 2 * H:].float() * qkv[:, 2 * H:].float()).sum().item(); rhs = (dctx.float() * c1.float()).sum().item()
-        res["dv_linearity_rel"] = abs(lhs - rhs) / max(abs(rhs), 1e-6)
+        # normalised by the norms, not by |rhs|: rhs is a random-sign sum and can be small by chance (the exact-mask check lives in
+        # tests/test_kernels_gpu.py::test_attention_dropout_exact_mask)
+        res["dv_linearity_rel"] = abs(lhs - rhs) / max((dctx.float().norm() * c1.float().norm()).item(), 1e-6)
         # softmax rows: sum_k dS = 0  =>  <dQ, Q> == <dK, K>
         a = (dqkv[:, :H].float() * qkv[:, :H].float()).sum().item(); b = (dqkv[:, H:2 * H].float() * qkv[:, H:2 * H].float()).sum().item()
         res["dq_dk_balance_rel"] = abs(a - b) / max(abs(a), abs(b), 1e-6)
-        res["ok"] = bool(res["mean_err"] < 0.08 and res["deterministic"] and res["dv_linearity_rel"] < 2e-2 and res["dq_dk_balance_rel"] < 5e-2)
+        res["ok"] = bool(res["mean_err"] < 0.08 and res["deterministic"] and res["dv_linearity_rel"] < 2e-3 and res["dq_dk_balance_rel"] < 5e-2)
     print(json.dumps(res), flush=True)
 
 

@@ -113,19 +113,27 @@ __device__ __forceinline__ void zero_acc(float (&c)[8][4]) {
   for (int j = 0; j < 8; ++j) c[j][0] = c[j][1] = c[j][2] = c[j][3] = 0.f;
 }
 
-// Dropout on attention probabilities: 16 random bits per (b,h,q,k); eight keys share one Philox call.
-// keep iff bits16 >= p * 65536.  Indexed only by logical coordinates so forward and both backward kernels agree.
+// Dropout on attention probabilities: 16 random bits per (b,h,q,k), keep iff bits16 >= p * 65536; indexed only by logical
+// coordinates so forward and both backward kernels agree.  One Philox call = 128 bits = 8 elements, and the element <-> bit assignment
+// follows the MMA fragment layout so that no call is wasted: for query row q and 64-key chunk c, call (t, h) -- t = 0..3 the thread's
+// column pair inside an 8-key block, h = 0..1 the half of the chunk -- holds in word i (low / high 16 bits) the keys
+// 64c + 8(4h+i) + 2t (+1), i.e. exactly the 8 keys one thread of the forward / dQ kernels owns for that row and half.  The dK/dV
+// kernel (keys as rows) needs per query one call for BOTH of its keys (they are 8 apart: adjacent words of the same call).
 struct ProbDropout {
   unsigned long long seed;
   const unsigned long long* seed_dev;
   unsigned site;
   uint32_t thr16;
   float scale;
-  int S8;  // ceil(S / 8)
-  // keep flags for keys (8*kblk + 2t, 8*kblk + 2t + 1) of query q
-  __device__ __forceinline__ void keep2(long long bh, int q, int kblk, int t, bool& k0, bool& k1) const {
-    const uint4 r = Philox(seed + (seed_dev ? *seed_dev : 0ull))((unsigned long long)((bh * 0x10000LL + q) * (long long)S8 + kblk), site);
-    const uint32_t w = t == 0 ? r.x : (t == 1 ? r.y : (t == 2 ? r.z : r.w));
+  int nchunk;  // ceil(S / 64)
+  __device__ __forceinline__ unsigned long long effective_seed() const { return seed + (seed_dev ? *seed_dev : 0ull); }
+  __device__ __forceinline__ uint4 bits(unsigned long long seed_eff, long long bh, int q, int chunk, int t, int half) const {
+    return Philox(seed_eff)((((unsigned long long)((bh * 0x10000LL + q) * (long long)nchunk + chunk)) << 3) + (unsigned)(t * 2 + half), site);
+  }
+  __device__ __forceinline__ static uint32_t word(const uint4& r, int i) { return i == 0 ? r.x : (i == 1 ? r.y : (i == 2 ? r.z : r.w)); }
+  // keep flags of the key pair of 8-key block j (0..7) of the chunk, given the two calls (halves) of this thread's row
+  __device__ __forceinline__ void keep_pair(const uint4& h0, const uint4& h1, int j, bool& k0, bool& k1) const {
+    const uint32_t w = word(j < 4 ? h0 : h1, j & 3);
     k0 = (w & 0xFFFFu) >= thr16;
     k1 = (w >> 16) >= thr16;
   }
@@ -176,6 +184,7 @@ __global__ void __launch_bounds__(kAttnThreads) attn_fwd_kernel(const AttnParams
   float m0 = -INFINITY, m1 = -INFINITY, l0 = 0.f, l1 = 0.f;
   const int qr0 = q0 + warp * 16 + g, qr1 = qr0 + 8;
   const long long bh = (long long)b * p.heads + h;
+  const unsigned long long seed_eff = DROP ? p.drop.effective_seed() : 0ull;
 
   for (int kc = 0; kc < S_pad; kc += kTile) {
     float s[8][4];
@@ -213,13 +222,15 @@ __global__ void __launch_bounds__(kAttnThreads) attn_fwd_kernel(const AttnParams
     l0 = l0 * al0 + rs0;
     l1 = l1 * al1 + rs1;
     if (DROP) {
+      const uint4 a0 = p.drop.bits(seed_eff, bh, qr0, kc >> 6, t, 0), a1 = p.drop.bits(seed_eff, bh, qr0, kc >> 6, t, 1);
+      const uint4 b0 = p.drop.bits(seed_eff, bh, qr1, kc >> 6, t, 0), b1 = p.drop.bits(seed_eff, bh, qr1, kc >> 6, t, 1);
 #pragma unroll
       for (int j = 0; j < 8; ++j) {
         bool k0, k1;
-        p.drop.keep2(bh, qr0, (kc >> 3) + j, t, k0, k1);
+        p.drop.keep_pair(a0, a1, j, k0, k1);
         s[j][0] = k0 ? s[j][0] * p.drop.scale : 0.f;
         s[j][1] = k1 ? s[j][1] * p.drop.scale : 0.f;
-        p.drop.keep2(bh, qr1, (kc >> 3) + j, t, k0, k1);
+        p.drop.keep_pair(b0, b1, j, k0, k1);
         s[j][2] = k0 ? s[j][2] * p.drop.scale : 0.f;
         s[j][3] = k1 ? s[j][3] * p.drop.scale : 0.f;
       }
@@ -310,12 +321,18 @@ __global__ void __launch_bounds__(kAttnThreads) attn_bwd_dq_kernel(const AttnPar
   load_a_frags(sdO, warp * 16, lo, adO);
   float dq[8][4];
   zero_acc(dq);
+  const unsigned long long seed_eff = DROP ? p.drop.effective_seed() : 0ull;
   for (int kc = 0; kc < S_pad; kc += kTile) {
     float s[8][4], dp[8][4];
     zero_acc(s);
     zero_acc(dp);
     mma_a_tn(s, aQ, sK, kc, lo);
     mma_a_tn(dp, adO, sV, kc, lo);
+    uint4 a0, a1, b0, b1;
+    if (DROP) {
+      a0 = p.drop.bits(seed_eff, bh, qr0, kc >> 6, t, 0); a1 = p.drop.bits(seed_eff, bh, qr0, kc >> 6, t, 1);
+      b0 = p.drop.bits(seed_eff, bh, qr1, kc >> 6, t, 0); b1 = p.drop.bits(seed_eff, bh, qr1, kc >> 6, t, 1);
+    }
 #pragma unroll
     for (int j = 0; j < 8; ++j) {
       const int key = kc + 8 * j + 2 * t;
@@ -326,10 +343,10 @@ __global__ void __launch_bounds__(kAttnThreads) attn_bwd_dq_kernel(const AttnPar
       const float p11 = v1 ? fast_exp2(s[j][3] * p.scale_log2 - lse1) : 0.f;
       if (DROP) {
         bool k0, k1;
-        p.drop.keep2(bh, qr0, (kc >> 3) + j, t, k0, k1);
+        p.drop.keep_pair(a0, a1, j, k0, k1);
         dp[j][0] = k0 ? dp[j][0] * p.drop.scale : 0.f;
         dp[j][1] = k1 ? dp[j][1] * p.drop.scale : 0.f;
-        p.drop.keep2(bh, qr1, (kc >> 3) + j, t, k0, k1);
+        p.drop.keep_pair(b0, b1, j, k0, k1);
         dp[j][2] = k0 ? dp[j][2] * p.drop.scale : 0.f;
         dp[j][3] = k1 ? dp[j][3] * p.drop.scale : 0.f;
       }
@@ -394,6 +411,7 @@ __global__ void __launch_bounds__(kAttnThreads) attn_bwd_dkv_kernel(const AttnPa
   float dk[8][4], dv[8][4];
   zero_acc(dk);
   zero_acc(dv);
+  const unsigned long long seed_eff = DROP ? p.drop.effective_seed() : 0ull;
   for (int qc = 0; qc < S_pad; qc += kTile) {
     float s[8][4], dp[8][4];
     zero_acc(s);
@@ -414,19 +432,18 @@ __global__ void __launch_bounds__(kAttnThreads) attn_bwd_dkv_kernel(const AttnPa
       float e00 = dp[j][0], e01 = dp[j][1], e10 = dp[j][2], e11 = dp[j][3];
       float pd00 = p00, pd01 = p01, pd10 = p10, pd11 = p11;
       if (DROP) {
-        // element (q, key): the forward drew keys (8*kblk + 2t', 8*kblk + 2t'+1) per call; find this key's slot
-        bool a0, a1;
-        p.drop.keep2(bh, q, kr0 >> 3, (kr0 & 7) >> 1, a0, a1);
-        bool keep = (kr0 & 1) ? a1 : a0;
+        // element (q, key): this thread's keys kr0 and kr1 = kr0 + 8 sit in 8-key blocks 2*warp and 2*warp + 1 of the CTA's chunk, at
+        // column pair t' = g >> 1, slot g & 1: adjacent words of ONE call of the forward's layout (see ProbDropout)
+        const int wsel = (warp & 1) * 2, sh = (g & 1) * 16;
+        const uint4 r0 = p.drop.bits(seed_eff, bh, q, kt, g >> 1, warp >> 1);
+        const uint4 r1 = p.drop.bits(seed_eff, bh, q + 1, kt, g >> 1, warp >> 1);
+        bool keep = ((ProbDropout::word(r0, wsel) >> sh) & 0xFFFFu) >= p.drop.thr16;
         pd00 = keep ? p00 * p.drop.scale : 0.f; e00 = keep ? e00 * p.drop.scale : 0.f;
-        p.drop.keep2(bh, q + 1, kr0 >> 3, (kr0 & 7) >> 1, a0, a1);
-        keep = (kr0 & 1) ? a1 : a0;
+        keep = ((ProbDropout::word(r1, wsel) >> sh) & 0xFFFFu) >= p.drop.thr16;
         pd01 = keep ? p01 * p.drop.scale : 0.f; e01 = keep ? e01 * p.drop.scale : 0.f;
-        p.drop.keep2(bh, q, kr1 >> 3, (kr1 & 7) >> 1, a0, a1);
-        keep = (kr1 & 1) ? a1 : a0;
+        keep = ((ProbDropout::word(r0, wsel + 1) >> sh) & 0xFFFFu) >= p.drop.thr16;
         pd10 = keep ? p10 * p.drop.scale : 0.f; e10 = keep ? e10 * p.drop.scale : 0.f;
-        p.drop.keep2(bh, q + 1, kr1 >> 3, (kr1 & 7) >> 1, a0, a1);
-        keep = (kr1 & 1) ? a1 : a0;
+        keep = ((ProbDropout::word(r1, wsel + 1) >> sh) & 0xFFFFu) >= p.drop.thr16;
         pd11 = keep ? p11 * p.drop.scale : 0.f; e11 = keep ? e11 * p.drop.scale : 0.f;
       }
       pt[j][0] = pd00; pt[j][1] = pd01; pt[j][2] = pd10; pt[j][3] = pd11;
@@ -469,7 +486,7 @@ static int fill_params(AttnParams& p, int B, int S, int heads, float dropout_p, 
   p.drop.seed = seed; p.drop.seed_dev = reinterpret_cast<const unsigned long long*>(seed_dev); p.drop.site = site;
   p.drop.thr16 = (uint32_t)(dropout_p * 65536.0f + 0.5f);
   p.drop.scale = 1.0f / (1.0f - dropout_p);
-  p.drop.S8 = (p.S_pad + 7) / 8;
+  p.drop.nchunk = p.S_pad / kTile;
   return VAULT_OK;
 }
 

@@ -27,8 +27,31 @@ ROOT = os.path.dirname(os.path.abspath(__file__))
 sys.path.insert(0, ROOT)
 
 METRIC = "VaultModel fine-tune samples/sec"
-WORKLOAD = dict(lm="bert-base-uncased (random init)", vilt="vilt-b32 (random init)", head="VaultForTMSC n_classes=3", per_gpu_batch=32,
-                text_len=40, image=[384, 384], patches=144, seq_len=185)
+# Named workloads of BASELINE.json.  The default (the one the driver runs) is config 3, the configuration the metric is quoted on.
+# train_gflop = dense-shape algorithmic FLOPs per sample of one training step (SURVEY.md section 8d / BASELINE.md section 4).
+WORKLOADS = {
+    "config3": dict(desc="VaultForTMSC fine-tune step (BASELINE config 3): fwd + CE + bwd + grad all-reduce + HF-AdamW", lm_kind="bert", freeze_lm=False,
+                    lm="bert-base-uncased (random init)", text_len=40, image=[384, 384], patches=144, seq_len=185, train_gflop=119.99),
+    "target": dict(desc="VaultForTMSC fine-tune step at the north-star target shape (bert-base + vilt-b32, 384x640 images, 128 text tokens)", lm_kind="bert",
+                   freeze_lm=False, lm="bert-base-uncased (random init)", text_len=128, image=[384, 640], patches=240, seq_len=369, train_gflop=272.41),
+    "config4": dict(desc="VaultForTMSC fine-tune step (BASELINE config 4): BERTweet-shaped RoBERTa + vilt-b32, max shape, variable-length text masks",
+                    lm_kind="roberta", freeze_lm=False, lm="BERTweet-base-shaped RoBERTa (vocab 64001, 130 positions; random init)", text_len=128,
+                    image=[384, 640], patches=240, seq_len=369, train_gflop=272.41),
+    "config5": dict(desc="VaultForTMSC fine-tune step (BASELINE config 5): frozen LM (forward only) + trainable ViLT", lm_kind="bert", freeze_lm=True,
+                    lm="bert-base-uncased (random init, frozen)", text_len=40, image=[384, 384], patches=144, seq_len=185, train_gflop=106.28),
+}
+COMMON = dict(vilt="vilt-b32 (random init)", head="VaultForTMSC n_classes=3", per_gpu_batch=32)
+
+
+def workload_config(name):
+    w = WORKLOADS[name]
+    return dict(lm=w["lm"], **COMMON, text_len=w["text_len"], image=w["image"], patches=w["patches"], seq_len=w["seq_len"], freeze_lm=w["freeze_lm"])
+
+
+def oracle_dims(name):
+    from oracle import synth
+
+    return synth.Dims.bertweet() if WORKLOADS[name]["lm_kind"] == "roberta" else synth.Dims.base()
 
 
 def parse():
@@ -37,20 +60,21 @@ def parse():
     ap.add_argument("--steps", type=int, default=30)
     ap.add_argument("--warmup", type=int, default=5)
     ap.add_argument("--impl", default="vault_b200", choices=["vault_b200", "reference"])
-    ap.add_argument("--batch", type=int, default=WORKLOAD["per_gpu_batch"])
+    ap.add_argument("--batch", type=int, default=COMMON["per_gpu_batch"])
+    ap.add_argument("--workload", default="config3", choices=sorted(WORKLOADS), help="named BASELINE workload (default: config 3, the metric's)")
     ap.add_argument("--no-graph", action="store_true")
     ap.add_argument("--skip-cpu-baseline", action="store_true")
     ap.add_argument("--skip-roofline", action="store_true")
     return ap.parse_args()
 
 
-def synth_batch(torch, B, T, hw, vocab, n_classes, seed, pin):
-    """TWITTER-15-shaped synthetic batch: ids ~ U, lengths ~ U{8..T} with trailing pad (id 0), pixels ~ N(0,1), mask all ones."""
+def synth_batch(torch, B, T, hw, vocab, n_classes, seed, pin, pad_id=0):
+    """TWITTER-15-shaped synthetic batch: ids ~ U, lengths ~ U{8..T} with trailing pad, pixels ~ N(0,1), mask all ones."""
     g = torch.Generator().manual_seed(seed)
     ids = torch.randint(1000, vocab, (B, T), generator=g)
     lens = torch.randint(8, T + 1, (B,), generator=g)
     am = (torch.arange(T)[None, :] < lens[:, None]).long()
-    ids = ids * am
+    ids = ids * am + pad_id * (1 - am)
     batch = dict(input_ids=ids, attention_mask=am, token_type_ids=torch.zeros_like(ids),
                  pixel_values=torch.randn((B, 3, hw[0], hw[1]), generator=g), pixel_mask=torch.ones((B, hw[0], hw[1]), dtype=torch.long),
                  labels=torch.randint(0, n_classes, (B,), generator=g))
@@ -99,28 +123,30 @@ class ClockSampler:
         return dict(sm_mhz=(busy[len(busy) // 2] if busy else None), sm_max_mhz=mx, samples=len(sm), reasons=sorted(reasons))
 
 
-def cpu_baseline(torch, steps=3, warmup=1, B=8):
+def cpu_baseline(torch, workload, steps=3, warmup=1, B=8):
     """Oracle port (fp32 restatement of the reference path, oracle/vault_oracle.py) on the host cores: forward + CE + backward +
     HF-AdamW, bounded sample of the same workload (B rows instead of 32)."""
     from oracle import synth, vault_oracle as O
 
+    w = WORKLOADS[workload]
     cores = os.cpu_count() or 1
     torch.set_num_threads(cores)
-    d = synth.Dims.base()
+    d = oracle_dims(workload)
     sd = synth.make_state_dict(d, seed=0)
-    batch = synth.make_inputs(d, batch=B, text_len=WORKLOAD["text_len"], image_hw=tuple(WORKLOAD["image"]), seed=1, var_text=True)
+    batch = synth.make_inputs(d, batch=B, text_len=w["text_len"], image_hw=tuple(w["image"]), seed=1, var_text=True)
     state = None
     times = []
     for i in range(warmup + steps):
         t0 = time.perf_counter()
-        out = O.train_step(sd, d, batch, lr=2e-5, state=state, train_mode=True)
+        out = O.train_step(sd, d, batch, lr=2e-5, freeze_lm=w["freeze_lm"], state=state, train_mode=True)
         state = out["state"]
         if i >= warmup:
             times.append(time.perf_counter() - t0)
     times.sort()
     med = times[len(times) // 2]
     return dict(value=B / med, unit="samples/s", cores=cores, kind="port",
-                sample=f"oracle train step (fwd+CE+bwd+HF-AdamW, fp32, dropout on), B={B} of the 32-row batch, T=40, 384x384; median of {steps} after {warmup} warm-up",
+                sample=f"oracle train step (fwd+CE+bwd+HF-AdamW, fp32, dropout on), B={B} of the 32-row batch, T={w['text_len']}, "
+                       f"{w['image'][0]}x{w['image'][1]}; median of {steps} after {warmup} warm-up",
                 ms_per_step=med * 1e3)
 
 
@@ -136,15 +162,16 @@ def run_reference(args):
     cores = os.cpu_count() or 1
     torch.set_num_threads(cores)
     B = 8
-    d = synth.Dims.base()
+    w = WORKLOADS[args.workload]
+    d = oracle_dims(args.workload)
     sd = synth.make_state_dict(d, seed=0)
-    batch = synth.make_inputs(d, batch=B, text_len=WORKLOAD["text_len"], image_hw=tuple(WORKLOAD["image"]), seed=1, var_text=True)
+    batch = synth.make_inputs(d, batch=B, text_len=w["text_len"], image_hw=tuple(w["image"]), seed=1, var_text=True)
     state = None
     t0 = None
     for i in range(args.warmup + args.steps):
         if i == args.warmup:
             t0 = time.perf_counter()
-        out = O.train_step(sd, d, batch, lr=2e-5, state=state, train_mode=True)
+        out = O.train_step(sd, d, batch, lr=2e-5, freeze_lm=w["freeze_lm"], state=state, train_mode=True)
         state = out["state"]
     dt = time.perf_counter() - t0
     v = B * args.steps / dt
@@ -152,7 +179,7 @@ def run_reference(args):
     print(json.dumps({
         "impl": "reference", "metric": METRIC, "value": v, "unit": "samples/s", "n_gpus": args.gpus, "steps": args.steps, "warmup": args.warmup,
         "ms_per_step": dt / args.steps * 1e3, "higher_is_better": True, "scaling": "weak", "vs_baseline": None, "dtype": "f32", "data": "synthetic",
-        "config": dict(workload="VaultForTMSC fine-tune step (config 3)", **WORKLOAD, parallelism="cpu", sample=sample),
+        "config": dict(workload=w["desc"], name=args.workload, **workload_config(args.workload), parallelism="cpu", sample=sample),
         "cpu_baseline": dict(value=v, unit="samples/s", cores=cores, kind="port", sample=sample),
         "e2e": dict(value=v, unit="samples/s", h2d_bytes_per_step=0, d2h_bytes_per_step=0),
     }), flush=True)
@@ -205,8 +232,10 @@ def gemm_roofline(torch, ts, batch_dev, peaks):
     peak = peaks.get("bf16_tflops_sustained") or 1400.0
     del keep
     return dict(bound="tensor", kernel="vb::gemm_bf16_kernel (tcgen05/TMEM/TMA)", achieved=achieved, peak=peak, unit="TFLOP/s", frac=achieved / peak,
-                traffic=dict(dram_bytes_per_launch=12.8e6, algorithmic_bytes_per_launch=40.0e6, launch="5920x2304x768 bias->bf16 (QKV forward)",
-                             source="profiles/r01_ncu_gemm_full.md (ncu --set full): operands and outputs of consecutive kernels stay in the 126 MB L2"),
+                traffic=12.8e6,
+                traffic_note=dict(dram_bytes_per_launch=12.8e6, algorithmic_bytes_per_launch=40.0e6, launch="5920x2304x768 bias->bf16 (QKV forward of config 3)",
+                                  source="profiles/r01_ncu_gemm_full.md (ncu --set full, dram__bytes_read.sum + dram__bytes_write.sum): operands and "
+                                         "outputs of consecutive kernels stay in the 126 MB L2"),
                 launches_per_step=len(gemms), gemm_ms_per_step=ms, flops_per_step=flops,
                 peak_source="MEASURED_PEAKS.json bf16_tflops_sustained (kernel replayed inside a multi-ms dense run)" if "bf16_tflops_sustained" in peaks
                 else "fallback (B200_PROFILING.md): 1.4 PFLOP/s sustained"), launches, calls
@@ -281,24 +310,33 @@ def main():
         os.environ.setdefault("MASTER_ADDR", "127.0.0.1")
         dist.init_process_group("nccl", device_id=dev)
 
-    from transformers import BertConfig, ViltConfig
+    from transformers import BertConfig, RobertaConfig, ViltConfig
 
     from vault_b200 import VaultForTMSC, VaultTrainStep
+    from vault_b200.model import set_parameter_requires_grad
 
+    W = WORKLOADS[args.workload]
     torch.manual_seed(0)
-    vc, bc = ViltConfig(), BertConfig()
+    vc = ViltConfig()
+    if W["lm_kind"] == "roberta":  # BERTweet-base shape
+        bc = RobertaConfig(vocab_size=64001, max_position_embeddings=130, type_vocab_size=1, pad_token_id=1, layer_norm_eps=1e-5, bos_token_id=0, eos_token_id=2)
+    else:
+        bc = BertConfig()
     model = VaultForTMSC(vc, n_classes=3, vilt_dropout_prob=0.1, bert_config=bc)
+    if W["freeze_lm"]:  # what VaultMixin.__init__(freeze_lm=True) does (ref:vault/models/vault/model.py:84-87); VaultForTMSC does not forward the flag
+        model.freeze_lm = True
+        set_parameter_requires_grad(model.bert, False)
     with torch.no_grad():  # HF leaves these at zero under random init
         model.embeddings.cls_token.normal_(0, 0.02)
         model.embeddings.position_embeddings.normal_(0, 0.02)
     model = model.to(dev).train()
-    B, T, hw = args.batch, WORKLOAD["text_len"], tuple(WORKLOAD["image"])
+    B, T, hw = args.batch, W["text_len"], tuple(W["image"])
     total_sched = 100000
     ts = VaultTrainStep(model, lr=2e-5, total_steps=total_sched, use_cuda_graph=not args.no_graph,
                         overlap_comm=os.environ.get("VB_OVERLAP", "1") == "1", comm_reserve_sms=int(os.environ.get("VB_COMM_RESERVE", "0")), grad_comm_dtype=os.environ.get("VB_COMM_DTYPE", "bf16"))
     ts.step_idx = total_sched // 5  # past warm-up: a non-zero learning rate so AdamW really moves the weights
     NB = 4
-    host = [synth_batch(torch, B, T, hw, bc.vocab_size, 3, seed=1000 * rank + i, pin=True) for i in range(NB)]
+    host = [synth_batch(torch, B, T, hw, bc.vocab_size, 3, seed=1000 * rank + i, pin=True, pad_id=bc.pad_token_id or 0) for i in range(NB)]
     devb = [{k: v.to(dev) for k, v in b.items()} for b in host]
     h2d = sum(v.numel() * v.element_size() for v in host[0].values())
 
@@ -351,18 +389,18 @@ def main():
         hbm = hbm_kernel_rates(torch, peaks) if (world == 1 and not args.skip_roofline) else None
         cpu = None
         if world == 1 and not args.skip_cpu_baseline:
-            cpu = cpu_baseline(torch)
+            cpu = cpu_baseline(torch, args.workload)
         gb = B * world
         value = gb * args.steps / (ms_dev * 1e-3)
         e2e = gb * args.steps / (ms_e2e * 1e-3)
-        train_gflop_per_sample = 119.99  # BASELINE.md section 4, shape A (dense-shape FLOPs)
+        train_gflop_per_sample = W["train_gflop"]  # BASELINE.md section 4 (dense-shape FLOPs of the named shape)
         out = {
             "metric": METRIC, "value": value, "unit": "samples/s", "n_gpus": world, "steps": args.steps, "warmup": args.warmup,
             "ms_per_step": ms_dev / args.steps, "higher_is_better": True, "scaling": "weak", "vs_baseline": None, "dtype": "bf16", "data": "synthetic",
-            "config": dict(workload="VaultForTMSC fine-tune step (BASELINE config 3): fwd + CE + bwd + grad all-reduce + HF-AdamW", **WORKLOAD,
+            "config": dict(workload=W["desc"], name=args.workload, **{**workload_config(args.workload), "per_gpu_batch": B},
                            global_batch=gb, parallelism=f"dp{world}", cuda_graph=not args.no_graph, comm_overlap=ts.overlap, grad_comm_dtype=("bf16" if ts.grad16 is not None else "fp32"),
                            gemm_ctas=ts.engine.gemm_max_ctas or ts.engine.sms,
-                           l2="per-step working set (0.44 GB bf16 weights + 0.79 GB fp32 grads + ~2 GB activations) >> 126 MB L2; 4 rotating input batches"),
+                           l2="per-step working set (0.44 GB bf16 weights + 0.79 GB fp32 grads + >= 2 GB activations) >> 126 MB L2; 4 rotating input batches"),
             "e2e": dict(value=e2e, unit="samples/s", h2d_bytes_per_step=h2d, d2h_bytes_per_step=4, ms_per_step=ms_e2e / args.steps,
                         api="vault_b200.VaultTrainStep.step(pinned host batch) -> StepResult.loss()"),
             "gpu_launches": (launches + 1) * args.steps if launches else None,

@@ -9,17 +9,30 @@
 // un-transposed, contraction over tokens, optional split-K with fp32 atomics).
 //
 // Warp roles (384 threads, 1 CTA/SM):  warp0 TMA producer | warp1 MMA issuer | warp2 TMEM alloc | warp3 idle | warps4-11 epilogue
+// (VB_EPI_WARPS=16: 640 threads, four epilogue warps per TMEM lane quadrant working in 16-column chunks)
 #include "common.cuh"
+
+#ifndef VB_EPI_WARPS
+#define VB_EPI_WARPS 8  // 16 (four warps per TMEM lane quadrant, 16-column chunks) measured 3-4 % SLOWER on every shape: kept for A/B builds
+#endif
 
 namespace vb {
 
 constexpr int BM = 128;
 constexpr int BK = 64;  // 64 bf16 = one 128-byte swizzle row
 constexpr int UMMA_K = 16;
-constexpr int kEpiWarps = 8;
+constexpr int kEpiWarps = VB_EPI_WARPS;
+static_assert(kEpiWarps == 8 || kEpiWarps == 16, "epilogue warps: 8 or 16");
 constexpr int kThreads = 128 + kEpiWarps * 32;
 constexpr int kRingBytes = 196608;                 // smem ring for A/B stages
-constexpr int kStagingBytes = kEpiWarps * 4096;    // per-warp 32x32 fp32 transpose buffers
+constexpr int kCW = kEpiWarps == 8 ? 32 : 16;      // columns of one transposed chunk (32 rows x kCW fp32 per warp)
+constexpr int kLPR = kCW / 4;                      // lanes per row after the transpose (one float4 each)
+constexpr int kRPP = 32 / kLPR;                    // rows per pass
+constexpr int kNP = 32 / kRPP;                     // passes per chunk
+constexpr int kStagingBytes = kEpiWarps * 32 * kCW * 4;  // per-warp 32 x kCW fp32 transpose buffers
+// XOR swizzle of the 16-byte slots of a staging row (row = 128 B for 32-column chunks, 64 B for 16-column chunks): conflict-free
+// for the row-per-lane writes and for the kRPP-rows-per-pass reads
+__device__ __forceinline__ int stg_swz(int row) { return kCW == 32 ? (row & 7) : ((row >> 1) & 3); }
 constexpr int kSchedDepth = 4;
 constexpr int kSmemBytes = kRingBytes + kStagingBytes + 1024 /*align slack*/ + 384 /*barriers + tile ring*/;
 
@@ -45,14 +58,14 @@ struct GemmParams {
 };
 
 // ---- fused epilogues -------------------------------------------------------------------------------------------------
-// After the smem transpose each lane owns 4 consecutive columns of 8 rows (row stride 4) of a 32x32 chunk.  Pointers are
+// After the smem transpose each lane owns 4 consecutive columns of kNP rows (row stride kRPP) of a 32 x kCW chunk.  Pointers are
 // formed once per chunk and advanced by a constant row stride; full tiles skip every bounds check (GUARD=false).
 template <int EPI>
 struct EpiPtrs {
   char* out;          // bf16 or fp32
   char* out2;         // bf16 (GELU pre-activation), may be null
   const char* side;   // fp32 residual or bf16 pre-activation
-  long long out_step, out2_step, side_step;  // bytes per 4 rows
+  long long out_step, out2_step, side_step;  // bytes per kRPP rows
 };
 
 template <int EPI>
@@ -62,13 +75,13 @@ __device__ __forceinline__ EpiPtrs<EPI> make_ptrs(const GemmParams& p, long long
   constexpr int osz = kOutF32 ? 4 : 2;
   EpiPtrs<EPI> e;
   e.out = reinterpret_cast<char*>(p.out) + (row * p.ldo + col) * osz;
-  e.out_step = 4 * p.ldo * osz;
+  e.out_step = kRPP * p.ldo * osz;
   e.out2 = nullptr; e.out2_step = 0; e.side = nullptr; e.side_step = 0;
   if constexpr (EPI == VAULT_EPI_BIAS_GELU_BF16) {
-    if (p.out2) { e.out2 = reinterpret_cast<char*>(p.out2) + (row * p.ldo2 + col) * 2; e.out2_step = 8 * p.ldo2; }
+    if (p.out2) { e.out2 = reinterpret_cast<char*>(p.out2) + (row * p.ldo2 + col) * 2; e.out2_step = 2 * kRPP * p.ldo2; }
   }
-  if constexpr (EPI == VAULT_EPI_BIAS_RESID_F32) { e.side = reinterpret_cast<const char*>(p.resid) + (row * p.ldr + col) * 4; e.side_step = 16 * p.ldr; }
-  if constexpr (EPI == VAULT_EPI_DGELU_BF16) { e.side = reinterpret_cast<const char*>(p.aux) + (row * p.ldaux + col) * 2; e.side_step = 8 * p.ldaux; }
+  if constexpr (EPI == VAULT_EPI_BIAS_RESID_F32) { e.side = reinterpret_cast<const char*>(p.resid) + (row * p.ldr + col) * 4; e.side_step = 4 * kRPP * p.ldr; }
+  if constexpr (EPI == VAULT_EPI_DGELU_BF16) { e.side = reinterpret_cast<const char*>(p.aux) + (row * p.ldaux + col) * 2; e.side_step = 2 * kRPP * p.ldaux; }
   return e;
 }
 
@@ -133,28 +146,28 @@ __device__ __forceinline__ void epilogue4(const GemmParams& p, float4 acc, const
   }
 }
 
-// one 32x32 chunk: side inputs of all 8 row groups are fetched before any store so the loads are in flight together
+// one 32 x kCW chunk: side inputs of all row groups are fetched before any store so the loads are in flight together
 template <int EPI, bool GUARD>
 __device__ __forceinline__ void epilogue_chunk(const GemmParams& p, const float4* stg, int lane, const float4& b4, unsigned long long seed,
                                                long long row0, int col) {
-  const int cg = lane & 7, rsub = lane >> 3;
+  const int cg = lane % kLPR, rsub = lane / kLPR;
   const long long rbase = row0 + rsub;
   if (GUARD && col >= p.N) return;
   EpiPtrs<EPI> e = make_ptrs<EPI>(p, rbase, col);
-  float4 side[8];
+  float4 side[kNP];
   if constexpr (EPI == VAULT_EPI_BIAS_RESID_F32 || EPI == VAULT_EPI_DGELU_BF16) {
 #pragma unroll
-    for (int i = 0; i < 8; ++i) {
-      if (!GUARD || rbase + 4 * i < p.M) side[i] = load_side<EPI>(e.side + i * e.side_step);
+    for (int i = 0; i < kNP; ++i) {
+      if (!GUARD || rbase + kRPP * i < p.M) side[i] = load_side<EPI>(e.side + i * e.side_step);
     }
   }
   const unsigned long long drop0 = (unsigned long long)(rbase * p.N + col) >> 2;
-  const unsigned long long drop_step = (unsigned long long)p.N;  // 4 rows * N / 4
+  const unsigned long long drop_step = (unsigned long long)p.N * (kRPP / 4);  // kRPP rows * N / 4
 #pragma unroll
-  for (int i = 0; i < 8; ++i) {
-    const int rl = 4 * i + rsub;
-    const float4 acc = stg[rl * 8 + (cg ^ (rl & 7))];
-    if (!GUARD || rbase + 4 * i < p.M)
+  for (int i = 0; i < kNP; ++i) {
+    const int rl = kRPP * i + rsub;
+    const float4 acc = stg[rl * kLPR + (cg ^ stg_swz(rl))];
+    if (!GUARD || rbase + kRPP * i < p.M)
       epilogue4<EPI>(p, acc, b4, side[i], seed, drop0 + i * drop_step, e.out + i * e.out_step, e.out2 ? e.out2 + i * e.out2_step : nullptr);
   }
 }
@@ -368,9 +381,10 @@ gemm_bf16_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant_
     // ===================== epilogue warps =====================
     const int ew = warp - 4;
     const int q = warp & 3;        // TMEM lane quadrant this warp may access
-    const int half = ew >> 2;      // which half of the tile's columns
-    constexpr int kColsPerWarp = BN / 2;
-    float4* stg = reinterpret_cast<float4*>(staging_gen + ew * 4096);
+    const int part = ew >> 2;      // which slice of the tile's columns
+    constexpr int kColsPerWarp = BN / (kEpiWarps / 4);
+    static_assert(kColsPerWarp % kCW == 0, "tile columns must split into whole chunks per epilogue warp");
+    float4* stg = reinterpret_cast<float4*>(staging_gen + ew * (32 * kCW * 4));
     const unsigned long long seed = p.seed + ((p.dropout_p > 0.f && p.seed_dev) ? *p.seed_dev : 0ull);
     int as = 0;
     uint32_t aphase = 0;
@@ -385,18 +399,18 @@ gemm_bf16_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant_
       tc_fence_after();
       const bool full_tile = (m0 + BM <= p.M) && (n0 + BN <= p.N);
 #pragma unroll 1
-      for (int c = half * kColsPerWarp; c < (half + 1) * kColsPerWarp; c += 32) {
-        uint32_t r[32];
-        tmem_ld32(tmem_base + ((uint32_t)(q * 32) << 16) + (uint32_t)(as * BN + c), r);
+      for (int c = part * kColsPerWarp; c < (part + 1) * kColsPerWarp; c += kCW) {
+        uint32_t r[kCW];
+        tmem_ld_cols(tmem_base + ((uint32_t)(q * 32) << 16) + (uint32_t)(as * BN + c), r);
         tmem_ld_wait();
-        // transpose through smem: thread = row -> (4 rows x 8 column-groups) per pass, XOR-swizzled 16B slots
+        // transpose through smem: thread = row -> (kRPP rows x kLPR column-groups) per pass, XOR-swizzled 16B slots
 #pragma unroll
-        for (int j = 0; j < 8; ++j) {
-          stg[lane * 8 + (j ^ (lane & 7))] =
+        for (int j = 0; j < kLPR; ++j) {
+          stg[lane * kLPR + (j ^ stg_swz(lane))] =
               make_float4(__uint_as_float(r[4 * j]), __uint_as_float(r[4 * j + 1]), __uint_as_float(r[4 * j + 2]), __uint_as_float(r[4 * j + 3]));
         }
         __syncwarp();
-        const int col = n0 + c + (lane & 7) * 4;
+        const int col = n0 + c + (lane % kLPR) * 4;
         float4 b4 = make_float4(0.f, 0.f, 0.f, 0.f);
         if constexpr (EPI == VAULT_EPI_BIAS_BF16 || EPI == VAULT_EPI_BIAS_GELU_BF16 || EPI == VAULT_EPI_BIAS_RESID_F32 || EPI == VAULT_EPI_BIAS_F32) {
           if (p.bias != nullptr && col < p.N) b4 = __ldg(reinterpret_cast<const float4*>(p.bias + col));

@@ -352,6 +352,10 @@ def main():
         barrier()
         e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
         prev, losses = None, []
+        # `ncu --profile-from-start off ... python bench.py` then lists exactly the launches of the device-resident timed region
+        prof = os.environ.get("VAULT_B200_PROFILE_RANGE") == "1" and not read_loss
+        if prof:
+            torch.cuda.profiler.start()
         e0.record()
         for i in range(args.steps):
             r = ts.step(batches[i % NB])
@@ -362,6 +366,8 @@ def main():
             losses.append(prev.loss())
         e1.record()
         barrier()
+        if prof:
+            torch.cuda.profiler.stop()
         ms = e0.elapsed_time(e1)
         t = torch.tensor([ms], device=dev)
         if world > 1:

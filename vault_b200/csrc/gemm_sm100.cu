@@ -12,6 +12,9 @@
 // (VB_EPI_WARPS=16: 640 threads, four epilogue warps per TMEM lane quadrant working in 16-column chunks)
 #include "common.cuh"
 
+#ifndef VB_EPI_DIRECT
+#define VB_EPI_DIRECT 0  // 1 = no smem transpose: every thread applies the epilogue to its own row (the TMEM lane) and stores 16-byte pieces
+#endif
 #ifndef VB_EPI_WARPS
 #define VB_EPI_WARPS 8  // 16 (four warps per TMEM lane quadrant, 16-column chunks) measured 3-4 % SLOWER on every shape: kept for A/B builds
 #endif
@@ -169,6 +172,72 @@ __device__ __forceinline__ void epilogue_chunk(const GemmParams& p, const float4
     const float4 acc = stg[rl * kLPR + (cg ^ stg_swz(rl))];
     if (!GUARD || rbase + kRPP * i < p.M)
       epilogue4<EPI>(p, acc, b4, side[i], seed, drop0 + i * drop_step, e.out + i * e.out_step, e.out2 ? e.out2 + i * e.out2_step : nullptr);
+  }
+}
+
+// Direct form (VB_EPI_DIRECT): thread = output row, kCW consecutive columns in registers; 16-byte loads / stores per thread, the
+// halves of a 32-byte sector arrive from consecutive instructions of the same thread.  No staging buffer, no warp synchronisation.
+template <int EPI, bool GUARD>
+__device__ __forceinline__ void epilogue_row(const GemmParams& p, const uint32_t (&r)[kCW], long long row, int col0, int split, unsigned long long seed) {
+  constexpr bool kOutF32 = EPI == VAULT_EPI_BIAS_RESID_F32 || EPI == VAULT_EPI_ATOMIC_F32 || EPI == VAULT_EPI_BIAS_F32 || EPI == VAULT_EPI_STORE_F32 ||
+                           EPI == VAULT_EPI_ATOMIC_BIAS_DROP_F32;
+  constexpr bool kBias = EPI == VAULT_EPI_BIAS_BF16 || EPI == VAULT_EPI_BIAS_GELU_BF16 || EPI == VAULT_EPI_BIAS_RESID_F32 || EPI == VAULT_EPI_BIAS_F32 ||
+                         EPI == VAULT_EPI_ATOMIC_BIAS_DROP_F32;
+  if (GUARD && row >= p.M) return;
+  const bool has_bias = kBias && p.bias != nullptr && (EPI != VAULT_EPI_ATOMIC_BIAS_DROP_F32 || split == 0);
+  const unsigned long long drop0 = (unsigned long long)(row * p.N + col0) >> 2;
+  if constexpr (kOutF32) {
+    float* out = reinterpret_cast<float*>(p.out) + row * p.ldo + col0;
+    float4 side[kCW / 4];
+    if constexpr (EPI == VAULT_EPI_BIAS_RESID_F32) {
+      const float* rs = p.resid + row * p.ldr + col0;
+#pragma unroll
+      for (int j = 0; j < kCW / 4; ++j)
+        if (!GUARD || col0 + 4 * j < p.N) side[j] = __ldg(reinterpret_cast<const float4*>(rs + 4 * j));
+    }
+#pragma unroll
+    for (int j = 0; j < kCW / 4; ++j) {
+      if (GUARD && col0 + 4 * j >= p.N) break;
+      const float4 acc = make_float4(__uint_as_float(r[4 * j]), __uint_as_float(r[4 * j + 1]), __uint_as_float(r[4 * j + 2]), __uint_as_float(r[4 * j + 3]));
+      const float4 b4 = has_bias ? __ldg(reinterpret_cast<const float4*>(p.bias + col0 + 4 * j)) : make_float4(0.f, 0.f, 0.f, 0.f);
+      epilogue4<EPI>(p, acc, b4, side[j], seed, drop0 + j, reinterpret_cast<char*>(out + 4 * j), nullptr);
+    }
+  } else {
+    bf16* out = reinterpret_cast<bf16*>(p.out) + row * p.ldo + col0;
+    bf16* out2 = (EPI == VAULT_EPI_BIAS_GELU_BF16 && p.out2) ? reinterpret_cast<bf16*>(p.out2) + row * p.ldo2 + col0 : nullptr;
+    uint4 aux[kCW / 8];
+    if constexpr (EPI == VAULT_EPI_DGELU_BF16) {
+      const bf16* ax = p.aux + row * p.ldaux + col0;
+#pragma unroll
+      for (int j = 0; j < kCW / 8; ++j)
+        if (!GUARD || col0 + 8 * j < p.N) aux[j] = __ldg(reinterpret_cast<const uint4*>(ax + 8 * j));
+    }
+#pragma unroll
+    for (int j = 0; j < kCW / 8; ++j) {  // N is a multiple of 8: an 8-column group is inside or outside as a whole
+      if (GUARD && col0 + 8 * j >= p.N) break;
+      float x[8];
+#pragma unroll
+      for (int e = 0; e < 8; ++e) x[e] = __uint_as_float(r[8 * j + e]);
+      if (has_bias) {
+        const float4 b0 = __ldg(reinterpret_cast<const float4*>(p.bias + col0 + 8 * j)), b1 = __ldg(reinterpret_cast<const float4*>(p.bias + col0 + 8 * j + 4));
+        x[0] += b0.x; x[1] += b0.y; x[2] += b0.z; x[3] += b0.w; x[4] += b1.x; x[5] += b1.y; x[6] += b1.z; x[7] += b1.w;
+      }
+      if constexpr (EPI == VAULT_EPI_BIAS_GELU_BF16) {
+        if (out2) *reinterpret_cast<uint4*>(out2 + 8 * j) = make_uint4(pack_bf16x2(x[0], x[1]), pack_bf16x2(x[2], x[3]), pack_bf16x2(x[4], x[5]), pack_bf16x2(x[6], x[7]));
+#pragma unroll
+        for (int e = 0; e < 8; ++e) x[e] = gelu_erf(x[e]);
+      }
+      if constexpr (EPI == VAULT_EPI_DGELU_BF16) {
+        const uint32_t w[4] = {aux[j].x, aux[j].y, aux[j].z, aux[j].w};
+#pragma unroll
+        for (int e = 0; e < 4; ++e) {
+          const float2 a = unpack_bf16x2(w[e]);
+          x[2 * e] *= gelu_erf_grad(a.x);
+          x[2 * e + 1] *= gelu_erf_grad(a.y);
+        }
+      }
+      *reinterpret_cast<uint4*>(out + 8 * j) = make_uint4(pack_bf16x2(x[0], x[1]), pack_bf16x2(x[2], x[3]), pack_bf16x2(x[4], x[5]), pack_bf16x2(x[6], x[7]));
+    }
   }
 }
 
@@ -403,6 +472,11 @@ gemm_bf16_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant_
         uint32_t r[kCW];
         tmem_ld_cols(tmem_base + ((uint32_t)(q * 32) << 16) + (uint32_t)(as * BN + c), r);
         tmem_ld_wait();
+#if VB_EPI_DIRECT
+        if (full_tile) epilogue_row<EPI, false>(p, r, (long long)m0 + q * 32 + lane, n0 + c, split, seed);
+        else epilogue_row<EPI, true>(p, r, (long long)m0 + q * 32 + lane, n0 + c, split, seed);
+        continue;
+#endif
         // transpose through smem: thread = row -> (kRPP rows x kLPR column-groups) per pass, XOR-swizzled 16B slots
 #pragma unroll
         for (int j = 0; j < kLPR; ++j) {

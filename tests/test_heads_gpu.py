@@ -76,3 +76,35 @@ def test_image_embeds_path_matches_reference_fixture():
         again = m(input_ids=inp["input_ids"].to(DEV), attention_mask=inp["attention_mask"].to(DEV), token_type_ids=inp["token_type_ids"].to(DEV),
                   image_embeds=image_embeds.to(DEV), pixel_mask=image_mask.to(DEV))
     assert torch.equal(again.pooler_output, out.pooler_output.detach())
+
+
+@pytest.mark.parametrize("vocab,tokens", [(510, 48), (30522, 80)])
+def test_mlm_decoder_on_the_gemm_kernel(vocab, tokens):
+    """``mlm_score.decoder`` of VaultForMaskedLM runs on the tcgen05 GEMM (forward, dgrad, wgrad, bias column sums), with the vocabulary
+    padded to a multiple of 8 columns: against torch fp32 on the same bf16-rounded operands.  Tolerance: bf16 rounding of dlogits."""
+    from vault_b200.model import _KernelDecoder
+
+    torch.manual_seed(3)
+    H = 128
+    lin = torch.nn.Linear(H, vocab).to(DEV)
+    with torch.no_grad():
+        lin.weight.copy_(lin.weight.to(torch.bfloat16).float())
+    ker = torch.nn.Linear(H, vocab).to(DEV)
+    ker.load_state_dict(lin.state_dict())
+    ker.__class__ = _KernelDecoder
+    x = torch.randn(2, tokens // 2, H, device=DEV).to(torch.bfloat16).float()
+    xa, xb = x.clone().requires_grad_(True), x.clone().requires_grad_(True)
+    labels = torch.randint(0, vocab, (tokens,), device=DEV)
+    labels[::3] = -100
+    ya, yb = lin(xa), ker(xb)
+    assert yb.shape == ya.shape == (2, tokens // 2, vocab)
+    assert rel_err(yb.detach().cpu(), ya.detach().cpu()) <= 1e-3
+    la = torch.nn.functional.cross_entropy(ya.view(-1, vocab), labels)
+    lb = torch.nn.functional.cross_entropy(yb.view(-1, vocab), labels)  # the HF head's own .view on the sliced logits
+    assert abs(la.item() - lb.item()) <= 1e-3
+    la.backward()
+    lb.backward()
+    for got, want in ((xb.grad, xa.grad), (ker.weight.grad, lin.weight.grad), (ker.bias.grad, lin.bias.grad)):
+        assert got is not None and got.shape == want.shape
+        assert cosine(got.float().cpu(), want.float().cpu()) >= 0.999
+        assert rel_err(got.float().cpu(), want.float().cpu()) <= 2e-2

@@ -203,3 +203,38 @@ def test_head_wrappers_route_the_trunk_through_the_engine(monkeypatch):
     assert eng.vp == "vilt." and eng._k("layernorm.weight") == "vilt.layernorm.weight" and eng._k("bert.embeddings.LayerNorm.bias").startswith("bert.")
     assert train[0] == "vilt.pooler.dense.weight" and all(n.startswith(("vilt.", "bert.")) for n in train)
     assert {"classifier.0.weight", "classifier.3.bias", "vilt.embeddings.text_embeddings.word_embeddings.weight"} <= set(static)
+
+
+def test_bench_workloads_are_consistent_with_baseline_shapes():
+    """bench.py's named workloads: ViLT sequence = text + CLS + patches, patch grid = image / 32, FLOPs per sample = the closed form of
+    SURVEY.md section 8d (3x forward, patch projection 2x, frozen LM 1x), and the oracle dims of each workload exist."""
+    import bench
+
+    assert bench.parse.__module__ == "bench" and set(bench.WORKLOADS) == {"config3", "target", "config4", "config5"}
+    for name, w in bench.WORKLOADS.items():
+        T, (hi, wi) = w["text_len"], w["image"]
+        P = (hi // 32) * (wi // 32)
+        assert w["patches"] == P and w["seq_len"] == T + 1 + P
+        enc = lambda n: 12 * (14155776 * n + 3072 * n * n)  # 12 layers: 24 n H^2 + 4 n^2 H
+        lm, vilt, patch = enc(T), enc(T + 1 + P), 4718592 * P
+        want = ((1 if w["freeze_lm"] else 3) * lm + 3 * vilt + 2 * patch) / 1e9
+        assert abs(w["train_gflop"] - want) / want < 2e-3, (name, w["train_gflop"], want)
+        cfg = bench.workload_config(name)
+        assert cfg["per_gpu_batch"] == 32 and cfg["text_len"] == T
+        d = bench.oracle_dims(name)
+        assert d.lm_kind == w["lm_kind"] and (d.lm_vocab == 64001) == (w["lm_kind"] == "roberta")
+
+
+def test_mlm_decoder_class_swap_keeps_the_state_dict():
+    from transformers import BertConfig, ViltConfig
+
+    from vault_b200.model import _KernelDecoder
+    from vault_b200.models.vault import VaultForMaskedLM
+
+    kw = dict(hidden_size=128, num_hidden_layers=2, num_attention_heads=2, intermediate_size=512, vocab_size=510)
+    m = VaultForMaskedLM(ViltConfig(**kw), bert_config=BertConfig(**kw))
+    assert isinstance(m.mlm_score.decoder, _KernelDecoder)
+    keys = set(m.state_dict())
+    assert {"mlm_score.decoder.weight", "mlm_score.decoder.bias", "mlm_score.transform.dense.weight"} <= keys
+    with pytest.raises(RuntimeError, match="CUDA"):  # no CPU path, as everywhere else
+        m.mlm_score.decoder(torch.zeros(1, 2, 128))

@@ -107,6 +107,69 @@ class _HeadFn(torch.autograd.Function):
         return dx, None, None, None, None, None
 
 
+class _DecoderFn(torch.autograd.Function):
+    """The MLM decoder ``Linear(hidden -> vocab)`` (HF:models/vilt/modeling_vilt.py ViltMLMHead.decoder) on the tcgen05 GEMM: forward
+    ``x W^T + b`` (bf16 operands, fp32 logits), backward dgrad ``dl W`` and wgrad ``dl^T x`` with the operands read un-transposed, bias
+    gradient by the column-sum kernel.  The vocabulary is padded to a multiple of 8 columns (30522 -> 30528: the GEMM stores 16-byte
+    groups) with zero weight rows; the caller slices the pad off, so its gradient columns arrive as zeros."""
+
+    @staticmethod
+    def forward(ctx, x, weight, bias, cache: dict):
+        from . import ops
+
+        ops._cuda(x, weight, bias)  # no CPU path
+        V, H = weight.shape
+        Vp = (V + 7) // 8 * 8
+        st = torch.cuda.current_stream().cuda_stream
+        x2 = x.reshape(-1, H).contiguous().float()
+        M = x2.shape[0]
+        x16 = torch.empty((M, H), device=x.device, dtype=torch.bfloat16)
+        _abi.call("vault_cast_f32_bf16", x2.data_ptr(), x16.data_ptr(), x2.numel(), st)
+        if cache.get("shape") != (Vp, H, x.device):  # padded operand buffers are allocated once; their contents are refreshed every call
+            cache.update(shape=(Vp, H, x.device), w16=torch.zeros((Vp, H), device=x.device, dtype=torch.bfloat16),
+                         b32=torch.zeros(Vp, device=x.device, dtype=torch.float32))
+        w32 = weight.detach().contiguous().float()
+        _abi.call("vault_cast_f32_bf16", w32.data_ptr(), cache["w16"].data_ptr(), w32.numel(), st)
+        if bias is not None:
+            cache["b32"][:V].copy_(bias.detach())
+        w16, b32 = cache["w16"], cache["b32"]
+        out = ops.gemm(x16, w16, ops.EPI_BIAS_F32, bias=b32)  # [M, Vp] fp32
+        ctx.save_for_backward(x16, w16)
+        ctx.dims = (V, Vp, H, bias is not None)
+        return out
+
+    @staticmethod
+    def backward(ctx, dout):
+        from . import ops
+
+        x16, w16 = ctx.saved_tensors
+        V, Vp, H, has_bias = ctx.dims
+        st = torch.cuda.current_stream().cuda_stream
+        dout = dout.contiguous().float()
+        M = dout.shape[0]
+        dl16 = torch.empty((M, Vp), device=dout.device, dtype=torch.bfloat16)
+        _abi.call("vault_cast_f32_bf16", dout.data_ptr(), dl16.data_ptr(), dout.numel(), st)
+        dx = dw = db = None
+        if ctx.needs_input_grad[0]:
+            dx = ops.gemm(dl16, w16, ops.EPI_STORE_F32, b_mn=True)  # [M, H]: contraction over the vocabulary, W read as stored
+        if ctx.needs_input_grad[1]:
+            dw = ops.gemm(dl16, x16, ops.EPI_STORE_F32, a_mn=True, b_mn=True)[:V]  # [V, H]: contraction over the tokens
+        if has_bias and ctx.needs_input_grad[2]:
+            dbp = torch.zeros(Vp, device=dout.device, dtype=torch.float32)
+            _abi.call("vault_colsum_bf16", dl16.data_ptr(), Vp, dbp.data_ptr(), M, Vp, st)
+            db = dbp[:V]
+        return dx, dw, db, None
+
+
+class _KernelDecoder(nn.Linear):
+    """``mlm_score.decoder`` with the same parameters / state-dict keys, served by the GEMM kernel."""
+
+    def forward(self, x):
+        cache = self.__dict__.setdefault("_vb_cache", {})
+        out = _DecoderFn.apply(x, self.weight, self.bias, cache)
+        return out[:, : self.out_features].view(*x.shape[:-1], self.out_features)
+
+
 class VaultMixin(nn.Module, ABC):
     """Mirror of ref:vault/models/vault/model.py:20-218 (inherit FIRST from this, then from the ViLT class).
 
@@ -348,7 +411,12 @@ class VaultForImagesAndTextClassification(VaultMixin, ViltForImagesAndTextClassi
 
 
 class VaultForMaskedLM(VaultMixin, ViltForMaskedLM):
-    """ref:vault/models/vault/model.py:455-456 -- MLM head on the text rows of the trunk output."""
+    """ref:vault/models/vault/model.py:455-456 -- MLM head on the text rows of the trunk output; the hidden -> vocab decoder product
+    (the one sizeable contraction of the head) runs on the tcgen05 GEMM, forward and backward."""
+
+    def __init__(self, *args, **kwargs):
+        super().__init__(*args, **kwargs)
+        self.mlm_score.decoder.__class__ = _KernelDecoder
 
 
 class VaultForQuestionAnswering(VaultMixin, ViltForQuestionAnswering):

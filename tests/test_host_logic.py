@@ -167,6 +167,8 @@ def test_head_wrappers_route_the_trunk_through_the_engine(monkeypatch):
         return lhs, torch.tanh(lhs[:, 0]), torch.ones(B, T + 5, dtype=torch.uint8)
 
     monkeypatch.setattr(VaultMixin, "_trunk", fake_trunk)
+    from vault_b200.model import _KernelDecoder
+    monkeypatch.setattr(_KernelDecoder, "forward", torch.nn.Linear.forward)  # the decoder GEMM is a kernel too: stubbed like the trunk (no GPU here)
     ids = torch.randint(5, 100, (2, 7))
     px = torch.randn(2, 3, 64, 64)
     common = dict(input_ids=ids, attention_mask=torch.ones_like(ids), token_type_ids=torch.zeros_like(ids))

@@ -136,6 +136,7 @@ class _DecoderFn(torch.autograd.Function):
         out = ops.gemm(x16, w16, ops.EPI_BIAS_F32, bias=b32)  # [M, Vp] fp32
         ctx.save_for_backward(x16, w16)
         ctx.dims = (V, Vp, H, bias is not None)
+        ctx.x_shape = tuple(x.shape)
         return out
 
     @staticmethod
@@ -151,7 +152,7 @@ class _DecoderFn(torch.autograd.Function):
         _abi.call("vault_cast_f32_bf16", dout.data_ptr(), dl16.data_ptr(), dout.numel(), st)
         dx = dw = db = None
         if ctx.needs_input_grad[0]:
-            dx = ops.gemm(dl16, w16, ops.EPI_STORE_F32, b_mn=True)  # [M, H]: contraction over the vocabulary, W read as stored
+            dx = ops.gemm(dl16, w16, ops.EPI_STORE_F32, b_mn=True).view(ctx.x_shape)  # [M, H]: contraction over the vocabulary, W as stored
         if ctx.needs_input_grad[1]:
             dw = ops.gemm(dl16, x16, ops.EPI_STORE_F32, a_mn=True, b_mn=True)[:V]  # [V, H]: contraction over the tokens
         if has_bias and ctx.needs_input_grad[2]:

@@ -94,6 +94,32 @@ def embeds_case(pkg):
     return m, d, inp, image_embeds, image_mask, w_pool, w_lhs
 
 
+TEXT_EMBEDS_KINDS = {"bert": {}, "roberta": dict(lm_kind="roberta", lm_type_vocab=1, lm_pad_id=1, lm_eps=1e-5), "nolm": dict(lm_layers=0)}
+TEXT_EMBEDS_GRAD_KEYS = ("pooler.dense.bias", "layernorm.weight", "embeddings.text_embeddings.token_type_embeddings.weight",
+                         "embeddings.text_embeddings.position_embeddings.weight", "embeddings.text_embeddings.LayerNorm.weight",
+                         "bert.embeddings.position_embeddings.weight", "bert.embeddings.token_type_embeddings.weight",
+                         "bert.embeddings.LayerNorm.bias", "bert.encoder.layer.1.output.dense.bias")
+
+
+def text_embeds_case(pkg, kind):
+    """VaultModel fed text ``inputs_embeds`` with ``input_ids=None`` (ref:vault/models/vault/model.py:170-200: they go to the LM in place
+    of its word-embedding lookup; without an LM, to ViLT's TextEmbeddings)."""
+    d = synth.Dims.tiny(**TEXT_EMBEDS_KINDS[kind])
+    vc, lc = hf_configs(d)
+    m = pkg.VaultModel(vc, bert_config=lc)
+    m.embeddings.text_embeddings.position_embedding_type = "absolute" if lc is None else "NOT_absolute"
+    shapes = {k: tuple(p.shape) for k, p in m.named_parameters()}
+    missing, unexpected = m.load_state_dict(synth.fill_parameters(shapes, d, seed=0), strict=False)
+    assert not unexpected
+    B, T = 3, 16
+    inp = synth.make_inputs(d, batch=B, text_len=T, seed=31, var_text=True)
+    g = torch.Generator().manual_seed(13)
+    text_embeds = torch.randn(B, T, d.hidden, generator=g) * 0.5
+    w_pool = torch.randn(B, d.hidden, generator=g)
+    w_text = torch.randn(B, T, d.hidden, generator=g) * 0.1
+    return m, d, inp, text_embeds, w_pool, w_text
+
+
 EMBEDS_GRAD_KEYS = ("pooler.dense.bias", "layernorm.weight", "embeddings.token_type_embeddings.weight", "encoder.layer.0.attention.attention.value.bias",
                     "bert.encoder.layer.1.output.dense.bias")
 
@@ -112,6 +138,30 @@ def main():
                     d_image_embeds=ie.grad.clone(), grads={k: named[k].grad.detach().clone() for k in EMBEDS_GRAD_KEYS}),
                os.path.join(OUT, "image_embeds.pt"))
     print("image_embeds", tuple(out.last_hidden_state.shape), float(loss))
+    for kind in TEXT_EMBEDS_KINDS:
+        m, d, inp, text_embeds, w_pool, w_text = text_embeds_case(mod, kind)
+        m.eval()
+        te = text_embeds.clone().requires_grad_(True)
+        torch.manual_seed(1234)
+        out = m(input_ids=None, attention_mask=inp["attention_mask"], token_type_ids=inp["token_type_ids"], pixel_values=inp["pixel_values"],
+                pixel_mask=inp["pixel_mask"], inputs_embeds=te)
+        T = text_embeds.shape[1]
+        loss = (out.pooler_output * w_pool).sum() + (out.last_hidden_state[:, :T] * w_text).sum()
+        loss.backward()
+        named = dict(m.named_parameters())
+        torch.save(dict(case="text_embeds_" + kind, pooler_output=out.pooler_output.detach().clone(), lhs_text=out.last_hidden_state[:, :T].detach().clone(),
+                        lhs_shape=tuple(out.last_hidden_state.shape), d_inputs_embeds=te.grad.clone(),
+                        grads={k: named[k].grad.detach().clone() for k in TEXT_EMBEDS_GRAD_KEYS if k in named and named[k].grad is not None}),
+                   os.path.join(OUT, f"text_embeds_{kind}.pt"))
+        # the restatement must agree with the reference right here
+        from oracle import vault_oracle as O
+        sd = {k: v.detach() for k, v in m.state_dict().items()}
+        with torch.no_grad():
+            o = O.vault_forward(sd, d, None, inp["attention_mask"], inp["token_type_ids"], inp["pixel_values"], inp["pixel_mask"], inputs_embeds=text_embeds)
+        print("text_embeds_" + kind, tuple(out.last_hidden_state.shape), float(loss), "restatement-vs-reference max-abs: pooler",
+              float((o["pooler_output"] - out.pooler_output).abs().max()), "text", float((o["last_hidden_state"][:, :T] - out.last_hidden_state[:, :T]).abs().max()))
+    if "--text-embeds-only" in sys.argv:
+        return
     for name in CASES:
         torch.manual_seed(0)
         m, d, (batch, text_len, n_images) = build(mod, name)

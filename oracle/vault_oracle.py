@@ -77,20 +77,25 @@ def roberta_position_ids(input_ids: Tensor, pad_id: int) -> Tensor:
     return torch.cumsum(m, dim=1) * m + pad_id
 
 
-def lm_forward(sd, d: Dims, input_ids: Tensor, attention_mask: Tensor, token_type_ids: Tensor, train: bool = False) -> Tensor:
+def lm_forward(sd, d: Dims, input_ids: Optional[Tensor], attention_mask: Tensor, token_type_ids: Optional[Tensor], train: bool = False,
+               inputs_embeds: Optional[Tensor] = None) -> Tensor:
     """BertModel / RobertaModel without pooler -> last_hidden_state.
 
     Embeddings HF:models/bert/modeling_bert.py:72-112 (RoBERTa: HF:models/roberta/modeling_roberta.py:79-126),
     post-LN layer HF:models/bert/modeling_bert.py:359-421, GELU = exact erf (BertIntermediate :330-342).
+    ``inputs_embeds`` (instead of ``input_ids``) replaces the word-embedding lookup; RoBERTa then numbers the positions
+    sequentially from pad+1 (create_position_ids_from_inputs_embeds: padding cannot be inferred from embeddings).
     """
-    B, T = input_ids.shape
+    B, T = input_ids.shape if input_ids is not None else inputs_embeds.shape[:2]
     if d.lm_kind == "roberta":
-        pos = roberta_position_ids(input_ids, d.lm_pad_id)
+        pos = roberta_position_ids(input_ids, d.lm_pad_id) if input_ids is not None else torch.arange(d.lm_pad_id + 1, T + d.lm_pad_id + 1)[None, :].expand(B, T)
     else:
         pos = torch.arange(T)[None, :].expand(B, T)
+    if token_type_ids is None:
+        token_type_ids = torch.zeros((B, T), dtype=torch.int64)
     p = d.lm_dropout
     x = (
-        sd["bert.embeddings.word_embeddings.weight"][input_ids]
+        (sd["bert.embeddings.word_embeddings.weight"][input_ids] if inputs_embeds is None else inputs_embeds)
         + sd["bert.embeddings.token_type_embeddings.weight"][token_type_ids]
         + sd["bert.embeddings.position_embeddings.weight"][pos]
     )
@@ -175,16 +180,20 @@ def vault_forward(
     train: bool = False,
     use_vilt_position_embeddings: bool = False,
     image_token_type_idx: int = 1,
+    inputs_embeds: Optional[Tensor] = None,
 ) -> Dict[str, Tensor]:
     """VaultMixin.forward (ref:vault/models/vault/model.py:151-218) -> ViltModel.forward
-    (HF:models/vilt/modeling_vilt.py:550-660) -> ViltPooler (:663-675)."""
+    (HF:models/vilt/modeling_vilt.py:550-660) -> ViltPooler (:663-675).  ``inputs_embeds`` with ``input_ids=None``: the text
+    embeddings handed to the LM (ref :170-190) -- or, without an LM, to ViLT's TextEmbeddings -- in place of the word lookup."""
+    if token_type_ids is None:  # HF: all-zero type ids
+        token_type_ids = torch.zeros((input_ids if input_ids is not None else inputs_embeds).shape[:2], dtype=torch.int64)
     if d.lm_layers > 0:
         # ref:vault/models/vault/model.py:174-180: LM copy of the type ids is zeroed iff the LM type vocab < 2
         lm_tt = torch.zeros_like(token_type_ids) if d.lm_type_vocab < 2 else token_type_ids
-        text_in = lm_forward(sd, d, input_ids, attention_mask, lm_tt, train)
+        text_in = lm_forward(sd, d, input_ids, attention_mask, lm_tt, train, inputs_embeds=inputs_embeds)
         use_pos = use_vilt_position_embeddings
     else:
-        text_in = sd["embeddings.text_embeddings.word_embeddings.weight"][input_ids]
+        text_in = sd["embeddings.text_embeddings.word_embeddings.weight"][input_ids] if inputs_embeds is None else inputs_embeds
         use_pos = True
     text = vilt_text_embed(sd, d, text_in, token_type_ids, use_pos)
     img, img_mask, patch_index = visual_embed_raster(sd, d, pixel_values, pixel_mask)

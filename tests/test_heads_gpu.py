@@ -108,3 +108,38 @@ def test_mlm_decoder_on_the_gemm_kernel(vocab, tokens):
         assert got is not None and got.shape == want.shape
         assert cosine(got.float().cpu(), want.float().cpu()) >= 0.999
         assert rel_err(got.float().cpu(), want.float().cpu()) <= 2e-2
+
+
+@pytest.mark.parametrize("kind", sorted(G.TEXT_EMBEDS_KINDS))
+def test_text_inputs_embeds_path_matches_reference_fixture(kind):
+    """VaultModel(input_ids=None, inputs_embeds=...) -- ref:vault/models/vault/model.py:170-200 -- against the REAL reference: BERT, RoBERTa
+    (sequential position ids from pad+1) and no-LM variants; outputs, the gradient returned for the caller's embeddings, embedding-table
+    gradients.  Tolerance as for the other fixtures of this file (bf16 trunk): 2e-2 relative, cosine >= 0.99."""
+    import vault_b200.models.vault as pkg
+
+    ref = torch.load(os.path.join(HEADS_DIR, f"text_embeds_{kind}.pt"), weights_only=False)
+    m, d, inp, text_embeds, w_pool, w_text = G.text_embeds_case(pkg, kind)
+    m = m.to(DEV).eval()
+    T = text_embeds.shape[1]
+    te = text_embeds.to(DEV).requires_grad_(True)
+    kw = dict(attention_mask=inp["attention_mask"].to(DEV), token_type_ids=inp["token_type_ids"].to(DEV), pixel_values=inp["pixel_values"].to(DEV),
+              pixel_mask=inp["pixel_mask"].to(DEV))
+    out = m(input_ids=None, inputs_embeds=te, **kw)
+    assert tuple(out.last_hidden_state.shape) == ref["lhs_shape"]
+    assert rel_err(out.pooler_output.detach().cpu(), ref["pooler_output"]) <= 2e-2
+    valid = inp["attention_mask"].bool()
+    assert rel_err(out.last_hidden_state.detach().cpu()[:, :T][valid], ref["lhs_text"][valid]) <= 2e-2
+    loss = (out.pooler_output * w_pool.to(DEV)).sum() + (out.last_hidden_state[:, :T] * w_text.to(DEV)).sum()
+    loss.backward()
+    assert te.grad is not None and cosine(te.grad.cpu(), ref["d_inputs_embeds"]) >= 0.99
+    named = dict(m.named_parameters())
+    for k, g_ref in ref["grads"].items():
+        assert named[k].grad is not None, k
+        assert cosine(named[k].grad.float().cpu(), g_ref) >= 0.99, k
+    word = "bert.embeddings.word_embeddings.weight" if kind != "nolm" else "embeddings.text_embeddings.word_embeddings.weight"
+    assert named[word].grad is None or float(named[word].grad.abs().max()) == 0.0  # the lookup never ran
+    with torch.no_grad():
+        again = m(input_ids=None, inputs_embeds=text_embeds.to(DEV), **kw)
+    assert torch.equal(again.pooler_output, out.pooler_output.detach())
+    with pytest.raises(ValueError):
+        m(input_ids=inp["input_ids"].to(DEV), inputs_embeds=te, **kw)

@@ -96,3 +96,37 @@ def test_linear_warmup_schedule():
 def test_roberta_position_ids():
     ids = torch.tensor([[5, 6, 7, 1, 1], [9, 1, 1, 1, 1]])
     assert O.roberta_position_ids(ids, 1).tolist() == [[2, 3, 4, 1, 1], [2, 1, 1, 1, 1]]
+
+
+@pytest.mark.parametrize("kind", ["bert", "roberta", "nolm"])
+def test_text_inputs_embeds_matches_reference(kind):
+    """``inputs_embeds`` with ``input_ids=None`` (ref:vault/models/vault/model.py:170-200): restatement vs the REAL reference fixture --
+    outputs, the gradient returned for the caller's embeddings and the LM / ViLT embedding-table gradients that replace the word lookup's."""
+    import os
+
+    from oracle import make_golden_heads as G
+    from oracle.ref_loader import hf_configs
+    from oracle import synth
+
+    ref = torch.load(os.path.join(os.path.dirname(os.path.abspath(__file__)), "golden", "heads", f"text_embeds_{kind}.pt"), weights_only=False)
+    d = synth.Dims.tiny(**G.TEXT_EMBEDS_KINDS[kind])
+    B, T = 3, 16
+    inp = synth.make_inputs(d, batch=B, text_len=T, seed=31, var_text=True)
+    g = torch.Generator().manual_seed(13)
+    text_embeds = torch.randn(B, T, d.hidden, generator=g) * 0.5
+    w_pool = torch.randn(B, d.hidden, generator=g)
+    w_text = torch.randn(B, T, d.hidden, generator=g) * 0.1
+    shapes = synth.param_shapes(d, head=False)
+    sd = synth.fill_parameters(shapes, d, seed=0)
+    params = {k: v.clone().requires_grad_(True) for k, v in sd.items()}
+    te = text_embeds.clone().requires_grad_(True)
+    o = O.vault_forward(params, d, None, inp["attention_mask"], inp["token_type_ids"], inp["pixel_values"], inp["pixel_mask"], inputs_embeds=te)
+    assert tuple(o["last_hidden_state"].shape) == ref["lhs_shape"]
+    assert (o["pooler_output"] - ref["pooler_output"]).abs().max() < 2e-5
+    assert (o["last_hidden_state"][:, :T] - ref["lhs_text"]).abs().max() < 2e-5
+    ((o["pooler_output"] * w_pool).sum() + (o["last_hidden_state"][:, :T] * w_text).sum()).backward()
+    assert cosine(te.grad, ref["d_inputs_embeds"]) > 1 - 1e-6
+    for k, g_ref in ref["grads"].items():
+        assert cosine(params[k].grad, g_ref) > 1 - 1e-6, k
+    word = "bert.embeddings.word_embeddings.weight" if kind != "nolm" else "embeddings.text_embeddings.word_embeddings.weight"
+    assert params[word].grad is None  # the lookup never ran

@@ -574,7 +574,7 @@ class VaultEngine:
 
     def forward_iter(self, input_ids, attention_mask, token_type_ids, pixel_values, pixel_mask, image_token_type_idx=1, training=False,
                      need_grad=False, hw: Optional[torch.Tensor] = None, pmax: Optional[int] = None, split_lm: bool = False,
-                     image_embeds: Optional[torch.Tensor] = None):
+                     image_embeds: Optional[torch.Tensor] = None, inputs_embeds: Optional[torch.Tensor] = None):
         """Generator form of forward.  With split_lm it yields "lm_done" once the language model's forward is enqueued and before
         anything reads a ViLT parameter, so a caller can start the LM while the previous step's AdamW is still updating the
         ViLT range (VaultTrainStep); the return value (StopIteration.value) is forward()'s tuple."""
@@ -587,7 +587,18 @@ class VaultEngine:
             torch.cuda.current_stream(dev).wait_stream(self._side)
         self.refresh_shadow()
         H = self.H
-        B, T = input_ids.shape
+        # text inputs_embeds [B,T,H] with input_ids=None (ref:vault/models/vault/model.py:170-200): they replace the LM's word-embedding lookup
+        # (without an LM: ViLT's own), HF:models/bert/modeling_bert.py:72-112 / RobertaEmbeddings with sequential position ids
+        text_embeds_mode = inputs_embeds is not None
+        if text_embeds_mode:
+            if input_ids is not None:
+                raise ValueError("You cannot specify both input_ids and inputs_embeds at the same time")
+            if inputs_embeds.dim() != 3 or inputs_embeds.shape[2] != H:
+                raise ValueError(f"inputs_embeds {tuple(inputs_embeds.shape)}: need [B, T, {H}]")
+            B, T = inputs_embeds.shape[:2]
+            inputs_embeds = inputs_embeds.contiguous().float()
+        else:
+            B, T = input_ids.shape
         if embeds_mode:
             if image_embeds.dim() != 3 or image_embeds.shape[0] != B or image_embeds.shape[2] != self.H:
                 raise ValueError(f"image_embeds {tuple(image_embeds.shape)}: need [B={B}, P, {self.H}]")
@@ -604,9 +615,10 @@ class VaultEngine:
             if Cc != self.C or Hi % self.patch or Wi % self.patch:
                 raise ValueError(f"pixel_values {tuple(pixel_values.shape)}: need {self.C} channels and sides divisible by {self.patch}")
             gh, gw = Hi // self.patch, Wi // self.patch
-        input_ids = input_ids.contiguous()
-        if input_ids.dtype != torch.int64:
-            input_ids = input_ids.to(torch.int64)
+        if input_ids is not None:
+            input_ids = input_ids.contiguous()
+            if input_ids.dtype != torch.int64:
+                input_ids = input_ids.to(torch.int64)
         if attention_mask is not None:
             attention_mask = attention_mask.contiguous() if attention_mask.dtype == torch.int64 else attention_mask.to(torch.int64)
         if token_type_ids is not None:
@@ -663,10 +675,20 @@ class VaultEngine:
             lsv = sv if lm_trains else None
             x_sum = self._new((Mt, H), torch.float32)
             lm_mask = self._new((B, T), torch.uint8)
-            _abi.check(lib.vault_lm_embed_fwd(input_ids.data_ptr(), lm_tt, self.w32("bert.embeddings.word_embeddings.weight"),
-                                              self.w32("bert.embeddings.token_type_embeddings.weight"),
-                                              self.w32("bert.embeddings.position_embeddings.weight"), x_sum.data_ptr(), am_ptr, lm_mask.data_ptr(), B, T,
-                                              H, self.lm_roberta_pad, st), "lm_embed_fwd")
+            if text_embeds_mode:
+                pos_off = self._lm_embeds_pos_offset(T)
+                _abi.check(lib.vault_vilt_text_embed_fwd(inputs_embeds.data_ptr(), lm_tt, self.w32("bert.embeddings.token_type_embeddings.weight"),
+                                                         self.w32("bert.embeddings.position_embeddings.weight") + 4 * H * pos_off, x_sum.data_ptr(),
+                                                         B, T, H, st), "lm_embeds_fwd")
+                if attention_mask is None:
+                    lm_mask.fill_(1)
+                else:
+                    lm_mask.copy_(attention_mask != 0)
+            else:
+                _abi.check(lib.vault_lm_embed_fwd(input_ids.data_ptr(), lm_tt, self.w32("bert.embeddings.word_embeddings.weight"),
+                                                  self.w32("bert.embeddings.token_type_embeddings.weight"),
+                                                  self.w32("bert.embeddings.position_embeddings.weight"), x_sum.data_ptr(), am_ptr, lm_mask.data_ptr(), B, T,
+                                                  H, self.lm_roberta_pad, st), "lm_embed_fwd")
             p_emb = self.lm_p if lm_train_mode else 0.0
             x16, r32, st0 = self.ln_fwd(x_sum, Mt, "bert.embeddings.LayerNorm.weight", "bert.embeddings.LayerNorm.bias", self.lm_eps, want32=True,
                                         p=p_emb, site=self.SITE_LM_EMB)
@@ -674,9 +696,14 @@ class VaultEngine:
                 lsv["lm.x_sum"], lsv["lm.st0"], lsv["lm.mask"] = x_sum, st0, lm_mask
             for i in range(self.lm_L):
                 r32, x16 = self.lm_layer_fwd(i, r32, x16, Mt, B, T, lm_mask, lsv, lm_train_mode)
-            inputs_embeds = r32
+            lm_out = r32
             if split_lm:
                 yield "lm_done"
+            text_pos = self.w32("embeddings.text_embeddings.position_embeddings.weight") if self.use_text_pos() else None
+            v_sum = self._new((Mt, H), torch.float32)
+            _abi.check(lib.vault_vilt_text_embed_fwd(lm_out.data_ptr(), tt_ptr, self.w32("embeddings.text_embeddings.token_type_embeddings.weight"),
+                                                     text_pos, v_sum.data_ptr(), B, T, H, st), "vilt_text_embed_fwd")
+        elif text_embeds_mode:
             text_pos = self.w32("embeddings.text_embeddings.position_embeddings.weight") if self.use_text_pos() else None
             v_sum = self._new((Mt, H), torch.float32)
             _abi.check(lib.vault_vilt_text_embed_fwd(inputs_embeds.data_ptr(), tt_ptr, self.w32("embeddings.text_embeddings.token_type_embeddings.weight"),
@@ -719,7 +746,7 @@ class VaultEngine:
             sv["v_sum"], sv["st_t"], sv["patches"], sv["hw"], sv["key_mask"] = v_sum, st_t, patches, hw, key_mask
             sv["ids"], sv["tt"], sv["am"] = input_ids, token_type_ids, attention_mask
             tape.meta.update(B=B, T=T, S=S, pmax=pmax, gh=gh, gw=gw, Hi=Hi, Wi=Wi, img_type=int(image_token_type_idx), training=training,
-                             lm_trains=lm_trains, embeds_mode=embeds_mode)
+                             lm_trains=lm_trains, embeds_mode=embeds_mode, text_embeds_mode=text_embeds_mode)
 
         # ---------------- ViLT encoder, final LN, pooler ----------------
         x32 = X.view(M, H)
@@ -833,7 +860,12 @@ class VaultEngine:
                     if off:
                         self._join_side()
                         yield off
-                yield from self._lm_backward(dv_sum, sv, B, T, mt["training"], segments)
+                yield from self._lm_backward(dv_sum, sv, B, T, mt["training"], segments, meta=mt)
+        elif mt.get("text_embeds_mode"):
+            gpos = self.g32("embeddings.text_embeddings.position_embeddings.weight") if self.use_text_pos() else 0
+            _abi.check(lib.vault_vilt_text_embed_bwd(tt_ptr, dv_sum.data_ptr(), self.g32("embeddings.text_embeddings.token_type_embeddings.weight") or None,
+                                                     gpos or None, B, T, H, st), "vilt_text_embed_bwd")
+            mt["d_inputs_embeds"] = dv_sum.view(B, T, H)  # gradient w.r.t. the caller's inputs_embeds (returned through autograd)
         else:
             _abi.check(lib.vault_lm_embed_bwd(sv["ids"].data_ptr(), tt_ptr, dv_sum.data_ptr(),
                                               self.g32("embeddings.text_embeddings.word_embeddings.weight") or None,
@@ -845,7 +877,15 @@ class VaultEngine:
         tape.done = True
         tape.t = {}
 
-    def _lm_backward(self, g32, sv, B, T, train, segments=False):
+    def _lm_embeds_pos_offset(self, T: int) -> int:
+        """First position-table row used with text inputs_embeds: 0 for BERT, pad+1 for RoBERTa (create_position_ids_from_inputs_embeds)."""
+        off = self.lm_roberta_pad + 1 if self.lm_roberta_pad >= 0 else 0
+        rows = self.lm.embeddings.position_embeddings.weight.shape[0]
+        if off + T > rows:
+            raise ValueError(f"inputs_embeds: {T} tokens need position rows {off}..{off + T - 1}, the LM's table has {rows}")
+        return off
+
+    def _lm_backward(self, g32, sv, B, T, train, segments=False, meta=None):
         lib, st = self._lib, self._st
         Mt, H = B * T, self.H
         gx16 = None
@@ -865,6 +905,12 @@ class VaultEngine:
         dx_sum, _ = self.ln_bwd(g32, gx16, sv["lm.x_sum"], sv["lm.st0"], Mt, "bert.embeddings.LayerNorm.weight", "bert.embeddings.LayerNorm.bias",
                                 want16=False, in_p=p_emb, in_site=self.SITE_LM_EMB)
         lm_tt = None if (self.lm_type_vocab < 2 or sv["tt"] is None) else sv["tt"].data_ptr()
+        if meta is not None and meta.get("text_embeds_mode"):
+            gpos = self.g32("bert.embeddings.position_embeddings.weight")
+            _abi.check(lib.vault_vilt_text_embed_bwd(lm_tt, dx_sum.data_ptr(), self.g32("bert.embeddings.token_type_embeddings.weight") or None,
+                                                     (gpos + 4 * H * self._lm_embeds_pos_offset(T)) if gpos else None, B, T, H, st), "lm_embeds_bwd")
+            meta["d_inputs_embeds"] = dx_sum.view(B, T, H)  # gradient w.r.t. the caller's inputs_embeds (returned through autograd)
+            return
         _abi.check(lib.vault_lm_embed_bwd(sv["ids"].data_ptr(), lm_tt, dx_sum.data_ptr(), self.g32("bert.embeddings.word_embeddings.weight") or None,
                                           self.g32("bert.embeddings.token_type_embeddings.weight") or None,
                                           self.g32("bert.embeddings.position_embeddings.weight") or None, B, T, H, self.lm_roberta_pad,

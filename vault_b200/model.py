@@ -17,8 +17,8 @@ forward and backward goes through ``vault_b200.engine.VaultEngine`` -> C ABI -> 
 Differences from the reference, all deliberate:
   * image tokens come out in raster order (valid patches first) instead of a random permutation -- ``pooler_output`` and the
     text rows are unaffected, image rows match after un-permuting the reference with its ``patch_index``;
-  * ``head_mask``, ``output_attentions``, ``output_hidden_states``, ``image_embeds`` and (with an LM) ``inputs_embeds`` are not
-    on the hot path and raise ``NotImplementedError``;
+  * ``head_mask``, ``output_attentions`` and ``output_hidden_states`` are not on the hot path and raise ``NotImplementedError``
+    (``image_embeds`` and text ``inputs_embeds`` are served by the kernels, gradients to the caller's tensors included);
   * gradients are written into one flat fp32 buffer and ``p.grad`` are views of it: zero (or ``None``) them between backward
     calls as the reference trainer does (ref:vault/tmsc_utils/trainer.py:364); accumulation across backwards is not supported.
 """
@@ -50,10 +50,11 @@ class _TrunkFn(torch.autograd.Function):
     into the engine's flat buffer and attached as ``p.grad`` views in ``backward``."""
 
     @staticmethod
-    def forward(ctx, anchor, engine: VaultEngine, kw: dict, image_embeds=None):
-        lhs, pooled, key_mask, tape = engine.forward(need_grad=True, image_embeds=image_embeds, **kw)
+    def forward(ctx, anchor, engine: VaultEngine, kw: dict, image_embeds=None, inputs_embeds=None):
+        lhs, pooled, key_mask, tape = engine.forward(need_grad=True, image_embeds=image_embeds, inputs_embeds=inputs_embeds, **kw)
         ctx.engine, ctx.tape = engine, tape
         ctx.embeds_grad = image_embeds is not None and image_embeds.requires_grad
+        ctx.text_embeds_grad = inputs_embeds is not None and inputs_embeds.requires_grad
         ctx.has_pooled = pooled is not None
         ctx.mark_non_differentiable(key_mask)
         if pooled is None:
@@ -66,7 +67,8 @@ class _TrunkFn(torch.autograd.Function):
         tape = ctx.tape
         engine.backward(tape, dlhs, dpooled if ctx.has_pooled else None)
         engine.attach_grads(exclude_prefix="classifier.")
-        return None, None, None, (tape.meta.get("d_image_embeds") if ctx.embeds_grad else None)
+        return (None, None, None, (tape.meta.get("d_image_embeds") if ctx.embeds_grad else None),
+                (tape.meta.get("d_inputs_embeds") if ctx.text_embeds_grad else None))  # None for a frozen LM: it runs under no_grad (ref :189)
 
 
 class _HeadFn(torch.autograd.Function):
@@ -253,10 +255,10 @@ class VaultMixin(nn.Module, ABC):
                return_dict=None, **extra):
         if head_mask is not None or output_attentions or output_hidden_states:
             raise NotImplementedError("vault_b200: head_mask / output_attentions / output_hidden_states are not on the hot path")
-        if inputs_embeds is not None:
-            raise NotImplementedError("vault_b200: text inputs_embeds are not on the hot path (pass input_ids; the LM runs inside the engine)")
-        if input_ids is None or (pixel_values is None and image_embeds is None):
-            raise ValueError("You have to specify input_ids and pixel_values (or image_embeds)")
+        if input_ids is not None and inputs_embeds is not None:
+            raise ValueError("You cannot specify both input_ids and inputs_embeds at the same time")
+        if (input_ids is None and inputs_embeds is None) or (pixel_values is None and image_embeds is None):
+            raise ValueError("You have to specify input_ids (or inputs_embeds) and pixel_values (or image_embeds)")
         if image_embeds is not None and pixel_values is not None:
             raise ValueError("You cannot specify both pixel_values and image_embeds at the same time")
         if not (pixel_values if pixel_values is not None else image_embeds).is_cuda:
@@ -272,7 +274,7 @@ class VaultMixin(nn.Module, ABC):
                   training=self.training)
         kw.update({k: v for k, v in extra.items() if k in ("hw", "pmax")})
         dev = (pixel_values if pixel_values is not None else image_embeds).device
-        need_grad = need_grad or (torch.is_grad_enabled() and image_embeds is not None and image_embeds.requires_grad)
+        need_grad = need_grad or (torch.is_grad_enabled() and any(e is not None and e.requires_grad for e in (image_embeds, inputs_embeds)))
         if need_grad:
             eng.ensure_packed(dev)
             if self.training and not self.__dict__.get("_seed_held", False):
@@ -283,9 +285,9 @@ class VaultMixin(nn.Module, ABC):
                     self.__dict__["_seed_held"] = True
             if self._anchor is None or self._anchor.device != dev:
                 self._anchor = torch.zeros(1, device=dev, requires_grad=True)
-            lhs, pooled, key_mask = _TrunkFn.apply(self._anchor, eng, kw, image_embeds)
+            lhs, pooled, key_mask = _TrunkFn.apply(self._anchor, eng, kw, image_embeds, inputs_embeds)
         else:
-            lhs, pooled, key_mask, _ = eng.forward(need_grad=False, image_embeds=image_embeds, **kw)
+            lhs, pooled, key_mask, _ = eng.forward(need_grad=False, image_embeds=image_embeds, inputs_embeds=inputs_embeds, **kw)
         if self._trunk_module().pooler is None:
             pooled = None
         return lhs, pooled, key_mask

@@ -241,6 +241,10 @@ def gemm_roofline(torch, ts, batch_dev, peaks):
                 else "fallback (B200_PROFILING.md): 1.4 PFLOP/s sustained"), launches, calls
 
 
+# one `ncu --set full` capture per kernel at exactly these shapes (profiles/r01_ncu_hbm_kernels.md): DRAM bytes per launch, read + write
+NCU_DRAM_BYTES = {"layernorm_fwd": 82.1e6, "layernorm_bwd": 258.9e6, "adamw": 1958.2e6}
+
+
 def hbm_kernel_rates(torch, peaks):
     """Achieved HBM GB/s of the bandwidth-bound kernels at the workload's shapes.  Every kernel runs round-robin over several
     independent operand sets whose total size is several times the 126 MB L2 (>= 650 MB per pass), so each launch finds its
@@ -269,7 +273,8 @@ def hbm_kernel_rates(torch, peaks):
         torch.cuda.synchronize()
         us = e0.elapsed_time(e1) * 1e3 / (reps * len(sets))
         gbs = nbytes / us / 1e3
-        out[name] = dict(achieved_gbs=gbs, frac_of_measured_peak=gbs / peak, algorithmic_bytes=nbytes, us_per_launch=us, operand_sets=len(sets))
+        out[name] = dict(achieved_gbs=gbs, frac_of_measured_peak=gbs / peak, algorithmic_bytes=nbytes, us_per_launch=us, operand_sets=len(sets),
+                         traffic=NCU_DRAM_BYTES[name])  # dram__bytes_read.sum + dram__bytes_write.sum of one launch, profiles/r01_ncu_hbm_kernels.md
 
     # LayerNorm forward: fp32 in, bf16 out (+ row statistics): 6 B / element
     fsets = [dict(x=torch.randn(rows, cols, device=dev), y=torch.empty(rows, cols, device=dev, dtype=torch.bfloat16),

@@ -1,0 +1,26 @@
+"""The three HBM-bound kernels of bench.py's `hbm_kernels` section, each launched twice on different operand sets (warm-up, then the
+launch to capture):  ncu --set full --clock-control none -k regex:"ln_fwd_kernel|ln_bwd_kernel|adamw_kernel" --launch-skip 3 -c 3 ... python tools/one_hbm.py"""
+import os, sys
+import torch
+sys.path.insert(0, os.path.dirname(os.path.dirname(os.path.abspath(__file__))))
+from vault_b200 import _abi
+dev = torch.device("cuda:0"); lib = _abi.lib(); st = torch.cuda.current_stream().cuda_stream
+rows, cols, n = 32 * 185 * 4, 768, 64 * 1024 * 1024
+g, b = torch.ones(cols, device=dev), torch.zeros(cols, device=dev)
+dg, db, dc = (torch.zeros(cols, device=dev) for _ in range(3))
+sets = []
+for _ in range(2):
+    sets.append(dict(x=torch.randn(rows, cols, device=dev), y=torch.empty(rows, cols, device=dev, dtype=torch.bfloat16), mean=torch.empty(rows, device=dev),
+                     rstd=torch.empty(rows, device=dev), dy=torch.randn(rows, cols, device=dev).to(torch.bfloat16), dres=torch.randn(rows, cols, device=dev),
+                     dx32=torch.empty(rows, cols, device=dev), dx16=torch.empty(rows, cols, device=dev, dtype=torch.bfloat16),
+                     p=torch.zeros(n, device=dev), g=torch.zeros(n, device=dev), m=torch.zeros(n, device=dev), v=torch.zeros(n, device=dev),
+                     sh=torch.zeros(n, device=dev, dtype=torch.bfloat16)))
+torch.cuda.synchronize()
+for s in sets:
+    lib.vault_layernorm_fwd(s["x"].data_ptr(), g.data_ptr(), b.data_ptr(), s["y"].data_ptr(), None, s["mean"].data_ptr(), s["rstd"].data_ptr(), rows, cols, 1e-12, st)
+    lib.vault_layernorm_bwd_drop(None, s["dy"].data_ptr(), s["x"].data_ptr(), s["mean"].data_ptr(), s["rstd"].data_ptr(), g.data_ptr(), s["dres"].data_ptr(),
+                                 s["dx32"].data_ptr(), s["dx16"].data_ptr(), dg.data_ptr(), db.data_ptr(), dc.data_ptr(), rows, cols, 0.0, 0, 0.0, 0, 0, None, st)
+    lib.vault_adamw_step(s["p"].data_ptr(), s["g"].data_ptr(), 0, s["m"].data_ptr(), s["v"].data_ptr(), s["sh"].data_ptr(), n, 1e-5, 0.9, 0.999, 1e-8, 0.0, 0, 1,
+                         1.0, None, st)
+torch.cuda.synchronize()
+print("done")

@@ -240,3 +240,54 @@ def test_mlm_decoder_class_swap_keeps_the_state_dict():
     assert {"mlm_score.decoder.weight", "mlm_score.decoder.bias", "mlm_score.transform.dense.weight"} <= keys
     with pytest.raises(RuntimeError, match="CUDA"):  # no CPU path, as everywhere else
         m.mlm_score.decoder(torch.zeros(1, 2, 128))
+
+
+def _check_bench_line(d, reference=False):
+    for k in ("metric", "value", "unit", "n_gpus", "steps", "warmup", "ms_per_step", "higher_is_better", "scaling", "vs_baseline", "dtype", "data", "config", "e2e"):
+        assert k in d, k
+    assert d["metric"] == "VaultModel fine-tune samples/sec" and d["unit"] == "samples/s" and d["higher_is_better"] is True and d["scaling"] == "weak"
+    assert d["vs_baseline"] is None and d["data"] == "synthetic" and "workload" in d["config"] and "model" not in d["config"]
+    assert {"value", "unit", "h2d_bytes_per_step", "d2h_bytes_per_step"} <= set(d["e2e"])
+    cb = d["cpu_baseline"]
+    assert cb is None or {"value", "unit", "cores", "kind", "sample"} <= set(cb)
+    if reference:
+        assert d["impl"] == "reference" and d["e2e"]["h2d_bytes_per_step"] == 0 and d["e2e"]["value"] == d["value"] and cb["kind"] == "port"
+    else:
+        r = d["roofline"]
+        assert {"bound", "achieved", "peak", "unit", "frac", "traffic"} <= set(r) and r["bound"] in ("hbm", "tensor")
+        assert abs(r["frac"] - r["achieved"] / r["peak"]) < 1e-9 and (r["traffic"] is None or isinstance(r["traffic"], (int, float)))
+        assert d["gpu_launches"] > 0 and {"sm_mhz", "sm_max_mhz", "reasons"} <= set(d["clocks"]) and d["e2e"]["h2d_bytes_per_step"] > 0
+
+
+def test_committed_bench_lines_follow_the_contract():
+    """The measured JSON lines kept under profiles/ (what bench.py printed on the B200) carry every key of the bench contract."""
+    import glob
+    import json
+
+    root = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+    files = sorted(glob.glob(os.path.join(root, "profiles", "r01_bench_*gpu*.json")))
+    assert files
+    for f in files:
+        d = json.loads(open(f).read().strip().splitlines()[-1])
+        _check_bench_line(d, reference=d.get("impl") == "reference")
+
+
+def test_reference_arm_prints_one_contract_line():
+    """`bench.py --impl reference` (the oracle port on the host cores) end to end: one JSON line, same metric / unit / config keys."""
+    import json
+    import subprocess
+
+    root = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+    r = subprocess.run([sys.executable, os.path.join(root, "bench.py"), "--impl", "reference", "--steps", "1", "--warmup", "0"], capture_output=True, text=True,
+                       timeout=600, cwd=root)
+    assert r.returncode == 0, r.stderr[-2000:]
+    lines = [ln for ln in r.stdout.splitlines() if ln.startswith("{")]
+    assert len(lines) == 1
+    d = json.loads(lines[0])
+    _check_bench_line(d, reference=True)
+    assert d["config"]["name"] == "config3" and d["value"] > 0
+    # under torchrun only rank 0 runs it; the other ranks exit 0 without work
+    env = dict(os.environ, RANK="1", WORLD_SIZE="2", LOCAL_RANK="1")
+    r = subprocess.run([sys.executable, os.path.join(root, "bench.py"), "--impl", "reference", "--gpus", "2", "--steps", "1", "--warmup", "0"], capture_output=True,
+                       text=True, timeout=120, cwd=root, env=env)
+    assert r.returncode == 0 and r.stdout.strip() == ""

@@ -48,6 +48,17 @@ def workload_config(name):
     return dict(lm=w["lm"], **COMMON, text_len=w["text_len"], image=w["image"], patches=w["patches"], seq_len=w["seq_len"], freeze_lm=w["freeze_lm"])
 
 
+def train_gflop_valid_tokens(text_lens, patches, freeze_lm):
+    """Algorithmic FLOPs per sample of one training step counting VALID tokens only (SURVEY.md section 8d asks for both figures): the same
+    closed form as the dense-shape number -- 12 layers x (24 n H^2 + 4 n^2 H), patch projection 2 x P x 3072 x 768, train = 3 x forward
+    (patch projection 2 x, a frozen LM 1 x) -- evaluated per sample with n = its number of un-padded text tokens (+ 1 + P for ViLT)."""
+    enc = lambda n: 12 * (14155776 * n + 3072 * n * n)
+    tot = 0.0
+    for t in text_lens:
+        tot += (1 if freeze_lm else 3) * enc(t) + 3 * enc(t + 1 + patches) + 2 * 4718592 * patches
+    return tot / max(len(text_lens), 1) / 1e9
+
+
 def oracle_dims(name):
     from oracle import synth
 
@@ -409,6 +420,8 @@ def main():
         value = gb * args.steps / (ms_dev * 1e-3)
         e2e = gb * args.steps / (ms_e2e * 1e-3)
         train_gflop_per_sample = W["train_gflop"]  # BASELINE.md section 4 (dense-shape FLOPs of the named shape)
+        lens = [int(n) for b_ in host for n in b_["attention_mask"].sum(dim=1).tolist()]
+        valid_gflop = train_gflop_valid_tokens(lens, W["patches"], W["freeze_lm"])  # padded text positions not counted
         out = {
             "metric": METRIC, "value": value, "unit": "samples/s", "n_gpus": world, "steps": args.steps, "warmup": args.warmup,
             "ms_per_step": ms_dev / args.steps, "higher_is_better": True, "scaling": "weak", "vs_baseline": None, "dtype": "bf16", "data": "synthetic",
@@ -421,6 +434,7 @@ def main():
             "gpu_launches": (launches + 1) * args.steps if launches else None,
             "launches_per_step": dict(total=(launches + 1) if launches else None, by_call=calls),
             "model_tflops_per_gpu": value / world * train_gflop_per_sample / 1e3,
+            "model_tflops_per_gpu_valid_tokens": value / world * valid_gflop / 1e3,
             "clocks": clocks,
             "roofline": roof,
             "hbm_kernels": hbm,

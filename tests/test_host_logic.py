@@ -221,6 +221,8 @@ def test_bench_workloads_are_consistent_with_baseline_shapes():
         lm, vilt, patch = enc(T), enc(T + 1 + P), 4718592 * P
         want = ((1 if w["freeze_lm"] else 3) * lm + 3 * vilt + 2 * patch) / 1e9
         assert abs(w["train_gflop"] - want) / want < 2e-3, (name, w["train_gflop"], want)
+        assert abs(bench.train_gflop_valid_tokens([T] * 3, P, w["freeze_lm"]) - want) / want < 1e-9  # all-valid text = the dense-shape figure
+        assert bench.train_gflop_valid_tokens([T // 2] * 3, P, w["freeze_lm"]) < want
         cfg = bench.workload_config(name)
         assert cfg["per_gpu_batch"] == 32 and cfg["text_len"] == T
         d = bench.oracle_dims(name)

@@ -293,3 +293,31 @@ def test_reference_arm_prints_one_contract_line():
     r = subprocess.run([sys.executable, os.path.join(root, "bench.py"), "--impl", "reference", "--gpus", "2", "--steps", "1", "--warmup", "0"], capture_output=True,
                        text=True, timeout=120, cwd=root, env=env)
     assert r.returncode == 0 and r.stdout.strip() == ""
+
+
+def test_processor_falls_back_to_the_stock_vilt_processor_and_swaps_the_tokenizer(monkeypatch):
+    """VaultProcessor.from_pretrained (ref:vault/models/vault/processor.py:7-18): checkpoints without processor files load the stock ViLT-B/32
+    processor, the LM's tokenizer replaces ViLT's; with nothing loadable the first error surfaces."""
+    import transformers
+
+    from vault_b200 import processor as P
+
+    calls = []
+
+    class FakeProc:
+        tokenizer = "vilt-tokenizer"
+
+    def fake_from_pretrained(cls, src, *a, **k):
+        calls.append(src)
+        if src != "dandelin/vilt-b32-mlm":
+            raise OSError(f"no processor files in {src}")
+        return FakeProc()
+
+    monkeypatch.setattr(transformers.ViltProcessor, "from_pretrained", classmethod(fake_from_pretrained))
+    monkeypatch.setattr(P.AutoTokenizer, "from_pretrained", staticmethod(lambda src: "tok:" + src))
+    p = P.VaultProcessor.from_pretrained("some/vilt-checkpoint", "vinai/bertweet-base")
+    assert calls == ["some/vilt-checkpoint", "dandelin/vilt-b32-mlm"] and p.tokenizer == "tok:vinai/bertweet-base"
+    assert P.VaultProcessor.from_pretrained("dandelin/vilt-b32-mlm").tokenizer == "vilt-tokenizer"
+    monkeypatch.setattr(P, "_FALLBACK_PROCESSORS", ())
+    with pytest.raises(OSError, match="some/other"):
+        P.VaultProcessor.from_pretrained("some/other")

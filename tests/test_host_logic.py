@@ -321,3 +321,32 @@ def test_processor_falls_back_to_the_stock_vilt_processor_and_swaps_the_tokenize
     monkeypatch.setattr(P, "_FALLBACK_PROCESSORS", ())
     with pytest.raises(OSError, match="some/other"):
         P.VaultProcessor.from_pretrained("some/other")
+
+
+def test_from_pretrained_with_local_checkpoints(tmp_path):
+    """VaultMixin.from_pretrained (ref:vault/models/vault/model.py:92-128) on local ViLT / BERT checkpoints written by save_pretrained: trunk and LM
+    weights arrive under the HF keys, the head is freshly initialised, freeze_lm / the position-embedding gate / n_classes behave as in the reference."""
+    from transformers import BertConfig, BertModel, ViltConfig, ViltModel
+
+    from vault_b200.models.vault import VaultForTMSC, VaultModel
+
+    kw = dict(hidden_size=128, num_hidden_layers=2, num_attention_heads=2, intermediate_size=512)
+    vd, bd = str(tmp_path / "vilt"), str(tmp_path / "bert")
+    torch.manual_seed(0)
+    v = ViltModel(ViltConfig(vocab_size=512, **kw))
+    v.save_pretrained(vd)
+    b = BertModel(BertConfig(vocab_size=512, max_position_embeddings=64, **kw), add_pooling_layer=False)
+    b.save_pretrained(bd)
+    m = VaultForTMSC.from_pretrained(vd, bd, freeze_lm=True, n_classes=3, vilt_dropout_prob=0.1)
+    assert m.freeze_lm and m.classifier[1].out_features == 3 and m.embeddings.text_embeddings.position_embedding_type == "NOT_absolute"
+    sd = m.state_dict()
+    assert torch.equal(sd["encoder.layer.1.output.dense.weight"], v.state_dict()["encoder.layer.1.output.dense.weight"])
+    assert torch.equal(sd["bert.encoder.layer.0.attention.self.query.weight"], b.state_dict()["encoder.layer.0.attention.self.query.weight"])
+    assert all(not p.requires_grad for p in m.bert.parameters()) and all(p.requires_grad for p in m.encoder.parameters())
+    assert not any(k.startswith("bert.pooler") for k in sd)  # add_pooling_layer=False
+    plain = VaultModel.from_pretrained(vd)
+    assert plain.bert is None and plain.embeddings.text_embeddings.position_embedding_type == "absolute"
+    keep_pos = VaultModel.from_pretrained(vd, bd, use_vilt_position_embeddings=True)
+    assert keep_pos.bert is not None and not keep_pos.freeze_lm and keep_pos.embeddings.text_embeddings.position_embedding_type == "absolute"
+    # the engine is built lazily from whatever LM is attached now
+    assert keep_pos.engine.lm is keep_pos.bert and plain.engine.lm is None

@@ -152,6 +152,9 @@ int vault_attn_set_impl(int32_t impl);
  *        x = word[ids] + type[tt] + pos[pid]  -> x_sum fp32 [B*T, H] (input of the embedding LayerNorm)
  * ViLT text: TextEmbeddings.forward with inputs_embeds HF:models/vilt/modeling_vilt.py:240-272 (4.48.0 gate):
  *        x = inputs_embeds + type[tt] (+ pos[t] if pos != NULL)
+ *        The same pair serves the LM when the caller passes text inputs_embeds instead of input_ids
+ *        (ref:vault/models/vault/model.py:170-190; BertEmbeddings / RobertaEmbeddings with inputs_embeds): pos then points at the
+ *        LM's position table, offset by pad+1 rows for RoBERTa (create_position_ids_from_inputs_embeds).
  * ------------------------------------------------------------------------------------------------------------------ */
 /* also converts attention_mask int64 [B,T] -> key_mask uint8 [B,T] for the attention kernels (both optional) */
 int vault_lm_embed_fwd(const int64_t* ids, const int64_t* tt, const float* word, const float* type, const float* pos,

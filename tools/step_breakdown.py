@@ -10,9 +10,10 @@ import bench
 dev = torch.device("cuda:0")
 torch.manual_seed(0)
 B = int(os.environ.get("VB_BATCH", "32"))
+W = bench.WORKLOADS[os.environ.get("VB_WORKLOAD", "config3")]
 m = VaultForTMSC(ViltConfig(), n_classes=3, vilt_dropout_prob=0.1, bert_config=BertConfig()).to(dev).train()
 ts = VaultTrainStep(m, lr=2e-5, use_cuda_graph=False)
-batch = {k: v.to(dev) for k, v in bench.synth_batch(torch, B, 40, (384, 384), 30522, 3, seed=1, pin=False).items()}
+batch = {k: v.to(dev) for k, v in bench.synth_batch(torch, B, W["text_len"], tuple(W["image"]), 30522, 3, seed=1, pin=False).items()}
 for _ in range(2):
     ts.step(batch)
 torch.cuda.synchronize()
@@ -40,10 +41,12 @@ trace = list(counter.trace)
 _abi.uninstall_counter()
 
 fams = {
-    "gemm_vilt": lambda n, a: n == "vault_gemm_bf16" and max(a[0].M, a[0].K if a[0].a_mn else 0) >= 4000,
-    "gemm_lm": lambda n, a: n == "vault_gemm_bf16" and max(a[0].M, a[0].K if a[0].a_mn else 0) < 4000,
-    "attn_fwd": lambda n, a: n == "vault_attn_fwd",
-    "attn_bwd": lambda n, a: n == "vault_attn_bwd",
+    "gemm_vilt": lambda n, a: n == "vault_gemm_bf16" and max(a[0].M, a[0].K if a[0].a_mn else 0) >= 4500,
+    "gemm_lm": lambda n, a: n == "vault_gemm_bf16" and max(a[0].M, a[0].K if a[0].a_mn else 0) < 4500,
+    "attn_fwd_vilt": lambda n, a: n == "vault_attn_fwd" and int(a[5]) != W["text_len"],
+    "attn_bwd_vilt": lambda n, a: n == "vault_attn_bwd" and int(a[8]) != W["text_len"],
+    "attn_fwd_lm": lambda n, a: n == "vault_attn_fwd" and int(a[5]) == W["text_len"],
+    "attn_bwd_lm": lambda n, a: n == "vault_attn_bwd" and int(a[8]) == W["text_len"],
     "ln_fwd": lambda n, a: n == "vault_layernorm_fwd_drop",
     "ln_bwd": lambda n, a: n == "vault_layernorm_bwd_drop",
     "colsum": lambda n, a: n == "vault_colsum_bf16",

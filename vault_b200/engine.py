@@ -94,6 +94,9 @@ class VaultEngine:
         self._g = GemmArgs()
         self.seed = 0x5EED5EED
         self.seed_dev: Optional[torch.Tensor] = None  # device counter added to the seed (advanced once per training step)
+        # what the kernels read the counter from: seed_dev itself (fused train step: forward and backward in one graph), or the per-forward
+        # snapshot a Tape carries (autograd path: several forwards may precede one backward, each must regenerate ITS OWN masks)
+        self._seed_buf: Optional[torch.Tensor] = None
         self.sms = 0
         self.gemm_max_ctas = 0  # >0: leave SMs free for a concurrently running collective (data-parallel overlap)
         self.dynamic_tiles = os.environ.get("VAULT_B200_DYNAMIC_TILES", "0") == "1"  # measured neutral on B200: opt-in
@@ -106,6 +109,7 @@ class VaultEngine:
         # the first backward of a generation zero-fills the accumulated gradient ranges, later ones of the same generation add.
         self._gen = 0
         self._accumulate = False
+        self._grads_live = False  # attach_grads() has handed out p.grad views since the last zeroing generation
 
     # ------------------------------------------------------------------------------------------------------------
     # parameter packing
@@ -183,6 +187,10 @@ class VaultEngine:
         if self._sig == sig and self.device == device and self._params_in_place():
             return
         _abi.check(_abi.lib().vault_check_device(device.index if device.index is not None else torch.cuda.current_device()), "check_device")
+        bad = [n for n, p in self.model.named_parameters() if p.dtype != torch.float32]
+        if bad:  # every parameter, once per (re)pack: a partially cast module (model.bert.half(), a bf16-loaded LM) must not be re-typed silently
+            raise RuntimeError("vault_b200 keeps fp32 master weights (bf16 tensor-core operands are derived): do not cast the module "
+                               f"({len(bad)} non-fp32 parameters, e.g. {bad[0]})")
         self.device = device
         self.sms = torch.cuda.get_device_properties(device).multi_processor_count
         named = dict(self.model.named_parameters())
@@ -213,6 +221,7 @@ class VaultEngine:
         self._grad_views = [(n, named[n], self.grad[s.off:s.off + s.numel].view(s.shape)) for n, s in slots.items() if s.trainable]
         self._versions = None
         self.seed_dev = torch.zeros(1, device=device, dtype=torch.int64)
+        self._seed_buf = self.seed_dev
         # gradient ranges that are ACCUMULATED into (atomics): zero-filled at the start of every backward
         self._zero_ranges = self._compute_zero_ranges()
         self.opt_state = None
@@ -309,7 +318,7 @@ class VaultEngine:
         g.aux, g.ldaux = aux or None, ldaux
         g.out, g.ldo, g.out2, g.ldo2 = out, ldo, out2 or None, ldo2
         g.dropout_p, g.seed, g.site = p, self.seed, site
-        g.seed_dev = self.seed_dev.data_ptr() if p > 0.0 else None
+        g.seed_dev = self._seed_buf.data_ptr() if p > 0.0 else None
         g.split_k, g.block_n, g.max_ctas = split_k, block_n, self.gemm_max_ctas
         if self.dynamic_tiles:
             self._sched_i = (self._sched_i + 1) % self._sched_slots
@@ -369,7 +378,7 @@ class VaultEngine:
         stats = self._new((2, rows), torch.float32)
         rc = self._lib.vault_layernorm_fwd_drop(x32.data_ptr(), self.w32(gname), self.w32(bname), y16.data_ptr() if want16 else None,
                                                 y32.data_ptr() if want32 else None, stats.data_ptr(), stats.data_ptr() + 4 * rows, rows, self.H, eps,
-                                                p, self.seed, self.seed_dev.data_ptr() if p > 0 else None, site, self._st)
+                                                p, self.seed, self._seed_buf.data_ptr() if p > 0 else None, site, self._st)
         if rc:
             _abi.check(rc, "vault_layernorm_fwd")
         return y16, y32, stats
@@ -385,7 +394,7 @@ class VaultEngine:
                                                 dres32.data_ptr() if dres32 is not None else None, dx32.data_ptr(),
                                                 dx16.data_ptr() if want16 else None, self.g32(gname) or None, self.g32(bname) or None,
                                                 (self.g32(colsum_to) or None) if (colsum_to and want16) else None, rows, self.H,
-                                                in_p, in_site, out_p, out_site, self.seed, self.seed_dev.data_ptr() if use_seed else None, self._st)
+                                                in_p, in_site, out_p, out_site, self.seed, self._seed_buf.data_ptr() if use_seed else None, self._st)
         if rc:
             _abi.check(rc, "vault_layernorm_bwd")
         return dx32, dx16
@@ -394,7 +403,7 @@ class VaultEngine:
         ctx = self._new((B * S, self.H), torch.bfloat16)
         lse = self._new((B, self.heads, S), torch.float32) if want_lse else None
         rc = self._lib.vault_attn_fwd(qkv.data_ptr(), key_mask.data_ptr(), ctx.data_ptr(), lse.data_ptr() if want_lse else None, B, S, self.heads, p,
-                                      self.seed, self.seed_dev.data_ptr() if p > 0 else None, site, self._st)
+                                      self.seed, self._seed_buf.data_ptr() if p > 0 else None, site, self._st)
         if rc:
             _abi.check(rc, "vault_attn_fwd")
         return ctx, lse
@@ -403,7 +412,7 @@ class VaultEngine:
         dqkv = self._new((B * S, 3 * self.H), torch.bfloat16)
         delta = self._new((B, self.heads, S), torch.float32)
         rc = self._lib.vault_attn_bwd(qkv.data_ptr(), key_mask.data_ptr(), ctx.data_ptr(), dctx.data_ptr(), lse.data_ptr(), delta.data_ptr(),
-                                      dqkv.data_ptr(), B, S, self.heads, p, self.seed, self.seed_dev.data_ptr() if p > 0 else None, site, self._st)
+                                      dqkv.data_ptr(), B, S, self.heads, p, self.seed, self._seed_buf.data_ptr() if p > 0 else None, site, self._st)
         if rc:
             _abi.check(rc, "vault_attn_bwd")
         return dqkv
@@ -574,7 +583,8 @@ class VaultEngine:
 
     def forward_iter(self, input_ids, attention_mask, token_type_ids, pixel_values, pixel_mask, image_token_type_idx=1, training=False,
                      need_grad=False, hw: Optional[torch.Tensor] = None, pmax: Optional[int] = None, split_lm: bool = False,
-                     image_embeds: Optional[torch.Tensor] = None, inputs_embeds: Optional[torch.Tensor] = None):
+                     image_embeds: Optional[torch.Tensor] = None, inputs_embeds: Optional[torch.Tensor] = None,
+                     seed_snapshot: Optional[torch.Tensor] = None):
         """Generator form of forward.  With split_lm it yields "lm_done" once the language model's forward is enqueued and before
         anything reads a ViLT parameter, so a caller can start the LM while the previous step's AdamW is still updating the
         ViLT range (VaultTrainStep); the return value (StopIteration.value) is forward()'s tuple."""
@@ -582,6 +592,9 @@ class VaultEngine:
         dev = image_embeds.device if embeds_mode else pixel_values.device
         self.ensure_packed(dev)
         self._lib, self._st = _abi.lib(), self._stream()
+        # seed_snapshot: device copy of seed_dev taken for THIS forward; its backward (and the head's) regenerate the masks from it even
+        # if later forwards have advanced the live counter in between
+        self._seed_buf = seed_snapshot if seed_snapshot is not None else self.seed_dev
         if not split_lm and not torch.cuda.is_current_stream_capturing():
             # an optimizer update issued on the side stream (VaultTrainStep) must have landed before weights are read here
             torch.cuda.current_stream(dev).wait_stream(self._side)
@@ -628,6 +641,7 @@ class VaultEngine:
         tape = Tape() if need_grad else None
         if tape is not None:
             tape.gen = self._gen
+            tape.meta["seed_buf"] = self._seed_buf
         sv = tape.t if tape is not None else None
         Mt = B * T
         am_ptr = attention_mask.data_ptr() if attention_mask is not None else None
@@ -764,6 +778,7 @@ class VaultEngine:
 
     def attach_grads(self, exclude_prefix: Optional[str] = None, only_prefix: Optional[str] = None):
         """p.grad <- view of the flat gradient buffer (no copy).  A foreign p.grad tensor is accumulated into instead."""
+        self._grads_live = True
         for n, p, view in self._grad_views:
             if only_prefix is not None and not n.startswith(only_prefix):
                 continue
@@ -777,6 +792,25 @@ class VaultEngine:
     def zero_accumulated_grads(self):
         for a, b in self._zero_ranges:
             self.grad[a:b].zero_()
+
+    def grads_pending(self, prefix: Optional[str] = None, exclude_prefix: Optional[str] = None) -> bool:
+        """True if some served Parameter's .grad still IS its view of the flat buffer, i.e. the caller has not dropped the previous
+        backward's gradients (no zero_grad(set_to_none=True)): torch semantics then are to ACCUMULATE into them.  The next
+        backward therefore adds (atomic weight-gradient epilogues, scratch copies for the overwriting kernels) instead of zero-filling;
+        after zero_grad(set_to_none=False) that adds into zeros, which is the same thing."""
+        if not self._grads_live:
+            return False
+        for n, p, v in self._grad_views:
+            if prefix is not None and not n.startswith(prefix):
+                continue
+            if exclude_prefix is not None and n.startswith(exclude_prefix):
+                continue
+            if p.grad is not None and p.grad.data_ptr() == v.data_ptr():
+                return True
+        return False
+
+    def __getstate__(self):
+        raise TypeError("VaultEngine holds device pointers and is not picklable; pickle / deepcopy the model instead (its engine is rebuilt lazily)")
 
     def backward(self, tape: Tape, dlhs: Optional[torch.Tensor], dpooled: Optional[torch.Tensor]):
         """Fills self.grad (fp32, flat) with dL/dparam for every trainable parameter; returns nothing."""
@@ -797,13 +831,16 @@ class VaultEngine:
         self._lib, self._st = _abi.lib(), self._stream()
         lib, st = self._lib, self._st
         sv, mt = tape.t, tape.meta
+        self._seed_buf = mt.get("seed_buf", self.seed_dev)
         B, T, S, pmax, gh, gw = mt["B"], mt["T"], mt["S"], mt["pmax"], mt["gh"], mt["gw"]
         H, M, Mt = self.H, B * S, B * T
         first = tape.gen >= self._gen
+        pending = first and self.grads_pending(exclude_prefix="classifier.")
         if first:
-            self.zero_accumulated_grads()
+            if not pending:
+                self.zero_accumulated_grads()
             self._gen = tape.gen + 1
-        self._accumulate = not first
+        self._accumulate = (not first) or pending
         if dlhs is not None:
             g_lhs = dlhs.contiguous().float().clone().view(M, H)
         else:

@@ -20,7 +20,7 @@ Differences from the reference, all deliberate:
   * ``head_mask``, ``output_attentions`` and ``output_hidden_states`` are not on the hot path and raise ``NotImplementedError``
     (``image_embeds`` and text ``inputs_embeds`` are served by the kernels, gradients to the caller's tensors included);
   * gradients are written into one flat fp32 buffer and ``p.grad`` are views of it: zero (or ``None``) them between backward
-    calls as the reference trainer does (ref:vault/tmsc_utils/trainer.py:364); accumulation across backwards is not supported.
+    calls as the reference trainer does (ref:vault/tmsc_utils/trainer.py:364); if a caller keeps ``p.grad`` across backward calls the next backward adds to it (torch semantics).
 """
 from __future__ import annotations
 
@@ -51,7 +51,9 @@ class _TrunkFn(torch.autograd.Function):
 
     @staticmethod
     def forward(ctx, anchor, engine: VaultEngine, kw: dict, image_embeds=None, inputs_embeds=None):
-        lhs, pooled, key_mask, tape = engine.forward(need_grad=True, image_embeds=image_embeds, inputs_embeds=inputs_embeds, **kw)
+        # the dropout counter as of THIS forward: a later forward may advance engine.seed_dev before this one's backward runs
+        snap = engine.seed_dev.clone() if kw.get("training") else None
+        lhs, pooled, key_mask, tape = engine.forward(need_grad=True, image_embeds=image_embeds, inputs_embeds=inputs_embeds, seed_snapshot=snap, **kw)
         ctx.engine, ctx.tape = engine, tape
         ctx.embeds_grad = image_embeds is not None and image_embeds.requires_grad
         ctx.text_embeds_grad = inputs_embeds is not None and inputs_embeds.requires_grad
@@ -82,7 +84,8 @@ class _HeadFn(torch.autograd.Function):
         x = pooled
         if p > 0.0:
             x = torch.empty_like(pooled)
-            _abi.check(lib.vault_dropout_f32(pooled.data_ptr(), x.data_ptr(), pooled.numel(), p, engine.seed, engine.seed_dev.data_ptr(),
+            ctx.seed_buf = engine._seed_buf  # the trunk forward's snapshot (or the live counter): read again by backward
+            _abi.check(lib.vault_dropout_f32(pooled.data_ptr(), x.data_ptr(), pooled.numel(), p, engine.seed, ctx.seed_buf.data_ptr(),
                                              engine.SITE_HEAD, st), "dropout_f32")
         logits = torch.empty((B, n_classes), device=pooled.device, dtype=torch.float32)
         _abi.check(lib.vault_small_linear_fwd(x.data_ptr(), H, engine.w32(wname), engine.w32(bname), logits.data_ptr(), B, n_classes, H, 0, st),
@@ -100,10 +103,18 @@ class _HeadFn(torch.autograd.Function):
         n = dlogits.shape[1]
         dlogits = dlogits.contiguous().float()
         dx = torch.empty_like(x)
+        gw, gb = engine.g32(wname), engine.g32(bname)
+        tmp = None
+        if gw and engine.grads_pending(prefix="classifier."):  # the kernel overwrites: gradients the caller kept are added to, as torch would
+            tmp = (torch.empty((n, H), device=x.device), torch.empty((n,), device=x.device))
+            gw, gb = tmp[0].data_ptr(), tmp[1].data_ptr()
         _abi.check(lib.vault_small_linear_bwd(dlogits.data_ptr(), None, x.data_ptr(), H, engine.w32(wname), dx.data_ptr(), H, 0,
-                                              engine.g32(wname) or None, engine.g32(bname) or None, B, n, H, 0, st), "classifier_bwd")
+                                              gw or None, gb or None, B, n, H, 0, st), "classifier_bwd")
+        if tmp is not None:
+            engine.grad_view(wname).add_(tmp[0])
+            engine.grad_view(bname).add_(tmp[1])
         if ctx.p > 0.0:
-            _abi.check(lib.vault_dropout_f32(dx.data_ptr(), dx.data_ptr(), dx.numel(), ctx.p, engine.seed, engine.seed_dev.data_ptr(),
+            _abi.check(lib.vault_dropout_f32(dx.data_ptr(), dx.data_ptr(), dx.numel(), ctx.p, engine.seed, ctx.seed_buf.data_ptr(),
                                              engine.SITE_HEAD, st), "dropout_f32_bwd")
         engine.attach_grads(only_prefix="classifier.")
         return dx, None, None, None, None, None
@@ -201,6 +212,12 @@ class VaultMixin(nn.Module, ABC):
         self._engine: Optional[VaultEngine] = None
         self._anchor = None
 
+    def __getstate__(self):
+        """copy.deepcopy(model) / torch.save(model): the engine (device pointers, ctypes structs, streams) is dropped and rebuilt lazily."""
+        st = self.__dict__.copy()
+        st["_engine"], st["_anchor"] = None, None
+        return st
+
     def _trunk_module(self):
         """The ViltModel holding the trunk parameters: the module itself, or ``.vilt`` of a head wrapper (ViltForMaskedLM & co.)."""
         return self.vilt if "vilt" in self._modules else self
@@ -263,10 +280,6 @@ class VaultMixin(nn.Module, ABC):
             raise ValueError("You cannot specify both pixel_values and image_embeds at the same time")
         if not (pixel_values if pixel_values is not None else image_embeds).is_cuda:
             raise RuntimeError("vault_b200 runs on CUDA (sm_100a) only: move the model and the batch to the GPU -- there is no CPU fallback")
-        for p in self.parameters():
-            if p.dtype != torch.float32:
-                raise RuntimeError("vault_b200 keeps fp32 master weights (bf16 tensor-core operands are derived): do not cast the module")
-            break
         eng = self.engine
         need_grad = torch.is_grad_enabled() and any(p.requires_grad for p in self.parameters())
         kw = dict(input_ids=input_ids, attention_mask=attention_mask, token_type_ids=token_type_ids, pixel_values=pixel_values,

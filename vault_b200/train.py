@@ -40,15 +40,27 @@ def allreduce_flat_(flat: torch.Tensor, group=None, bucket_elems: int = 16 * 102
     return works
 
 
-class StepResult:
-    """Handle on a step's loss: ``loss()`` waits for that step's device->host copy only."""
+LOSS_RING = 4096  # steps whose loss may be outstanding (unread) at once
 
-    def __init__(self, host: torch.Tensor, event: torch.cuda.Event, lr: float):
-        self._host, self._event, self.lr = host, event, lr
+
+class StepResult:
+    """Handle on a step's loss: ``loss()`` waits for that step's device->host copy only.  Every step owns one entry (and one event)
+    of a pinned ring of LOSS_RING floats, so handles may be resolved late and in any order -- the reference accumulates
+    ``loss.item() * batch_len`` per step (ref:vault/tmsc_utils/trainer.py:369); a caller that defers the read gets the same numbers."""
+
+    def __init__(self, owner, step_no: int, lr: float):
+        self._owner, self._step, self.lr = owner, step_no, lr
+        self._value: Optional[float] = None
 
     def loss(self) -> float:
-        self._event.synchronize()
-        return float(self._host[0])
+        if self._value is None:
+            o = self._owner
+            if o.step_idx - self._step > LOSS_RING:
+                raise RuntimeError(f"StepResult.loss(): step {self._step} is more than {LOSS_RING} steps old, its read-back entry was reused")
+            i = self._step % LOSS_RING
+            o._loss_events[i].synchronize()
+            self._value = float(o._loss_ring[i])
+        return self._value
 
 
 class _Slot:
@@ -57,8 +69,6 @@ class _Slot:
         self.ready = torch.cuda.Event()
         self.free = torch.cuda.Event()
         self.graphs = None   # list of (CUDAGraph, grad offset reached when it finishes)
-        self.loss_host = None
-        self.loss_event = torch.cuda.Event()
 
 
 class VaultTrainStep:
@@ -122,6 +132,8 @@ class VaultTrainStep:
         self.sched_dev = torch.zeros(2, device=self.dev, dtype=torch.float32)
         self.step_idx = 0
         self._states: Dict[tuple, list] = {}
+        self._loss_ring = torch.zeros(LOSS_RING, dtype=torch.float32).pin_memory()
+        self._loss_events = [None] * LOSS_RING
         self._pool = None
         self._turn = 0
 
@@ -147,7 +159,6 @@ class VaultTrainStep:
         s.buf["hw"] = torch.empty((B, 2), device=self.dev, dtype=torch.int32)
         s.buf["loss"] = torch.zeros(1, device=self.dev, dtype=torch.float32)
         s.buf["logits"] = torch.zeros((B, self.n_classes), device=self.dev, dtype=torch.float32)
-        s.loss_host = torch.zeros(1, dtype=torch.float32).pin_memory()
         s.free.record(torch.cuda.current_stream(self.dev))
         return s
 
@@ -271,6 +282,8 @@ class VaultTrainStep:
         step_size = lr
         if self.correct_bias:
             step_size = lr * (1.0 - b2 ** step_no) ** 0.5 / (1.0 - b1 ** step_no)
+        if self._ev_rest is not None:
+            cs.wait_event(self._ev_rest)  # split_lm: the previous step's ViLT-range AdamW (side stream) still reads sched_dev
         self.sched_dev.copy_(torch.tensor([step_size, lr * self.wd if self.wd > 0 else 0.0], dtype=torch.float32), non_blocking=True)
         hp = dict(step=step_no, lr=lr, b1=b1, b2=b2)
         if self.use_graph:
@@ -329,7 +342,11 @@ class VaultTrainStep:
             ev = torch.cuda.Event()
             ev.record(eng._side)
             cs.wait_event(ev)  # every range's AdamW (and all-reduce) is done before the next step touches weights or gradients
-        s.loss_host.copy_(s.buf["loss"], non_blocking=True)
-        s.loss_event.record(cs)
+        i = self.step_idx % LOSS_RING
+        self._loss_ring[i:i + 1].copy_(s.buf["loss"], non_blocking=True)
+        if self._loss_events[i] is None:
+            self._loss_events[i] = torch.cuda.Event()
+        self._loss_events[i].record(cs)
+        res = StepResult(self, self.step_idx, lr)
         self.step_idx += 1
-        return StepResult(s.loss_host, s.loss_event, lr)
+        return res

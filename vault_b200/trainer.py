@@ -229,6 +229,9 @@ class Twitter201XTrainer:
                 kw = dict(self.input_batch_kwargs(batch))
                 kw["labels"] = self.batch_labels(batch)
                 pending.append((self.train_step.step(kw), self.batch_len(batch)))  # H2D + graph replay are enqueued; nothing waits here
+                if len(pending) >= 1024:  # bound the outstanding read-backs (each step owns an entry of the step's pinned loss ring)
+                    tl, ns = self._flush_losses(pending)
+                    train_loss, n_samples = train_loss + tl, n_samples + ns
                 if (step + 1) % eval_steps == 0:
                     tl, ns = self._flush_losses(pending)
                     tl, ns = self._allreduce_sums(train_loss + tl, n_samples + ns)

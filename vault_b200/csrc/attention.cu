@@ -504,13 +504,20 @@ int attn_fwd_tc(const void* qkv, const uint8_t* key_mask, void* ctx, float* lse,
 int attn_bwd_tc(const void* qkv, const uint8_t* key_mask, const void* ctx, const void* dctx, const float* lse, float* delta, void* dqkv, int B, int S,
                 int heads, cudaStream_t st);
 void attn_set_impl(int impl);
+// pipelined tcgen05 kernels of attention_sm100.cu (S <= 384, no dropout)
+bool attn_sm100_ok(int S, float dropout_p);
+void attn_sm100_enable(int on);
+int attn_fwd_sm100(const void* qkv, const uint8_t* key_mask, void* ctx, float* lse, int B, int S, int heads, cudaStream_t st);
+int attn_bwd_sm100(const void* qkv, const uint8_t* key_mask, const void* ctx, const void* dctx, const float* lse, float* delta, void* dqkv, int B, int S,
+                   int heads, cudaStream_t st);
 
 }  // namespace vb
 
 extern "C" int vault_attn_set_impl(int32_t impl) {
   using namespace vb;
-  VB_REQUIRE(impl >= 0 && impl <= 2, "vault_attn_set_impl: impl=%d (0 auto, 1 mma.sync, 2 tcgen05 where the shape allows)", impl);
+  VB_REQUIRE(impl >= 0 && impl <= 2, "vault_attn_set_impl: impl=%d (0 auto, 1 mma.sync, 2 first-generation tcgen05 kernels where the shape allows)", impl);
   attn_set_impl(impl);
+  attn_sm100_enable(impl == 0 ? 1 : 0);
   return VAULT_OK;
 }
 
@@ -521,6 +528,7 @@ extern "C" int vault_attn_fwd(const void* qkv, const uint8_t* key_mask, void* ct
   AttnParams p{};
   int rc = fill_params(p, B, S, heads, dropout_p, seed, seed_dev, site);
   if (rc) return rc;
+  if (attn_sm100_ok(S, dropout_p)) return attn_fwd_sm100(qkv, key_mask, ctx, lse, B, S, heads, reinterpret_cast<cudaStream_t>(stream));
   if (attn_tc_fwd_ok(S, dropout_p)) return attn_fwd_tc(qkv, key_mask, ctx, lse, B, S, heads, reinterpret_cast<cudaStream_t>(stream));
   p.qkv = reinterpret_cast<const bf16*>(qkv); p.key_mask = key_mask; p.ctx = reinterpret_cast<bf16*>(ctx); p.lse = lse;
   const int smem = (kTile + 2 * p.S_pad) * 128 + p.S_pad;
@@ -544,6 +552,8 @@ extern "C" int vault_attn_bwd(const void* qkv, const uint8_t* key_mask, const vo
   AttnParams p{};
   int rc = fill_params(p, B, S, heads, dropout_p, seed, seed_dev, site);
   if (rc) return rc;
+  if (attn_sm100_ok(S, dropout_p))
+    return attn_bwd_sm100(qkv, key_mask, ctx, dctx, lse, delta, dqkv, B, S, heads, reinterpret_cast<cudaStream_t>(stream));
   if (attn_tc_bwd_ok(S, dropout_p))
     return attn_bwd_tc(qkv, key_mask, ctx, dctx, lse, delta, dqkv, B, S, heads, reinterpret_cast<cudaStream_t>(stream));
   p.qkv = reinterpret_cast<const bf16*>(qkv); p.key_mask = key_mask; p.ctx = reinterpret_cast<bf16*>(const_cast<void*>(ctx));

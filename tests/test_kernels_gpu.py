@@ -180,8 +180,12 @@ def _mid_mask(dev, B, S):
 
 
 @pytest.mark.parametrize("B,S,heads", [(2, 64, 2), (3, 185, 12), (2, 369, 12), (2, 40, 12), (1, 17, 2), (2, 209, 12), (1, 512, 2), (2, 65, 2),
-                                       (2, 128, 4), (3, 129, 2), (2, 192, 4), (2, 193, 2), (1, 256, 2), (2, 257, 2)])
+                                       (2, 128, 4), (3, 129, 2), (2, 192, 4), (2, 193, 2), (1, 256, 2), (2, 257, 2), (1, 384, 2), (5, 300, 12),
+                                       (13, 369, 12)])
 def test_attention_fwd_bwd(dev, B, S, heads):
+    """vault_attn_fwd / vault_attn_bwd against torch fp32 (HF:models/vilt/modeling_vilt.py:306-365 semantics: scores / 8, key mask, softmax, @V) at
+    every kernel family's shapes: mma.sync (<= 64, > 384), whole-row tcgen05 (65..192), pipelined tcgen05 (193..384; 13 x 12 = 156 (sample, head)
+    items = more than one item per persistent CTA)."""
     from vault_b200 import _abi
 
     lib, st = _abi.lib(), torch.cuda.current_stream().cuda_stream
@@ -205,10 +209,12 @@ def test_attention_fwd_bwd(dev, B, S, heads):
     assert _rel(dqkv, dref) < 2e-2
 
 
-@pytest.mark.parametrize("B,S,heads", [(3, 185, 12), (2, 100, 2), (2, 192, 2), (1, 241, 2)])
-def test_attention_tcgen05_matches_mma_sync(dev, B, S, heads):
-    """The tensor-memory kernels (attention_tc.cu) and the mma.sync kernels implement the same contract: same LSE convention (either
-    forward feeds either backward), outputs equal to bf16 rounding, every output row written, nothing written past a sample's rows."""
+@pytest.mark.parametrize("B,S,heads,tc_impl", [(3, 185, 12, 0), (2, 100, 2, 0), (2, 192, 2, 0), (1, 241, 2, 0), (2, 369, 12, 0),
+                                               (1, 17, 2, 3), (2, 40, 12, 3), (2, 128, 2, 3), (3, 185, 12, 3), (2, 256, 2, 3), (25, 128, 12, 3)])
+def test_attention_tcgen05_matches_mma_sync(dev, B, S, heads, tc_impl):
+    """The tensor-memory kernels (attention_tc.cu, attention_sm100.cu; tc_impl 3 forces the pipelined kernels at every length) and the
+    mma.sync kernels implement the same contract: same LSE convention (either forward feeds either backward), outputs equal to bf16
+    rounding, every output row written, nothing written past a sample's rows."""
     from vault_b200 import _abi
 
     lib, st = _abi.lib(), torch.cuda.current_stream().cuda_stream
@@ -219,7 +225,7 @@ def test_attention_tcgen05_matches_mma_sync(dev, B, S, heads):
     dctx = _rnd(dev, B * S, H, scale=0.5)
     out = {}
     try:
-        for impl in (1, 0):
+        for impl in (1, tc_impl):
             _abi.set_attn_impl(impl)
             ctx = torch.full((B * S + 64, H), float("nan"), device=dev, dtype=torch.bfloat16)
             ctx[B * S:] = 7.0  # 64 guard rows behind the last sample
@@ -227,23 +233,23 @@ def test_attention_tcgen05_matches_mma_sync(dev, B, S, heads):
             _abi.check(lib.vault_attn_fwd(qkv.data_ptr(), mask.data_ptr(), ctx.data_ptr(), lse.data_ptr(), B, S, heads, 0.0, 0, None, 0, st))
             assert torch.all(ctx[B * S:] == 7.0) and not torch.isnan(ctx.float()).any() and not torch.isnan(lse).any()
             out[impl] = (ctx[:B * S].clone(), lse)
-        (c1, l1), (c0, l0) = out[1], out[0]
+        (c1, l1), (c0, l0) = out[1], out[tc_impl]
         assert (c0.float() - c1.float()).abs().max() <= 2 ** -8 * max(1.0, c1.float().abs().max().item())
         assert (l0 - l1).abs().max() < 1e-5
-        if S <= 192:
+        if True:
             grads = {}
-            for impl in (1, 0):
+            for impl in (1, tc_impl):
                 _abi.set_attn_impl(impl)
                 dqkv = torch.full((B * S + 64, 3 * H), float("nan"), device=dev, dtype=torch.bfloat16)
                 dqkv[B * S:] = 7.0
                 delta = torch.empty(B, heads, S, device=dev)
                 # forward of the OTHER family feeds this backward
-                cf, lf = out[1 - impl]
+                cf, lf = out[tc_impl if impl == 1 else 1]
                 _abi.check(lib.vault_attn_bwd(qkv.data_ptr(), mask.data_ptr(), cf.data_ptr(), dctx.data_ptr(), lf.data_ptr(), delta.data_ptr(),
                                               dqkv.data_ptr(), B, S, heads, 0.0, 0, None, 0, st))
                 assert torch.all(dqkv[B * S:] == 7.0) and not torch.isnan(dqkv.float()).any()
                 grads[impl] = dqkv[:B * S].float()
-            assert _rel(grads[0], grads[1]) < 1e-2
+            assert _rel(grads[tc_impl], grads[1]) < 1e-2
     finally:
         _abi.set_attn_impl(0)
 

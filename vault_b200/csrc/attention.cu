@@ -515,9 +515,10 @@ int attn_bwd_sm100(const void* qkv, const uint8_t* key_mask, const void* ctx, co
 
 extern "C" int vault_attn_set_impl(int32_t impl) {
   using namespace vb;
-  VB_REQUIRE(impl >= 0 && impl <= 2, "vault_attn_set_impl: impl=%d (0 auto, 1 mma.sync, 2 first-generation tcgen05 kernels where the shape allows)", impl);
-  attn_set_impl(impl);
-  attn_sm100_enable(impl == 0 ? 1 : 0);
+  VB_REQUIRE(impl >= 0 && impl <= 3, "vault_attn_set_impl: impl=%d (0 auto, 1 mma.sync only, 2 whole-row tcgen05 kernels where the shape allows, "
+             "3 pipelined tcgen05 kernels for every S <= 384)", impl);
+  attn_set_impl(impl == 3 ? 0 : impl);
+  attn_sm100_enable(impl == 0 ? 1 : (impl == 3 ? 2 : 0));
   return VAULT_OK;
 }
 

@@ -45,15 +45,26 @@ struct AParams {
   bf16* dqkv;               // B: out [B*S, 3H]
   int B, S, heads, nblk, n_items;
   float scale_log2, scale;
+  long long* trace;  // VAULT_B200_ATTN_TRACE=1 (debug): (clock64, event id) pairs of CTA 0's MMA thread [0..1023] and first softmax warp [1024..2047]
 };
+
+#define VB_TR(who, id)                                                                                     \
+  do {                                                                                                     \
+    if (p.trace != nullptr && blockIdx.x == 0 && tr_n < 1023) {                                            \
+      p.trace[((who) * 1024 + tr_n) * 2] = clock64();                                                      \
+      p.trace[((who) * 1024 + tr_n) * 2 + 1] = (id);                                                       \
+      ++tr_n;                                                                                              \
+    }                                                                                                      \
+  } while (0)
 
 // shared memory map (bytes from the 1024-aligned base)
 constexpr uint32_t kBlk = 16384;                 // one [128 x 64] bf16 operand block (two 64-row TMA boxes)
 constexpr uint32_t oR1 = 0, oR2 = 3 * kBlk;      // resident operands, up to 3 blocks each
 constexpr uint32_t oT = 6 * kBlk;                // per-tile operands: F: Q_t x 2 (double buffer); B: T1, T2
 constexpr uint32_t oOP = 8 * kBlk;               // P / dS staging: 4 x 16 KB
-constexpr uint32_t oMisc = 12 * kBlk;            // barriers, exchange arrays
-constexpr uint32_t kSmemA = 12 * kBlk + 6144 + 1024;  // misc: 512 B barriers + 2 KB xm + 2 KB xl + mask words
+constexpr uint32_t oStage = 12 * kBlk;           // epilogue staging: 2 KB per softmax warp (32 rows x 32 bf16), coalesced global stores
+constexpr uint32_t oMisc = 13 * kBlk;            // barriers, exchange arrays
+constexpr uint32_t kSmemA = 13 * kBlk + 6144 + 1024;  // misc: 512 B barriers + 2 KB xm + 2 KB xl + mask words
 
 // barrier indices
 constexpr int bR1F = 0, bR1E = 3, bR2F = 6, bR2E = 9, bTF = 12, bTE = 14, bSF = 16, bSE = 19, bDPF = 22, bDPE = 23, bOPF = 24, bOPE = 28, bOF = 32,
@@ -73,12 +84,35 @@ __device__ __forceinline__ void store_row32a(uint32_t buf, int row, int c, const
     st_shared_v4a(rowaddr + (seg << 4), pk[4 * i], pk[4 * i + 1], pk[4 * i + 2], pk[4 * i + 3]);
   }
 }
+__device__ __forceinline__ uint4 ld_shared_v4a(uint32_t addr) {
+  uint4 v;
+  asm volatile("ld.shared.v4.b32 {%0, %1, %2, %3}, [%4];" : "=r"(v.x), "=r"(v.y), "=r"(v.z), "=r"(v.w) : "r"(addr));
+  return v;
+}
+// A warp owns 32 accumulator rows (lane = row) x 32 fp32 columns in registers and writes them, scaled and rounded to bf16, to 32 rows
+// (64 bytes each) of a row-major global matrix.  A lane storing its own row costs 32 L1 wavefronts per instruction, so the rows go
+// through the warp's 2 KB of shared memory (16-byte segments XOR-swizzled) and leave 8 rows per instruction.
+__device__ __forceinline__ void store_rows32_staged(const uint32_t (&r)[32], float mul, uint32_t stage, bf16* gptr0, long long row_stride, int n_valid,
+                                                    int lane) {
+#pragma unroll
+  for (int i = 0; i < 4; ++i) {
+    const uint32_t seg = (uint32_t)i ^ (((uint32_t)lane >> 1) & 3u);
+    st_shared_v4a(stage + (uint32_t)lane * 64u + (seg << 4),
+                  pack_bf16x2(__uint_as_float(r[8 * i]) * mul, __uint_as_float(r[8 * i + 1]) * mul),
+                  pack_bf16x2(__uint_as_float(r[8 * i + 2]) * mul, __uint_as_float(r[8 * i + 3]) * mul),
+                  pack_bf16x2(__uint_as_float(r[8 * i + 4]) * mul, __uint_as_float(r[8 * i + 5]) * mul),
+                  pack_bf16x2(__uint_as_float(r[8 * i + 6]) * mul, __uint_as_float(r[8 * i + 7]) * mul));
+  }
+  __syncwarp();
+#pragma unroll
+  for (int it = 0; it < 4; ++it) {
+    const int rr = 8 * it + (lane >> 2), sg = lane & 3;
+    const uint4 v = ld_shared_v4a(stage + (uint32_t)rr * 64u + (uint32_t)((sg ^ ((rr >> 1) & 3)) << 4));
+    if (rr < n_valid) *reinterpret_cast<uint4*>(gptr0 + (long long)rr * row_stride + sg * 8) = v;
+  }
+  __syncwarp();
+}
 __device__ __forceinline__ void bar_sync_256() { asm volatile("bar.sync 1, 256;" ::: "memory"); }
-
-// position in this CTA's stream of score blocks
-struct Cursor {
-  int it, tile, j, n, nt;
-};
 
 template <int MODE>
 __global__ void __launch_bounds__(kThreadsA, 1)
@@ -91,10 +125,12 @@ attn_sm100_kernel(const __grid_constant__ CUtensorMap tmQKV, const __grid_consta
   const int S = p.S, H = p.heads * 64, nblk = p.nblk;
   const int ntiles = nblk;                             // 128-row tiles per item (queries in F / BQ, keys in BKV)
   const int L = MODE == MODE_F ? 2 * nblk - 1 : nblk;  // score blocks per tile
-  constexpr int kRing = MODE == MODE_F ? 3 : 2;        // TMEM score ring
-  constexpr int kLook = MODE == MODE_F ? 2 : 1;        // score MMAs issued ahead of the output MMAs
-  constexpr bool kTwoAcc = MODE != MODE_BKV;           // double-buffered accumulators
-  constexpr uint32_t colDP = 256, colAcc = 384;
+  // TMEM map.  F: score ring 3 x 128 | O 2 x 64.  BQ / BKV: S 128 | dP 128 | accumulators 2 x 128 (BQ uses 64 of each): in the backward
+  // a softmax warp has its piece of S and dP in registers half-way through the block, so a single buffer each already lets the
+  // next block's score MMAs run under the second half, and the spare columns double-buffer the accumulators (epilogues drain
+  // under the next tile).
+  constexpr int kRing = MODE == MODE_F ? 3 : 1;
+  constexpr uint32_t colDP = 128, colAcc = MODE == MODE_F ? 384u : 256u, accStride = MODE == MODE_F ? 64u : 128u;
 
   const uint32_t bars = base + oMisc;
   auto bar = [&](int i) { return bars + 8u * (uint32_t)i; };
@@ -109,8 +145,11 @@ attn_sm100_kernel(const __grid_constant__ CUtensorMap tmQKV, const __grid_consta
     if (MODE != MODE_F) tma_prefetch_desc(&tmDO);
   }
   if (warp == 1 && lane == 0) {
+    // resident-block "empty" barriers: one arrival per issuer thread that reads the block (score MMAs and / or output MMAs)
+    const uint32_t r1e = MODE == MODE_F ? 1u : 2u;                       // F: K_b scores only; BQ: K_b scores + dQ; BKV: Q_b scores + dK
+    const uint32_t r2e = MODE == MODE_BKV ? 2u : 1u;                     // F: V_b output only; BQ: V_b dP only; BKV: dO_b dP + dV
     for (int i = 0; i < 3; ++i) {
-      mbar_init(bar(bR1F + i), 1); mbar_init(bar(bR1E + i), 1); mbar_init(bar(bR2F + i), 1); mbar_init(bar(bR2E + i), 1);
+      mbar_init(bar(bR1F + i), 1); mbar_init(bar(bR1E + i), r1e); mbar_init(bar(bR2F + i), 1); mbar_init(bar(bR2E + i), r2e);
       mbar_init(bar(bSF + i), 1); mbar_init(bar(bSE + i), 8);
     }
     for (int i = 0; i < 2; ++i) {
@@ -118,7 +157,7 @@ attn_sm100_kernel(const __grid_constant__ CUtensorMap tmQKV, const __grid_consta
     }
     mbar_init(bar(bDPF), 1); mbar_init(bar(bDPE), 8);
     for (int i = 0; i < 4; ++i) {
-      mbar_init(bar(bOPF + i), MODE == MODE_BKV ? 8 : 4);
+      mbar_init(bar(bOPF + i), 8);  // P / dS of one score block: all eight softmax warps
       mbar_init(bar(bOPE + i), 1);
     }
     mbar_fence_init();
@@ -130,14 +169,6 @@ attn_sm100_kernel(const __grid_constant__ CUtensorMap tmQKV, const __grid_consta
   const uint32_t tmem = *tmem_slot_gen;
   pdl_enter();
 
-  auto valid = [&](const Cursor& c) { return (int)blockIdx.x + c.it * (int)gridDim.x < p.n_items; };
-  auto advance = [&](Cursor& c) {
-    ++c.n;
-    if (++c.j == L) {
-      c.j = 0; ++c.nt;
-      if (++c.tile == ntiles) { c.tile = 0; ++c.it; }
-    }
-  };
   // block index / kind of stream position j of tile nt (F: kind 0 = max only, 1 = max + exp, 2 = exp; B modes: always 2).  In F the
   // direction of the walk alternates from tile to tile (b0 .. b_last .. b0, then b_last .. b0 .. b_last): a tile ends on the block the
   // next one does NOT start with, so across an item boundary the blocks the next item needs first were released first.
@@ -151,12 +182,13 @@ attn_sm100_kernel(const __grid_constant__ CUtensorMap tmQKV, const __grid_consta
   // sequences the next item's blocks land in free slots while the current item is still being worked on)
   auto rslot = [&](int it, int b) { return (it * nblk + b) % 3; };
   auto rpar = [&](int it, int b) { return (uint32_t)(((it * nblk + b) / 3) & 1); };
+  const int my_items = ((int)p.n_items - (int)blockIdx.x + (int)gridDim.x - 1) / (int)gridDim.x;
 
   if (warp == 0) {
     // =========================================== TMA producer ===========================================
     if (lane == 0) {
       int nt = 0;
-      for (int it = 0; (int)blockIdx.x + it * (int)gridDim.x < p.n_items; ++it) {
+      for (int it = 0; it < my_items; ++it) {
         const int item = (int)blockIdx.x + it * (int)gridDim.x;
         const int b_ = item / p.heads, h_ = item % p.heads;
         const int row0 = b_ * S;
@@ -215,126 +247,112 @@ attn_sm100_kernel(const __grid_constant__ CUtensorMap tmQKV, const __grid_consta
       }
     }
   } else if (warp == 1) {
-    // =========================================== MMA issuer (one thread) ===========================================
+    // =========================================== score-MMA issuer (one thread) ===========================================
+    // Runs as far ahead of the softmax warps as the TMEM score ring allows; every wait is an in-order blocking one.
     if (lane == 0) {
-      const uint32_t id_s = umma_idesc(1u, 128u, 128u, 0u, 0u);    // score blocks: both operands K-major (dh contiguous)
-      const uint32_t id_o = umma_idesc(1u, 128u, 64u, 0u, 1u);     // F / BQ output: A = P / dS chunk K-major, B = V / K rows MN-major
-      const uint32_t id_t = umma_idesc(1u, 128u, 64u, 1u, 1u);     // BKV output: A = P / dS read MN-major (M = keys), B = dO / Q rows MN-major
-      int opn = 0;                                                 // exp-kind blocks whose output MMAs have been issued (operand ring position)
-      // Every wait below is on a barrier the MMA thread really needs; `probe` turns the same sequence into a non-blocking readiness test,
-      // used for the score blocks issued AHEAD of the output MMAs (a look-ahead that blocked could wait for a resident block of the
-      // next item whose slot is only released by an output MMA this thread has not issued yet).
-      auto need = [&](uint32_t barrier, uint32_t parity, bool probe) -> bool {
-        if (probe) return mbar_test_wait(barrier, parity);
-        mbar_wait(barrier, parity);
-        return true;
-      };
-      auto scores_waits = [&](const Cursor& c, bool probe) -> bool {
-        const int b = blk_of(c.j, c.nt);
-        const int ts = MODE == MODE_F ? (c.nt & 1) : 0;
-        if (c.j == 0 && !need(bar(bTF + ts), (uint32_t)((MODE == MODE_F ? (c.nt >> 1) : c.nt) & 1), probe)) return false;
-        if (!need(bar(bR1F + rslot(c.it, b)), rpar(c.it, b), probe)) return false;
-        if (!need(bar(bSE + c.n % kRing), (uint32_t)((c.n / kRing) & 1) ^ 1u, probe)) return false;
-        if (MODE != MODE_F) {
-          if (!need(bar(bR2F + rslot(c.it, b)), rpar(c.it, b), probe)) return false;
-          if (!need(bar(bDPE), (uint32_t)(c.n & 1) ^ 1u, probe)) return false;
-        }
-        return true;
-      };
-      auto issue_scores = [&](const Cursor& c) {
-        const int b = blk_of(c.j, c.nt), kind = kind_of(c.j);
-        scores_waits(c, false);
-        tc_fence_after();
-        const int ts = MODE == MODE_F ? (c.nt & 1) : 0;
-        const int sl = c.n % kRing, rs = rslot(c.it, b);
-        const uint32_t sT1 = base + oT + (MODE == MODE_F ? (uint32_t)ts * kBlk : 0u), sT2 = base + oT + kBlk;
-        const uint32_t sR1b = base + oR1 + (uint32_t)rs * kBlk, sR2b = base + oR2 + (uint32_t)rs * kBlk;
-        const uint32_t aS = MODE == MODE_BKV ? sR1b : sT1, bS = MODE == MODE_BKV ? sT1 : sR1b;
+      const uint32_t id_s = umma_idesc(1u, 128u, 128u, 0u, 0u);  // both operands K-major (dh contiguous)
+      int n = 0, nt = 0, tr_n = 0;
+      for (int it = 0; it < my_items; ++it) {
+        uint32_t seen = 0;  // bit b: R1_b of this item already waited for, bit 4 + b: R2_b
+        for (int tile = 0; tile < ntiles; ++tile, ++nt) {
+          const int ts = MODE == MODE_F ? (nt & 1) : 0;
+          const bool last_tile = tile == ntiles - 1;
+          for (int j = 0; j < L; ++j, ++n) {
+            const int b = blk_of(j, nt), kind = kind_of(j);
+            const int sl = n % kRing, rs = rslot(it, b);
+            VB_TR(0, 100 + n);
+            if (j == 0) mbar_wait(bar(bTF + ts), (uint32_t)((MODE == MODE_F ? (nt >> 1) : nt) & 1));
+            if (!(seen & (1u << b))) { mbar_wait(bar(bR1F + rs), rpar(it, b)); seen |= 1u << b; }
+            mbar_wait(bar(bSE + sl), (uint32_t)((n / kRing) & 1) ^ 1u);
+            tc_fence_after();
+            const uint32_t sT1 = base + oT + (MODE == MODE_F ? (uint32_t)ts * kBlk : 0u), sT2 = base + oT + kBlk;
+            const uint32_t sR1b = base + oR1 + (uint32_t)rs * kBlk, sR2b = base + oR2 + (uint32_t)rs * kBlk;
+            const uint32_t aS = MODE == MODE_BKV ? sR1b : sT1, bS = MODE == MODE_BKV ? sT1 : sR1b;
 #pragma unroll
-        for (int k = 0; k < 4; ++k)
-          tc_mma_f16(tmem + (uint32_t)(sl * 128), umma_desc_sw128(aS + k * 32u, 16u, 1024u), umma_desc_sw128(bS + k * 32u, 16u, 1024u), id_s, k > 0 ? 1u : 0u);
-        tc_commit(bar(bSF + sl));
-        if (MODE != MODE_F) {
-          const uint32_t aD = MODE == MODE_BKV ? sR2b : sT2, bD = MODE == MODE_BKV ? sT2 : sR2b;
+            for (int k = 0; k < 4; ++k)
+              tc_mma_f16(tmem + (uint32_t)(sl * 128), umma_desc_sw128(aS + k * 32u, 16u, 1024u), umma_desc_sw128(bS + k * 32u, 16u, 1024u), id_s,
+                         k > 0 ? 1u : 0u);
+            tc_commit(bar(bSF + sl));
+            if (MODE != MODE_F) {
+              if (!(seen & (16u << b))) { mbar_wait(bar(bR2F + rs), rpar(it, b)); seen |= 16u << b; }
+              mbar_wait(bar(bDPE), (uint32_t)(n & 1) ^ 1u);
+              tc_fence_after();
+              const uint32_t aD = MODE == MODE_BKV ? sR2b : sT2, bD = MODE == MODE_BKV ? sT2 : sR2b;
 #pragma unroll
-          for (int k = 0; k < 4; ++k)
-            tc_mma_f16(tmem + colDP, umma_desc_sw128(aD + k * 32u, 16u, 1024u), umma_desc_sw128(bD + k * 32u, 16u, 1024u), id_s, k > 0 ? 1u : 0u);
-          tc_commit(bar(bDPF));
-        }
-        const bool last_tile = c.tile == ntiles - 1;
-        if (c.j == L - 1) tc_commit(bar(bTE + ts));                                    // the tile's operands are dead
-        // K_b's last use in this item: its exp-kind visit in the last tile (every block is visited exactly once with kind != 0 there)
-        if (MODE == MODE_F && last_tile && kind != 0) tc_commit(bar(bR1E + rs));
-        if (MODE == MODE_BQ && last_tile) tc_commit(bar(bR2E + rs));                   // V_b's last use (dP)
-      };
-      auto out_waits = [&](const Cursor& c, bool probe) -> bool {
-        const int b = blk_of(c.j, c.nt), kind = kind_of(c.j);
-        if (kind == 0) return true;
-        const bool first = MODE == MODE_F ? kind == 1 : c.j == 0;
-        const int ob = kTwoAcc ? (c.nt & 1) : 0;
-        if (first && !need(bar(bOE + ob), (uint32_t)((kTwoAcc ? (c.nt >> 1) : c.nt) & 1) ^ 1u, probe)) return false;
-        if (MODE == MODE_BKV) {
-          if (!need(bar(bOPF + 0), (uint32_t)(opn & 1), probe)) return false;
-          if (!need(bar(bOPF + 1), (uint32_t)(opn & 1), probe)) return false;
-        } else {
-          if (MODE == MODE_F && !need(bar(bR2F + rslot(c.it, b)), rpar(c.it, b), probe)) return false;
-          if (!need(bar(bOPF + 0 * 2 + (opn & 1)), (uint32_t)((opn >> 1) & 1), probe)) return false;
-          if (!need(bar(bOPF + 1 * 2 + (opn & 1)), (uint32_t)((opn >> 1) & 1), probe)) return false;
-        }
-        return true;
-      };
-      auto issue_out = [&](const Cursor& c) {
-        const int b = blk_of(c.j, c.nt), kind = kind_of(c.j);
-        if (kind == 0) return;
-        out_waits(c, false);
-        tc_fence_after();
-        const bool first = MODE == MODE_F ? kind == 1 : c.j == 0;
-        const bool last = c.j == L - 1;
-        const bool last_tile = c.tile == ntiles - 1;
-        const int ob = kTwoAcc ? (c.nt & 1) : 0;
-        const int slot = opn & 1, rs = rslot(c.it, b);
-        if (MODE != MODE_BKV) {
-          const uint32_t acc = tmem + colAcc + (uint32_t)(ob * 64);
-          const uint32_t sRb = base + (MODE == MODE_F ? oR2 : oR1) + (uint32_t)rs * kBlk;
-#pragma unroll
-          for (int g = 0; g < 2; ++g) {
-            const uint32_t sP = base + oOP + (uint32_t)(g * 2 + slot) * kBlk;
-#pragma unroll
-            for (int ks = 0; ks < 4; ++ks)
-              tc_mma_f16(acc, umma_desc_sw128(sP + ks * 32u, 16u, 1024u), umma_desc_sw128(sRb + (uint32_t)g * 8192u + ks * 2048u, 8192u, 1024u), id_o,
-                         (first && g == 0 && ks == 0) ? 0u : 1u);
-            tc_commit(bar(bOPE + g * 2 + slot));
+              for (int k = 0; k < 4; ++k)
+                tc_mma_f16(tmem + colDP, umma_desc_sw128(aD + k * 32u, 16u, 1024u), umma_desc_sw128(bD + k * 32u, 16u, 1024u), id_s, k > 0 ? 1u : 0u);
+              tc_commit(bar(bDPF));
+            }
+            if (j == L - 1) tc_commit(bar(bTE + ts));  // the tile's operands are dead
+            if (last_tile) {
+              // last score-side use of the resident blocks in this item (F: K_b at its exp-kind visit; B modes: every block once)
+              if (MODE == MODE_F) { if (kind != 0) tc_commit(bar(bR1E + rs)); }
+              else { tc_commit(bar(bR1E + rs)); if (MODE == MODE_BQ || MODE == MODE_BKV) tc_commit(bar(bR2E + rs)); }
+            }
+            VB_TR(0, 200 + n);
           }
-          if (last_tile) tc_commit(bar((MODE == MODE_F ? bR2E : bR1E) + rs));  // F: V_b, BQ: K_b -- last use in this item
-        } else {
-          // dV_t += P_b^T dO_b ; dK_t += dS_b^T Q_b  (A read MN-major: M = keys, two 64-key chunks 16 KB apart; K = the block's 128 queries)
-          const uint32_t sP = base + oOP, sDS = base + oOP + 2 * kBlk;
-          const uint32_t sQb = base + oR1 + (uint32_t)rs * kBlk, sDOb = base + oR2 + (uint32_t)rs * kBlk;
-#pragma unroll
-          for (int ks = 0; ks < 8; ++ks)
-            tc_mma_f16(tmem + colAcc, umma_desc_sw128(sP + ks * 2048u, 16384u, 1024u), umma_desc_sw128(sDOb + ks * 2048u, 8192u, 1024u), id_t,
-                       (first && ks == 0) ? 0u : 1u);
-          tc_commit(bar(bOPE + 0));
-#pragma unroll
-          for (int ks = 0; ks < 8; ++ks)
-            tc_mma_f16(tmem + colAcc + 64u, umma_desc_sw128(sDS + ks * 2048u, 16384u, 1024u), umma_desc_sw128(sQb + ks * 2048u, 8192u, 1024u), id_t,
-                       (first && ks == 0) ? 0u : 1u);
-          tc_commit(bar(bOPE + 1));
-          if (last_tile) { tc_commit(bar(bR1E + rs)); tc_commit(bar(bR2E + rs)); }
         }
-        if (last) tc_commit(bar(bOF + ob));
-        ++opn;
-      };
-      Cursor cs{0, 0, 0, 0, 0}, co{0, 0, 0, 0, 0};
-      while (valid(co)) {
-        while (valid(cs) && cs.n <= co.n) { issue_scores(cs); advance(cs); }  // the block the output MMAs below consume
-        // until the output operands of block co are ready, keep issuing score blocks ahead whenever one can go without waiting
-        for (;;) {
-          if (valid(cs) && cs.n <= co.n + kLook && scores_waits(cs, true)) { issue_scores(cs); advance(cs); continue; }
-          if (out_waits(co, true)) break;
+      }
+    }
+  } else if (warp == 3) {
+    // =========================================== output-MMA issuer (one thread) ===========================================
+    if (lane == 0) {
+      const uint32_t id_o = umma_idesc(1u, 128u, 64u, 0u, 1u);  // F / BQ: A = P / dS chunk K-major, B = V / K rows MN-major
+      const uint32_t id_t = umma_idesc(1u, 128u, 64u, 1u, 1u);  // BKV: A = P / dS read MN-major (M = keys), B = dO / Q rows MN-major
+      int opn = 0, nt = 0, tr_n = 1 << 20;
+      (void)tr_n;
+      for (int it = 0; it < my_items; ++it) {
+        uint32_t seen = 0;
+        for (int tile = 0; tile < ntiles; ++tile, ++nt) {
+          const bool last_tile = tile == ntiles - 1;
+          const int ob = nt & 1;
+          for (int j = 0; j < L; ++j) {
+            const int b = blk_of(j, nt), kind = kind_of(j);
+            if (kind == 0) continue;
+            const bool first = MODE == MODE_F ? kind == 1 : j == 0;
+            const int slot = opn & 1, rs = rslot(it, b);
+            if (first) mbar_wait(bar(bOE + ob), (uint32_t)((nt >> 1) & 1) ^ 1u);
+            if (!(seen & (1u << b))) {  // the MN-major operand rows of this block (loaded by TMA: observe its barrier in this thread too)
+              if (MODE != MODE_F) mbar_wait(bar(bR1F + rs), rpar(it, b));
+              if (MODE != MODE_BQ) mbar_wait(bar(bR2F + rs), rpar(it, b));
+              seen |= 1u << b;
+            }
+            if (MODE != MODE_BKV) {
+              mbar_wait(bar(bOPF + slot), (uint32_t)((opn >> 1) & 1));
+              tc_fence_after();
+              const uint32_t acc = tmem + colAcc + (uint32_t)ob * accStride;
+              const uint32_t sRb = base + (MODE == MODE_F ? oR2 : oR1) + (uint32_t)rs * kBlk;
+#pragma unroll
+              for (int g = 0; g < 2; ++g) {
+                const uint32_t sP = base + oOP + (uint32_t)(g * 2 + slot) * kBlk;
+#pragma unroll
+                for (int ks = 0; ks < 4; ++ks)
+                  tc_mma_f16(acc, umma_desc_sw128(sP + ks * 32u, 16u, 1024u), umma_desc_sw128(sRb + (uint32_t)g * 8192u + ks * 2048u, 8192u, 1024u), id_o,
+                             (first && g == 0 && ks == 0) ? 0u : 1u);
+              }
+              tc_commit(bar(bOPE + slot));
+              if (last_tile) tc_commit(bar((MODE == MODE_F ? bR2E : bR1E) + rs));  // F: V_b, BQ: K_b -- last output-side use in this item
+            } else {
+              // dV_t += P_b^T dO_b ; dK_t += dS_b^T Q_b  (A read MN-major: M = keys, two 64-key chunks 16 KB apart; K = the block's 128 queries)
+              mbar_wait(bar(bOPF + 0), (uint32_t)(opn & 1));
+              tc_fence_after();
+              const uint32_t sP = base + oOP, sDS = base + oOP + 2 * kBlk;
+              const uint32_t sQb = base + oR1 + (uint32_t)rs * kBlk, sDOb = base + oR2 + (uint32_t)rs * kBlk;
+#pragma unroll
+              for (int ks = 0; ks < 8; ++ks)
+                tc_mma_f16(tmem + colAcc + (uint32_t)ob * accStride, umma_desc_sw128(sP + ks * 2048u, 16384u, 1024u), umma_desc_sw128(sDOb + ks * 2048u, 8192u, 1024u), id_t,
+                           (first && ks == 0) ? 0u : 1u);
+#pragma unroll
+              for (int ks = 0; ks < 8; ++ks)
+                tc_mma_f16(tmem + colAcc + (uint32_t)ob * accStride + 64u, umma_desc_sw128(sDS + ks * 2048u, 16384u, 1024u), umma_desc_sw128(sQb + ks * 2048u, 8192u, 1024u), id_t,
+                           (first && ks == 0) ? 0u : 1u);
+              tc_commit(bar(bOPE + 0));
+              if (last_tile) { tc_commit(bar(bR1E + rs)); tc_commit(bar(bR2E + rs)); }
+            }
+            if (j == L - 1) tc_commit(bar(bOF + ob));
+            ++opn;
+          }
         }
-        issue_out(co);
-        advance(co);
       }
     }
   } else if (warp >= 4) {
@@ -343,46 +361,53 @@ attn_sm100_kernel(const __grid_constant__ CUtensorMap tmQKV, const __grid_consta
     const int row = q * 32 + lane;
     const uint32_t lanef = (uint32_t)(q * 32) << 16;
     int opn = 0;
-    // deferred epilogue state (F / BQ): the accumulator of tile `pend_nt` is drained under the next tile's first block
+    int tr_n = (warp == 4 && lane == 0) ? 0 : 1 << 20;
+    // deferred epilogue state (F / BQ): the accumulator of tile `pend_nt` is drained while the next tile is in flight
     bool pend = false;
     int pend_nt = 0, pend_item = 0, pend_tile = 0;
     float pend_msc = 0.f;
 
-    auto epilogue_fq = [&](int nt, int item, int tile, float msc) {
+    // Drain the accumulator of tile `nt` (F: the caller has passed a 256-thread barrier since both warpgroups wrote the tile's partial
+    // row sums).  F / BQ: warpgroup g owns output columns [32g, 32g+32); BKV: warpgroup 0 = dV_t, warpgroup 1 = dK_t (x softmax scale).
+    const uint32_t stage = base + oStage + (uint32_t)ew * 2048u;
+    auto epilogue = [&](int nt, int item, int tile, float msc) {
       const int b_ = item / p.heads, h_ = item % p.heads;
       const int ob = nt & 1;
+      VB_TR(1, 8000 + nt);
       mbar_wait(bar(bOF + ob), (uint32_t)((nt >> 1) & 1));
       tc_fence_after();
-      float mul = p.scale;
-      float l_tot = 0.f;
-      if (MODE == MODE_F) {
-        bar_sync_256();
-        l_tot = xl[(nt & 1) * 256 + row] + xl[(nt & 1) * 256 + 128 + row];
-        mul = l_tot > 0.f ? 1.f / l_tot : 0.f;
-      }
-      uint32_t r[32];
-      tmem_ld32(tmem + lanef + colAcc + (uint32_t)(ob * 64 + g * 32), r);
-      tmem_ld_wait();
-      tc_fence_before();
-      __syncwarp();
-      if (lane == 0) mbar_arrive(bar(bOE + ob));
-      const int qg = tile * 128 + row;
-      if (qg < S) {
-        uint4* dst;
-        if (MODE == MODE_F) dst = reinterpret_cast<uint4*>(p.ctx + ((long long)b_ * S + qg) * H + h_ * 64 + g * 32);
-        else dst = reinterpret_cast<uint4*>(p.dqkv + ((long long)b_ * S + qg) * 3LL * H + h_ * 64 + g * 32);
-#pragma unroll
-        for (int i = 0; i < 4; ++i) {
-          uint4 v;
-          v.x = pack_bf16x2(__uint_as_float(r[8 * i]) * mul, __uint_as_float(r[8 * i + 1]) * mul);
-          v.y = pack_bf16x2(__uint_as_float(r[8 * i + 2]) * mul, __uint_as_float(r[8 * i + 3]) * mul);
-          v.z = pack_bf16x2(__uint_as_float(r[8 * i + 4]) * mul, __uint_as_float(r[8 * i + 5]) * mul);
-          v.w = pack_bf16x2(__uint_as_float(r[8 * i + 6]) * mul, __uint_as_float(r[8 * i + 7]) * mul);
-          dst[i] = v;
+      const int r0g = tile * 128 + q * 32;  // first row (query, or key in BKV) of this warp inside the sample
+      if (MODE != MODE_BKV) {
+        uint32_t r[32];
+        tmem_ld32(tmem + lanef + colAcc + (uint32_t)ob * accStride + (uint32_t)(g * 32), r);
+        float mul = p.scale;
+        float l_tot = 0.f;
+        if (MODE == MODE_F) {
+          l_tot = xl[(nt & 1) * 256 + row] + xl[(nt & 1) * 256 + 128 + row];
+          mul = l_tot > 0.f ? 1.f / l_tot : 0.f;
         }
-        if (MODE == MODE_F && g == 0 && p.lse != nullptr)
-          p.lse[((long long)b_ * p.heads + h_) * S + qg] = msc * kLn2A + __logf(fmaxf(l_tot, 1e-30f));
+        tmem_ld_wait();
+        tc_fence_before();
+        __syncwarp();
+        if (lane == 0) mbar_arrive(bar(bOE + ob));
+        bf16* g0 = MODE == MODE_F ? p.ctx + ((long long)b_ * S + r0g) * H + h_ * 64 + g * 32 : p.dqkv + ((long long)b_ * S + r0g) * 3LL * H + h_ * 64 + g * 32;
+        store_rows32_staged(r, mul, stage, g0, MODE == MODE_F ? (long long)H : 3LL * H, S - r0g, lane);
+        if (MODE == MODE_F && g == 0 && r0g + lane < S && p.lse != nullptr)
+          p.lse[((long long)b_ * p.heads + h_) * S + r0g + lane] = msc * kLn2A + __logf(fmaxf(l_tot, 1e-30f));
+      } else {
+        uint32_t ra[32], rb[32];
+        tmem_ld32(tmem + lanef + colAcc + (uint32_t)ob * accStride + (uint32_t)(g * 64), ra);
+        tmem_ld32(tmem + lanef + colAcc + (uint32_t)ob * accStride + (uint32_t)(g * 64 + 32), rb);
+        tmem_ld_wait();
+        tc_fence_before();
+        __syncwarp();
+        if (lane == 0) mbar_arrive(bar(bOE + ob));
+        bf16* g0 = p.dqkv + ((long long)b_ * S + r0g) * 3LL * H + (g == 0 ? 2 * H : H) + h_ * 64;
+        const float mul = g == 0 ? 1.f : p.scale;
+        store_rows32_staged(ra, mul, stage, g0, 3LL * H, S - r0g, lane);
+        store_rows32_staged(rb, mul, stage, g0 + 32, 3LL * H, S - r0g, lane);
       }
+      VB_TR(1, 8500 + nt);
     };
 
     // key-validity bytes of the NEXT item are fetched one item ahead (two keys per lane per warp: words ew and ew + 8)
@@ -394,7 +419,7 @@ attn_sm100_kernel(const __grid_constant__ CUtensorMap tmQKV, const __grid_consta
     uint32_t nx0 = mask_bytes((int)blockIdx.x, ew), nx1 = mask_bytes((int)blockIdx.x, ew + 8);
 
     int n = 0, nt = 0;
-    for (int it = 0; (int)blockIdx.x + it * (int)gridDim.x < p.n_items; ++it) {
+    for (int it = 0; it < my_items; ++it) {
       const int item = (int)blockIdx.x + it * (int)gridDim.x;
       const int b_ = item / p.heads, h_ = item % p.heads;
       const long long bh = (long long)b_ * p.heads + h_;
@@ -435,23 +460,26 @@ attn_sm100_kernel(const __grid_constant__ CUtensorMap tmQKV, const __grid_consta
             const int qn = (b + 1) * 128 + row;
             if (b + 1 < nblk && qn < S) { lse2_n = p.lse[bh * S + qn] * kLog2eA; dl_n = p.delta[bh * S + qn]; }
           }
+          const int slot = opn & 1;
+          VB_TR(1, 1000 + n);
           mbar_wait(bar(bSF + sl), (uint32_t)((n / kRing) & 1));
           tc_fence_after();
+          VB_TR(1, 2000 + n);
           const uint32_t tS = tmem + lanef + (uint32_t)(sl * 128 + g * 64);
-          if (MODE == MODE_F && kind != 2) {
-            // ---- row maximum over my 64 columns ----
-#pragma unroll
-            for (int c = 0; c < 2; ++c) {
-              uint32_t r[32];
-              tmem_ld32(tS + (uint32_t)(c * 32), r);
-              tmem_ld_wait();
-              if (kind == 0 && c == 1) {  // max-only block: the buffer is free as soon as it is in registers
-                tc_fence_before();
-                __syncwarp();
-                if (lane == 0) mbar_arrive(bar(bSE + sl));
-              }
-              const uint32_t mw = c == 0 ? mw0 : mw1;
-              if (warp_active) {
+          if (MODE == MODE_F) {
+            // ---- my 32 x 64 piece of the block goes to registers in one go; the TMEM buffer is free again right away ----
+            uint32_t r0[32], r1[32];
+            tmem_ld32(tS, r0);
+            tmem_ld32(tS + 32u, r1);
+            const uint32_t sP = base + oOP + (uint32_t)(g * 2 + slot) * kBlk;
+            if (kind != 0) mbar_wait(bar(bOPE + slot), (uint32_t)((opn >> 1) & 1) ^ 1u);  // under the load latency
+            tmem_ld_wait();
+            tc_fence_before();
+            __syncwarp();
+            if (lane == 0) mbar_arrive(bar(bSE + sl));
+            if (kind != 2 && warp_active) {
+              // ---- row maximum over my 64 columns ----
+              auto rmax = [&](const uint32_t (&r)[32], uint32_t mw) {
                 if (mw == 0xffffffffu) {
                   float m0 = __uint_as_float(r[0]), m1 = __uint_as_float(r[1]), m2 = __uint_as_float(r[2]), m3 = __uint_as_float(r[3]);
 #pragma unroll
@@ -461,53 +489,31 @@ attn_sm100_kernel(const __grid_constant__ CUtensorMap tmQKV, const __grid_consta
                   }
                   m_run = fmaxf(m_run, fmaxf(fmaxf(m0, m1), fmaxf(m2, m3)));
                 } else if (mw != 0u) {
+                  float m0 = -INFINITY, m1 = -INFINITY;
 #pragma unroll
-                  for (int i = 0; i < 32; ++i) m_run = fmaxf(m_run, ((mw >> i) & 1u) ? __uint_as_float(r[i]) : -INFINITY);
+                  for (int i = 0; i < 32; i += 2) {
+                    m0 = fmaxf(m0, ((mw >> i) & 1u) ? __uint_as_float(r[i]) : -INFINITY);
+                    m1 = fmaxf(m1, ((mw >> (i + 1)) & 1u) ? __uint_as_float(r[i + 1]) : -INFINITY);
+                  }
+                  m_run = fmaxf(m_run, fmaxf(m0, m1));
                 }
-              }
+              };
+              rmax(r0, mw0);
+              rmax(r1, mw1);
             }
-            if (kind == 0) {
-              if (pend && j == 0) {  // previous tile's accumulator: drained under this tile's next score block
-                epilogue_fq(pend_nt, pend_item, pend_tile, pend_msc);
-                pend = false;
-              }
-              continue;
+            if (kind == 0) continue;
+            if (kind == 1) {
+              // ---- the two warpgroups exchange their partial maxima (the one 256-thread barrier of the tile) ----
+              VB_TR(1, 3000 + n);
+              xm[(nt & 1) * 256 + g * 128 + row] = m_run;
+              bar_sync_256();
+              m_run = fmaxf(m_run, xm[(nt & 1) * 256 + (g ^ 1) * 128 + row]);
+              msc = m_run == -INFINITY ? 0.f : m_run * p.scale_log2;
+              VB_TR(1, 4000 + n);
             }
-            // ---- the two warpgroups exchange their partial maxima ----
-            xm[(nt & 1) * 256 + g * 128 + row] = m_run;
-            bar_sync_256();
-            m_run = fmaxf(m_run, xm[(nt & 1) * 256 + (g ^ 1) * 128 + row]);
-            msc = m_run == -INFINITY ? 0.f : m_run * p.scale_log2;
-          }
-          // ---- exp pass: P (F) / dS (BQ) / P and dS (BKV) for my 64 columns ----
-          if (MODE != MODE_F) {
-            mbar_wait(bar(bDPF), (uint32_t)(n & 1));
-            tc_fence_after();
-          }
-          const int slot = opn & 1;
-          uint32_t sP, sDS = 0;
-          if (MODE == MODE_BKV) {
-            sP = base + oOP + (uint32_t)g * kBlk;
-            sDS = base + oOP + 2 * kBlk + (uint32_t)g * kBlk;
-            mbar_wait(bar(bOPE + 0), (uint32_t)(opn & 1) ^ 1u);
-            mbar_wait(bar(bOPE + 1), (uint32_t)(opn & 1) ^ 1u);
-          } else {
-            sP = base + oOP + (uint32_t)(g * 2 + slot) * kBlk;
-            mbar_wait(bar(bOPE + g * 2 + slot), (uint32_t)((opn >> 1) & 1) ^ 1u);
-          }
-#pragma unroll
-          for (int c = 0; c < 2; ++c) {
-            uint32_t r[32];
-            uint32_t pk[16];
-            const uint32_t mw = c == 0 ? mw0 : mw1;
-            tmem_ld32(tS + (uint32_t)(c * 32), r);
-            if (MODE == MODE_F) {
-              tmem_ld_wait();
-              if (c == 1) {
-                tc_fence_before();
-                __syncwarp();
-                if (lane == 0) mbar_arrive(bar(bSE + sl));
-              }
+            // ---- exp pass: P for my 64 columns ----
+            auto pexp = [&](const uint32_t (&r)[32], uint32_t mw, int c) {
+              uint32_t pk[16];
               if (warp_active && mw == 0xffffffffu) {
                 float l0 = 0.f, l1 = 0.f;
 #pragma unroll
@@ -531,9 +537,45 @@ attn_sm100_kernel(const __grid_constant__ CUtensorMap tmQKV, const __grid_consta
                 for (int i = 0; i < 16; ++i) pk[i] = 0u;
               }
               store_row32a(sP, row, c, pk);
+            };
+            VB_TR(1, 5000 + n);
+            pexp(r0, mw0, 0);
+            pexp(r1, mw1, 1);
+            VB_TR(1, 6000 + n);
+            fence_async_smem_a();
+            __syncwarp();
+            if (lane == 0) mbar_arrive(bar(bOPF + slot));
+            ++opn;
+            if (j == L - 1) xl[(nt & 1) * 256 + g * 128 + row] = l;
+            VB_TR(1, 7000 + n);
+            if (kind == 1 && pend) {
+              // previous tile's accumulator (its row sums were published before this tile's exchange barrier): drained while the
+              // tensor pipe works on this tile
+              epilogue(pend_nt, pend_item, pend_tile, pend_msc);
+              pend = false;
+            }
+          } else {
+            // ---- BQ / BKV: P and dS for my 64 columns ----
+            mbar_wait(bar(bDPF), (uint32_t)(n & 1));
+            tc_fence_after();
+            uint32_t sP, sDS = 0;
+            if (MODE == MODE_BKV) {
+              sP = base + oOP + (uint32_t)g * kBlk;
+              sDS = base + oOP + 2 * kBlk + (uint32_t)g * kBlk;
             } else {
-              uint32_t d[32];
+              sP = base + oOP + (uint32_t)(g * 2 + slot) * kBlk;
+            }
+#pragma unroll
+            for (int c = 0; c < 2; ++c) {
+              uint32_t r[32], d[32];
+              uint32_t pk[16];
+              const uint32_t mw = c == 0 ? mw0 : mw1;
+              tmem_ld32(tS + (uint32_t)(c * 32), r);
               tmem_ld32(tmem + lanef + colDP + (uint32_t)(g * 64 + c * 32), d);
+              if (c == 0) {  // the staging buffers of this block must have been read by the output MMAs of the previous use
+                if (MODE == MODE_BKV) mbar_wait(bar(bOPE + 0), (uint32_t)(opn & 1) ^ 1u);
+                else mbar_wait(bar(bOPE + slot), (uint32_t)((opn >> 1) & 1) ^ 1u);
+              }
               tmem_ld_wait();
               if (c == 1) {
                 tc_fence_before();
@@ -564,59 +606,27 @@ attn_sm100_kernel(const __grid_constant__ CUtensorMap tmQKV, const __grid_consta
                 store_row32a(sP, row, c, pk);
               }
             }
-          }
-          fence_async_smem_a();
-          __syncwarp();
-          if (lane == 0) {
-            if (MODE == MODE_BKV) { mbar_arrive(bar(bOPF + 0)); mbar_arrive(bar(bOPF + 1)); }
-            else mbar_arrive(bar(bOPF + g * 2 + slot));
-          }
-          ++opn;
-          if (MODE != MODE_BKV && pend && j == 0) {  // previous tile's accumulator: drained under this tile's next score block
-            epilogue_fq(pend_nt, pend_item, pend_tile, pend_msc);
-            pend = false;
-          }
-        }
-        if (MODE == MODE_F) xl[(nt & 1) * 256 + g * 128 + row] = l;
-        if (MODE != MODE_BKV) {
-          if (pend) {  // (single-block tiles whose first block was max-only never get here with pend set; safety for L == 1 streams)
-            epilogue_fq(pend_nt, pend_item, pend_tile, pend_msc);
-          }
-          pend = true; pend_nt = nt; pend_item = item; pend_tile = tile; pend_msc = msc;
-        } else {
-          // dV_t (warpgroup 0) / dK_t (warpgroup 1, x softmax scale): rows = keys of the tile
-          mbar_wait(bar(bOF + 0), (uint32_t)(nt & 1));
-          tc_fence_after();
-          const int key = tile * 128 + row;
-          const float mul = g == 0 ? 1.f : p.scale;
-          bf16* dst0 = p.dqkv + ((long long)b_ * S + key) * 3LL * H + (g == 0 ? 2 * H : H) + h_ * 64;
-#pragma unroll
-          for (int c = 0; c < 2; ++c) {
-            uint32_t r[32];
-            tmem_ld32(tmem + lanef + colAcc + (uint32_t)(g * 64 + c * 32), r);
-            tmem_ld_wait();
-            if (c == 1) {
-              tc_fence_before();
-              __syncwarp();
-              if (lane == 0) mbar_arrive(bar(bOE + 0));
-            }
-            if (key < S) {
-              uint4* dst = reinterpret_cast<uint4*>(dst0 + c * 32);
-#pragma unroll
-              for (int i = 0; i < 4; ++i) {
-                uint4 v;
-                v.x = pack_bf16x2(__uint_as_float(r[8 * i]) * mul, __uint_as_float(r[8 * i + 1]) * mul);
-                v.y = pack_bf16x2(__uint_as_float(r[8 * i + 2]) * mul, __uint_as_float(r[8 * i + 3]) * mul);
-                v.z = pack_bf16x2(__uint_as_float(r[8 * i + 4]) * mul, __uint_as_float(r[8 * i + 5]) * mul);
-                v.w = pack_bf16x2(__uint_as_float(r[8 * i + 6]) * mul, __uint_as_float(r[8 * i + 7]) * mul);
-                dst[i] = v;
-              }
+            fence_async_smem_a();
+            __syncwarp();
+            if (lane == 0) mbar_arrive(bar(bOPF + (MODE == MODE_BKV ? 0 : slot)));
+            ++opn;
+            if (pend && j == 0) {  // previous tile's accumulators: drained under this tile's next score block
+              epilogue(pend_nt, pend_item, pend_tile, pend_msc);
+              pend = false;
             }
           }
         }
+        if (pend) {  // not reached: every tile drains its predecessor at its max+exp block (F) / first block (BQ, BKV)
+          if (MODE == MODE_F) bar_sync_256();
+          epilogue(pend_nt, pend_item, pend_tile, pend_msc);
+        }
+        pend = true; pend_nt = nt; pend_item = item; pend_tile = tile; pend_msc = msc;
       }
     }
-    if (MODE != MODE_BKV && pend) epilogue_fq(pend_nt, pend_item, pend_tile, pend_msc);
+    if (pend) {
+      if (MODE == MODE_F) bar_sync_256();  // the last tile's row sums
+      epilogue(pend_nt, pend_item, pend_tile, pend_msc);
+    }
   }
 
   tc_fence_before();
@@ -661,6 +671,28 @@ int set_smem_a(K kernel) {
   return VAULT_OK;
 }
 
+long long* trace_buf() {
+  static long long* buf = nullptr;
+  const char* e = getenv("VAULT_B200_ATTN_TRACE");
+  if (e == nullptr || e[0] != '1') return nullptr;
+  if (!buf) cudaMalloc(&buf, 2 * 1024 * 2 * sizeof(long long));
+  cudaMemset(buf, 0, 2 * 1024 * 2 * sizeof(long long));
+  return buf;
+}
+void trace_dump(const char* what, long long* dbuf) {
+  if (!dbuf) return;
+  static long long h[2 * 1024 * 2];
+  cudaDeviceSynchronize();
+  cudaMemcpy(h, dbuf, sizeof(h), cudaMemcpyDeviceToHost);
+  long long t0 = h[0] ? h[0] : h[2048];
+  for (int who = 0; who < 2; ++who) {
+    printf("TRACE %s %s:", what, who ? "softmax" : "mma");
+    for (int i = 0; i < 1024 && h[(who * 1024 + i) * 2]; ++i) printf(" %lld@%lld", h[(who * 1024 + i) * 2 + 1], h[(who * 1024 + i) * 2] - t0);
+    printf("\n");
+  }
+  fflush(stdout);
+}
+
 int fill(AParams& p, int B, int S, int heads) {
   p.B = B; p.S = S; p.heads = heads;
   p.nblk = (S + 127) / 128;
@@ -674,7 +706,13 @@ int fill(AParams& p, int B, int S, int heads) {
 
 int g_attn_sm100 = 1;  // 0: disabled (A/B switch through vault_attn_set_impl)
 
-bool attn_sm100_ok(int S, float dropout_p) { return g_attn_sm100 != 0 && dropout_p == 0.f && S >= 1 && S <= 384; }
+// Shapes served: no dropout, 193..384 keys (measured on B200, B = 32, 12 heads: S = 369 forward 56 us / backward 125 us against 75 / 313 us
+// for the mma.sync kernels; at S <= 192 the whole-row kernels of attention_tc.cu -- 2 CTAs / SM, no key-block loop -- are still ahead:
+// 22 / 49 us against 28 / 56 us at S = 185).  g_attn_sm100 = 2 forces these kernels for every S <= 384 (tests).
+bool attn_sm100_ok(int S, float dropout_p) {
+  if (g_attn_sm100 == 0 || dropout_p != 0.f || S < 1 || S > 384) return false;
+  return g_attn_sm100 == 2 || S > 192;
+}
 void attn_sm100_enable(int on) { g_attn_sm100 = on; }
 
 int attn_fwd_sm100(const void* qkv, const uint8_t* key_mask, void* ctx, float* lse, int B, int S, int heads, cudaStream_t st) {
@@ -687,7 +725,9 @@ int attn_fwd_sm100(const void* qkv, const uint8_t* key_mask, void* ctx, float* l
   if (rc) return rc;
   if ((rc = set_smem_a(attn_sm100_kernel<MODE_F>))) return rc;
   const int grid = p.n_items < device_sm_count() ? p.n_items : device_sm_count();
+  p.trace = trace_buf();
   launch(attn_sm100_kernel<MODE_F>, dim3(grid), dim3(kThreadsA), (size_t)kSmemA, st, tm, tm, p);
+  trace_dump("F", p.trace);
   return check_launch("attn_sm100_kernel<F>");
 }
 
@@ -709,9 +749,13 @@ int attn_bwd_sm100(const void* qkv, const uint8_t* key_mask, const void* ctx, co
          B, S, heads);
   if ((rc = check_launch("attn_delta_kernel"))) return rc;
   const int grid = p.n_items < device_sm_count() ? p.n_items : device_sm_count();
+  p.trace = trace_buf();
   launch(attn_sm100_kernel<MODE_BQ>, dim3(grid), dim3(kThreadsA), (size_t)kSmemA, st, tmQ, tmD, p);
+  trace_dump("BQ", p.trace);
   if ((rc = check_launch("attn_sm100_kernel<BQ>"))) return rc;
+  p.trace = trace_buf();
   launch(attn_sm100_kernel<MODE_BKV>, dim3(grid), dim3(kThreadsA), (size_t)kSmemA, st, tmQ, tmD, p);
+  trace_dump("BKV", p.trace);
   return check_launch("attn_sm100_kernel<BKV>");
 }
 

@@ -4,14 +4,16 @@
     python bench.py [--gpus N] [--steps K] [--warmup W]                 # this repo's CUDA path (one rank per GPU under torchrun)
     python bench.py --impl reference [--gpus N] [--steps K] [--warmup W]  # the reference path on the box's host cores (CPU)
 
-Workload (config 3 of BASELINE.json, the one the metric is quoted on): bert-base + vilt-b32 VaultForTMSC, n_classes 3,
-batch 32 per GPU, T=40 text tokens with TWITTER-15-like trailing padding, 384x384 images (144 patches, S=185), synthetic
-inputs, random-init weights, dropout active in the LM stack and head as in the reference's model.train().
+Workload (default `target`, the shape BASELINE.json's north-star "Target:" sentence names): bert-base + vilt-b32 VaultForTMSC, n_classes 3,
+batch 32 per GPU, T=128 text tokens with trailing padding, 384x640 images (240 patches, S=369), synthetic inputs, random-init weights,
+dropout active in the LM stack and head as in the reference's model.train().  `--workload config3` (T=40, 384x384, S=185: BASELINE config 3)
+/ config4 / config5 select the other named configurations; the default line also carries a short config-3 run under "also".
 A "step" = host batch -> H2D -> forward -> CE -> backward -> (gradient all-reduce) -> AdamW -> loss read-back.
 
 Prints ONE JSON line (see the task contract): `value` = device-resident-input throughput, `e2e` = through VaultTrainStep.step()
 with pinned HOST batches and per-step loss read-back, plus `roofline` (the tcgen05 GEMM, replayed launch by launch with CUDA
-events), `cpu_baseline` (oracle port on the host cores, bounded sample) and `clocks`.
+events), `cpu_baseline` (the reference's own VaultForTMSC on the host cores, bounded sample) and `clocks`.  `--impl reference` steps the REAL
+reference class (oracle/_ref, copied from /root/reference by oracle/build_ref.py) on the host cores at the same batch and shapes.
 """
 from __future__ import annotations
 
@@ -27,7 +29,7 @@ ROOT = os.path.dirname(os.path.abspath(__file__))
 sys.path.insert(0, ROOT)
 
 METRIC = "VaultModel fine-tune samples/sec"
-# Named workloads of BASELINE.json.  The default (the one the driver runs) is config 3, the configuration the metric is quoted on.
+# Named workloads of BASELINE.json.  The default (the one the driver runs) is `target`, the shape of the north-star's "Target:" sentence.
 # train_gflop = dense-shape algorithmic FLOPs per sample of one training step (SURVEY.md section 8d / BASELINE.md section 4).
 WORKLOADS = {
     "config3": dict(desc="VaultForTMSC fine-tune step (BASELINE config 3): fwd + CE + bwd + grad all-reduce + HF-AdamW", lm_kind="bert", freeze_lm=False,
@@ -48,6 +50,14 @@ def workload_config(name):
     return dict(lm=w["lm"], **COMMON, text_len=w["text_len"], image=w["image"], patches=w["patches"], seq_len=w["seq_len"], freeze_lm=w["freeze_lm"])
 
 
+def bench_config(name, B, world):
+    """`config` of the JSON line: the workload only (identical in this repo's arm and in the reference arm); how an arm runs it goes to `impl_config`."""
+    w = WORKLOADS[name]
+    return dict(workload=w["desc"], name=name, **{**workload_config(name), "per_gpu_batch": B}, global_batch=B * world, parallelism=f"dp{world}",
+                optimizer="HF-AdamW (transformers 4.48.0 rule, correct_bias=False), lr 2e-5, linear warm-up schedule past warm-up",
+                l2="per-step working set (0.44 GB bf16 weights + 0.79 GB fp32 grads + >= 2 GB activations) >> 126 MB L2; 4 rotating input batches")
+
+
 def train_gflop_valid_tokens(text_lens, patches, freeze_lm):
     """Algorithmic FLOPs per sample of one training step counting VALID tokens only (SURVEY.md section 8d asks for both figures): the same
     closed form as the dense-shape number -- 12 layers x (24 n H^2 + 4 n^2 H), patch projection 2 x P x 3072 x 768, train = 3 x forward
@@ -59,12 +69,6 @@ def train_gflop_valid_tokens(text_lens, patches, freeze_lm):
     return tot / max(len(text_lens), 1) / 1e9
 
 
-def oracle_dims(name):
-    from oracle import synth
-
-    return synth.Dims.bertweet() if WORKLOADS[name]["lm_kind"] == "roberta" else synth.Dims.base()
-
-
 def parse():
     ap = argparse.ArgumentParser()
     ap.add_argument("--gpus", type=int, default=1)
@@ -72,7 +76,7 @@ def parse():
     ap.add_argument("--warmup", type=int, default=5)
     ap.add_argument("--impl", default="vault_b200", choices=["vault_b200", "reference"])
     ap.add_argument("--batch", type=int, default=COMMON["per_gpu_batch"])
-    ap.add_argument("--workload", default="config3", choices=sorted(WORKLOADS), help="named BASELINE workload (default: config 3, the metric's)")
+    ap.add_argument("--workload", default="target", choices=sorted(WORKLOADS), help="named BASELINE workload (default: the north-star target shape)")
     ap.add_argument("--no-graph", action="store_true")
     ap.add_argument("--skip-cpu-baseline", action="store_true")
     ap.add_argument("--skip-roofline", action="store_true")
@@ -134,64 +138,117 @@ class ClockSampler:
         return dict(sm_mhz=(busy[len(busy) // 2] if busy else None), sm_max_mhz=mx, samples=len(sm), reasons=sorted(reasons))
 
 
-def cpu_baseline(torch, workload, steps=3, warmup=1, B=8):
-    """Oracle port (fp32 restatement of the reference path, oracle/vault_oracle.py) on the host cores: forward + CE + backward +
-    HF-AdamW, bounded sample of the same workload (B rows instead of 32)."""
-    from oracle import synth, vault_oracle as O
+def _hf_lm_config(name):
+    from transformers import BertConfig, RobertaConfig
 
-    w = WORKLOADS[workload]
-    cores = os.cpu_count() or 1
-    torch.set_num_threads(cores)
-    d = oracle_dims(workload)
-    sd = synth.make_state_dict(d, seed=0)
-    batch = synth.make_inputs(d, batch=B, text_len=w["text_len"], image_hw=tuple(w["image"]), seed=1, var_text=True)
-    state = None
+    if WORKLOADS[name]["lm_kind"] == "roberta":  # BERTweet-base shape
+        return RobertaConfig(vocab_size=64001, max_position_embeddings=130, type_vocab_size=1, pad_token_id=1, layer_norm_eps=1e-5, bos_token_id=0, eos_token_id=2)
+    return BertConfig()
+
+
+class ReferenceStepper:
+    """The reference's fine-tuning step on the host CPU: its own ``VaultForTMSC`` (ref:vault/models/vault/model.py:512-570, loaded from
+    oracle/_ref or /root/reference by oracle/ref_loader.py over the installed HF ViLT / BERT modules, transformers==4.48.0 position-embedding
+    gate restored), driven exactly as ref:vault/tmsc_utils/trainer.py:353-369 drives it: model(**kwargs) -> CrossEntropyLoss -> zero_grad ->
+    backward -> HF-AdamW.step -> loss.item().  Falls back to the pinned oracle port (kind "port") only if the reference files are absent."""
+
+    def __init__(self, torch, workload, B):
+        from oracle import ref_loader, synth
+
+        self.torch, self.B = torch, B
+        w = WORKLOADS[workload]
+        self.w = w
+        self.cores = os.cpu_count() or 1
+        torch.set_num_threads(self.cores)
+        bc = _hf_lm_config(workload)
+        self.batch = synth_batch(torch, B, w["text_len"], tuple(w["image"]), bc.vocab_size, 3, seed=1, pin=False, pad_id=bc.pad_token_id or 0)
+        self.kind = "reference" if ref_loader.available() else "port"
+        if self.kind == "reference":
+            from transformers import ViltConfig
+
+            mod = ref_loader.load_reference_module()
+            torch.manual_seed(0)
+            m = mod.VaultForTMSC(ViltConfig(), n_classes=3, vilt_dropout_prob=0.1, bert_config=bc)
+            m.embeddings.text_embeddings.position_embedding_type = "NOT_absolute"  # what from_pretrained does (ref:...model.py:112-116)
+            if w["freeze_lm"]:
+                m.freeze_lm = True
+                for p_ in m.bert.parameters():
+                    p_.requires_grad_(False)
+            with torch.no_grad():
+                m.embeddings.cls_token.normal_(0, 0.02)
+                m.embeddings.position_embeddings.normal_(0, 0.02)
+            self.model = m.train()
+            self.opt = ref_loader.HFAdamW([p_ for p_ in m.parameters() if p_.requires_grad], lr=2e-5, betas=(0.9, 0.999), eps=1e-8, weight_decay=0.0,
+                                          correct_bias=False)
+            self.loss_fn = torch.nn.CrossEntropyLoss()
+        else:
+            self.d = synth.Dims.bertweet() if w["lm_kind"] == "roberta" else synth.Dims.base()
+            self.sd = synth.make_state_dict(self.d, seed=0)
+            self.state = None
+
+    def step(self):
+        torch = self.torch
+        b = self.batch
+        if self.kind == "reference":
+            logits = self.model(input_ids=b["input_ids"], attention_mask=b["attention_mask"], token_type_ids=b["token_type_ids"],
+                                pixel_values=b["pixel_values"], pixel_mask=b["pixel_mask"])
+            loss = self.loss_fn(logits, b["labels"])
+            self.opt.zero_grad()
+            loss.backward()
+            self.opt.step()
+            return loss.item()
+        from oracle import vault_oracle as O
+
+        out = O.train_step(self.sd, self.d, b, lr=2e-5, freeze_lm=self.w["freeze_lm"], state=self.state, train_mode=True)
+        self.state = out["state"]
+        return float(out["loss"])
+
+    def describe(self, what):
+        w = self.w
+        src = ("the reference's own VaultForTMSC (oracle/_ref: ref:vault/models/vault/model.py over HF ViLT/BERT) + HF-AdamW" if self.kind == "reference"
+               else "oracle port (oracle/vault_oracle.py; reference files absent)")
+        return f"{what}: {src}, fwd + CE + bwd + optimizer step, fp32, dropout on, B={self.B}, T={w['text_len']}, {w['image'][0]}x{w['image'][1]}, {self.cores} host threads"
+
+
+def cpu_baseline(torch, workload, steps=2, warmup=1, B=8):
+    """Bounded sample (about 10-20 s of CPU work) of the reference step on the host cores, run next to the GPU measurement."""
+    st = ReferenceStepper(torch, workload, B)
     times = []
     for i in range(warmup + steps):
         t0 = time.perf_counter()
-        out = O.train_step(sd, d, batch, lr=2e-5, freeze_lm=w["freeze_lm"], state=state, train_mode=True)
-        state = out["state"]
+        st.step()
         if i >= warmup:
             times.append(time.perf_counter() - t0)
     times.sort()
     med = times[len(times) // 2]
-    return dict(value=B / med, unit="samples/s", cores=cores, kind="port",
-                sample=f"oracle train step (fwd+CE+bwd+HF-AdamW, fp32, dropout on), B={B} of the 32-row batch, T={w['text_len']}, "
-                       f"{w['image'][0]}x{w['image'][1]}; median of {steps} after {warmup} warm-up",
-                ms_per_step=med * 1e3)
+    return dict(value=B / med, unit="samples/s", cores=st.cores, kind=st.kind,
+                sample=st.describe(f"B={B} rows of the 32-row per-GPU batch, median of {steps} steps after {warmup} warm-up"), ms_per_step=med * 1e3)
 
 
 def run_reference(args):
-    """Reference arm: the reference's algorithm on the host CPU (the Python reference cannot travel to the GPU box and has no
-    compiled component, so this is the pinned oracle port -- oracle/vault_oracle.py -- with all host threads)."""
+    """Reference arm: the reference's own CPU implementation of the path on the host cores, same workload, same per-GPU batch (each step is
+    ONE rank's 32-row batch: a CPU has no ranks; under torchrun rank 0 alone runs it), all host threads."""
     rank = int(os.environ.get("RANK", "0"))
     if rank != 0:
         return
     import torch
-    from oracle import synth, vault_oracle as O
 
-    cores = os.cpu_count() or 1
-    torch.set_num_threads(cores)
-    B = 8
-    w = WORKLOADS[args.workload]
-    d = oracle_dims(args.workload)
-    sd = synth.make_state_dict(d, seed=0)
-    batch = synth.make_inputs(d, batch=B, text_len=w["text_len"], image_hw=tuple(w["image"]), seed=1, var_text=True)
-    state = None
+    world = int(os.environ.get("WORLD_SIZE", str(args.gpus)))
+    st = ReferenceStepper(torch, args.workload, args.batch)
     t0 = None
     for i in range(args.warmup + args.steps):
         if i == args.warmup:
             t0 = time.perf_counter()
-        out = O.train_step(sd, d, batch, lr=2e-5, freeze_lm=w["freeze_lm"], state=state, train_mode=True)
-        state = out["state"]
+        st.step()
     dt = time.perf_counter() - t0
-    v = B * args.steps / dt
-    sample = f"B={B} rows of the 32-row per-GPU batch per step (bounded sample), fp32, {cores} host threads"
+    v = args.batch * args.steps / dt
+    sample = st.describe(f"every step = one {args.batch}-row per-GPU batch of the workload")
     print(json.dumps({
         "impl": "reference", "metric": METRIC, "value": v, "unit": "samples/s", "n_gpus": args.gpus, "steps": args.steps, "warmup": args.warmup,
         "ms_per_step": dt / args.steps * 1e3, "higher_is_better": True, "scaling": "weak", "vs_baseline": None, "dtype": "f32", "data": "synthetic",
-        "config": dict(workload=w["desc"], name=args.workload, **workload_config(args.workload), parallelism="cpu", sample=sample),
-        "cpu_baseline": dict(value=v, unit="samples/s", cores=cores, kind="port", sample=sample),
+        "config": bench_config(args.workload, args.batch, world),
+        "impl_config": dict(device="cpu", threads=st.cores, kind=st.kind),
+        "cpu_baseline": dict(value=v, unit="samples/s", cores=st.cores, kind=st.kind, sample=sample),
         "e2e": dict(value=v, unit="samples/s", h2d_bytes_per_step=0, d2h_bytes_per_step=0),
     }), flush=True)
 
@@ -242,29 +299,39 @@ def gemm_roofline(torch, ts, batch_dev, peaks):
     achieved = flops / (ms * 1e-3) / 1e12
     peak = peaks.get("bf16_tflops_sustained") or 1400.0
     del keep
+    tr = NCU_TRAFFIC.get("gemm")  # one `ncu --set full` capture of this round (profiles/r02_ncu_traffic.json), per launch; None if not captured
     return dict(bound="tensor", kernel="vb::gemm_bf16_kernel (tcgen05/TMEM/TMA)", achieved=achieved, peak=peak, unit="TFLOP/s", frac=achieved / peak,
-                traffic=12.8e6,
-                traffic_note=dict(dram_bytes_per_launch=12.8e6, algorithmic_bytes_per_launch=40.0e6, launch="5920x2304x768 bias->bf16 (QKV forward of config 3)",
-                                  source="profiles/r01_ncu_gemm_full.md (ncu --set full, dram__bytes_read.sum + dram__bytes_write.sum): operands and "
-                                         "outputs of consecutive kernels stay in the 126 MB L2"),
+                traffic=(tr or {}).get("dram_bytes_per_launch"), traffic_note=tr,
                 launches_per_step=len(gemms), gemm_ms_per_step=ms, flops_per_step=flops,
                 peak_source="MEASURED_PEAKS.json bf16_tflops_sustained (kernel replayed inside a multi-ms dense run)" if "bf16_tflops_sustained" in peaks
                 else "fallback (B200_PROFILING.md): 1.4 PFLOP/s sustained"), launches, calls
 
 
-# one `ncu --set full` capture per kernel at exactly these shapes (profiles/r01_ncu_hbm_kernels.md): DRAM bytes per launch, read + write
-NCU_DRAM_BYTES = {"layernorm_fwd": 82.1e6, "layernorm_bwd": 258.9e6, "adamw": 1958.2e6}
+def _load_ncu_traffic():
+    """DRAM bytes per launch (dram__bytes_read.sum + dram__bytes_write.sum) of one `ncu --set full` capture per kernel, taken this round at
+    the workload's own launch shapes and committed under profiles/ with the command that produced it.  Not a per-run measurement: a run
+    under ncu is never a bench value, so the capture is a separate call; absent file / kernel -> traffic is null."""
+    try:
+        return json.load(open(os.path.join(ROOT, "profiles", "r02_ncu_traffic.json")))
+    except Exception:
+        return {}
 
 
-def hbm_kernel_rates(torch, peaks):
-    """Achieved HBM GB/s of the bandwidth-bound kernels at the workload's shapes.  Every kernel runs round-robin over several
-    independent operand sets whose total size is several times the 126 MB L2 (>= 650 MB per pass), so each launch finds its
-    operands in HBM without a flush kernel in between (a memset flush leaves the L2 full of dirty lines whose write-back the next
-    launch pays for); all launches of `reps` passes sit between one pair of CUDA events; algorithmic bytes per DESIGN.md section 3."""
+NCU_TRAFFIC = _load_ncu_traffic()
+
+
+def hbm_kernel_rates(torch, peaks, rows_vilt, n_params):
+    """Achieved HBM GB/s of the bandwidth-bound kernels AT THE WORKLOAD'S REAL LAUNCH SHAPES: LayerNorm forward / backward over the
+    ViLT stack's `rows_vilt` = B x S token rows (11,808 at the target shape, 5,920 at config 3), AdamW over the model's `n_params` trainable
+    parameters.  Every kernel runs round-robin over independent operand sets whose total size is several times the 126 MB L2, so each
+    launch finds its operands in HBM without a flush kernel in between (a memset flush leaves the L2 full of dirty lines whose
+    write-back the next launch pays for); all launches of `reps` passes sit between one pair of CUDA events; algorithmic bytes per
+    DESIGN.md section 3.  (In the step itself consecutive kernels hand activations over through the L2, so the in-step times are shorter
+    than these HBM-resident ones; profiles/ holds the in-graph family times.)"""
     from vault_b200 import _abi
 
     dev = torch.device("cuda", torch.cuda.current_device())
-    rows, cols = 32 * 185 * 4, 768  # four ViLT-layer activations' worth of rows: 73 MB fp32 per tensor
+    rows, cols = rows_vilt, 768
     st = torch.cuda.current_stream().cuda_stream
     lib = _abi.lib()
     g, b = torch.ones(cols, device=dev), torch.zeros(cols, device=dev)
@@ -272,7 +339,7 @@ def hbm_kernel_rates(torch, peaks):
     peak = peaks.get("hbm_gbs") or 6650.0
     out = {}
 
-    def run(name, sets, fn, nbytes, reps=4):
+    def run(name, sets, fn, nbytes, reps=6):
         for s_ in sets:  # warm-up pass (also fills statistics the backward reads)
             fn(s_)
         torch.cuda.synchronize()
@@ -285,29 +352,32 @@ def hbm_kernel_rates(torch, peaks):
         us = e0.elapsed_time(e1) * 1e3 / (reps * len(sets))
         gbs = nbytes / us / 1e3
         out[name] = dict(achieved_gbs=gbs, frac_of_measured_peak=gbs / peak, algorithmic_bytes=nbytes, us_per_launch=us, operand_sets=len(sets),
-                         traffic=NCU_DRAM_BYTES[name])  # dram__bytes_read.sum + dram__bytes_write.sum of one launch, profiles/r01_ncu_hbm_kernels.md
+                         shape=[rows, cols] if name != "adamw" else [n_params], traffic=(NCU_TRAFFIC.get(name) or {}).get("dram_bytes_per_launch"))
 
+    # enough operand sets that one pass touches > 4 x L2
+    nset_f = max(4, int(4 * 126e6 / (rows * cols * 6)) + 1)
+    nset_b = max(3, int(4 * 126e6 / (rows * cols * 16)) + 1)
     # LayerNorm forward: fp32 in, bf16 out (+ row statistics): 6 B / element
     fsets = [dict(x=torch.randn(rows, cols, device=dev), y=torch.empty(rows, cols, device=dev, dtype=torch.bfloat16),
-                  mean=torch.empty(rows, device=dev), rstd=torch.empty(rows, device=dev)) for _ in range(6)]
+                  mean=torch.empty(rows, device=dev), rstd=torch.empty(rows, device=dev)) for _ in range(nset_f)]
     run("layernorm_fwd", fsets, lambda s_: lib.vault_layernorm_fwd(s_["x"].data_ptr(), g.data_ptr(), b.data_ptr(), s_["y"].data_ptr(), None,
                                                                     s_["mean"].data_ptr(), s_["rstd"].data_ptr(), rows, cols, 1e-12, st), rows * cols * 6)
     # LayerNorm backward: x fp32 + dy bf16 + residual gradient fp32 in, dx fp32 + dx bf16 out: 16 B / element
     dg, db, dc = (torch.zeros(cols, device=dev) for _ in range(3))
     bsets = [dict(fsets[i], dy=torch.randn(rows, cols, device=dev).to(torch.bfloat16), dres=torch.randn(rows, cols, device=dev),
-                  dx32=torch.empty(rows, cols, device=dev), dx16=torch.empty(rows, cols, device=dev, dtype=torch.bfloat16)) for i in range(3)]
+                  dx32=torch.empty(rows, cols, device=dev), dx16=torch.empty(rows, cols, device=dev, dtype=torch.bfloat16)) for i in range(min(nset_b, nset_f))]
     run("layernorm_bwd", bsets, lambda s_: lib.vault_layernorm_bwd_drop(None, s_["dy"].data_ptr(), s_["x"].data_ptr(), s_["mean"].data_ptr(), s_["rstd"].data_ptr(),
                                                                          g.data_ptr(), s_["dres"].data_ptr(), s_["dx32"].data_ptr(), s_["dx16"].data_ptr(), dg.data_ptr(),
                                                                          db.data_ptr(), dc.data_ptr(), rows, cols, 0.0, 0, 0.0, 0, 0, None, st), rows * cols * 16)
     del fsets, bsets
-    # fused AdamW: 64 Mi parameters = 2 GB of state per launch (>> L2): 30 B / parameter
-    n = 64 * 1024 * 1024
+    # fused AdamW at the model's own size (197 M parameters = 5.9 GB of state per launch >> L2): 30 B / parameter
+    n = int(n_params)
     p_, g_, m_, v_ = (torch.zeros(n, device=dev) for _ in range(4))
     sh = torch.zeros(n, device=dev, dtype=torch.bfloat16)
     run("adamw", [0], lambda _s: lib.vault_adamw_step(p_.data_ptr(), g_.data_ptr(), 0, m_.data_ptr(), v_.data_ptr(), sh.data_ptr(), n, 1e-5, 0.9, 0.999, 1e-8,
                                                       0.0, 0, 1, 1.0, None, st), n * 30, reps=5)
     out["peak_gbs"] = peak
-    out["method"] = "round-robin over operand sets >> L2, all launches between one CUDA-event pair (no flush kernel)"
+    out["method"] = "the workload's own launch shapes, round-robin over operand sets >> L2, all launches between one CUDA-event pair (no flush kernel)"
     return out
 
 
@@ -330,7 +400,7 @@ def main():
         os.environ.setdefault("MASTER_ADDR", "127.0.0.1")
         dist.init_process_group("nccl", device_id=dev)
 
-    from transformers import BertConfig, RobertaConfig, ViltConfig
+    from transformers import ViltConfig
 
     from vault_b200 import VaultForTMSC, VaultTrainStep
     from vault_b200.model import set_parameter_requires_grad
@@ -338,10 +408,7 @@ def main():
     W = WORKLOADS[args.workload]
     torch.manual_seed(0)
     vc = ViltConfig()
-    if W["lm_kind"] == "roberta":  # BERTweet-base shape
-        bc = RobertaConfig(vocab_size=64001, max_position_embeddings=130, type_vocab_size=1, pad_token_id=1, layer_norm_eps=1e-5, bos_token_id=0, eos_token_id=2)
-    else:
-        bc = BertConfig()
+    bc = _hf_lm_config(args.workload)
     model = VaultForTMSC(vc, n_classes=3, vilt_dropout_prob=0.1, bert_config=bc)
     if W["freeze_lm"]:  # what VaultMixin.__init__(freeze_lm=True) does (ref:vault/models/vault/model.py:84-87); VaultForTMSC does not forward the flag
         model.freeze_lm = True
@@ -365,8 +432,12 @@ def main():
             dist.barrier()
         torch.cuda.synchronize()
 
-    def timed(batches, read_loss):
-        for i in range(args.warmup):
+    def timed(batches, read_loss, steps=None, warmup=None):
+        steps_, warm_ = steps or args.steps, warmup or args.warmup
+        return _timed(batches, read_loss, steps_, warm_)
+
+    def _timed(batches, read_loss, n_steps, n_warm):
+        for i in range(n_warm):
             r = ts.step(batches[i % NB])
         r.loss()
         barrier()
@@ -377,7 +448,7 @@ def main():
         if prof:
             torch.cuda.profiler.start()
         e0.record()
-        for i in range(args.steps):
+        for i in range(n_steps):
             r = ts.step(batches[i % NB])
             if read_loss and prev is not None:
                 losses.append(prev.loss())
@@ -400,6 +471,19 @@ def main():
     ms_dev, _ = timed(devb, read_loss=False)
     ms_e2e, losses = timed(host, read_loss=True)
     clocks = sampler.stop() if sampler else None
+    # BASELINE config 3 (T=40, 384x384, S=185) on the same model and step object, a short run next to the headline shape
+    also = None
+    if args.workload == "target" and os.environ.get("VB_BENCH_ALSO", "1") == "1":
+        W3 = WORKLOADS["config3"]
+        host3 = [synth_batch(torch, B, W3["text_len"], tuple(W3["image"]), bc.vocab_size, 3, seed=7000 + 1000 * rank + i, pin=True, pad_id=bc.pad_token_id or 0)
+                 for i in range(NB)]
+        dev3 = [{k: v.to(dev) for k, v in b.items()} for b in host3]
+        ms3, _ = timed(dev3, read_loss=False, steps=10, warmup=4)
+        ms3e, _ = timed(host3, read_loss=True, steps=10, warmup=4)
+        also = dict(config3=dict(config=bench_config("config3", B, world), steps=10, warmup=4, ms_per_step=ms3 / 10, value=B * world * 10 / (ms3 * 1e-3),
+                                 e2e=B * world * 10 / (ms3e * 1e-3), unit="samples/s",
+                                 model_tflops_per_gpu=B * 10 / (ms3 * 1e-3) * W3["train_gflop"] / 1e3))
+        del host3, dev3
 
     if rank == 0:
         peaks = {}
@@ -412,7 +496,7 @@ def main():
             roof, launches, calls = gemm_roofline(torch, ts, devb[0], peaks)
         else:
             launches = 0
-        hbm = hbm_kernel_rates(torch, peaks) if (world == 1 and not args.skip_roofline) else None
+        hbm = hbm_kernel_rates(torch, peaks, B * W["seq_len"], ts.engine.n_train) if (world == 1 and not args.skip_roofline) else None
         cpu = None
         if world == 1 and not args.skip_cpu_baseline:
             cpu = cpu_baseline(torch, args.workload)
@@ -425,10 +509,9 @@ def main():
         out = {
             "metric": METRIC, "value": value, "unit": "samples/s", "n_gpus": world, "steps": args.steps, "warmup": args.warmup,
             "ms_per_step": ms_dev / args.steps, "higher_is_better": True, "scaling": "weak", "vs_baseline": None, "dtype": "bf16", "data": "synthetic",
-            "config": dict(workload=W["desc"], name=args.workload, **{**workload_config(args.workload), "per_gpu_batch": B},
-                           global_batch=gb, parallelism=f"dp{world}", cuda_graph=not args.no_graph, comm_overlap=ts.overlap, grad_comm_dtype=("bf16" if ts.grad16 is not None else "fp32"),
-                           gemm_ctas=ts.engine.gemm_max_ctas or ts.engine.sms,
-                           l2="per-step working set (0.44 GB bf16 weights + 0.79 GB fp32 grads + >= 2 GB activations) >> 126 MB L2; 4 rotating input batches"),
+            "config": bench_config(args.workload, B, world),
+            "impl_config": dict(device="cuda", cuda_graph=not args.no_graph, comm_overlap=ts.overlap, grad_comm_dtype=("bf16" if ts.grad16 is not None else "fp32"),
+                                gemm_ctas=ts.engine.gemm_max_ctas or ts.engine.sms),
             "e2e": dict(value=e2e, unit="samples/s", h2d_bytes_per_step=h2d, d2h_bytes_per_step=4, ms_per_step=ms_e2e / args.steps,
                         api="vault_b200.VaultTrainStep.step(pinned host batch) -> StepResult.loss()"),
             "gpu_launches": (launches + 1) * args.steps if launches else None,
@@ -440,6 +523,7 @@ def main():
             "hbm_kernels": hbm,
             "cpu_baseline": cpu,
             "loss_first_last": [losses[0], losses[-1]] if losses else None,
+            "also": also,
         }
         print(json.dumps(out), flush=True)
     if world > 1:

@@ -225,8 +225,11 @@ def test_bench_workloads_are_consistent_with_baseline_shapes():
         assert bench.train_gflop_valid_tokens([T // 2] * 3, P, w["freeze_lm"]) < want
         cfg = bench.workload_config(name)
         assert cfg["per_gpu_batch"] == 32 and cfg["text_len"] == T
-        d = bench.oracle_dims(name)
-        assert d.lm_kind == w["lm_kind"] and (d.lm_vocab == 64001) == (w["lm_kind"] == "roberta")
+        lc = bench._hf_lm_config(name)
+        assert (lc.model_type == "roberta") == (w["lm_kind"] == "roberta") and (lc.vocab_size == 64001) == (w["lm_kind"] == "roberta")
+        # one `config` for both arms of the bench (the driver compares them): workload-only keys, nothing about how an arm runs it
+        c1 = bench.bench_config(name, 32, 2)
+        assert c1["global_batch"] == 64 and c1["parallelism"] == "dp2" and c1["name"] == name and "cuda_graph" not in c1 and "model" not in c1
 
 
 def test_mlm_decoder_class_swap_keeps_the_state_dict():
@@ -253,7 +256,7 @@ def _check_bench_line(d, reference=False):
     cb = d["cpu_baseline"]
     assert cb is None or {"value", "unit", "cores", "kind", "sample"} <= set(cb)
     if reference:
-        assert d["impl"] == "reference" and d["e2e"]["h2d_bytes_per_step"] == 0 and d["e2e"]["value"] == d["value"] and cb["kind"] == "port"
+        assert d["impl"] == "reference" and d["e2e"]["h2d_bytes_per_step"] == 0 and d["e2e"]["value"] == d["value"] and cb["kind"] in ("port", "reference")
     else:
         r = d["roofline"]
         assert {"bound", "achieved", "peak", "unit", "frac", "traffic"} <= set(r) and r["bound"] in ("hbm", "tensor")
@@ -267,7 +270,7 @@ def test_committed_bench_lines_follow_the_contract():
     import json
 
     root = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
-    files = sorted(glob.glob(os.path.join(root, "profiles", "r01_bench_*gpu*.json")))
+    files = sorted(glob.glob(os.path.join(root, "profiles", "r0[12]_bench_*gpu*.json")))
     assert files
     for f in files:
         d = json.loads(open(f).read().strip().splitlines()[-1])
@@ -275,19 +278,24 @@ def test_committed_bench_lines_follow_the_contract():
 
 
 def test_reference_arm_prints_one_contract_line():
-    """`bench.py --impl reference` (the oracle port on the host cores) end to end: one JSON line, same metric / unit / config keys."""
+    """`bench.py --impl reference` (the reference's own VaultForTMSC on the host cores; oracle port only where the reference files are absent)
+    end to end: one JSON line, same metric / unit, and a `config` identical to the one this repo's arm prints for the same command."""
     import json
     import subprocess
 
     root = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
-    r = subprocess.run([sys.executable, os.path.join(root, "bench.py"), "--impl", "reference", "--steps", "1", "--warmup", "0"], capture_output=True, text=True,
-                       timeout=600, cwd=root)
+    r = subprocess.run([sys.executable, os.path.join(root, "bench.py"), "--impl", "reference", "--steps", "1", "--warmup", "0", "--batch", "2"], capture_output=True,
+                       text=True, timeout=600, cwd=root)
     assert r.returncode == 0, r.stderr[-2000:]
     lines = [ln for ln in r.stdout.splitlines() if ln.startswith("{")]
     assert len(lines) == 1
     d = json.loads(lines[0])
     _check_bench_line(d, reference=True)
-    assert d["config"]["name"] == "config3" and d["value"] > 0
+    import bench
+    from oracle import ref_loader
+
+    assert d["config"] == bench.bench_config("target", 2, 1) and d["value"] > 0  # default workload = the north-star target shape
+    assert d["cpu_baseline"]["kind"] == ("reference" if ref_loader.available() else "port")
     # under torchrun only rank 0 runs it; the other ranks exit 0 without work
     env = dict(os.environ, RANK="1", WORLD_SIZE="2", LOCAL_RANK="1")
     r = subprocess.run([sys.executable, os.path.join(root, "bench.py"), "--impl", "reference", "--gpus", "2", "--steps", "1", "--warmup", "0"], capture_output=True,

@@ -98,6 +98,20 @@ int vault_gemm_bf16(const vault_gemm_args* args, void* stream);
  *   out [B*(Hi/32)*(Wi/32), N] fp32, row = b*gh*gw + i*gw + j                                                     */
 int vault_patch_embed_fwd(const float* pixels, const float* weight, const float* bias, float* out, int32_t B, int32_t C,
                           int32_t Hi, int32_t Wi, int32_t P, int32_t N, void* stream);
+/* Its weight gradient, im2col-free as well (backward of HF:models/vilt/modeling_vilt.py:293-303 w.r.t. projection.weight):
+ *   dW[n, (c,kh,kw)] += sum over patches of dpatch[patch, n] * pixel(patch, c, kh, kw)
+ * TF32 tcgen05 GEMM with the contraction over the patches: the pixel operand comes through the SAME 5-D TMA map as the forward
+ * (one box = [patch rows] x [32 kw] = a 32-wide atom of an MN-major operand), dpatch fp32 [B*gh*gw, N] is read MN-major too.
+ * dW fp32 [N, C*32*32] is ACCUMULATED into (red.global.add; caller zero-fills).  vault_patch_embed_wgrad_ok() says whether the
+ * patch grid admits the kernel's k-blocks (whole patch rows of <= 64 patches: images up to 2048 px wide); returns 1 / 0.     */
+int vault_patch_embed_wgrad_ok(int32_t C, int32_t Hi, int32_t Wi, int32_t P, int32_t N);
+int vault_patch_embed_wgrad(const float* pixels, const float* dpatch_f32, float* dW, int32_t B, int32_t C, int32_t Hi,
+                            int32_t Wi, int32_t P, int32_t N, void* stream);
+/* fp32 patch-gradient rows for the kernel above, gathered from the gradient of the assembled sequence, + the projection's
+ * bias gradient:  dpatch[b, i*gw+j] = dX[b, T+1+i*w_b+j] inside the sample's valid rectangle hw[b] = (h_b, w_b), zero rows
+ * elsewhere;  dbias[n] += column sums (atomics; may be NULL).  dX fp32 [B, T+1+Pmax, H]; dpatch fp32 [B*gh*gw, H].        */
+int vault_patch_grad_rows_f32(const float* dX, const int32_t* hw, float* dpatch_f32, float* dbias, int32_t B, int32_t T,
+                              int32_t Pmax, int32_t gh, int32_t gw, int32_t H, void* stream);
 
 /* ------------------------------------------------------------------------------------------------------------------
  * LayerNorm (HF nn.LayerNorm call sites: 25 in the LM, 26 in ViLT).  x fp32 [rows, cols].

@@ -376,6 +376,54 @@ def test_patch_embed_tma_tf32(dev, B, Hi, Wi, N):
     assert _rel(out, ref) < 2e-3
 
 
+@pytest.mark.parametrize("B,Hi,Wi,N,T", [(2, 384, 384, 768, 8), (5, 384, 640, 768, 40), (3, 640, 384, 128, 5), (33, 384, 384, 256, 16), (32, 384, 640, 768, 128),
+                                         (2, 512, 512, 128, 3), (3, 416, 608, 128, 7), (2, 32, 32, 128, 2)])
+def test_patch_embed_wgrad_tma_tf32(dev, B, Hi, Wi, N, T):
+    """im2col-free weight gradient of the patch projection (vault_patch_grad_rows_f32 + vault_patch_embed_wgrad) against torch's conv2d
+    backward (HF:models/vilt/modeling_vilt.py:293-303): dW, and the bias gradient, with mixed per-sample valid patch rectangles (rows of
+    invalid patches are zero); TF32 operands -> 2e-3 relative.  The result is ACCUMULATED into dW (a second call doubles it)."""
+    from vault_b200 import _abi
+
+    lib, st = _abi.lib(), torch.cuda.current_stream().cuda_stream
+    gh, gw = Hi // 32, Wi // 32
+    assert lib.vault_patch_embed_wgrad_ok(3, Hi, Wi, 32, N) == 1
+    torch.manual_seed(B + Hi)
+    px = torch.randn(B, 3, Hi, Wi, device=dev)
+    hw = torch.tensor([[gh, gw]] + [[max(1, gh - (b * 3) % gh), max(1, gw - (b * 5) % gw)] for b in range(1, B)], dtype=torch.int32, device=dev)
+    pmax = int((hw[:, 0] * hw[:, 1]).max())
+    S = T + 1 + pmax
+    dX = torch.randn(B, S, N, device=dev)
+    # reference: dpatch rows in the full-grid layout, zero outside each sample's rectangle
+    dpatch_ref = torch.zeros(B, gh, gw, N, device=dev)
+    for b in range(B):
+        h, w = int(hw[b, 0]), int(hw[b, 1])
+        dpatch_ref[b, :h, :w] = dX[b, T + 1:T + 1 + h * w].view(h, w, N)
+    wt = torch.zeros(N, 3, 32, 32, device=dev, requires_grad=True)
+    bias = torch.zeros(N, device=dev, requires_grad=True)
+    y = torch.nn.functional.conv2d(px, wt, bias, stride=32)  # [B, N, gh, gw]
+    y.backward(dpatch_ref.permute(0, 3, 1, 2).contiguous())
+    dp32 = torch.full((B * gh * gw, N), float("nan"), device=dev)
+    db = torch.zeros(N, device=dev)
+    dW = torch.zeros(N, 3 * 32 * 32, device=dev)
+    for rep in (1, 2):
+        _abi.check(lib.vault_patch_grad_rows_f32(dX.data_ptr(), hw.data_ptr(), dp32.data_ptr(), db.data_ptr(), B, T, pmax, gh, gw, N, st))
+        _abi.check(lib.vault_patch_embed_wgrad(px.data_ptr(), dp32.data_ptr(), dW.data_ptr(), B, 3, Hi, Wi, 32, N, st))
+        assert torch.equal(dp32.view(B, gh, gw, N), dpatch_ref)
+        assert _rel(dW, rep * wt.grad.view(N, -1)) < 2e-3
+        assert _rel(db, rep * bias.grad) < 1e-5
+
+
+def test_patch_embed_wgrad_rejects_grids_without_a_k_block(dev):
+    from vault_b200 import _abi
+
+    lib = _abi.lib()
+    assert lib.vault_patch_embed_wgrad_ok(3, 384, 416, 32, 768) == 1    # 13 patches per row: k-blocks of 4 rows = 52 patches, zero-padded to 56
+    assert lib.vault_patch_embed_wgrad_ok(3, 32, 32, 32, 768) == 1      # one patch per image: k-block of 1, padded to 8
+    assert lib.vault_patch_embed_wgrad_ok(3, 64, 32 * 65, 32, 768) == 0  # a patch row of 65 patches does not fit a k-block
+    assert lib.vault_patch_embed_wgrad_ok(3, 384, 384, 16, 768) == 0    # patch size
+    assert lib.vault_patch_embed_wgrad_ok(3, 384, 384, 32, 100) == 0    # N % 128
+
+
 @pytest.mark.parametrize("cl,M,N,K,a_mn,b_mn,bn", [
     (1, 5920, 2304, 768, False, False, 256), (1, 5920, 768, 2304, False, True, 256), (1, 300, 256, 192, False, False, 128),
     (2, 1280, 768, 768, False, False, 64), (2, 2304, 768, 1280, True, True, 128), (2, 128, 192, 64, False, False, 64), (1, 128, 256, 64, True, True, 128),

@@ -39,6 +39,9 @@ SIGNATURES = {
     "vault_check_device": [c_i32],
     "vault_gemm_bf16": [C.POINTER(GemmArgs), c_p],
     "vault_patch_embed_fwd": [c_p, c_p, c_p, c_p, c_i32, c_i32, c_i32, c_i32, c_i32, c_i32, c_p],
+    "vault_patch_embed_wgrad_ok": [c_i32, c_i32, c_i32, c_i32, c_i32],
+    "vault_patch_embed_wgrad": [c_p, c_p, c_p, c_i32, c_i32, c_i32, c_i32, c_i32, c_i32, c_p],
+    "vault_patch_grad_rows_f32": [c_p, c_p, c_p, c_p, c_i32, c_i32, c_i32, c_i32, c_i32, c_i32, c_p],
     "vault_layernorm_fwd": [c_p, c_p, c_p, c_p, c_p, c_p, c_p, c_i64, c_i32, c_f32, c_p],
     "vault_layernorm_bwd": [c_p, c_p, c_p, c_p, c_p, c_p, c_p, c_p, c_p, c_p, c_p, c_i64, c_i32, c_p],
     "vault_layernorm_fwd_drop": [c_p, c_p, c_p, c_p, c_p, c_p, c_p, c_i64, c_i32, c_f32, c_f32, c_u64, c_p, c_u32, c_p],
@@ -137,7 +140,8 @@ class CountingLib:
 
     def __getattr__(self, name):
         fn = getattr(self._inner, name)
-        if not name.startswith("vault_") or name in ("vault_version", "vault_last_error", "vault_check_device", "vault_attn_set_impl"):
+        if not name.startswith("vault_") or name in ("vault_version", "vault_last_error", "vault_check_device", "vault_attn_set_impl",
+                                                     "vault_patch_embed_wgrad_ok"):
             return fn
 
         def wrapped(*args):

@@ -319,6 +319,18 @@ __device__ __forceinline__ uint64_t umma_desc_sw128(uint32_t smem_addr, uint32_t
   d |= (uint64_t)2 << 61;  // SWIZZLE_128B
   return d;
 }
+// Same for an MN-major operand of 4-byte elements (tf32): the swizzle works on 32-byte pieces (TMA CU_TENSOR_MAP_SWIZZLE_128B_ATOM_32B,
+// descriptor layout type 1 "128B, base 32B").  Canonical atom = 4 k-rows x 128 B (32 MN elements): SBO = bytes between consecutive
+// 4-row groups (512 when the rows are dense), LBO = bytes between consecutive 32-wide MN atoms.
+__device__ __forceinline__ uint64_t umma_desc_sw128_base32(uint32_t smem_addr, uint32_t lbo_bytes, uint32_t sbo_bytes) {
+  uint64_t d = 0;
+  d |= (uint64_t)((smem_addr & 0x3FFFFu) >> 4);
+  d |= (uint64_t)((lbo_bytes >> 4) & 0x3FFFu) << 16;
+  d |= (uint64_t)((sbo_bytes >> 4) & 0x3FFFu) << 32;
+  d |= (uint64_t)1 << 46;  // version
+  d |= (uint64_t)1 << 61;  // SWIZZLE_128B_BASE32B
+  return d;
+}
 // Instruction descriptor (kind::f16 / kind::tf32): fp32 accumulate, dense, no negate.
 //   fmt: 0 = f16, 1 = bf16, 2 = tf32;  a_mn/b_mn: 1 = operand is MN-major in shared memory
 __host__ __device__ __forceinline__ uint32_t umma_idesc(uint32_t fmt, uint32_t M, uint32_t N, uint32_t a_mn, uint32_t b_mn) {

@@ -534,8 +534,14 @@ EncodeTiledFn get_encode_fn() {
 }
 
 // 2-D bf16 tensor [outer rows, inner contiguous], 128B swizzle, zero fill out of bounds
+int encode_tmap_2d_sw(CUtensorMap* tm, CUtensorMapDataType dt, int elem_bytes, const void* base, uint64_t inner, uint64_t outer,
+                      uint64_t ld_elems, uint32_t box_inner, uint32_t box_outer, CUtensorMapSwizzle swizzle);
 int encode_tmap_2d(CUtensorMap* tm, CUtensorMapDataType dt, int elem_bytes, const void* base, uint64_t inner, uint64_t outer,
                    uint64_t ld_elems, uint32_t box_inner, uint32_t box_outer) {
+  return encode_tmap_2d_sw(tm, dt, elem_bytes, base, inner, outer, ld_elems, box_inner, box_outer, CU_TENSOR_MAP_SWIZZLE_128B);
+}
+int encode_tmap_2d_sw(CUtensorMap* tm, CUtensorMapDataType dt, int elem_bytes, const void* base, uint64_t inner, uint64_t outer,
+                      uint64_t ld_elems, uint32_t box_inner, uint32_t box_outer, CUtensorMapSwizzle swizzle) {
   EncodeTiledFn fn = get_encode_fn();
   if (!fn) return fail(VAULT_ERR_DRIVER, "cuTensorMapEncodeTiled entry point not available");
   if ((reinterpret_cast<uintptr_t>(base) & 15) != 0 || ((ld_elems * elem_bytes) & 15) != 0)
@@ -544,7 +550,7 @@ int encode_tmap_2d(CUtensorMap* tm, CUtensorMapDataType dt, int elem_bytes, cons
   cuuint64_t gstr[1] = {ld_elems * (uint64_t)elem_bytes};
   cuuint32_t box[2] = {box_inner, box_outer};
   cuuint32_t estr[2] = {1, 1};
-  CUresult r = fn(tm, dt, 2, const_cast<void*>(base), gdim, gstr, box, estr, CU_TENSOR_MAP_INTERLEAVE_NONE, CU_TENSOR_MAP_SWIZZLE_128B,
+  CUresult r = fn(tm, dt, 2, const_cast<void*>(base), gdim, gstr, box, estr, CU_TENSOR_MAP_INTERLEAVE_NONE, swizzle,
                   CU_TENSOR_MAP_L2_PROMOTION_L2_256B, CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
   if (r != CUDA_SUCCESS) return fail(VAULT_ERR_DRIVER, "cuTensorMapEncodeTiled failed (%d): inner %llu outer %llu ld %llu box %ux%u", (int)r,
                                      (unsigned long long)inner, (unsigned long long)outer, (unsigned long long)ld_elems, box_inner, box_outer);

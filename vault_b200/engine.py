@@ -102,6 +102,7 @@ class VaultEngine:
         self.dynamic_tiles = os.environ.get("VAULT_B200_DYNAMIC_TILES", "0") == "1"  # measured neutral on B200: opt-in
         self.wgrad_side_stream = os.environ.get("VAULT_B200_WGRAD_SIDE", "1") != "0"
         self.small_m_split_k = os.environ.get("VAULT_B200_SMALL_M_SPLITK", "1") != "0"
+        self.patch_wgrad_tma = os.environ.get("VAULT_B200_PATCH_WGRAD_TMA", "1") != "0"  # 0: bf16 im2col + GEMM (A/B switch)
         self._side = None
         self._side_keep = []
         self._side_dirty = False
@@ -670,8 +671,10 @@ class VaultEngine:
                 _abi.check(lib.vault_patchify_bf16(pixel_values.data_ptr(), patches.data_ptr(), B, self.C, Hi, Wi, self.patch, st), "patchify")
                 self.gemm(patches.data_ptr(), Kp, 0, self.w16("embeddings.patch_embeddings.projection.weight"), Kp, 0, B * G, H, Kp, EPI_BIAS_F32,
                           patch_out.data_ptr(), H, bias=self.w32("embeddings.patch_embeddings.projection.bias"))
-            if sv is not None and patches is None and self.g32("embeddings.patch_embeddings.projection.weight"):
-                # the projection's wgrad (dW = dpatch^T * patches) reads the patch matrix as its MN-major B operand: bf16 im2col, training only
+            if (sv is not None and patches is None and self.g32("embeddings.patch_embeddings.projection.weight")
+                    and not (self.patch_wgrad_tma and lib.vault_patch_embed_wgrad_ok(self.C, Hi, Wi, self.patch, H))):
+                # patch grids the im2col-free weight-gradient kernel does not take (a patch row of more than 64 patches; other patch sizes): the
+                # projection's wgrad (dW = dpatch^T * patches) then reads a bf16 patch matrix as its MN-major B operand (training only)
                 patches = self._new((B * G, Kp), torch.bfloat16)
                 _abi.check(lib.vault_patchify_bf16(pixel_values.data_ptr(), patches.data_ptr(), B, self.C, Hi, Wi, self.patch, st), "patchify")
             ev1 = torch.cuda.Event()
@@ -759,6 +762,7 @@ class VaultEngine:
         if sv is not None:
             sv["v_sum"], sv["st_t"], sv["patches"], sv["hw"], sv["key_mask"] = v_sum, st_t, patches, hw, key_mask
             sv["ids"], sv["tt"], sv["am"] = input_ids, token_type_ids, attention_mask
+            sv["pixels"] = None if embeds_mode else pixel_values  # the patch projection's weight gradient reads them through TMA (no im2col)
             tape.meta.update(B=B, T=T, S=S, pmax=pmax, gh=gh, gw=gw, Hi=Hi, Wi=Wi, img_type=int(image_token_type_idx), training=training,
                              lm_trains=lm_trains, embeds_mode=embeds_mode, text_embeds_mode=text_embeds_mode)
 
@@ -875,8 +879,10 @@ class VaultEngine:
                        "vilt_assemble_embeds_bwd")
             tape.meta["d_image_embeds"] = d_img
         else:
-            dpatch = self._new((B * gh * gw, H), torch.bfloat16)
-            _abi.check(lib.vault_vilt_assemble_bwd(g32.data_ptr(), sv["hw"].data_ptr(), dtext_ln.data_ptr(), dpatch.data_ptr(),
+            gw_ptr = self.g32("embeddings.patch_embeddings.projection.weight")
+            tma_wgrad = bool(gw_ptr) and sv["patches"] is None and sv.get("pixels") is not None
+            dpatch = self._new((B * gh * gw, H), torch.bfloat16) if (sv["patches"] is not None) else None
+            _abi.check(lib.vault_vilt_assemble_bwd(g32.data_ptr(), sv["hw"].data_ptr(), dtext_ln.data_ptr(), dpatch.data_ptr() if dpatch is not None else None,
                                                    self.g32("embeddings.cls_token") or None, self.g32("embeddings.position_embeddings") or None,
                                                    self.g32("embeddings.token_type_embeddings.weight") or None, B, T, pmax, gh, gw, self.grid, H,
                                                    mt["img_type"], st), "vilt_assemble_bwd")
@@ -884,6 +890,23 @@ class VaultEngine:
             if sv["patches"] is not None:
                 self.linear_wgrad(dpatch, sv["patches"], B * gh * gw, "embeddings.patch_embeddings.projection.weight",
                                   "embeddings.patch_embeddings.projection.bias", H, Kp)
+            elif tma_wgrad:
+                # im2col-free: dW += dpatch^T * pixels with the pixel operand taken through the forward's 5-D TMA map (TF32 tcgen05, contraction
+                # over the patches); fp32 patch-gradient rows + the bias gradient by one gather kernel.  Off the critical path: side stream.
+                dp32 = self._new((B * gh * gw, H), torch.float32)
+                wst = st
+                if self.wgrad_side_stream:
+                    ev = torch.cuda.Event()
+                    ev.record(torch.cuda.current_stream(self.device))
+                    self._side.wait_event(ev)
+                    wst = self._side.cuda_stream
+                    self._side_keep.append((dp32, sv["pixels"], g32))
+                    self._side_dirty = True
+                _abi.check(lib.vault_patch_grad_rows_f32(g32.data_ptr(), sv["hw"].data_ptr(), dp32.data_ptr(),
+                                                         self.g32("embeddings.patch_embeddings.projection.bias") or None, B, T, pmax, gh, gw, H, wst),
+                           "patch_grad_rows_f32")
+                _abi.check(lib.vault_patch_embed_wgrad(sv["pixels"].data_ptr(), dp32.data_ptr(), gw_ptr, B, self.C, mt["Hi"], mt["Wi"], self.patch, H, wst),
+                           "patch_embed_wgrad")
         dv_sum, _ = self.ln_bwd(dtext_ln, None, sv["v_sum"], sv["st_t"], Mt, "embeddings.text_embeddings.LayerNorm.weight",
                                 "embeddings.text_embeddings.LayerNorm.bias", want16=False)
         tt_ptr = sv["tt"].data_ptr() if sv["tt"] is not None else None

@@ -38,6 +38,7 @@ def _rel(got, ref):
     (128, 256, 64, False, True, 256), (5920, 768, 2304, False, True, 0), (130, 3072, 768, False, True, 0),       # dgrad layout
     (128, 128, 64, True, True, 128), (256, 256, 1000, True, True, 0), (2304, 768, 5920, True, True, 128),          # wgrad layout
     (128, 128, 64, True, False, 128),
+    (4096, 768, 768, False, False, 192), (4096, 768, 3072, False, True, 192), (304, 384, 200, True, True, 192), (4096, 768, 2304, False, True, 0),   # 128x192 tiles
 ])
 def test_gemm_layouts(dev, ops, M, N, K, a_mn, b_mn, bn):
     """bit-level claim: bf16 x bf16 products accumulated in fp32 -> relative error <= 1e-4 of the fp32 torch result."""

@@ -13,7 +13,8 @@ torch.manual_seed(0)
 B = int(os.environ.get("VB_BATCH", "32"))
 m = VaultForTMSC(ViltConfig(), n_classes=3, vilt_dropout_prob=0.1, bert_config=BertConfig()).to(dev).train()
 ts = VaultTrainStep(m, lr=2e-5, use_cuda_graph=False)
-batch = {k: v.to(dev) for k, v in bench.synth_batch(torch, B, 40, (384, 384), 30522, 3, seed=1, pin=False).items()}
+W = bench.WORKLOADS[os.environ.get("VB_WORKLOAD", "config3")]
+batch = {k: v.to(dev) for k, v in bench.synth_batch(torch, B, W["text_len"], tuple(W["image"]), 30522, 3, seed=1, pin=False).items()}
 for _ in range(2):
     ts.step(batch)
 torch.cuda.synchronize()

@@ -248,7 +248,7 @@ gemm_bf16_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant_
   constexpr int kBStage = BN * BK * 2;
   constexpr int kStage = kAStage + kBStage;
   constexpr int kStages = kRingBytes / kStage;
-  constexpr uint32_t kTmemCols = 2 * BN;  // two accumulator buffers (power of two >= 32 for BN in {64,128,256})
+  constexpr uint32_t kTmemCols = BN == 192 ? 512u : 2u * BN;  // two accumulator buffers; the allocation is a power of two >= 32
 
   extern __shared__ uint8_t smem_raw[];
   const uint32_t smem_base = (smem_u32(smem_raw) + 1023u) & ~1023u;
@@ -574,23 +574,34 @@ template <int EPI>
 int dispatch_bn(int bn, const CUtensorMap& tmA, const CUtensorMap& tmB, const GemmParams& p, int grid, cudaStream_t st) {
   switch (bn) {
     case 256: return launch_gemm<256, EPI>(tmA, tmB, p, grid, st);
+    case 192: return launch_gemm<192, EPI>(tmA, tmB, p, grid, st);
     case 128: return launch_gemm<128, EPI>(tmA, tmB, p, grid, st);
     case 64: return launch_gemm<64, EPI>(tmA, tmB, p, grid, st);
   }
-  return fail(VAULT_ERR_INVALID, "block_n must be 64, 128 or 256 (got %d)", bn);
+  return fail(VAULT_ERR_INVALID, "block_n must be 64, 128, 192 or 256 (got %d)", bn);
 }
 
 // Tile-N choice: fill whole waves of SMs; wider tiles amortise the A-tile smem traffic (N=256 runs the MMA at full rate with
-// 96 B/clk of smem reads, N=128 needs 128 B/clk, N=64 is smem-bound).
+// 96 B/clk of smem reads, N=128 needs 128 B/clk, N=64 is smem-bound).  N=192 exists for the 768-wide outputs at 4,096 tokens (the LM stack
+// of the target shape): 32 x 4 = 128 tiles fill 86 % of the SMs in one wave where 128x256 tiles (96) fill 65 %.
+static bool no_bn192() {  // VAULT_B200_NO_BN192=1: A/B switch
+  static int v = -1;
+  if (v < 0) {
+    const char* e = getenv("VAULT_B200_NO_BN192");
+    v = (e != nullptr && e[0] == '1') ? 1 : 0;
+  }
+  return v != 0;
+}
 static int pick_block_n(int M, int N, int split_k, int sms) {
-  const int cands[3] = {256, 128, 64};
-  const float rate[3] = {1.0f, 0.85f, 0.55f};
+  const int cands[4] = {256, 192, 128, 64};
+  const float rate[4] = {1.0f, 0.93f, 0.85f, 0.55f};
   float best = -1.f;
   int best_bn = 128;
   const int mb = (M + BM - 1) / BM;
-  for (int i = 0; i < 3; ++i) {
+  for (int i = 0; i < 4; ++i) {
     const int bn = cands[i];
     if (bn > 64 && N < bn) continue;
+    if (bn == 192 && (N % 192 != 0 || no_bn192())) continue;
     const int nb = (N + bn - 1) / bn;
     const long long tiles = (long long)mb * nb * split_k;
     const long long waves = (tiles + sms - 1) / sms;
@@ -622,6 +633,7 @@ extern "C" int vault_gemm_bf16(const vault_gemm_args* a, void* stream) {
   int cl = a->cluster > 0 ? a->cluster : 0;  // 0 / negative: no cluster (the CTA-pair multicast measured +2 % at best, so there is no automatic choice)
   VB_REQUIRE(cl <= 2, "vault_gemm_bf16: cluster mode %d (0/-1 off, 1 pair along M, 2 pair along N)", a->cluster);
   if (cl == 1 && a->b_mn && bn < 128) cl = 0;  // an MN-major B tile of one 64-wide box cannot be split across the pair
+  if (bn == 192) cl = 0;                       // three 64-wide boxes do not split evenly across a CTA pair
   CUtensorMap tmA, tmB;
   int rc;
   if (!a->a_mn) rc = encode_tmap_2d(&tmA, CU_TENSOR_MAP_DATA_TYPE_BFLOAT16, 2, a->A, (uint64_t)a->K, (uint64_t)a->M, (uint64_t)a->lda, BK, cl == 2 ? 64 : BM);

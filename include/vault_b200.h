@@ -154,8 +154,9 @@ int vault_attn_fwd(const void* qkv, const uint8_t* key_mask, void* ctx, float* l
 int vault_attn_bwd(const void* qkv, const uint8_t* key_mask, const void* ctx, const void* dctx, const float* lse,
                    float* delta, void* dqkv, int32_t B, int32_t S, int32_t heads, float dropout_p, uint64_t seed,
                    const uint64_t* seed_dev, uint32_t site, void* stream);
-/* Kernel family used by vault_attn_fwd / vault_attn_bwd: 0 = automatic (dropout-free calls: pipelined tcgen05 kernels for 193..384 keys,
- * whole-row tcgen05 kernels for 65..256 keys forward / 65..192 keys backward; mma.sync kernels otherwise), 1 = mma.sync kernels only,
+/* Kernel family used by vault_attn_fwd / vault_attn_bwd: 0 = automatic (pipelined tcgen05 kernels for 193..384 keys, and for 65..384
+ * keys with probability dropout; whole-row tcgen05 kernels for dropout-free calls with 65..192 keys; mma.sync kernels otherwise),
+ * 1 = mma.sync kernels only,
  * 2 = whole-row tcgen05 kernels wherever their shape limits allow, 3 = pipelined tcgen05 kernels for every dropout-free call with
  * <= 384 keys.  Process-wide; meant for tests and A/B measurements. */
 int vault_attn_set_impl(int32_t impl);

@@ -255,7 +255,7 @@ def test_attention_tcgen05_matches_mma_sync(dev, B, S, heads, tc_impl):
         _abi.set_attn_impl(0)
 
 
-@pytest.mark.parametrize("S", [40, 64, 100, 128, 185])
+@pytest.mark.parametrize("S", [40, 64, 100, 128, 185, 257, 369])
 def test_attention_dropout_exact_mask(dev, S):
     """With V = identity over one 64-key chunk the context IS that chunk of the dropped probability matrix: recover the Philox mask chunk
     by chunk (the mask depends only on seed / site / (b, h, q, k), never on the data), then check forward and backward against torch

@@ -148,7 +148,8 @@ class CountingLib:
             n = KERNELS_PER_CALL.get(name, 1)
             if name == "vault_attn_bwd" and ATTN_IMPL != 1 and float(args[10]) == 0.0 and 64 < int(args[8]) <= 192:
                 n = 1  # fused tcgen05 backward (attention_tc.cu) instead of the dQ + dK/dV pair
-            elif name == "vault_attn_bwd" and ATTN_IMPL in (0, 3) and float(args[10]) == 0.0 and 192 < int(args[8]) <= 384:
+            elif name == "vault_attn_bwd" and ATTN_IMPL in (0, 3) and ((float(args[10]) == 0.0 and 192 < int(args[8]) <= 384)
+                                                                        or (float(args[10]) > 0.0 and 64 < int(args[8]) <= 384)):
                 n = 3  # delta + dQ + dK/dV kernels of attention_sm100.cu
             self.launches += n
             self.calls[name] = self.calls.get(name, 0) + 1

@@ -507,9 +507,10 @@ void attn_set_impl(int impl);
 // pipelined tcgen05 kernels of attention_sm100.cu (S <= 384, no dropout)
 bool attn_sm100_ok(int S, float dropout_p);
 void attn_sm100_enable(int on);
-int attn_fwd_sm100(const void* qkv, const uint8_t* key_mask, void* ctx, float* lse, int B, int S, int heads, cudaStream_t st);
+int attn_fwd_sm100(const void* qkv, const uint8_t* key_mask, void* ctx, float* lse, int B, int S, int heads, float dropout_p, unsigned long long seed,
+                   const unsigned long long* seed_dev, unsigned site, cudaStream_t st);
 int attn_bwd_sm100(const void* qkv, const uint8_t* key_mask, const void* ctx, const void* dctx, const float* lse, float* delta, void* dqkv, int B, int S,
-                   int heads, cudaStream_t st);
+                   int heads, float dropout_p, unsigned long long seed, const unsigned long long* seed_dev, unsigned site, cudaStream_t st);
 
 }  // namespace vb
 
@@ -529,7 +530,9 @@ extern "C" int vault_attn_fwd(const void* qkv, const uint8_t* key_mask, void* ct
   AttnParams p{};
   int rc = fill_params(p, B, S, heads, dropout_p, seed, seed_dev, site);
   if (rc) return rc;
-  if (attn_sm100_ok(S, dropout_p)) return attn_fwd_sm100(qkv, key_mask, ctx, lse, B, S, heads, reinterpret_cast<cudaStream_t>(stream));
+  if (attn_sm100_ok(S, dropout_p))
+    return attn_fwd_sm100(qkv, key_mask, ctx, lse, B, S, heads, dropout_p, seed, reinterpret_cast<const unsigned long long*>(seed_dev), site,
+                          reinterpret_cast<cudaStream_t>(stream));
   if (attn_tc_fwd_ok(S, dropout_p)) return attn_fwd_tc(qkv, key_mask, ctx, lse, B, S, heads, reinterpret_cast<cudaStream_t>(stream));
   p.qkv = reinterpret_cast<const bf16*>(qkv); p.key_mask = key_mask; p.ctx = reinterpret_cast<bf16*>(ctx); p.lse = lse;
   const int smem = (kTile + 2 * p.S_pad) * 128 + p.S_pad;
@@ -554,7 +557,8 @@ extern "C" int vault_attn_bwd(const void* qkv, const uint8_t* key_mask, const vo
   int rc = fill_params(p, B, S, heads, dropout_p, seed, seed_dev, site);
   if (rc) return rc;
   if (attn_sm100_ok(S, dropout_p))
-    return attn_bwd_sm100(qkv, key_mask, ctx, dctx, lse, delta, dqkv, B, S, heads, reinterpret_cast<cudaStream_t>(stream));
+    return attn_bwd_sm100(qkv, key_mask, ctx, dctx, lse, delta, dqkv, B, S, heads, dropout_p, seed, reinterpret_cast<const unsigned long long*>(seed_dev), site,
+                          reinterpret_cast<cudaStream_t>(stream));
   if (attn_tc_bwd_ok(S, dropout_p))
     return attn_bwd_tc(qkv, key_mask, ctx, dctx, lse, delta, dqkv, B, S, heads, reinterpret_cast<cudaStream_t>(stream));
   p.qkv = reinterpret_cast<const bf16*>(qkv); p.key_mask = key_mask; p.ctx = reinterpret_cast<bf16*>(const_cast<void*>(ctx));

@@ -1,5 +1,5 @@
-// Pipelined, warp-specialised fused attention for sm_100a (tcgen05.mma + tensor memory + TMA), head_dim 64, S <= 384, no dropout:
-// the ViLT stack's masked-softmax attention (HF:models/vilt/modeling_vilt.py:306-365) forward and backward at every shape the
+// Pipelined, warp-specialised fused attention for sm_100a (tcgen05.mma + tensor memory + TMA), head_dim 64, S <= 384, with or without
+// probability dropout: the ViLT stack's masked-softmax attention (HF:models/vilt/modeling_vilt.py:306-365) forward and backward at every shape the
 // reference pipeline produces (T <= 128 text tokens + CLS + <= 240 patches = 369 keys).
 //
 // One skeleton, three instantiations.  A CTA is persistent over (sample, head) items; per item two [S x 64] operands stay resident
@@ -45,6 +45,10 @@ struct AParams {
   bf16* dqkv;               // B: out [B*S, 3H]
   int B, S, heads, nblk, n_items;
   float scale_log2, scale;
+  float dropout_p;                       // probability dropout (HF:models/bert/modeling_bert.py eager attention: dropout(softmax(...)) before @V)
+  unsigned long long seed;
+  const unsigned long long* seed_dev;    // device counter added to the seed (advanced once per training step), may be NULL
+  unsigned site;
   long long* trace;  // VAULT_B200_ATTN_TRACE=1 (debug): (clock64, event id) pairs of CTA 0's MMA thread [0..1023] and first softmax warp [1024..2047]
 };
 
@@ -114,7 +118,12 @@ __device__ __forceinline__ void store_rows32_staged(const uint32_t (&r)[32], flo
 }
 __device__ __forceinline__ void bar_sync_256() { asm volatile("bar.sync 1, 256;" ::: "memory"); }
 
-template <int MODE>
+// Probability dropout (DROP): one Philox4x32 call yields eight 16-bit draws = the keep decisions of 8 consecutive keys of one query row,
+// counter = ((sample * heads + head) * S + query) * 64 + key / 8, stream = dropout site.  Lanes are queries and a thread walks keys in
+// aligned groups of 32 in all three kernels, so forward, dQ and dK/dV regenerate the same mask without exchanging a bit.
+//   forward:  O = (P o keep / (1 - p)) V, row sums / LSE over the undropped P
+//   backward: dP = (dO V^T) o keep / (1 - p);  dS = P o (dP - delta);  dV = (P o keep / (1 - p))^T dO;  delta = sum_d dO o O
+template <int MODE, bool DROP>
 __global__ void __launch_bounds__(kThreadsA, 1)
 attn_sm100_kernel(const __grid_constant__ CUtensorMap tmQKV, const __grid_constant__ CUtensorMap tmDO, const AParams p) {
   extern __shared__ uint8_t smem_raw[];
@@ -362,6 +371,15 @@ attn_sm100_kernel(const __grid_constant__ CUtensorMap tmQKV, const __grid_consta
     const uint32_t lanef = (uint32_t)(q * 32) << 16;
     int opn = 0;
     int tr_n = (warp == 4 && lane == 0) ? 0 : 1 << 20;
+    const unsigned long long dseed = DROP ? p.seed + (p.seed_dev != nullptr ? *p.seed_dev : 0ull) : 0ull;
+    const uint32_t thr16 = DROP ? (uint32_t)fminf(p.dropout_p * 65536.0f, 65535.0f) : 0u;
+    const float inv_keep = DROP ? 1.0f / (1.0f - p.dropout_p) : 1.0f;
+    // keep decisions of elements 2i, 2i+1 (i = 0..3) of an 8-key group from one Philox call
+    auto keep2 = [&](const uint4& rb, int i, bool& k0, bool& k1) {
+      const uint32_t w = i == 0 ? rb.x : (i == 1 ? rb.y : (i == 2 ? rb.z : rb.w));
+      k0 = (w & 0xffffu) >= thr16;
+      k1 = (w >> 16) >= thr16;
+    };
     // deferred epilogue state (F / BQ): the accumulator of tile `pend_nt` is drained while the next tile is in flight
     bool pend = false;
     int pend_nt = 0, pend_item = 0, pend_tile = 0;
@@ -512,9 +530,30 @@ attn_sm100_kernel(const __grid_constant__ CUtensorMap tmQKV, const __grid_consta
               VB_TR(1, 4000 + n);
             }
             // ---- exp pass: P for my 64 columns ----
+            const unsigned long long rowctr = DROP ? ((unsigned long long)(bh * S + tile * 128 + row) << 6) + (unsigned)((b * 128 + g * 64) >> 3) : 0ull;
             auto pexp = [&](const uint32_t (&r)[32], uint32_t mw, int c) {
               uint32_t pk[16];
-              if (warp_active && mw == 0xffffffffu) {
+              if (DROP) {
+                if (warp_active && mw != 0u) {
+#pragma unroll
+                  for (int j = 0; j < 4; ++j) {
+                    const uint4 rb = Philox(dseed)(rowctr + (unsigned)(c * 4 + j), p.site);
+#pragma unroll
+                    for (int e = 0; e < 4; ++e) {
+                      const int i = 4 * j + e;
+                      const float p0 = ((mw >> (2 * i)) & 1u) ? fast_exp2(fmaf(__uint_as_float(r[2 * i]), p.scale_log2, -msc)) : 0.f;
+                      const float p1 = ((mw >> (2 * i + 1)) & 1u) ? fast_exp2(fmaf(__uint_as_float(r[2 * i + 1]), p.scale_log2, -msc)) : 0.f;
+                      l += p0 + p1;
+                      bool k0, k1;
+                      keep2(rb, e, k0, k1);
+                      pk[i] = pack_bf16x2(k0 ? p0 * inv_keep : 0.f, k1 ? p1 * inv_keep : 0.f);
+                    }
+                  }
+                } else {
+#pragma unroll
+                  for (int i = 0; i < 16; ++i) pk[i] = 0u;
+                }
+              } else if (warp_active && mw == 0xffffffffu) {
                 float l0 = 0.f, l1 = 0.f;
 #pragma unroll
                 for (int i = 0; i < 16; ++i) {
@@ -583,7 +622,25 @@ attn_sm100_kernel(const __grid_constant__ CUtensorMap tmQKV, const __grid_consta
                 if (lane == 0) { mbar_arrive(bar(bSE + sl)); mbar_arrive(bar(bDPE)); }
               }
               uint32_t pp[16];
-              if (warp_active && mw != 0u) {
+              if (DROP && warp_active && mw != 0u) {
+                const int qg = MODE == MODE_BKV ? b * 128 + row : tile * 128 + row;
+                const unsigned long long rowctr = ((unsigned long long)(bh * S + qg) << 6) + (unsigned)((kb * 128 + g * 64 + c * 32) >> 3);
+#pragma unroll
+                for (int j = 0; j < 4; ++j) {
+                  const uint4 rb = Philox(dseed)(rowctr + (unsigned)j, p.site);
+#pragma unroll
+                  for (int e = 0; e < 4; ++e) {
+                    const int i = 4 * j + e;
+                    const float p0 = ((mw >> (2 * i)) & 1u) ? fast_exp2(fmaf(__uint_as_float(r[2 * i]), p.scale_log2, -lse2)) : 0.f;
+                    const float p1 = ((mw >> (2 * i + 1)) & 1u) ? fast_exp2(fmaf(__uint_as_float(r[2 * i + 1]), p.scale_log2, -lse2)) : 0.f;
+                    bool k0, k1;
+                    keep2(rb, e, k0, k1);
+                    const float d0 = k0 ? __uint_as_float(d[2 * i]) * inv_keep : 0.f, d1 = k1 ? __uint_as_float(d[2 * i + 1]) * inv_keep : 0.f;
+                    pk[i] = pack_bf16x2(p0 * (d0 - dl), p1 * (d1 - dl));
+                    if (MODE == MODE_BKV) pp[i] = pack_bf16x2(k0 ? p0 * inv_keep : 0.f, k1 ? p1 * inv_keep : 0.f);
+                  }
+                }
+              } else if (warp_active && mw != 0u) {
 #pragma unroll
                 for (int i = 0; i < 16; ++i) {
                   float p0 = fast_exp2(fmaf(__uint_as_float(r[2 * i]), p.scale_log2, -lse2));
@@ -710,31 +767,41 @@ int g_attn_sm100 = 1;  // 0: disabled (A/B switch through vault_attn_set_impl)
 // for the mma.sync kernels; at S <= 192 the whole-row kernels of attention_tc.cu -- 2 CTAs / SM, no key-block loop -- are still ahead:
 // 22 / 49 us against 28 / 56 us at S = 185).  g_attn_sm100 = 2 forces these kernels for every S <= 384 (tests).
 bool attn_sm100_ok(int S, float dropout_p) {
-  if (g_attn_sm100 == 0 || dropout_p != 0.f || S < 1 || S > 384) return false;
-  return g_attn_sm100 == 2 || S > 192;
+  if (g_attn_sm100 == 0 || S < 1 || S > 384) return false;
+  if (g_attn_sm100 == 2) return true;
+  // with probability dropout (the LM stack in training) the alternative is the mma.sync family: ahead only up to 64 keys
+  return dropout_p > 0.f ? S > 64 : S > 192;
 }
 void attn_sm100_enable(int on) { g_attn_sm100 = on; }
 
-int attn_fwd_sm100(const void* qkv, const uint8_t* key_mask, void* ctx, float* lse, int B, int S, int heads, cudaStream_t st) {
+int attn_fwd_sm100(const void* qkv, const uint8_t* key_mask, void* ctx, float* lse, int B, int S, int heads, float dropout_p, unsigned long long seed,
+                   const unsigned long long* seed_dev, unsigned site, cudaStream_t st) {
   AParams p{};
   fill(p, B, S, heads);
+  p.dropout_p = dropout_p; p.seed = seed; p.seed_dev = seed_dev; p.site = site;
   p.key_mask = key_mask; p.ctx = reinterpret_cast<bf16*>(ctx); p.lse = lse;
   const int H = heads * 64;
   CUtensorMap tm;
   int rc = encode_tmap_2d(&tm, CU_TENSOR_MAP_DATA_TYPE_BFLOAT16, 2, qkv, (uint64_t)3 * H, (uint64_t)B * S, (uint64_t)3 * H, 64, 64);
   if (rc) return rc;
-  if ((rc = set_smem_a(attn_sm100_kernel<MODE_F>))) return rc;
   const int grid = p.n_items < device_sm_count() ? p.n_items : device_sm_count();
   p.trace = trace_buf();
-  launch(attn_sm100_kernel<MODE_F>, dim3(grid), dim3(kThreadsA), (size_t)kSmemA, st, tm, tm, p);
+  if (dropout_p > 0.f) {
+    if ((rc = set_smem_a(attn_sm100_kernel<MODE_F, true>))) return rc;
+    launch(attn_sm100_kernel<MODE_F, true>, dim3(grid), dim3(kThreadsA), (size_t)kSmemA, st, tm, tm, p);
+  } else {
+    if ((rc = set_smem_a(attn_sm100_kernel<MODE_F, false>))) return rc;
+    launch(attn_sm100_kernel<MODE_F, false>, dim3(grid), dim3(kThreadsA), (size_t)kSmemA, st, tm, tm, p);
+  }
   trace_dump("F", p.trace);
   return check_launch("attn_sm100_kernel<F>");
 }
 
 int attn_bwd_sm100(const void* qkv, const uint8_t* key_mask, const void* ctx, const void* dctx, const float* lse, float* delta, void* dqkv, int B, int S,
-                   int heads, cudaStream_t st) {
+                   int heads, float dropout_p, unsigned long long seed, const unsigned long long* seed_dev, unsigned site, cudaStream_t st) {
   AParams p{};
   fill(p, B, S, heads);
+  p.dropout_p = dropout_p; p.seed = seed; p.seed_dev = seed_dev; p.site = site;
   p.key_mask = key_mask; p.lse = const_cast<float*>(lse); p.delta = delta; p.dqkv = reinterpret_cast<bf16*>(dqkv);
   const int H = heads * 64;
   CUtensorMap tmQ, tmD;
@@ -742,19 +809,22 @@ int attn_bwd_sm100(const void* qkv, const uint8_t* key_mask, const void* ctx, co
   if (rc) return rc;
   rc = encode_tmap_2d(&tmD, CU_TENSOR_MAP_DATA_TYPE_BFLOAT16, 2, dctx, (uint64_t)H, (uint64_t)B * S, (uint64_t)H, 64, 64);
   if (rc) return rc;
-  if ((rc = set_smem_a(attn_sm100_kernel<MODE_BQ>))) return rc;
-  if ((rc = set_smem_a(attn_sm100_kernel<MODE_BKV>))) return rc;
+  const bool drop = dropout_p > 0.f;
+  if ((rc = drop ? set_smem_a(attn_sm100_kernel<MODE_BQ, true>) : set_smem_a(attn_sm100_kernel<MODE_BQ, false>))) return rc;
+  if ((rc = drop ? set_smem_a(attn_sm100_kernel<MODE_BKV, true>) : set_smem_a(attn_sm100_kernel<MODE_BKV, false>))) return rc;
   const long long total = (long long)B * S * heads * 8;
   launch(attn_delta_kernel, dim3((unsigned)((total + 255) / 256)), dim3(256), 0, st, reinterpret_cast<const bf16*>(ctx), reinterpret_cast<const bf16*>(dctx), delta,
          B, S, heads);
   if ((rc = check_launch("attn_delta_kernel"))) return rc;
   const int grid = p.n_items < device_sm_count() ? p.n_items : device_sm_count();
   p.trace = trace_buf();
-  launch(attn_sm100_kernel<MODE_BQ>, dim3(grid), dim3(kThreadsA), (size_t)kSmemA, st, tmQ, tmD, p);
+  if (drop) launch(attn_sm100_kernel<MODE_BQ, true>, dim3(grid), dim3(kThreadsA), (size_t)kSmemA, st, tmQ, tmD, p);
+  else launch(attn_sm100_kernel<MODE_BQ, false>, dim3(grid), dim3(kThreadsA), (size_t)kSmemA, st, tmQ, tmD, p);
   trace_dump("BQ", p.trace);
   if ((rc = check_launch("attn_sm100_kernel<BQ>"))) return rc;
   p.trace = trace_buf();
-  launch(attn_sm100_kernel<MODE_BKV>, dim3(grid), dim3(kThreadsA), (size_t)kSmemA, st, tmQ, tmD, p);
+  if (drop) launch(attn_sm100_kernel<MODE_BKV, true>, dim3(grid), dim3(kThreadsA), (size_t)kSmemA, st, tmQ, tmD, p);
+  else launch(attn_sm100_kernel<MODE_BKV, false>, dim3(grid), dim3(kThreadsA), (size_t)kSmemA, st, tmQ, tmD, p);
   trace_dump("BKV", p.trace);
   return check_launch("attn_sm100_kernel<BKV>");
 }

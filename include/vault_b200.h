@@ -158,7 +158,8 @@ int vault_attn_bwd(const void* qkv, const uint8_t* key_mask, const void* ctx, co
  * keys with probability dropout; whole-row tcgen05 kernels for dropout-free calls with 65..192 keys; mma.sync kernels otherwise),
  * 1 = mma.sync kernels only,
  * 2 = whole-row tcgen05 kernels wherever their shape limits allow, 3 = pipelined tcgen05 kernels for every dropout-free call with
- * <= 384 keys.  Process-wide; meant for tests and A/B measurements. */
+ * <= 384 keys, 4 = as 3 with the alternative forward that gives each softmax warpgroup its own tile (measured slower, see
+ * attention_sm100.cu).  Process-wide; meant for tests and A/B measurements. */
 int vault_attn_set_impl(int32_t impl);
 
 /* ------------------------------------------------------------------------------------------------------------------

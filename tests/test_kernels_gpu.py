@@ -211,9 +211,11 @@ def test_attention_fwd_bwd(dev, B, S, heads):
 
 
 @pytest.mark.parametrize("B,S,heads,tc_impl", [(3, 185, 12, 0), (2, 100, 2, 0), (2, 192, 2, 0), (1, 241, 2, 0), (2, 369, 12, 0),
-                                               (1, 17, 2, 3), (2, 40, 12, 3), (2, 128, 2, 3), (3, 185, 12, 3), (2, 256, 2, 3), (25, 128, 12, 3)])
+                                               (1, 17, 2, 3), (2, 40, 12, 3), (2, 128, 2, 3), (3, 185, 12, 3), (2, 256, 2, 3), (25, 128, 12, 3),
+                                               (2, 369, 12, 4), (27, 128, 12, 4), (13, 300, 12, 4), (3, 185, 2, 4)])
 def test_attention_tcgen05_matches_mma_sync(dev, B, S, heads, tc_impl):
-    """The tensor-memory kernels (attention_tc.cu, attention_sm100.cu; tc_impl 3 forces the pipelined kernels at every length) and the
+    """The tensor-memory kernels (attention_tc.cu, attention_sm100.cu; tc_impl 3 forces the pipelined kernels at every length, 4 additionally
+    its one-tile-per-warpgroup forward; the multi-item cases put several (sample, head) items on one persistent CTA) and the
     mma.sync kernels implement the same contract: same LSE convention (either forward feeds either backward), outputs equal to bf16
     rounding, every output row written, nothing written past a sample's rows."""
     from vault_b200 import _abi

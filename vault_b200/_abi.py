@@ -118,7 +118,8 @@ ATTN_IMPL = 0  # mirror of vault_attn_set_impl (set through set_attn_impl below)
 
 
 def set_attn_impl(impl: int) -> None:
-    """0 = automatic (tcgen05 attention where the shape allows), 1 = mma.sync kernels only."""
+    """0 = automatic routing, 1 = mma.sync kernels only, 2 = whole-row tcgen05 kernels where allowed, 3 = pipelined tcgen05 kernels for every
+    S <= 384, 4 = 3 with the one-tile-per-warpgroup forward (include/vault_b200.h)."""
     global ATTN_IMPL
     call("vault_attn_set_impl", int(impl))
     ATTN_IMPL = int(impl)
@@ -148,7 +149,7 @@ class CountingLib:
             n = KERNELS_PER_CALL.get(name, 1)
             if name == "vault_attn_bwd" and ATTN_IMPL != 1 and float(args[10]) == 0.0 and 64 < int(args[8]) <= 192:
                 n = 1  # fused tcgen05 backward (attention_tc.cu) instead of the dQ + dK/dV pair
-            elif name == "vault_attn_bwd" and ATTN_IMPL in (0, 3) and ((float(args[10]) == 0.0 and 192 < int(args[8]) <= 384)
+            elif name == "vault_attn_bwd" and ATTN_IMPL in (0, 3, 4) and ((float(args[10]) == 0.0 and 192 < int(args[8]) <= 384)
                                                                         or (float(args[10]) > 0.0 and 64 < int(args[8]) <= 384)):
                 n = 3  # delta + dQ + dK/dV kernels of attention_sm100.cu
             self.launches += n

@@ -507,6 +507,7 @@ void attn_set_impl(int impl);
 // pipelined tcgen05 kernels of attention_sm100.cu (S <= 384, no dropout)
 bool attn_sm100_ok(int S, float dropout_p);
 void attn_sm100_enable(int on);
+void attn_sm100_fwd_pp(int on);
 int attn_fwd_sm100(const void* qkv, const uint8_t* key_mask, void* ctx, float* lse, int B, int S, int heads, float dropout_p, unsigned long long seed,
                    const unsigned long long* seed_dev, unsigned site, cudaStream_t st);
 int attn_bwd_sm100(const void* qkv, const uint8_t* key_mask, const void* ctx, const void* dctx, const float* lse, float* delta, void* dqkv, int B, int S,
@@ -516,10 +517,11 @@ int attn_bwd_sm100(const void* qkv, const uint8_t* key_mask, const void* ctx, co
 
 extern "C" int vault_attn_set_impl(int32_t impl) {
   using namespace vb;
-  VB_REQUIRE(impl >= 0 && impl <= 3, "vault_attn_set_impl: impl=%d (0 auto, 1 mma.sync only, 2 whole-row tcgen05 kernels where the shape allows, "
-             "3 pipelined tcgen05 kernels for every S <= 384)", impl);
-  attn_set_impl(impl == 3 ? 0 : impl);
-  attn_sm100_enable(impl == 0 ? 1 : (impl == 3 ? 2 : 0));
+  VB_REQUIRE(impl >= 0 && impl <= 4, "vault_attn_set_impl: impl=%d (0 auto, 1 mma.sync only, 2 whole-row tcgen05 kernels where the shape allows, "
+             "3 pipelined tcgen05 kernels for every S <= 384, 4 = 3 with the one-tile-per-warpgroup forward)", impl);
+  attn_set_impl(impl >= 3 ? 0 : impl);
+  attn_sm100_enable(impl == 0 ? 1 : (impl >= 3 ? 2 : 0));
+  attn_sm100_fwd_pp(impl == 4 ? 1 : 0);
   return VAULT_OK;
 }
 

@@ -694,6 +694,410 @@ attn_sm100_kernel(const __grid_constant__ CUtensorMap tmQKV, const __grid_consta
   }
 }
 
+// ============================================ forward, one tile per warpgroup ("ping-pong") ============================================
+// Same resident-block ring, block stream and two-pass softmax as MODE_F above, but the two softmax warpgroups do not share a tile: the
+// CTA's tile stream alternates between them (tile nt -> warpgroup nt & 1), each with its own Q buffer, TMEM columns (S 128 + O 2 x 64),
+// P staging (two 64-key halves) and issuer thread (warp 1 for warpgroup 0, warp 3 for warpgroup 1: score MMA of block n+1, then the two
+// half-block output MMAs of block n).  A thread owns a whole query row: no cross-warpgroup exchange and no CTA-wide barrier inside an
+// item, and -- the point -- the warpgroups drift apart, so one's exp pass (MUFU) runs under the other's TMEM loads, row-max passes,
+// mbarrier waits and epilogue instead of all eight warps queueing for the same unit at the same time.
+constexpr int pR1F = 0, pR1E = 3, pR2F = 6, pR2E = 9, pTF = 12, pTE = 14, pSF = 16, pSE = 18, pOPF = 20, pOPE = 24, pOF = 28, pOE = 32, kNumBarsPP = 36;
+
+template <bool DROP>
+__global__ void __launch_bounds__(kThreadsA, 1) attn_fwd_pp_kernel(const __grid_constant__ CUtensorMap tmQKV, const AParams p) {
+  extern __shared__ uint8_t smem_raw[];
+  const uint32_t raw = smem_u32(smem_raw);
+  const uint32_t base = (raw + 1023u) & ~1023u;
+  uint8_t* gen = smem_raw + (base - raw);
+  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+  const int S = p.S, H = p.heads * 64, nblk = p.nblk;
+  const int ntiles = nblk, L = 2 * nblk - 1;
+  const uint32_t bars = base + oMisc;
+  auto bar = [&](int i) { return bars + 8u * (uint32_t)i; };
+  const uint32_t tmem_slot = bars + 8u * kNumBarsPP;
+  volatile uint32_t* tmem_slot_gen = reinterpret_cast<volatile uint32_t*>(gen + oMisc + 8 * kNumBarsPP);
+  uint32_t* mws = reinterpret_cast<uint32_t*>(gen + oMisc + 512);  // [2 wg][2 parity][12] key-validity words
+
+  if (warp == 0 && lane == 0) tma_prefetch_desc(&tmQKV);
+  if (warp == 1 && lane == 0) {
+    for (int i = 0; i < 3; ++i) {
+      mbar_init(bar(pR1F + i), 1); mbar_init(bar(pR1E + i), 2);  // K_b / V_b: released by both issuer threads
+      mbar_init(bar(pR2F + i), 1); mbar_init(bar(pR2E + i), 2);
+    }
+    for (int i = 0; i < 2; ++i) {
+      mbar_init(bar(pTF + i), 1); mbar_init(bar(pTE + i), 1);
+      mbar_init(bar(pSF + i), 1); mbar_init(bar(pSE + i), 4);
+    }
+    for (int i = 0; i < 4; ++i) {
+      mbar_init(bar(pOPF + i), 4); mbar_init(bar(pOPE + i), 1);
+      mbar_init(bar(pOF + i), 1); mbar_init(bar(pOE + i), 4);
+    }
+    mbar_fence_init();
+  }
+  if (warp == 2) tmem_alloc(tmem_slot, 512u);
+  tc_fence_before();
+  __syncthreads();
+  tc_fence_after();
+  const uint32_t tmem = *tmem_slot_gen;
+  pdl_enter();
+
+  auto blk_of = [&](int j, int nt) {
+    const int i = j < nblk ? j : 2 * nblk - 2 - j;
+    return (nt & 1) ? nblk - 1 - i : i;
+  };
+  auto kind_of = [&](int j) { return j < nblk - 1 ? 0 : (j == nblk - 1 ? 1 : 2); };
+  auto rslot = [&](int it, int b) { return (it * nblk + b) % 3; };
+  auto rpar = [&](int it, int b) { return (uint32_t)(((it * nblk + b) / 3) & 1); };
+  const int my_items = ((int)p.n_items - (int)blockIdx.x + (int)gridDim.x - 1) / (int)gridDim.x;
+  const int n_tiles_total = my_items * ntiles;
+
+  if (warp == 0) {
+    // =========================================== TMA producer ===========================================
+    if (lane == 0) {
+      // Issue order inside an item: Q tiles 0 and 1 (one per warpgroup), the K blocks, the V blocks, then the remaining Q tiles.  An
+      // issuer thread runs its score MMAs one block AHEAD of its output MMAs, and the V slots of the previous item are only released by
+      // those output MMAs: everything a look-ahead score block needs (its Q tile, the K blocks) must therefore sit in front of the V
+      // loads in this in-order queue.
+      for (int it = 0; it < my_items; ++it) {
+        const int item = (int)blockIdx.x + it * (int)gridDim.x;
+        const int b_ = item / p.heads, h_ = item % p.heads;
+        const int row0 = b_ * S;
+        auto load_t = [&](int tile) {
+          const int nt = it * ntiles + tile, w = nt & 1;
+          mbar_wait(bar(pTE + w), (uint32_t)((nt >> 1) & 1) ^ 1u);
+          const uint32_t fb = bar(pTF + w);
+          mbar_expect_tx(fb, kBlk);
+          const uint32_t d = base + oT + (uint32_t)w * kBlk;
+          tma_load_2d(d, &tmQKV, fb, h_ * 64, row0 + tile * 128);
+          tma_load_2d(d + 8192u, &tmQKV, fb, h_ * 64, row0 + tile * 128 + 64);
+        };
+        auto load_r = [&](int which, int bb) {
+          const int sl = rslot(it, bb);
+          mbar_wait(bar((which ? pR2E : pR1E) + sl), rpar(it, bb) ^ 1u);
+          const uint32_t f = bar((which ? pR2F : pR1F) + sl);
+          mbar_expect_tx(f, kBlk);
+          const uint32_t dd = base + (which ? oR2 : oR1) + (uint32_t)sl * kBlk;
+          const int c = which ? 2 * H + h_ * 64 : H + h_ * 64;
+          tma_load_2d(dd, &tmQKV, f, c, row0 + bb * 128);
+          tma_load_2d(dd + 8192u, &tmQKV, f, c, row0 + bb * 128 + 64);
+        };
+        load_t(0);
+        if (ntiles > 1) load_t(1);
+        const int dir0 = (it * ntiles) & 1;
+        for (int i = 0; i < nblk; ++i) load_r(0, dir0 ? nblk - 1 - i : i);
+        for (int i = 0; i < nblk; ++i) load_r(1, dir0 ? i : nblk - 1 - i);
+        for (int tile = 2; tile < ntiles; ++tile) load_t(tile);
+      }
+    }
+  } else if (warp == 1 || warp == 3) {
+    // =========================================== MMA issuer of warpgroup w (one thread) ===========================================
+    if (lane == 0) {
+      const int w = warp == 1 ? 0 : 1;
+      const uint32_t id_s = umma_idesc(1u, 128u, 128u, 0u, 0u), id_o = umma_idesc(1u, 128u, 64u, 0u, 1u);
+      const uint32_t tS = tmem + (uint32_t)(w * 256);
+      const uint32_t sQ = base + oT + (uint32_t)w * kBlk;
+      int nb = 0, ne = 0;  // score blocks / exp-kind blocks of this warpgroup so far
+      int tr_n = w == 0 ? 0 : 1 << 20;
+      auto issue_score = [&](int nt, int j, uint32_t& seen) {
+        const int it = nt / ntiles, k = nt >> 1;
+        const int b = blk_of(j, nt), kind = kind_of(j), rs = rslot(it, b);
+        VB_TR(0, 100 + nb);
+        if (j == 0) mbar_wait(bar(pTF + w), (uint32_t)(k & 1));
+        if (!(seen & (1u << b))) { mbar_wait(bar(pR1F + rs), rpar(it, b)); seen |= 1u << b; }
+        mbar_wait(bar(pSE + w), (uint32_t)(nb & 1) ^ 1u);
+        tc_fence_after();
+        const uint32_t sK = base + oR1 + (uint32_t)rs * kBlk;
+#pragma unroll
+        for (int kk = 0; kk < 4; ++kk)
+          tc_mma_f16(tS, umma_desc_sw128(sQ + kk * 32u, 16u, 1024u), umma_desc_sw128(sK + kk * 32u, 16u, 1024u), id_s, kk > 0 ? 1u : 0u);
+        tc_commit(bar(pSF + w));
+        VB_TR(0, 200 + nb);
+        if (j == L - 1) tc_commit(bar(pTE + w));
+        // this warpgroup's last score-side use of K_b in the item: the exp-kind visit in its last tile of the item
+        const bool my_last_tile = (nt + 2) / ntiles != it;
+        if (my_last_tile && kind != 0) tc_commit(bar(pR1E + rs));
+        ++nb;
+      };
+      int cur_it = -1;
+      uint32_t seen_s = 0, seen_o = 0;
+      int seen_s_it = -1;
+      // cursor of the score block issued ahead
+      int s_nt = w, s_j = 0;
+      auto score_next = [&]() {
+        if (s_nt >= n_tiles_total) return;
+        const int it = s_nt / ntiles;
+        if (it != seen_s_it) {
+          // items this warpgroup never touches (single-tile items go to the warpgroups alternately): it still owes their K / V slots
+          // one arrival each, or the producer would wait for it forever.  Through tcgen05.commit, not a plain arrive: the arrival
+          // must stay ordered behind this thread's earlier commits on the same slot (a plain arrive would overtake a commit whose
+          // MMAs are still running and complete the slot's PREVIOUS phase too early)
+          for (int skipped = seen_s_it + 1; skipped < it; ++skipped)
+            for (int b = 0; b < nblk; ++b) { tc_commit(bar(pR1E + rslot(skipped, b))); tc_commit(bar(pR2E + rslot(skipped, b))); }
+          seen_s_it = it; seen_s = 0;
+        }
+        issue_score(s_nt, s_j, seen_s);
+        if (++s_j == L) { s_j = 0; s_nt += 2; }
+      };
+      score_next();
+      for (int nt = w; nt < n_tiles_total; nt += 2) {
+        const int it = nt / ntiles, k = nt >> 1;
+        if (it != cur_it) { cur_it = it; seen_o = 0; }
+        const bool my_last_tile = (nt + 2) / ntiles != it;
+        const uint32_t acc = tS + 128u + (uint32_t)((k & 1) * 64);
+        for (int j = 0; j < L; ++j) {
+          score_next();  // block n+1 (its TMEM buffer is free once the warps hold block n in registers)
+          const int b = blk_of(j, nt), kind = kind_of(j), rs = rslot(it, b);
+          if (kind == 0) continue;
+          if (kind == 1) mbar_wait(bar(pOE + w * 2 + (k & 1)), (uint32_t)((k >> 1) & 1) ^ 1u);
+          if (!(seen_o & (1u << b))) { mbar_wait(bar(pR2F + rs), rpar(it, b)); seen_o |= 1u << b; }
+          const uint32_t sV = base + oR2 + (uint32_t)rs * kBlk;
+          // the max+exp block delivers its second half first (still in registers after the max pass), the exp blocks the first
+#pragma unroll
+          for (int hh = 0; hh < 2; ++hh) {
+            const int half = kind == 1 ? 1 - hh : hh;
+            VB_TR(0, 500 + ne * 2 + hh);
+            mbar_wait(bar(pOPF + w * 2 + half), (uint32_t)(ne & 1));
+            tc_fence_after();
+            VB_TR(0, 600 + ne * 2 + hh);
+            const uint32_t sP = base + oOP + (uint32_t)(w * 2 + half) * kBlk;
+#pragma unroll
+            for (int ks = 0; ks < 4; ++ks)
+              tc_mma_f16(acc, umma_desc_sw128(sP + ks * 32u, 16u, 1024u), umma_desc_sw128(sV + (uint32_t)half * 8192u + ks * 2048u, 8192u, 1024u), id_o,
+                         (kind == 1 && hh == 0 && ks == 0) ? 0u : 1u);
+            tc_commit(bar(pOPE + w * 2 + half));
+          }
+          if (my_last_tile) tc_commit(bar(pR2E + rs));
+          if (j == L - 1) tc_commit(bar(pOF + w * 2 + (k & 1)));
+          ++ne;
+        }
+      }
+      // trailing items of the CTA this warpgroup never touched
+      for (int skipped = (seen_s_it < 0 ? 0 : seen_s_it + 1); skipped < my_items; ++skipped)
+        for (int b = 0; b < nblk; ++b) { tc_commit(bar(pR1E + rslot(skipped, b))); tc_commit(bar(pR2E + rslot(skipped, b))); }
+    }
+  } else if (warp >= 4) {
+    // =========================================== softmax / epilogue warps ===========================================
+    const int ew = warp - 4, w = ew >> 2, q = warp & 3;
+    const int row = q * 32 + lane;
+    const uint32_t lanef = (uint32_t)(q * 32) << 16;
+    const uint32_t tS = tmem + lanef + (uint32_t)(w * 256);
+    const uint32_t stage = base + oStage + (uint32_t)ew * 2048u;
+    const unsigned long long dseed = DROP ? p.seed + (p.seed_dev != nullptr ? *p.seed_dev : 0ull) : 0ull;
+    const uint32_t thr16 = DROP ? (uint32_t)fminf(p.dropout_p * 65536.0f, 65535.0f) : 0u;
+    const float inv_keep = DROP ? 1.0f / (1.0f - p.dropout_p) : 1.0f;
+    uint32_t* mw_wg = mws + w * 24;
+    int nb = 0, ne = 0;
+    int tr_n = (warp == 4 && lane == 0) ? 0 : 1 << 20;
+    bool pend = false;
+    int pend_k = 0, pend_item = 0, pend_tile = 0;
+    float pend_msc = 0.f, pend_l = 0.f;
+
+    auto epilogue = [&](int k, int item, int tile, float msc, float l) {
+      const int b_ = item / p.heads, h_ = item % p.heads;
+      VB_TR(1, 8000 + k);
+      mbar_wait(bar(pOF + w * 2 + (k & 1)), (uint32_t)((k >> 1) & 1));
+      tc_fence_after();
+      VB_TR(1, 8500 + k);
+      uint32_t ra[32], rb[32];
+      tmem_ld32(tS + 128u + (uint32_t)((k & 1) * 64), ra);
+      tmem_ld32(tS + 128u + (uint32_t)((k & 1) * 64 + 32), rb);
+      tmem_ld_wait();
+      tc_fence_before();
+      __syncwarp();
+      if (lane == 0) mbar_arrive(bar(pOE + w * 2 + (k & 1)));
+      const float mul = l > 0.f ? 1.f / l : 0.f;
+      const int r0g = tile * 128 + q * 32;
+      bf16* g0 = p.ctx + ((long long)b_ * S + r0g) * H + h_ * 64;
+      store_rows32_staged(ra, mul, stage, g0, (long long)H, S - r0g, lane);
+      store_rows32_staged(rb, mul, stage, g0 + 32, (long long)H, S - r0g, lane);
+      if (r0g + lane < S && p.lse != nullptr) p.lse[((long long)b_ * p.heads + h_) * S + r0g + lane] = msc * kLn2A + __logf(fmaxf(l, 1e-30f));
+      VB_TR(1, 9000 + k);
+    };
+    auto mask_bit = [&](int item, int wd) -> bool {
+      if (item >= p.n_items || wd >= nblk * 4) return false;
+      const int key = 32 * wd + lane;
+      return key < S && p.key_mask[(long long)(item / p.heads) * S + key] != 0;
+    };
+
+    int cur_it = -1, ci = 0;  // ci: items this warpgroup has started (double-buffers its mask words)
+    for (int nt = w, k = 0; nt < n_tiles_total; nt += 2, ++k) {
+      const int it = nt / ntiles, tile = nt % ntiles;
+      const int item = (int)blockIdx.x + it * (int)gridDim.x;
+      const long long bh = item;  // = b * heads + h
+      if (it != cur_it) {
+        // key-validity words of the item, per warpgroup: warp q computes words q, q+4, q+8 (a 128-thread barrier publishes them; a warp is
+        // at most one such barrier ahead of its neighbours, hence two buffers)
+        cur_it = it;
+        ++ci;
+#pragma unroll
+        for (int i = 0; i < 3; ++i) {
+          const uint32_t wv = __ballot_sync(0xffffffffu, mask_bit(item, q + 4 * i));
+          if (lane == 0) mw_wg[(ci & 1) * 12 + q + 4 * i] = wv;
+        }
+        asm volatile("bar.sync %0, 128;" ::"r"(2 + w) : "memory");
+      }
+      const uint32_t* mw_item = mw_wg + (ci & 1) * 12;
+      const bool warp_active = tile * 128 + q * 32 < S;
+      float m_run = -INFINITY, msc = 0.f, l = 0.f;
+      const unsigned long long rowbase = DROP ? ((unsigned long long)(bh * S + tile * 128 + row) << 6) : 0ull;
+
+      auto rmax = [&](const uint32_t (&r)[32], uint32_t mw) {
+        if (mw == 0xffffffffu) {
+          float m0 = __uint_as_float(r[0]), m1 = __uint_as_float(r[1]), m2 = __uint_as_float(r[2]), m3 = __uint_as_float(r[3]);
+#pragma unroll
+          for (int i = 4; i < 32; i += 4) {
+            m0 = fmaxf(m0, __uint_as_float(r[i])); m1 = fmaxf(m1, __uint_as_float(r[i + 1]));
+            m2 = fmaxf(m2, __uint_as_float(r[i + 2])); m3 = fmaxf(m3, __uint_as_float(r[i + 3]));
+          }
+          m_run = fmaxf(m_run, fmaxf(fmaxf(m0, m1), fmaxf(m2, m3)));
+        } else if (mw != 0u) {
+          float m0 = -INFINITY, m1 = -INFINITY;
+#pragma unroll
+          for (int i = 0; i < 32; i += 2) {
+            m0 = fmaxf(m0, ((mw >> i) & 1u) ? __uint_as_float(r[i]) : -INFINITY);
+            m1 = fmaxf(m1, ((mw >> (i + 1)) & 1u) ? __uint_as_float(r[i + 1]) : -INFINITY);
+          }
+          m_run = fmaxf(m_run, fmaxf(m0, m1));
+        }
+      };
+      // exp of 32 columns (chunk c of half `half` of block b) -> bf16 P in the half's staging chunk
+      auto pexp = [&](const uint32_t (&r)[32], uint32_t mw, int b, int half, int c) {
+        uint32_t pk[16];
+        const uint32_t sP = base + oOP + (uint32_t)(w * 2 + half) * kBlk;
+        if (DROP) {
+          if (warp_active && mw != 0u) {
+            const unsigned long long ctr = rowbase + (unsigned)((b * 128 + half * 64 + c * 32) >> 3);
+#pragma unroll
+            for (int jj = 0; jj < 4; ++jj) {
+              const uint4 rb = Philox(dseed)(ctr + (unsigned)jj, p.site);
+#pragma unroll
+              for (int e = 0; e < 4; ++e) {
+                const int i = 4 * jj + e;
+                const float p0 = ((mw >> (2 * i)) & 1u) ? fast_exp2(fmaf(__uint_as_float(r[2 * i]), p.scale_log2, -msc)) : 0.f;
+                const float p1 = ((mw >> (2 * i + 1)) & 1u) ? fast_exp2(fmaf(__uint_as_float(r[2 * i + 1]), p.scale_log2, -msc)) : 0.f;
+                l += p0 + p1;
+                const uint32_t wd = e == 0 ? rb.x : (e == 1 ? rb.y : (e == 2 ? rb.z : rb.w));
+                pk[i] = pack_bf16x2((wd & 0xffffu) >= thr16 ? p0 * inv_keep : 0.f, (wd >> 16) >= thr16 ? p1 * inv_keep : 0.f);
+              }
+            }
+          } else {
+#pragma unroll
+            for (int i = 0; i < 16; ++i) pk[i] = 0u;
+          }
+        } else if (warp_active && mw == 0xffffffffu) {
+          float l0 = 0.f, l1 = 0.f;
+#pragma unroll
+          for (int i = 0; i < 16; ++i) {
+            const float p0 = fast_exp2(fmaf(__uint_as_float(r[2 * i]), p.scale_log2, -msc));
+            const float p1 = fast_exp2(fmaf(__uint_as_float(r[2 * i + 1]), p.scale_log2, -msc));
+            l0 += p0; l1 += p1;
+            pk[i] = pack_bf16x2(p0, p1);
+          }
+          l += l0 + l1;
+        } else if (warp_active && mw != 0u) {
+#pragma unroll
+          for (int i = 0; i < 16; ++i) {
+            const float p0 = ((mw >> (2 * i)) & 1u) ? fast_exp2(fmaf(__uint_as_float(r[2 * i]), p.scale_log2, -msc)) : 0.f;
+            const float p1 = ((mw >> (2 * i + 1)) & 1u) ? fast_exp2(fmaf(__uint_as_float(r[2 * i + 1]), p.scale_log2, -msc)) : 0.f;
+            l += p0 + p1;
+            pk[i] = pack_bf16x2(p0, p1);
+          }
+        } else {
+#pragma unroll
+          for (int i = 0; i < 16; ++i) pk[i] = 0u;
+        }
+        store_row32a(sP, row, c, pk);
+      };
+      auto release_s = [&]() {
+        tc_fence_before();
+        __syncwarp();
+        if (lane == 0) mbar_arrive(bar(pSE + w));
+      };
+      auto publish_half = [&](int half) {
+        fence_async_smem_a();
+        __syncwarp();
+        if (lane == 0) mbar_arrive(bar(pOPF + w * 2 + half));
+      };
+
+      for (int j = 0; j < L; ++j, ++nb) {
+        const int b = blk_of(j, nt), kind = kind_of(j);
+        VB_TR(1, 1000 + nb);
+        mbar_wait(bar(pSF + w), (uint32_t)(nb & 1));
+        tc_fence_after();
+        VB_TR(1, 2000 + nb);
+        uint32_t r0[32], r1[32];
+        if (kind == 0) {
+          // ---- row maximum only: both halves through the same 64 registers ----
+#pragma unroll
+          for (int half = 0; half < 2; ++half) {
+            tmem_ld32(tS + (uint32_t)(half * 64), r0);
+            tmem_ld32(tS + (uint32_t)(half * 64 + 32), r1);
+            tmem_ld_wait();
+            if (half == 1) release_s();
+            if (warp_active) { rmax(r0, mw_item[b * 4 + half * 2]); rmax(r1, mw_item[b * 4 + half * 2 + 1]); }
+          }
+        } else if (kind == 1) {
+          // ---- max over the whole row, then exp: second half straight from the registers of the max pass, first half re-read ----
+          tmem_ld32(tS, r0);
+          tmem_ld32(tS + 32u, r1);
+          tmem_ld_wait();
+          if (warp_active) { rmax(r0, mw_item[b * 4]); rmax(r1, mw_item[b * 4 + 1]); }
+          tmem_ld32(tS + 64u, r0);
+          tmem_ld32(tS + 96u, r1);
+          mbar_wait(bar(pOPE + w * 2 + 1), (uint32_t)(ne & 1) ^ 1u);
+          tmem_ld_wait();
+          if (warp_active) { rmax(r0, mw_item[b * 4 + 2]); rmax(r1, mw_item[b * 4 + 3]); }
+          msc = m_run == -INFINITY ? 0.f : m_run * p.scale_log2;
+          VB_TR(1, 4000 + nb);
+          pexp(r0, mw_item[b * 4 + 2], b, 1, 0);
+          pexp(r1, mw_item[b * 4 + 3], b, 1, 1);
+          publish_half(1);
+          VB_TR(1, 5000 + nb);
+          tmem_ld32(tS, r0);
+          tmem_ld32(tS + 32u, r1);
+          mbar_wait(bar(pOPE + w * 2 + 0), (uint32_t)(ne & 1) ^ 1u);
+          tmem_ld_wait();
+          release_s();
+          VB_TR(1, 6000 + nb);
+          pexp(r0, mw_item[b * 4], b, 0, 0);
+          pexp(r1, mw_item[b * 4 + 1], b, 0, 1);
+          publish_half(0);
+          ++ne;
+        } else {
+#pragma unroll
+          for (int half = 0; half < 2; ++half) {
+            tmem_ld32(tS + (uint32_t)(half * 64), r0);
+            tmem_ld32(tS + (uint32_t)(half * 64 + 32), r1);
+            mbar_wait(bar(pOPE + w * 2 + half), (uint32_t)(ne & 1) ^ 1u);
+            tmem_ld_wait();
+            if (half == 1) release_s();
+            VB_TR(1, 6000 + nb);
+            pexp(r0, mw_item[b * 4 + half * 2], b, half, 0);
+            pexp(r1, mw_item[b * 4 + half * 2 + 1], b, half, 1);
+            publish_half(half);
+          }
+          ++ne;
+        }
+        VB_TR(1, 7000 + nb);
+        if (pend && j == 0) {  // this warpgroup's previous tile: drained while the tensor pipe works on the next score block
+          epilogue(pend_k, pend_item, pend_tile, pend_msc, pend_l);
+          pend = false;
+        }
+      }
+      if (pend) epilogue(pend_k, pend_item, pend_tile, pend_msc, pend_l);  // (not reached: every tile drains its predecessor at j == 0)
+      pend = true; pend_k = k; pend_item = item; pend_tile = tile; pend_msc = msc; pend_l = l;
+    }
+    if (pend) epilogue(pend_k, pend_item, pend_tile, pend_msc, pend_l);
+  }
+
+  tc_fence_before();
+  __syncthreads();
+  if (warp == 2) {
+    tc_fence_after();
+    tmem_dealloc(tmem, 512u);
+  }
+}
+
 // delta[b,h,q] = sum_d dO[q,d] O[q,d]  (one 16-byte segment per lane, 8 lanes per (row, head))
 __global__ void __launch_bounds__(256) attn_delta_kernel(const bf16* __restrict__ ctx, const bf16* __restrict__ dctx, float* __restrict__ delta, int B, int S,
                                                          int heads) {
@@ -762,6 +1166,7 @@ int fill(AParams& p, int B, int S, int heads) {
 }  // namespace
 
 int g_attn_sm100 = 1;  // 0: disabled (A/B switch through vault_attn_set_impl)
+int g_attn_fwd_pp = 0;
 
 // Shapes served: no dropout, 193..384 keys (measured on B200, B = 32, 12 heads: S = 369 forward 56 us / backward 125 us against 75 / 313 us
 // for the mma.sync kernels; at S <= 192 the whole-row kernels of attention_tc.cu -- 2 CTAs / SM, no key-block loop -- are still ahead:
@@ -773,6 +1178,7 @@ bool attn_sm100_ok(int S, float dropout_p) {
   return dropout_p > 0.f ? S > 64 : S > 192;
 }
 void attn_sm100_enable(int on) { g_attn_sm100 = on; }
+void attn_sm100_fwd_pp(int on) { g_attn_fwd_pp = on; }
 
 int attn_fwd_sm100(const void* qkv, const uint8_t* key_mask, void* ctx, float* lse, int B, int S, int heads, float dropout_p, unsigned long long seed,
                    const unsigned long long* seed_dev, unsigned site, cudaStream_t st) {
@@ -786,7 +1192,20 @@ int attn_fwd_sm100(const void* qkv, const uint8_t* key_mask, void* ctx, float* l
   if (rc) return rc;
   const int grid = p.n_items < device_sm_count() ? p.n_items : device_sm_count();
   p.trace = trace_buf();
-  if (dropout_p > 0.f) {
+  // g_attn_fwd_pp (vault_attn_set_impl(4)): the forward with one tile per warpgroup instead of the shared-tile MODE_F.  Measured on B200
+  // (B = 32, 12 heads): S = 369 60.5 us against 56.0 us, S = 209 (B = 64) 49.1 against 53.4 us -- the warpgroups do drift apart as intended,
+  // but each now walks whole 128-column blocks alone behind a single score buffer (a row-max-only block waits ~300 cycles for the next
+  // score MMA), and because they finish an item at different times the next item's K / V blocks, released only when BOTH have retired
+  // their last MMA on a slot, arrive late: ~8 k idle cycles per item.  Kept as a tested alternative, not routed by default.
+  if (g_attn_fwd_pp) {
+    if (dropout_p > 0.f) {
+      if ((rc = set_smem_a(attn_fwd_pp_kernel<true>))) return rc;
+      launch(attn_fwd_pp_kernel<true>, dim3(grid), dim3(kThreadsA), (size_t)kSmemA, st, tm, p);
+    } else {
+      if ((rc = set_smem_a(attn_fwd_pp_kernel<false>))) return rc;
+      launch(attn_fwd_pp_kernel<false>, dim3(grid), dim3(kThreadsA), (size_t)kSmemA, st, tm, p);
+    }
+  } else if (dropout_p > 0.f) {
     if ((rc = set_smem_a(attn_sm100_kernel<MODE_F, true>))) return rc;
     launch(attn_sm100_kernel<MODE_F, true>, dim3(grid), dim3(kThreadsA), (size_t)kSmemA, st, tm, tm, p);
   } else {

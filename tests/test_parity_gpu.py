@@ -2,7 +2,11 @@
 reference fixtures, plus size-independent properties at the BASELINE batch sizes.
 
 Stated tolerance (bf16 tensor-core operands, fp32 accumulation / residual stream / statistics, 24 transformer layers):
-  pooler_output : per-row relative L2 <= 1e-2  and  max-abs / max|ref| <= 2e-2
+  pooler_output : per-row relative L2 <= 1e-2 (the north-star's "within 1e-2 relative of the reference"; measured 5.5e-3 at the base
+                  shapes)  and  max-abs / max|ref| <= 1.5e-2 -- the single worst ELEMENT of a 768-wide tanh output relative to the largest
+                  one; measured 0.9e-2 .. 1.1e-2 at the base shapes, 4e-4 at the tiny ones.  It cannot be brought under 1e-2 without
+                  leaving bf16: 24 layers of bf16-rounded GEMM operands put ~1e-2 on individual elements while the row as a whole (the
+                  relative-L2 figure, what the target sentence bounds) stays at half of that
   loss          : |d| <= 5e-3 ;  gradients: per-parameter cosine >= 0.99, global cosine >= 0.999
 """
 import pytest
@@ -46,7 +50,7 @@ def test_forward_vs_reference_fixture_and_oracle(name):
     assert tuple(lhs.shape) == g["lhs_shape"]  # same dynamic sequence length as the reference (max valid patches in the batch)
     ref = g["pooler_output"]  # REAL reference output
     assert ((pooled - ref).norm(dim=1) / ref.norm(dim=1)).max() <= 1e-2
-    assert (pooled - ref).abs().max() / ref.abs().max() <= 2e-2
+    assert (pooled - ref).abs().max() / ref.abs().max() <= 1.5e-2
     assert (lhs[:, 0] - g["lhs_cls"]).abs().max() <= 6e-2 and (lhs[:, T] - g["lhs_image_cls"]).abs().max() <= 6e-2
     with torch.no_grad():
         o = O.vault_forward(sd, d, use_vilt_position_embeddings=g["options"].get("use_vilt_pos", False), **{k: inp[k] for k in FWD})
@@ -255,4 +259,4 @@ def test_inference_config2_batch64_matches_oracle_rows():
         o = O.vault_forward(sd, d, **sub)
     got, ref = pooled[rows].float().cpu(), o["pooler_output"]
     assert ((got - ref).norm(dim=1) / ref.norm(dim=1)).max() <= 1e-2
-    assert (got - ref).abs().max() / ref.abs().max() <= 2e-2
+    assert (got - ref).abs().max() / ref.abs().max() <= 1.5e-2  # worst element (see the module docstring)

@@ -510,7 +510,7 @@ def main():
             "metric": METRIC, "value": value, "unit": "samples/s", "n_gpus": world, "steps": args.steps, "warmup": args.warmup,
             "ms_per_step": ms_dev / args.steps, "higher_is_better": True, "scaling": "weak", "vs_baseline": None, "dtype": "bf16", "data": "synthetic",
             "config": bench_config(args.workload, B, world),
-            "impl_config": dict(device="cuda", cuda_graph=not args.no_graph, comm_overlap=ts.overlap, grad_comm_dtype=("bf16" if ts.grad16 is not None else "fp32"),
+            "impl_config": dict(device="cuda", cuda_graph=not args.no_graph, comm_overlap=ts.overlap, grad_comm_dtype=ts.grad_comm, comm=("multimem" if ts.mc is not None else ("nccl" if world > 1 else "none")),
                                 gemm_ctas=ts.engine.gemm_max_ctas or ts.engine.sms),
             "e2e": dict(value=e2e, unit="samples/s", h2d_bytes_per_step=h2d, d2h_bytes_per_step=4, ms_per_step=ms_e2e / args.steps,
                         api="vault_b200.VaultTrainStep.step(pinned host batch) -> StepResult.loss()"),

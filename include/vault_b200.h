@@ -87,6 +87,9 @@ typedef struct vault_gemm_args {
                              counter) instead of round-robin, so SMs held by a concurrent kernel / collective do not stretch the launch.
                              One pair per launch that may run concurrently with another. */
   int32_t cluster;        /* CTA-pair operand multicast: 0/-1 off, 1 pair along M (B tile shared), 2 pair along N (A tile shared) */
+  float* a_colsum;        /* optional DEVICE fp32 [M], ACCUMULATED (caller zero-fills): a_colsum[m] += sum_k A[m,k].  a_mn = 1 and an fp32
+                             epilogue only: in a weight-gradient launch A = dy^T, so this is the bias gradient of the same nn.Linear
+                             (replaces a separate column-sum pass over dy); the sums are taken from the A tiles already in shared memory. */
 } vault_gemm_args;
 
 int vault_gemm_bf16(const vault_gemm_args* args, void* stream);
@@ -284,6 +287,24 @@ int vault_colsum_bf16(const void* x, int64_t ldx, float* out, int64_t rows, int3
 int vault_adamw_step(float* p, const void* g, int32_t grad_is_bf16, float* m, float* v, void* shadow_bf16, int64_t n, double lr,
                      double beta1, double beta2, double eps, double weight_decay, int32_t correct_bias, int32_t step,
                      float grad_scale, const float* sched_dev, void* stream);
+/* Data-parallel form of the step above as ONE kernel over NVSwitch multicast (replaces NCCL all-reduce + a full-range AdamW per gradient
+ * range; optimizer rule ref:vault/tmsc_utils/trainer.py:244-254, data parallelism SURVEY.md 8e).  The caller owns slice [0, n) of a
+ * finished gradient range (1/world of it, n % 8 == 0); every pointer is already offset to that slice:
+ *   g_mc      multicast address of the gradients, fp32 or (grad_is_bf16) a bf16 copy: multimem.ld_reduce returns the SUM over all ranks,
+ *             added in the switch with fp32 accumulation
+ *   p_local   this rank's fp32 masters (read; written too when p_mc is NULL)
+ *   p_mc      multicast address of the masters, or NULL: NULL = the masters are SHARDED (a rank's copy is current only for the slices it
+ *             owns; vault_mc_broadcast_f32 consolidates them), non-NULL = the new masters are stored to every replica
+ *   shadow_mc multicast address of the bf16 shadow: always stored to EVERY replica (the next forward reads it)
+ *   m, v      this rank's AdamW moments of the slice (only the owner of a slice ever touches them)
+ * The flat buffers must be symmetric memory mapped into one multicast object (torch.distributed._symmetric_memory).  Ordering across
+ * ranks is the caller's: a barrier before the launch (all ranks' gradients of the range are final) and one after the last launch of
+ * the step (all slices written everywhere).  `ctas` bounds the grid (the kernel is NVLink-latency bound; two CTAs fit on an SM). */
+int vault_mc_adamw_step(float* p_local, float* p_mc, const void* g_mc, int32_t grad_is_bf16, float* m, float* v, void* shadow_mc,
+                        int64_t n, double lr, double beta1, double beta2, double eps, double weight_decay, int32_t correct_bias,
+                        int32_t step, float grad_scale, const float* sched_dev, int32_t ctas, void* stream);
+/* src_local fp32 [n] -> the same range of every replica through its multicast address (n % 4 == 0) */
+int vault_mc_broadcast_f32(const float* src_local, float* dst_mc, int64_t n, int32_t ctas, void* stream);
 /* fp32 -> bf16 cast of a flat range (shadow refresh after an external optimizer touched the masters) */
 int vault_cast_f32_bf16(const float* src, void* dst_bf16, int64_t n, void* stream);
 

@@ -51,6 +51,26 @@ def test_gemm_layouts(dev, ops, M, N, K, a_mn, b_mn, bn):
     assert _rel(got, ref) < 1e-4
 
 
+@pytest.mark.parametrize("n_out,k_in,tokens,split,bn", [
+    (2304, 768, 11808, 2, 192), (3072, 768, 4096, 2, 256), (768, 768, 5920, 8, 256), (768, 3072, 1000, 2, 256), (136, 128, 70, 1, 128),
+    (384, 384, 1280, 1, 128),   # several tiles per m block and (grid < tiles) several tiles per CTA
+])
+def test_gemm_wgrad_fused_bias_gradient(dev, ops, n_out, k_in, tokens, split, bn):
+    """a_colsum: db = column sums of dy taken from the A tiles of the weight-gradient launch itself == torch sum over tokens (fp32 sum of
+    the bf16 values), and dW is unchanged by the extra readers of the smem ring."""
+    torch.manual_seed(n_out + k_in + tokens)
+    dy, x = _rnd(dev, tokens, n_out, scale=0.5), _rnd(dev, tokens, k_in, scale=0.5)
+    ref_w = dy.float().t() @ x.float()
+    ref_b = dy.float().sum(0)
+    for max_ctas in (0, 3):
+        gw = torch.zeros(n_out, k_in, device=dev)
+        gb = torch.zeros(n_out, device=dev)
+        ops.gemm(dy, x, ops.EPI_ATOMIC_F32 if split > 1 else ops.EPI_STORE_F32, a_mn=True, b_mn=True, split_k=split, out=gw, block_n=bn,
+                 a_colsum=gb, max_ctas=max_ctas)
+        assert _rel(gw, ref_w) < 1e-4
+        assert _rel(gb, ref_b) < 1e-5, (max_ctas, (gb - ref_b).abs().max().item())
+
+
 @pytest.mark.parametrize("split", [2, 4, 8])
 def test_gemm_split_k_atomic(dev, ops, split):
     a, b = _rnd(dev, 768, 5920, scale=0.5), _rnd(dev, 768, 5920, scale=0.5)

@@ -29,6 +29,7 @@ class GemmArgs(C.Structure):
         ("out", c_p), ("ldo", c_i64), ("out2", c_p), ("ldo2", c_i64),
         ("dropout_p", c_f32), ("seed", c_u64), ("seed_dev", c_p), ("site", c_u32),
         ("split_k", c_i32), ("block_n", c_i32), ("max_ctas", c_i32), ("sched", c_p), ("cluster", c_i32),
+        ("a_colsum", c_p),
     ]
 
 
@@ -67,6 +68,9 @@ SIGNATURES = {
     "vault_head_loss": [c_p, c_p, c_p, c_p, c_i32, c_i32, c_i32, c_f32, c_p],
     "vault_colsum_bf16": [c_p, c_i64, c_p, c_i64, c_i32, c_p],
     "vault_adamw_step": [c_p, c_p, c_i32, c_p, c_p, c_p, c_i64, C.c_double, C.c_double, C.c_double, C.c_double, C.c_double, c_i32, c_i32, c_f32, c_p, c_p],
+    "vault_mc_adamw_step": [c_p, c_p, c_p, c_i32, c_p, c_p, c_p, c_i64, C.c_double, C.c_double, C.c_double, C.c_double, C.c_double, c_i32, c_i32, c_f32,
+                            c_p, c_i32, c_p],
+    "vault_mc_broadcast_f32": [c_p, c_p, c_i64, c_i32, c_p],
     "vault_cast_f32_bf16": [c_p, c_p, c_i64, c_p],
 }
 _RESTYPES = {"vault_last_error": C.c_size_t}

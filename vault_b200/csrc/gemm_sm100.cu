@@ -58,6 +58,7 @@ struct GemmParams {
   unsigned long long seed;
   const unsigned long long* seed_dev;
   unsigned site;
+  float* a_colsum;  // optional (MN-major A, fp32 epilogues): [M] += sum_k A[m,k], taken from the A tiles as they pass through the smem ring
 };
 
 // ---- fused epilogues -------------------------------------------------------------------------------------------------
@@ -267,6 +268,14 @@ gemm_bf16_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant_
   auto sfull_bar = [&](int s) { return bars + 8u * (2 * kStages + 5 + s); };
   auto sempty_bar = [&](int s) { return bars + 8u * (2 * kStages + 5 + kSchedDepth + s); };
   volatile int* tile_ring = reinterpret_cast<volatile int*>(smem_gen + kRingBytes + kStagingBytes + 8 * (2 * kStages + 5 + 2 * kSchedDepth));
+  // A-operand column sums (weight-gradient launches: the bias gradient).  csfull[kStages]: the MMA thread passes on "this slot holds a k-block
+  // you sum" (one arrival); csdone[kStages]: one arrival per epilogue warp once it has read the slot.  Both advance only on the k-blocks that
+  // are summed and each such k-block is held in its slot until csdone completes, so neither can run more than one phase ahead of its waiters.
+  constexpr bool kColsum = EPI == VAULT_EPI_ATOMIC_F32 || EPI == VAULT_EPI_STORE_F32;
+  auto csfull_bar = [&](int s) { return bars + 8u * (2 * kStages + 5 + 2 * kSchedDepth + 2 + s); };
+  auto csdone_bar = [&](int s) { return bars + 8u * (2 * kStages + 5 + 2 * kSchedDepth + 2 + kStages + s); };
+  static_assert(8 * (2 * kStages + 5 + 2 * kSchedDepth + 2 + 2 * kStages) <= 384, "barrier block overflows its 384 bytes");
+  const bool colsum = kColsum && p.a_colsum != nullptr;
 
   const int warp = threadIdx.x >> 5;
   const int lane = threadIdx.x & 31;
@@ -287,6 +296,12 @@ gemm_bf16_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant_
     for (int s = 0; s < kSchedDepth; ++s) {
       mbar_init(sfull_bar(s), 1);
       mbar_init(sempty_bar(s), 1 + kEpiWarps);  // MMA thread + 8 epilogue warps each take every tile id the producer publishes
+    }
+    if constexpr (kColsum) {
+      for (int s = 0; s < kStages; ++s) {
+        mbar_init(csfull_bar(s), 1);
+        mbar_init(csdone_bar(s), kEpiWarps);
+      }
     }
     mbar_fence_init();
   }
@@ -341,6 +356,7 @@ gemm_bf16_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant_
       uint32_t phase = 0;
       int t = unit0, pslot = 0;
       uint32_t pph = 0;
+      uint32_t cs_pending = 0, cs_phase = 0;  // per-stage bits: slot last filled for a column-sum tile / parity of its csdone barrier
       for (;;) {
         int t_next = t + unit_step;
         if (dyn) {
@@ -357,8 +373,22 @@ gemm_bf16_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant_
         const int n0 = tile_n0(rem);
         const int kb0 = split * p.kb_per_split;
         const int kb1 = min(kb0 + p.kb_per_split, p.num_k_blocks);
+        // the n_units tiles of one m block share its A rows: tile j sums the k-blocks with kb % n_units == j
+        int cs_next = colsum ? kb0 + ((rem % n_units - kb0 % n_units) + n_units) % n_units : -1;
         for (int kb = kb0; kb < kb1; ++kb) {
           mbar_wait(empty_bar(stage), phase ^ 1u);
+          if constexpr (kColsum) {
+            // a slot that fed the column sums is also read by the epilogue warps: refill only after they have let go of it
+            if ((cs_pending >> stage) & 1u) {
+              mbar_wait(csdone_bar(stage), (cs_phase >> stage) & 1u);
+              cs_phase ^= 1u << stage;
+              cs_pending &= ~(1u << stage);
+            }
+            if (kb == cs_next) {
+              cs_pending |= 1u << stage;
+              cs_next += n_units;
+            }
+          }
           const uint32_t sA = ring + stage * kStage;
           const uint32_t sB = sA + kAStage;
           const uint32_t fb = full_bar(stage);
@@ -423,11 +453,24 @@ gemm_bf16_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant_
         const int split = t / tiles_mn;
         const int kb0 = split * p.kb_per_split;
         const int kb1 = min(kb0 + p.kb_per_split, p.num_k_blocks);
+        int cs_next = -1;
+        if constexpr (kColsum) {
+          if (colsum) {
+            const int rem = t - split * tiles_mn;
+            cs_next = kb0 + ((rem % n_units - kb0 % n_units) + n_units) % n_units;
+          }
+        }
         mbar_wait(tempty_bar(as), aphase ^ 1u);
         tc_fence_after();
         const uint32_t d_tmem = tmem_base + (uint32_t)(as * BN);
         for (int kb = kb0; kb < kb1; ++kb) {
           mbar_wait(full_bar(stage), phase);
+          if constexpr (kColsum) {
+            if (kb == cs_next) {  // the k-block has landed: the epilogue warps may add it up while the MMAs below read it
+              mbar_arrive(csfull_bar(stage));
+              cs_next += n_units;
+            }
+          }
           tc_fence_after();
           const uint32_t sA = ring + stage * kStage;
           const uint32_t sB = sA + kAStage;
@@ -457,6 +500,8 @@ gemm_bf16_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant_
     const unsigned long long seed = p.seed + ((p.dropout_p > 0.f && p.seed_dev) ? *p.seed_dev : 0ull);
     int as = 0;
     uint32_t aphase = 0;
+    uint32_t gkb = 0;  // k-blocks this CTA has been through so far: ring slot = gkb % kStages, as in the producer
+    uint32_t csf_phase = 0;  // per-slot parity of csfull
     TileIter it = iter_begin();
     while (iter_next(it, lane == 0, true)) {
       const int t = it.t;
@@ -464,6 +509,41 @@ gemm_bf16_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant_
       const int rem = t - split * tiles_mn;
       const int m0 = tile_m0(rem);
       const int n0 = tile_n0(rem);
+      if constexpr (kColsum) {
+        const int kb0 = split * p.kb_per_split;
+        const int nkb = min(kb0 + p.kb_per_split, p.num_k_blocks) - kb0;
+        if (colsum) {
+          // Bias gradient for free: while the MMAs of this tile run, the (otherwise idle) epilogue warps add up MN-major A tiles
+          // (64 k-rows x two 128-byte m boxes, 128B-swizzled) along k.  The n_units tiles of an m block see the same A rows, so tile j
+          // takes every n_units-th k-block (kb % n_units == j): the extra shared-memory reads are spread over all CTAs of the launch.
+          // Warp -> (m box, k-row group), lane -> 2 adjacent m: a warp reads one whole 128-byte row per instruction (conflict-free
+          // whatever the swizzle phase of the row).
+          constexpr int kRowsPerWarp = 64 / (kEpiWarps / 2);
+          const int box = ew & 1, r0 = (ew >> 1) * kRowsPerWarp;
+          const int nblk = rem % n_units;
+          float s0 = 0.f, s1 = 0.f;
+          for (int kb = kb0 + ((nblk - kb0 % n_units) + n_units) % n_units; kb < kb0 + nkb; kb += n_units) {
+            const int stage = (int)((gkb + (uint32_t)(kb - kb0)) % (uint32_t)kStages);
+            mbar_wait(csfull_bar(stage), (csf_phase >> stage) & 1u);
+            csf_phase ^= 1u << stage;
+            const uint32_t sA = ring + stage * kStage + box * 8192;
+#pragma unroll
+            for (int r = r0; r < r0 + kRowsPerWarp; ++r) {
+              const float2 v = unpack_bf16x2(lds_u32(sA + r * 128 + ((((lane >> 2) ^ (r & 7))) << 4) + (lane & 3) * 4));
+              s0 += v.x;
+              s1 += v.y;
+            }
+            __syncwarp();
+            if (lane == 0) mbar_arrive(csdone_bar(stage));
+          }
+          const int m = m0 + box * 64 + 2 * lane;  // M is even (checked on the host)
+          if (m < p.M) {
+            atomicAdd(p.a_colsum + m, s0);
+            atomicAdd(p.a_colsum + m + 1, s1);
+          }
+        }
+        gkb += (uint32_t)nkb;
+      }
       mbar_wait(tfull_bar(as), aphase);
       tc_fence_after();
       const bool full_tile = (m0 + BM <= p.M) && (n0 + BN <= p.N);
@@ -634,6 +714,11 @@ extern "C" int vault_gemm_bf16(const vault_gemm_args* a, void* stream) {
   VB_REQUIRE(cl <= 2, "vault_gemm_bf16: cluster mode %d (0/-1 off, 1 pair along M, 2 pair along N)", a->cluster);
   if (cl == 1 && a->b_mn && bn < 128) cl = 0;  // an MN-major B tile of one 64-wide box cannot be split across the pair
   if (bn == 192) cl = 0;                       // three 64-wide boxes do not split evenly across a CTA pair
+  if (a->a_colsum) {
+    VB_REQUIRE(a->a_mn == 1 && a->M % 2 == 0, "vault_gemm_bf16: a_colsum needs an MN-major A operand and an even M");
+    VB_REQUIRE(a->epilogue == VAULT_EPI_ATOMIC_F32 || a->epilogue == VAULT_EPI_STORE_F32, "vault_gemm_bf16: a_colsum needs EPI_ATOMIC_F32 / EPI_STORE_F32");
+    cl = 0;
+  }
   CUtensorMap tmA, tmB;
   int rc;
   if (!a->a_mn) rc = encode_tmap_2d(&tmA, CU_TENSOR_MAP_DATA_TYPE_BFLOAT16, 2, a->A, (uint64_t)a->K, (uint64_t)a->M, (uint64_t)a->lda, BK, cl == 2 ? 64 : BM);
@@ -657,6 +742,7 @@ extern "C" int vault_gemm_bf16(const vault_gemm_args* a, void* stream) {
   p.aux = reinterpret_cast<const bf16*>(a->aux); p.ldaux = a->ldaux;
   p.out = a->out; p.ldo = a->ldo; p.out2 = a->out2; p.ldo2 = a->ldo2;
   p.dropout_p = a->dropout_p; p.seed = a->seed; p.seed_dev = reinterpret_cast<const unsigned long long*>(a->seed_dev); p.site = a->site;
+  p.a_colsum = a->a_colsum;
   p.cl = cl;
   p.sched = cl ? nullptr : a->sched;
   int grid;

@@ -102,6 +102,8 @@ class VaultEngine:
         self.dynamic_tiles = os.environ.get("VAULT_B200_DYNAMIC_TILES", "0") == "1"  # measured neutral on B200: opt-in
         self.wgrad_side_stream = os.environ.get("VAULT_B200_WGRAD_SIDE", "1") != "0"
         self.small_m_split_k = os.environ.get("VAULT_B200_SMALL_M_SPLITK", "1") != "0"
+        self.flat_alloc = None  # optional allocator of the flat master / shadow / gradient buffers (see ensure_packed)
+        self.fuse_bias_grad = os.environ.get("VAULT_B200_FUSE_BIAS_GRAD", "1") != "0"  # A/B switch: 0 = separate vault_colsum_bf16 launches
         self.patch_wgrad_tma = os.environ.get("VAULT_B200_PATCH_WGRAD_TMA", "1") != "0"  # 0: bf16 im2col + GEMM (A/B switch)
         self._side = None
         self._side_keep = []
@@ -206,15 +208,17 @@ class VaultEngine:
             slots[n] = Slot(n, off, named[n].numel(), tuple(named[n].shape), False)
             off += _round_up(named[n].numel(), ALIGN)
         self.n_total = off
-        master = torch.zeros(self.n_total, device=device, dtype=torch.float32)
+        # flat_alloc(numel, dtype) -> zero-filled 1-D tensor: the data-parallel multicast path (train.py) supplies symmetric memory here
+        alloc = self.flat_alloc or (lambda numel, dt: torch.zeros(numel, device=device, dtype=dt))
+        master = alloc(self.n_total, torch.float32)
         with torch.no_grad():
             for n, s in slots.items():
                 view = master[s.off:s.off + s.numel].view(s.shape)
                 view.copy_(named[n].detach())
                 named[n].data = view  # the nn.Parameter now aliases the flat master buffer
         self.master = master
-        self.shadow = torch.empty(self.n_total, device=device, dtype=torch.bfloat16)
-        self.grad = torch.zeros(max(self.n_train, ALIGN), device=device, dtype=torch.float32)
+        self.shadow = alloc(self.n_total, torch.bfloat16)
+        self.grad = alloc(max(self.n_train, ALIGN), torch.float32)
         self.slots = slots
         self._sig = sig
         self._ptrs = {n: named[n].data_ptr() for n in slots}
@@ -232,6 +236,12 @@ class VaultEngine:
         self._sched_slots = 512
         self._sched = torch.zeros(2 * self._sched_slots, device=device, dtype=torch.int32)  # dynamic tile-scheduler counters
         self._sched_i = 0
+
+    def repack(self, device: torch.device, flat_alloc=None):
+        """Move the flat buffers to memory from `flat_alloc` (values kept; optimizer state dropped)."""
+        self.flat_alloc = flat_alloc
+        self._sig = None
+        self.ensure_packed(device)
 
     def _params_in_place(self) -> bool:
         named = dict(self.model.named_parameters())
@@ -277,16 +287,24 @@ class VaultEngine:
 
     def _wgrad_cfg(self, n_out: int, k_out: int, tokens: int) -> Tuple[int, int]:
         """(tile N, split-K) of a weight-gradient GEMM dW[n_out, k_out] = dy^T x (contraction over `tokens`).  Measured on B200
-        (tools/wgrad_sweep.py): 128x256 tiles with the token contraction split over a power-of-two number of CTAs so that the
-        launch fills the SMs (54-72 tiles -> 2, 18 tiles -> 8) beat un-split 128x128 tiles by 25-30 %; partial sums meet in the
-        zero-filled fp32 gradient slot through red.global.add.v4.f32."""
-        bn = 256 if k_out >= 256 else 128
-        tiles = ((n_out + 127) // 128) * ((k_out + bn - 1) // bn)
+        (tools/wgrad_sweep.py): 128x256 tiles with the token contraction split over several CTAs so that the launch fills the SMs
+        (72 tiles -> 2, 18 tiles -> 8) beat un-split 128x128 tiles by 25-30 %; partial sums meet in the zero-filled fp32 gradient
+        slot through red.global.add.v4.f32.  The 2304 x 768 QKV gradient is 54 tiles of 128x256 (x2 = 108 CTAs, 73 % of the SMs):
+        128x192 tiles make it 72 x 2 = 144.  Score = SM fill x relative MMA rate of the tile width (as in the kernel's own choice)."""
         nkb = (tokens + 63) // 64
-        split = 1
-        while split * 2 * tiles <= self.sms and split * 2 <= 8 and nkb // (split * 2) >= 2:
-            split *= 2
-        return bn, split
+        best = (-1.0, 128, 1)
+        for bn, rate in ((256, 1.0), (192, 0.93), (128, 0.85)):
+            if bn > 128 and (k_out < bn or (bn == 192 and k_out % 192 != 0)):
+                continue
+            tiles = ((n_out + 127) // 128) * ((k_out + bn - 1) // bn)
+            split = 1
+            while split * 2 * tiles <= self.sms and split * 2 <= 8 and nkb // (split * 2) >= 2:
+                split *= 2
+            waves = -(-(tiles * split) // self.sms)
+            score = rate * tiles * split / (waves * self.sms)
+            if score > best[0] + 1e-6:
+                best = (score, bn, split)
+        return best[1], best[2]
 
     def _compute_zero_ranges(self):
         """Every trainable gradient slot is ACCUMULATED into (split-K weight gradients, bias / LayerNorm / embedding atomics), except the
@@ -309,7 +327,7 @@ class VaultEngine:
         return torch.empty(shape, device=self.device, dtype=dtype)
 
     def gemm(self, A, lda, a_mn, B, ldb, b_mn, M, N, K, epi, out, ldo, bias=0, resid=0, ldr=0, aux=0, ldaux=0, out2=0, ldo2=0, p=0.0, site=0,
-             split_k=1, block_n=0, stream=None):
+             split_k=1, block_n=0, stream=None, a_colsum=0):
         g = self._g
         g.M, g.N, g.K = M, N, K
         g.A, g.lda, g.a_mn = A, lda, a_mn
@@ -321,6 +339,7 @@ class VaultEngine:
         g.dropout_p, g.seed, g.site = p, self.seed, site
         g.seed_dev = self._seed_buf.data_ptr() if p > 0.0 else None
         g.split_k, g.block_n, g.max_ctas = split_k, block_n, self.gemm_max_ctas
+        g.a_colsum = a_colsum or None
         if self.dynamic_tiles:
             self._sched_i = (self._sched_i + 1) % self._sched_slots
             g.sched = self._sched.data_ptr() + 8 * self._sched_i
@@ -357,8 +376,14 @@ class VaultEngine:
             self._side_dirty = True
         if gw:
             bn, split = self._wgrad_cfg(N_out, K_in, M)  # the slot was zero-filled by zero_accumulated_grads()
+            # db = column sums of dy = row sums of the GEMM's MN-major A operand: taken from the A tiles in shared memory by the
+            # epilogue warps of the same launch (they idle during a weight gradient's long contraction) instead of a second pass over dy
+            fused = gb if (self.fuse_bias_grad and N_out % 2 == 0) else 0
             self.gemm(dy16.data_ptr(), N_out, 1, x16.data_ptr(), K_in, 1, N_out, K_in, M,
-                      EPI_ATOMIC_F32 if (split > 1 or self._accumulate) else EPI_STORE_F32, gw, K_in, split_k=split, block_n=bn, stream=st)
+                      EPI_ATOMIC_F32 if (split > 1 or self._accumulate) else EPI_STORE_F32, gw, K_in, split_k=split, block_n=bn, stream=st,
+                      a_colsum=fused)
+            if fused:
+                gb = 0
         if gb:
             rc = self._lib.vault_colsum_bf16(dy16.data_ptr(), N_out, gb, M, N_out, st)
             if rc:

@@ -30,7 +30,7 @@ def _cuda(*ts):
 
 def gemm(a: torch.Tensor, b: torch.Tensor, epilogue: int, *, a_mn: bool = False, b_mn: bool = False, bias=None, resid=None,
          aux=None, out=None, out2=None, dropout_p: float = 0.0, seed: int = 0, site: int = 0, split_k: int = 1,
-         block_n: int = 0, max_ctas: int = 0, cluster: int = 0, sched=None) -> torch.Tensor:
+         block_n: int = 0, max_ctas: int = 0, cluster: int = 0, sched=None, a_colsum=None) -> torch.Tensor:
     """C[M,N] = sum_k A[m,k] B[n,k] with a fused epilogue.  a: [M,K] (or [K,M] if a_mn), b: [N,K] (or [K,N] if b_mn), bf16,
     last dim contiguous."""
     _cuda(a, b, bias, resid, aux, out, out2)
@@ -55,6 +55,7 @@ def gemm(a: torch.Tensor, b: torch.Tensor, epilogue: int, *, a_mn: bool = False,
     g.dropout_p, g.seed, g.site = dropout_p, seed, site
     g.split_k, g.block_n, g.max_ctas, g.cluster = split_k, block_n, max_ctas, cluster
     g.sched = _ptr(sched)
+    g.a_colsum = _ptr(a_colsum)
     _abi.call("vault_gemm_bf16", C.byref(g), _stream())
     return out
 

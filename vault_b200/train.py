@@ -40,6 +40,79 @@ def allreduce_flat_(flat: torch.Tensor, group=None, bucket_elems: int = 16 * 102
     return works
 
 
+class _McBuffers:
+    """Symmetric-memory home of the engine's flat buffers for the multicast data-parallel path: fp32 masters, bf16 shadow and fp32
+    gradients are allocated with torch.distributed._symmetric_memory.empty, exchanged with rendezvous() (CUDA VMM handles + one NVSwitch
+    multicast object per buffer) and addressed through `multicast_ptr` by vault_mc_adamw_step."""
+
+    BARRIER_TIMEOUT_MS = 60000
+
+    def __init__(self):
+        self.master_mc = self.shadow_mc = self.grad_mc = self.grad16_mc = 0
+        self.grad16 = None
+        self.handles = []
+        self._ptrs = ()
+
+    @classmethod
+    def create(cls, engine: VaultEngine, dev, group, required: bool, payload: str = "bf16"):
+        import torch.distributed as dist
+        try:
+            import torch.distributed._symmetric_memory as symm_mem
+        except Exception as e:  # pragma: no cover
+            if required:
+                raise RuntimeError(f"comm='multimem' needs torch.distributed._symmetric_memory: {e}")
+            return None
+        pg = group if group is not None else dist.group.WORLD
+        if dist.get_backend(pg) != "nccl":
+            if required:
+                raise RuntimeError("comm='multimem' needs an NCCL process group on CUDA devices")
+            return None
+        self = cls()
+        made = []
+
+        def alloc(numel, dt):
+            t = symm_mem.empty(numel, dtype=dt, device=dev)
+            t.zero_()
+            made.append(t)
+            return t
+
+        try:
+            engine.repack(dev, flat_alloc=alloc)
+            bufs = [engine.master, engine.shadow, engine.grad]
+            if payload == "bf16":  # gradients travel as a bf16 copy of each finished range (half the link bytes; the switch accumulates in fp32)
+                self.grad16 = alloc(engine.grad.numel(), torch.bfloat16)
+                bufs.append(self.grad16)
+            torch.cuda.synchronize(dev)
+            for t in bufs:
+                self.handles.append(symm_mem.rendezvous(t, pg))
+            ok = all(int(h.multicast_ptr) != 0 for h in self.handles)
+        except Exception as e:
+            if required:
+                raise
+            ok = False
+            self._why = repr(e)
+        # every rank must take the same path
+        flag = torch.tensor([1 if ok else 0], device=dev, dtype=torch.int32)
+        dist.all_reduce(flag, op=dist.ReduceOp.MIN, group=group)
+        if int(flag.item()) == 0:
+            if required:
+                raise RuntimeError("comm='multimem': this system has no NVSwitch multicast support (multicast_ptr == 0 on some rank)")
+            engine.repack(dev, flat_alloc=None)
+            return None
+        self.master_mc, self.shadow_mc, self.grad_mc = (int(h.multicast_ptr) for h in self.handles[:3])
+        self.grad16_mc = int(self.handles[3].multicast_ptr) if self.grad16 is not None else 0
+        self._ptrs = (engine.master.data_ptr(), engine.shadow.data_ptr(), engine.grad.data_ptr())
+        return self
+
+    def check(self, engine: VaultEngine):
+        if (engine.master.data_ptr(), engine.shadow.data_ptr(), engine.grad.data_ptr()) != self._ptrs:
+            raise RuntimeError("the engine re-packed its parameters (requires_grad changed?) after VaultTrainStep mapped them into multicast "
+                               "memory: create a new VaultTrainStep")
+
+    def barrier(self):
+        self.handles[2].barrier(channel=0, timeout_ms=self.BARRIER_TIMEOUT_MS)
+
+
 LOSS_RING = 4096  # steps whose loss may be outstanding (unread) at once
 
 
@@ -74,7 +147,8 @@ class _Slot:
 class VaultTrainStep:
     def __init__(self, model, lr: float = 2e-5, betas=(0.9, 0.999), eps: float = 1e-8, weight_decay: float = 0.0, correct_bias: bool = False,
                  total_steps: Optional[int] = None, warmup_ratio: float = 0.1, process_group=None, use_cuda_graph: bool = True,
-                 dropout: bool = True, overlap_comm: bool = True, comm_reserve_sms: int = 0, grad_comm_dtype: str = "bf16", loss: str = "auto"):
+                 dropout: bool = True, overlap_comm: bool = True, comm_reserve_sms: int = 0, grad_comm_dtype: str = "bf16", loss: str = "auto",
+                 comm: str = "nccl", mc_ctas: int = 0):
         self.model = model
         self.engine: VaultEngine = model.engine
         self.lr, self.betas, self.eps, self.wd, self.correct_bias = lr, betas, eps, weight_decay, correct_bias
@@ -93,15 +167,36 @@ class VaultTrainStep:
         self.dev = next(model.parameters()).device
         if self.dev.type != "cuda":
             raise RuntimeError("VaultTrainStep needs the model on a CUDA device (sm_100a); there is no CPU path")
-        self.engine.ensure_packed(self.dev)
-        self.engine.refresh_shadow(force=True)
-        self.engine.init_opt_state()
         self.world, self.rank, self.pg = 1, 0, process_group
         import torch.distributed as dist
 
         if dist.is_available() and dist.is_initialized():
             self.world = dist.get_world_size(process_group)
             self.rank = dist.get_rank(process_group)
+        # Gradient exchange of the data-parallel step:
+        #   "multimem": the flat master / shadow / gradient buffers live in symmetric memory mapped into one NVSwitch multicast object and
+        #               each finished gradient range is handled by ONE kernel per rank (vault_mc_adamw_step: in-switch reduce of the rank's
+        #               1/world slice, AdamW with the slice's own moments, multicast store of the new weights to every replica);
+        #   "nccl":     cast -> NCCL all-reduce -> full-range AdamW on every rank.
+        #   "auto":     multimem when the system has multicast support, else nccl.
+        if grad_comm_dtype not in ("bf16", "fp32"):
+            raise ValueError("grad_comm_dtype must be 'bf16' or 'fp32'")
+        comm = os.environ.get("VAULT_B200_COMM", comm)
+        if comm not in ("auto", "multimem", "nccl"):
+            raise ValueError("comm must be 'auto', 'multimem' or 'nccl'")
+        self.mc = None
+        if self.world > 1 and comm != "nccl":
+            self.mc = _McBuffers.create(self.engine, self.dev, process_group, required=(comm == "multimem"), payload=grad_comm_dtype)
+        if self.mc is None:
+            self.engine.ensure_packed(self.dev)
+        self.mc_ctas = int(os.environ.get("VAULT_B200_MC_CTAS", mc_ctas or 64))
+        # multimem: fp32 masters SHARDED by default -- only the bf16 shadow of an updated slice is multicast (2 B/parameter instead of 6);
+        # synchronize() brings every replica's masters up to date before anybody reads the Parameters (evaluation, state_dict)
+        self.mc_shard_master = os.environ.get("VAULT_B200_MC_SHARD_MASTER", "1") != "0"
+        self._mc_segments = set()
+        self._mc_stale = False
+        self.engine.refresh_shadow(force=True)
+        self.engine.init_opt_state()
         if self.world > 1:
             # identical replicas: rank 0's weights everywhere; decorrelated dropout streams per rank
             dist.broadcast(self.engine.master, src=dist.get_global_rank(process_group, 0) if process_group is not None else 0, group=process_group)
@@ -127,7 +222,9 @@ class VaultTrainStep:
         # by NCCL, and AdamW reads the bf16 sums); "fp32" reduces the fp32 buffer in place (bit-faithful sum of the ranks' gradients)
         if grad_comm_dtype not in ("bf16", "fp32"):
             raise ValueError("grad_comm_dtype must be 'bf16' or 'fp32'")
-        self.grad16 = torch.empty(self.engine.n_train, device=self.dev, dtype=torch.bfloat16) if (self.world > 1 and grad_comm_dtype == "bf16") else None
+        self.grad16 = (torch.empty(self.engine.n_train, device=self.dev, dtype=torch.bfloat16)
+                       if (self.world > 1 and grad_comm_dtype == "bf16" and self.mc is None) else None)
+        self.grad_comm = grad_comm_dtype if self.world > 1 else "none"
         self.copy_stream = torch.cuda.Stream(device=self.dev)
         self.sched_dev = torch.zeros(2, device=self.dev, dtype=torch.float32)
         self.step_idx = 0
@@ -136,6 +233,7 @@ class VaultTrainStep:
         self._loss_events = [None] * LOSS_RING
         self._pool = None
         self._turn = 0
+        self._mc_dirty = False
 
     # ------------------------------------------------------------------------------------------------------------
     def lr_at(self, step: int) -> float:
@@ -221,9 +319,28 @@ class VaultTrainStep:
         return reached
 
     def synchronize(self):
-        """Wait for everything this object has enqueued (incl. the trailing AdamW on the side stream)."""
+        """Wait for everything this object has enqueued (incl. the trailing AdamW on the side stream).  Multicast data parallelism with
+        sharded masters: also brings every replica's fp32 Parameters up to date (each rank multicasts the slices it owns) -- a COLLECTIVE
+        then: every rank must call it (the trainer does, before evaluation and before a checkpoint)."""
         torch.cuda.current_stream(self.dev).wait_stream(self.engine._side)
+        if self.mc is not None and self._mc_stale:
+            eng, mc = self.engine, self.mc
+            mc.check(eng)
+            st = torch.cuda.current_stream(self.dev).cuda_stream
+            mc.barrier()
+            for lo, hi in sorted(self._mc_segments):
+                a, b = self._mc_slice(lo, hi)
+                if b > a:
+                    _abi.call("vault_mc_broadcast_f32", eng.master.data_ptr() + 4 * a, mc.master_mc + 4 * a, b - a, 2 * eng.sms, st)
+            mc.barrier()
+            self._mc_stale = False
         torch.cuda.synchronize(self.dev)
+
+    def _mc_slice(self, lo: int, hi: int):
+        """This rank's share [a, b) of the gradient range [lo, hi): equal slices in units of 8 parameters."""
+        n = hi - lo
+        per = (-(-n // self.world) + 7) // 8 * 8
+        return lo + min(n, per * self.rank), lo + min(n, per * (self.rank + 1))
 
     def _finish_range(self, lo: int, hi: int, hp):
         """Gradients in [lo, hi) are final on the main stream: all-reduce them (async) and apply AdamW to that range on the side
@@ -236,6 +353,9 @@ class VaultTrainStep:
         ev.record(torch.cuda.current_stream(self.dev))
         side.wait_event(ev)
         with torch.cuda.stream(side):
+            if self.mc is not None:
+                self._mc_range(lo, hi, hp, side)
+                return
             works = []
             if self.world > 1:
                 if self.grad16 is not None:
@@ -247,6 +367,28 @@ class VaultTrainStep:
                 w.wait()
             eng.adamw_range(lo, hi, hp["step"], hp["lr"], hp["b1"], hp["b2"], self.eps, self.wd, self.correct_bias, 1.0 / self.world, self.sched_dev,
                             side.cuda_stream, grad16=self.grad16)
+
+    def _mc_range(self, lo: int, hi: int, hp, side):
+        """Multicast path, on the side stream: barrier (every rank's gradients of [lo, hi) are final), then the fused kernel on this
+        rank's slice of the range.  The barrier is the symmetric-memory handle's (stream-ordered, traps after a timeout instead of
+        hanging); the matching end-of-step barrier is issued by step()."""
+        eng, mc = self.engine, self.mc
+        mc.check(eng)
+        n = hi - lo
+        a, b = self._mc_slice(lo, hi)
+        g16 = mc.grad16 is not None
+        if g16:
+            _abi.call("vault_cast_f32_bf16", eng.grad.data_ptr() + 4 * lo, mc.grad16.data_ptr() + 2 * lo, n, side.cuda_stream)
+        mc.barrier()
+        if b > a and os.environ.get("VAULT_B200_MC_SKIP_KERNEL", "0") != "1":  # (diagnostic switch: cast + barriers only)
+            st = eng.opt_state
+            _abi.call("vault_mc_adamw_step", eng.master.data_ptr() + 4 * a, None if self.mc_shard_master else mc.master_mc + 4 * a,
+                      (mc.grad16_mc + 2 * a) if g16 else (mc.grad_mc + 4 * a), int(g16), st["m"].data_ptr() + 4 * a, st["v"].data_ptr() + 4 * a,
+                      mc.shadow_mc + 2 * a, b - a, hp["lr"], hp["b1"], hp["b2"], self.eps, self.wd, int(self.correct_bias), max(1, hp["step"]),
+                      1.0 / self.world, self.sched_dev.data_ptr(), self.mc_ctas, side.cuda_stream)
+        self._mc_segments.add((lo, hi))
+        self._mc_stale = self.mc_shard_master
+        self._mc_dirty = True
 
     def _get_slot(self, batch) -> _Slot:
         key = tuple((k, tuple(batch[k].shape)) for k in _INPUT_KEYS if batch.get(k) is not None)
@@ -339,6 +481,10 @@ class VaultTrainStep:
                 self._ev_rest = torch.cuda.Event()
                 self._ev_rest.record(side)
         else:
+            if self.mc is not None and self._mc_dirty:
+                with torch.cuda.stream(eng._side):
+                    self.mc.barrier()  # every rank has stored every slice to every replica; gradients may be overwritten from here on
+                self._mc_dirty = False
             ev = torch.cuda.Event()
             ev.record(eng._side)
             cs.wait_event(ev)  # every range's AdamW (and all-reduce) is done before the next step touches weights or gradients

@@ -470,6 +470,7 @@ def main():
         sampler.start()
     ms_dev, _ = timed(devb, read_loss=False)
     ms_e2e, losses = timed(host, read_loss=True)
+    h2d_copied = int(getattr(ts, "last_h2d_bytes", 0)) or h2d  # what step() really copied (a host pixel mask is reduced to patch-grid sizes first)
     clocks = sampler.stop() if sampler else None
     # BASELINE config 3 (T=40, 384x384, S=185) on the same model and step object, a short run next to the headline shape
     also = None
@@ -512,7 +513,7 @@ def main():
             "config": bench_config(args.workload, B, world),
             "impl_config": dict(device="cuda", cuda_graph=not args.no_graph, comm_overlap=ts.overlap, grad_comm_dtype=ts.grad_comm, comm=("multimem" if ts.mc is not None else ("nccl" if world > 1 else "none")),
                                 gemm_ctas=ts.engine.gemm_max_ctas or ts.engine.sms),
-            "e2e": dict(value=e2e, unit="samples/s", h2d_bytes_per_step=h2d, d2h_bytes_per_step=4, ms_per_step=ms_e2e / args.steps,
+            "e2e": dict(value=e2e, unit="samples/s", h2d_bytes_per_step=h2d_copied, host_batch_bytes=h2d, d2h_bytes_per_step=4, ms_per_step=ms_e2e / args.steps,
                         api="vault_b200.VaultTrainStep.step(pinned host batch) -> StepResult.loss()"),
             "gpu_launches": (launches + 1) * args.steps if launches else None,
             "launches_per_step": dict(total=(launches + 1) if launches else None, by_call=calls),

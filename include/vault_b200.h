@@ -292,16 +292,18 @@ int vault_adamw_step(float* p, const void* g, int32_t grad_is_bf16, float* m, fl
  * finished gradient range (1/world of it, n % 8 == 0); every pointer is already offset to that slice:
  *   g_mc      multicast address of the gradients, fp32 or (grad_is_bf16) a bf16 copy: multimem.ld_reduce returns the SUM over all ranks,
  *             added in the switch with fp32 accumulation
- *   p_local   this rank's fp32 masters (read; written too when p_mc is NULL)
- *   p_mc      multicast address of the masters, or NULL: NULL = the masters are SHARDED (a rank's copy is current only for the slices it
- *             owns; vault_mc_broadcast_f32 consolidates them), non-NULL = the new masters are stored to every replica
+ *   p_local   this rank's fp32 masters;  p_mc  multicast address of the same range: the new masters are stored to every replica, except
+ *             in the 64-parameter blocks whose bit is set in local_only_bits (DEVICE bitmap over the whole flat buffer, block b = parameters
+ *             [64b, 64b+64), or NULL = none; first_param = flat index of the slice's first parameter): those masters stay SHARDED -- a
+ *             rank's copy is current only for the slices it owns, vault_mc_broadcast_f32 consolidates them.  Meant for the dense
+ *             projection matrices, which the forward / backward only ever read through the bf16 shadow
  *   shadow_mc multicast address of the bf16 shadow: always stored to EVERY replica (the next forward reads it)
  *   m, v      this rank's AdamW moments of the slice (only the owner of a slice ever touches them)
  * The flat buffers must be symmetric memory mapped into one multicast object (torch.distributed._symmetric_memory).  Ordering across
  * ranks is the caller's: a barrier before the launch (all ranks' gradients of the range are final) and one after the last launch of
  * the step (all slices written everywhere).  `ctas` bounds the grid (the kernel is NVLink-latency bound; two CTAs fit on an SM). */
-int vault_mc_adamw_step(float* p_local, float* p_mc, const void* g_mc, int32_t grad_is_bf16, float* m, float* v, void* shadow_mc,
-                        int64_t n, double lr, double beta1, double beta2, double eps, double weight_decay, int32_t correct_bias,
+int vault_mc_adamw_step(float* p_local, float* p_mc, const uint32_t* local_only_bits, int64_t first_param, const void* g_mc,
+                        int32_t grad_is_bf16, float* m, float* v, void* shadow_mc, int64_t n, double lr, double beta1, double beta2, double eps, double weight_decay, int32_t correct_bias,
                         int32_t step, float grad_scale, const float* sched_dev, int32_t ctas, void* stream);
 /* src_local fp32 [n] -> the same range of every replica through its multicast address (n % 4 == 0) */
 int vault_mc_broadcast_f32(const float* src_local, float* dst_mc, int64_t n, int32_t ctas, void* stream);

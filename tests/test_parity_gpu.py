@@ -120,6 +120,25 @@ def test_train_step_matches_oracle_one_step():
         assert torch.equal(after[k], before[k])
 
 
+def test_train_step_host_pixel_mask_reduced_on_host():
+    """A HOST batch's pixel mask never crosses PCIe: step() reduces it to (patch rows, patch columns) per sample, exactly what
+    vault_patch_grid computes from a device mask.  Same model, same batch: host path and device path give the same loss, bit for bit."""
+    from vault_b200 import VaultTrainStep
+
+    d = synth.Dims.tiny()
+    sd = synth.make_state_dict(d, seed=0)
+    batch = synth.make_inputs(d, batch=4, text_len=16, seed=5, var_text=True, mixed_images=True, image_hw=(384, 640))
+    losses = []
+    for on_host in (True, False):
+        m = build(d, sd).train()
+        ts = VaultTrainStep(m, lr=1e-3, dropout=False, use_cuda_graph=True)
+        b = {k: (v.pin_memory() if on_host else v.to(DEV)) for k, v in batch.items()}
+        losses.append([ts.step(b).loss() for _ in range(2)])
+        if on_host:
+            assert ts.last_h2d_bytes < sum(v.numel() * v.element_size() for v in batch.values()) - batch["pixel_mask"].numel() * 8 + 64
+    assert losses[0] == losses[1], losses
+
+
 @pytest.mark.parametrize("kind,n_classes", [("bce", 1), ("ce2", 6)])
 def test_train_step_other_trainer_losses_match_oracle(kind, n_classes):
     """The Bloomberg (one logit, BCE-with-logits) and raw-MVSA (two label groups) losses through the fused step vs the oracle."""

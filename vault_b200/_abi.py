@@ -68,7 +68,7 @@ SIGNATURES = {
     "vault_head_loss": [c_p, c_p, c_p, c_p, c_i32, c_i32, c_i32, c_f32, c_p],
     "vault_colsum_bf16": [c_p, c_i64, c_p, c_i64, c_i32, c_p],
     "vault_adamw_step": [c_p, c_p, c_i32, c_p, c_p, c_p, c_i64, C.c_double, C.c_double, C.c_double, C.c_double, C.c_double, c_i32, c_i32, c_f32, c_p, c_p],
-    "vault_mc_adamw_step": [c_p, c_p, c_p, c_i32, c_p, c_p, c_p, c_i64, C.c_double, C.c_double, C.c_double, C.c_double, C.c_double, c_i32, c_i32, c_f32,
+    "vault_mc_adamw_step": [c_p, c_p, c_p, c_i64, c_p, c_i32, c_p, c_p, c_p, c_i64, C.c_double, C.c_double, C.c_double, C.c_double, C.c_double, c_i32, c_i32, c_f32,
                             c_p, c_i32, c_p],
     "vault_mc_broadcast_f32": [c_p, c_p, c_i64, c_i32, c_p],
     "vault_cast_f32_bf16": [c_p, c_p, c_i64, c_p],

@@ -5,9 +5,11 @@
 //      and adds them: one NVLink load returns the reduced value, no rank ever sees another rank's partial gradients),
 //   2. applies the transformers==4.48.0 AdamW rule (same arithmetic as adamw.cu) with ITS OWN m / v -- the optimizer state of a slice is
 //      only ever touched by its owner, so the 30 B/parameter of AdamW HBM traffic become 30/world + 10,
-//   3. pushes the new bf16 shadow (what the next forward reads) -- and, when p_mc is given, the new fp32 masters -- to EVERY replica (itself
-//      included) with multimem.st.  Without p_mc the masters are SHARDED: a rank's copy is current for the slices it owns only, and
-//      vault_mc_broadcast_f32 brings all replicas up to date when somebody wants to read the parameters (evaluation, checkpoint).
+//   3. pushes the new bf16 shadow (what the next forward's GEMMs read) to EVERY replica (itself included) with multimem.st, and the new
+//      fp32 masters too -- except for the 64-parameter blocks flagged in `local_only_bits`: the dense projection matrices (86 % of the
+//      model) are only ever read through their shadow, so their masters stay SHARDED (a rank's copy is current for the slices it owns;
+//      vault_mc_broadcast_f32 brings all replicas up to date when somebody wants to read the Parameters: evaluation, checkpoint), while
+//      biases, LayerNorm affines and embedding tables, which kernels read in fp32, are replicated at once.
 // Gradients travel as fp32 (bit-faithful sum) or as a bf16 copy (half the NVLink bytes; the switch accumulates in fp32).  Link bytes per
 // parameter and GPU: up 2-4 (its gradients, read once by the switch) + 2/world, down 2-4/world + 2 -- the NVLS all-reduce's, while the
 // AdamW traffic on HBM drops by (world-1)/world.
@@ -46,8 +48,10 @@ __device__ __forceinline__ void mm_st_bf16x8(void* mc, const uint4& v) {
 }
 
 struct McAdamParams {
-  const float* p_local;  // this rank's copy of the masters (identical on every rank), read side
-  float* p_mc;           // multicast address of the same range (write side), or the local address again when the masters are sharded
+  float* p_local;        // this rank's copy of the masters
+  float* p_mc;           // multicast address of the same range (write side)
+  const uint32_t* local_only_bits;  // bit b = 1: the masters of 64-parameter block b (counted from parameter 0 of the flat buffer) stay local
+  long long first_param; // flat index of this slice's first parameter
   const void* g_mc;      // multicast address of the gradients (fp32, or the bf16 copy)
   float* m;
   float* v;
@@ -78,7 +82,7 @@ constexpr int kMcUnrollMax = 8;  // (per-kernel unroll: 4 fp32 / 8 bf16 units) i
                               // so the kernel is sized by bytes in flight -- 2 CTAs/SM x 512 threads x 128 B = 128 KB per SM, ~30 SMs cover the
                               // bandwidth-latency product of the link and the rest of the GPU stays with the backward pass
 
-template <bool G16, bool PUSH_P>
+template <bool G16>
 __global__ void __launch_bounds__(kMcThreads, 2) mc_adamw_kernel(const McAdamParams a) {
   constexpr int kMcUnroll = G16 ? 8 : 4;  // 128 bytes of gradient pulls in flight per thread either way
   pdl_enter();
@@ -108,6 +112,11 @@ __global__ void __launch_bounds__(kMcThreads, 2) mc_adamw_kernel(const McAdamPar
       const long long i = i0 + u * stride;
       if (i < a.n8) {
         uint32_t pk[4];
+        bool local_only = false;
+        if (a.local_only_bits) {
+          const long long blk = (a.first_param + 8 * i) >> 6;
+          local_only = (__ldg(a.local_only_bits + (blk >> 5)) >> (blk & 31)) & 1u;
+        }
 #pragma unroll
         for (int h = 0; h < 2; ++h) {  // one half (4 parameters) at a time: the moments of a unit never all live in registers together
           float4 p = *reinterpret_cast<const float4*>(a.p_local + 8 * i + 4 * h);
@@ -123,8 +132,8 @@ __global__ void __launch_bounds__(kMcThreads, 2) mc_adamw_kernel(const McAdamPar
           adam4(p, gh, m, v, a, step_size, lr_wd);
           *reinterpret_cast<float4*>(a.m + 8 * i + 4 * h) = m;
           *reinterpret_cast<float4*>(a.v + 8 * i + 4 * h) = v;
-          if constexpr (PUSH_P) mm_st_f32x4(a.p_mc + 8 * i + 4 * h, p);
-          else *reinterpret_cast<float4*>(a.p_mc + 8 * i + 4 * h) = p;
+          if (local_only) *reinterpret_cast<float4*>(a.p_local + 8 * i + 4 * h) = p;
+          else mm_st_f32x4(a.p_mc + 8 * i + 4 * h, p);
           pk[2 * h] = pack_bf16x2(p.x, p.y);
           pk[2 * h + 1] = pack_bf16x2(p.z, p.w);
         }
@@ -148,10 +157,11 @@ __global__ void __launch_bounds__(kMcThreads) mc_broadcast_f32_kernel(const floa
 
 using namespace vb;
 
-extern "C" int vault_mc_adamw_step(float* p_local, float* p_mc, const void* g_mc, int32_t grad_is_bf16, float* m, float* v, void* shadow_mc,
-                                   int64_t n, double lr, double beta1, double beta2, double eps, double weight_decay, int32_t correct_bias,
+extern "C" int vault_mc_adamw_step(float* p_local, float* p_mc, const uint32_t* local_only_bits, int64_t first_param, const void* g_mc,
+                                   int32_t grad_is_bf16, float* m, float* v, void* shadow_mc, int64_t n, double lr, double beta1, double beta2, double eps, double weight_decay, int32_t correct_bias,
                                    int32_t step, float grad_scale, const float* sched_dev, int32_t ctas, void* stream) {
-  VB_REQUIRE(p_local && g_mc && m && v && shadow_mc && n >= 0, "mc_adamw_step: null pointer");
+  VB_REQUIRE(p_local && p_mc && g_mc && m && v && shadow_mc && n >= 0, "mc_adamw_step: null pointer");
+  VB_REQUIRE(first_param >= 0 && first_param % 8 == 0, "mc_adamw_step: first_param must be a multiple of 8");
   VB_REQUIRE(n % 8 == 0, "mc_adamw_step: a slice must be a multiple of 8 parameters (n = %lld)", (long long)n);
   VB_REQUIRE((((uintptr_t)p_local | (uintptr_t)p_mc | (uintptr_t)g_mc | (uintptr_t)m | (uintptr_t)v | (uintptr_t)shadow_mc) & 15) == 0,
              "mc_adamw_step: buffers must be 16-byte aligned");
@@ -163,7 +173,7 @@ extern "C" int vault_mc_adamw_step(float* p_local, float* p_mc, const void* g_mc
     step_size = lr * sqrt(1.0 - pow(beta2, step)) / (1.0 - pow(beta1, step));
   }
   McAdamParams a;
-  a.p_local = p_local; a.p_mc = p_mc ? p_mc : p_local; a.g_mc = g_mc; a.m = m; a.v = v; a.shadow_mc = shadow_mc;
+  a.p_local = p_local; a.p_mc = p_mc; a.local_only_bits = local_only_bits; a.first_param = first_param; a.g_mc = g_mc; a.m = m; a.v = v; a.shadow_mc = shadow_mc;
   a.n8 = n / 8;
   a.step_size = (float)step_size;
   a.lr_wd = weight_decay > 0.0 ? (float)(lr * weight_decay) : 0.f;
@@ -173,13 +183,8 @@ extern "C" int vault_mc_adamw_step(float* p_local, float* p_mc, const void* g_mc
   const long long need = (a.n8 + (long long)kMcThreads * unroll - 1) / ((long long)kMcThreads * unroll);
   const dim3 grid((unsigned)(need < ctas ? need : ctas)), block(kMcThreads);
   cudaStream_t st = (cudaStream_t)stream;
-  if (grad_is_bf16) {
-    if (p_mc) launch(mc_adamw_kernel<true, true>, grid, block, 0, st, a);
-    else launch(mc_adamw_kernel<true, false>, grid, block, 0, st, a);
-  } else {
-    if (p_mc) launch(mc_adamw_kernel<false, true>, grid, block, 0, st, a);
-    else launch(mc_adamw_kernel<false, false>, grid, block, 0, st, a);
-  }
+  if (grad_is_bf16) launch(mc_adamw_kernel<true>, grid, block, 0, st, a);
+  else launch(mc_adamw_kernel<false>, grid, block, 0, st, a);
   return check_launch("mc_adamw_kernel");
 }
 

@@ -102,6 +102,7 @@ class VaultEngine:
         self.dynamic_tiles = os.environ.get("VAULT_B200_DYNAMIC_TILES", "0") == "1"  # measured neutral on B200: opt-in
         self.wgrad_side_stream = os.environ.get("VAULT_B200_WGRAD_SIDE", "1") != "0"
         self.small_m_split_k = os.environ.get("VAULT_B200_SMALL_M_SPLITK", "1") != "0"
+        self.comm_stream = None  # see _cut()
         self.flat_alloc = None  # optional allocator of the flat master / shadow / gradient buffers (see ensure_packed)
         self.fuse_bias_grad = os.environ.get("VAULT_B200_FUSE_BIAS_GRAD", "1") != "0"  # A/B switch: 0 = separate vault_colsum_bf16 launches
         self.patch_wgrad_tma = os.environ.get("VAULT_B200_PATCH_WGRAD_TMA", "1") != "0"  # 0: bf16 im2col + GEMM (A/B switch)
@@ -242,6 +243,21 @@ class VaultEngine:
         self.flat_alloc = flat_alloc
         self._sig = None
         self.ensure_packed(device)
+
+    def shadow_only_bitmap(self) -> torch.Tensor:
+        """int32 bitmap over the 64-parameter blocks of the trainable flat range: bit = 1 where the block belongs to a dense projection matrix
+        of an encoder layer (q/k/v, attention output, MLP), i.e. a parameter the kernels read through its bf16 shadow ONLY (linear_fwd /
+        linear_dgrad take w16; nothing takes w32 of these).  Used by the multicast optimizer step to leave those fp32 masters sharded."""
+        import re
+        pat = re.compile(r"encoder\.layer\.\d+\.(attention\.(attention|self)\.(query|key|value)|attention\.output\.dense|intermediate\.dense|output\.dense)\.weight$")
+        nblk = (self.n_train + ALIGN - 1) // ALIGN
+        bits = torch.zeros((nblk + 31) // 32 * 32, dtype=torch.bool)
+        for n, sl in self.slots.items():
+            if sl.trainable and pat.search(n):
+                bits[sl.off // ALIGN:(sl.off + sl.numel + ALIGN - 1) // ALIGN] = True
+        w = (bits.view(-1, 32).to(torch.int64) << torch.arange(32, dtype=torch.int64)).sum(1)
+        w = torch.where(w >= 2 ** 31, w - 2 ** 32, w).to(torch.int32)
+        return w.to(self.device)
 
     def _params_in_place(self) -> bool:
         named = dict(self.model.named_parameters())
@@ -388,6 +404,21 @@ class VaultEngine:
             rc = self._lib.vault_colsum_bf16(dy16.data_ptr(), N_out, gb, M, N_out, st)
             if rc:
                 _abi.check(rc, "vault_colsum_bf16")
+
+    def _cut(self):
+        """A gradient range is complete once the chain AND the weight-gradient stream get here.  Default: the chain waits for the side
+        stream (the caller reduces the range from the host between two graph replays).  With `comm_stream` set (the whole step is ONE
+        captured graph, train.py) only that stream waits for both -- the dependency chain does not stop at the cut."""
+        if self.comm_stream is None:
+            self._join_side()
+            return
+        ev = torch.cuda.Event()
+        ev.record(torch.cuda.current_stream(self.device))
+        self.comm_stream.wait_event(ev)
+        if self._side_dirty:
+            ev2 = torch.cuda.Event()
+            ev2.record(self._side)
+            self.comm_stream.wait_event(ev2)
 
     def _join_side(self):
         """Main stream waits for every weight-gradient kernel issued on the side stream so far."""
@@ -893,7 +924,7 @@ class VaultEngine:
             if segments and i > 0 and i in (self.L * 2 // 3, self.L // 3):
                 off = self._first_off(f"encoder.layer.{i - 1}.")
                 if off:
-                    self._join_side()
+                    self._cut()
                     yield off
         # ---- embeddings ----
         dtext_ln = self._new((Mt, H), torch.float32)
@@ -943,7 +974,7 @@ class VaultEngine:
                 if segments:
                     off = self._first_off("bert.")
                     if off:
-                        self._join_side()
+                        self._cut()
                         yield off
                 yield from self._lm_backward(dv_sum, sv, B, T, mt["training"], segments, meta=mt)
         elif mt.get("text_embeds_mode"):
@@ -979,12 +1010,12 @@ class VaultEngine:
             if segments and i > 0 and i in (self.lm_L * 2 // 3, self.lm_L // 3):
                 off = self._first_off(f"bert.encoder.layer.{i - 1}.")
                 if off:
-                    self._join_side()
+                    self._cut()
                     yield off
         if segments:
             off = self._first_off("bert.embeddings.")
             if off:
-                self._join_side()
+                self._cut()
                 yield off
         p_emb = self.lm_p if train else 0.0
         dx_sum, _ = self.ln_bwd(g32, gx16, sv["lm.x_sum"], sv["lm.st0"], Mt, "bert.embeddings.LayerNorm.weight", "bert.embeddings.LayerNorm.bias",

@@ -142,13 +142,15 @@ class _Slot:
         self.ready = torch.cuda.Event()
         self.free = torch.cuda.Event()
         self.graphs = None   # list of (CUDAGraph, grad offset reached when it finishes)
+        self.host_hw = False  # the per-sample patch-grid sizes arrive from the host (the pixel mask itself is never copied)
+        self.hw_pinned = None
 
 
 class VaultTrainStep:
     def __init__(self, model, lr: float = 2e-5, betas=(0.9, 0.999), eps: float = 1e-8, weight_decay: float = 0.0, correct_bias: bool = False,
                  total_steps: Optional[int] = None, warmup_ratio: float = 0.1, process_group=None, use_cuda_graph: bool = True,
                  dropout: bool = True, overlap_comm: bool = True, comm_reserve_sms: int = 0, grad_comm_dtype: str = "bf16", loss: str = "auto",
-                 comm: str = "nccl", mc_ctas: int = 0):
+                 comm: str = "auto", mc_ctas: int = 0):
         self.model = model
         self.engine: VaultEngine = model.engine
         self.lr, self.betas, self.eps, self.wd, self.correct_bias = lr, betas, eps, weight_decay, correct_bias
@@ -189,12 +191,20 @@ class VaultTrainStep:
             self.mc = _McBuffers.create(self.engine, self.dev, process_group, required=(comm == "multimem"), payload=grad_comm_dtype)
         if self.mc is None:
             self.engine.ensure_packed(self.dev)
-        self.mc_ctas = int(os.environ.get("VAULT_B200_MC_CTAS", mc_ctas or 64))
-        # multimem: fp32 masters SHARDED by default -- only the bf16 shadow of an updated slice is multicast (2 B/parameter instead of 6);
-        # synchronize() brings every replica's masters up to date before anybody reads the Parameters (evaluation, state_dict)
+        self.mc_ctas = int(os.environ.get("VAULT_B200_MC_CTAS", mc_ctas or 128))
+        # multimem: the fp32 masters of the dense projection matrices (read through their bf16 shadow only) are SHARDED by default -- only
+        # the shadow of an updated slice is multicast (2 B/parameter instead of 6); everything kernels read in fp32 (biases, LayerNorm,
+        # embedding tables, patch projection, pooler, head) is replicated at once.  synchronize() brings every replica's masters up to date
+        # before anybody reads the Parameters (evaluation, state_dict).
         self.mc_shard_master = os.environ.get("VAULT_B200_MC_SHARD_MASTER", "1") != "0"
+        self._mc_local_bits = self.engine.shadow_only_bitmap() if (self.mc is not None and self.mc_shard_master) else None
         self._mc_segments = set()
         self._mc_stale = False
+        # multimem + CUDA graphs: the WHOLE step -- forward, backward, per-range barrier + fused optimizer kernel on a third (comm) stream,
+        # end-of-step barrier -- is ONE captured graph: no host launch between gradient ranges, and the dependency chain does not wait for
+        # the weight-gradient stream at the range boundaries (only the comm stream does, VaultEngine._cut).
+        self.mc_in_graph = self.mc is not None and use_cuda_graph and os.environ.get("VAULT_B200_MC_IN_GRAPH", "1") != "0"
+        self._comm_stream = torch.cuda.Stream(device=self.dev) if self.mc is not None else None
         self.engine.refresh_shadow(force=True)
         self.engine.init_opt_state()
         if self.world > 1:
@@ -234,6 +244,7 @@ class VaultTrainStep:
         self._pool = None
         self._turn = 0
         self._mc_dirty = False
+        self.last_h2d_bytes = 0
 
     # ------------------------------------------------------------------------------------------------------------
     def lr_at(self, step: int) -> float:
@@ -247,14 +258,20 @@ class VaultTrainStep:
 
     def _make_slot(self, batch) -> _Slot:
         s = _Slot()
+        # A HOST pixel mask is reduced on the host to what the path needs from it -- (valid patch rows, valid patch columns) per sample, the
+        # same two counts vault_patch_grid takes from the first patch column / row -- so 8 bytes per sample cross PCIe instead of the int64
+        # mask (63 MB of the 157 MB a 32 x 384 x 640 batch would otherwise copy per step).
+        s.host_hw = batch.get("pixel_mask") is not None and not batch["pixel_mask"].is_cuda
         for k in _INPUT_KEYS:
             v = batch.get(k)
-            if v is None:
+            if v is None or (k == "pixel_mask" and s.host_hw):
                 continue
             dt = torch.float32 if (k == "pixel_values" or (k == "labels" and self.loss_kind == 1)) else torch.int64
             s.buf[k] = torch.empty(v.shape, device=self.dev, dtype=dt)
         B = batch["input_ids"].shape[0]
         s.buf["hw"] = torch.empty((B, 2), device=self.dev, dtype=torch.int32)
+        if s.host_hw:
+            s.hw_pinned = torch.empty((B, 2), dtype=torch.int32).pin_memory()
         s.buf["loss"] = torch.zeros(1, device=self.dev, dtype=torch.float32)
         s.buf["logits"] = torch.zeros((B, self.n_classes), device=self.dev, dtype=torch.float32)
         s.free.record(torch.cuda.current_stream(self.dev))
@@ -279,6 +296,8 @@ class VaultTrainStep:
         eng.seed_dev.add_(1)
         if "pixel_mask" in b:
             _abi.check(lib.vault_patch_grid(b["pixel_mask"].data_ptr(), 0, b["hw"].data_ptr(), B, Hi, Wi, eng.patch, st), "patch_grid")
+        elif s.host_hw:
+            pass  # b["hw"] was filled by step()'s host->device copy
         else:
             b["hw"][:, 0] = gh
             b["hw"][:, 1] = gw
@@ -348,7 +367,7 @@ class VaultTrainStep:
         if hi <= lo:
             return
         eng = self.engine
-        side = eng._side
+        side = eng._side if eng.comm_stream is None else eng.comm_stream
         ev = torch.cuda.Event()
         ev.record(torch.cuda.current_stream(self.dev))
         side.wait_event(ev)
@@ -382,7 +401,8 @@ class VaultTrainStep:
         mc.barrier()
         if b > a and os.environ.get("VAULT_B200_MC_SKIP_KERNEL", "0") != "1":  # (diagnostic switch: cast + barriers only)
             st = eng.opt_state
-            _abi.call("vault_mc_adamw_step", eng.master.data_ptr() + 4 * a, None if self.mc_shard_master else mc.master_mc + 4 * a,
+            _abi.call("vault_mc_adamw_step", eng.master.data_ptr() + 4 * a, mc.master_mc + 4 * a,
+                      self._mc_local_bits.data_ptr() if self.mc_shard_master else None, a,
                       (mc.grad16_mc + 2 * a) if g16 else (mc.grad_mc + 4 * a), int(g16), st["m"].data_ptr() + 4 * a, st["v"].data_ptr() + 4 * a,
                       mc.shadow_mc + 2 * a, b - a, hp["lr"], hp["b1"], hp["b2"], self.eps, self.wd, int(self.correct_bias), max(1, hp["step"]),
                       1.0 / self.world, self.sched_dev.data_ptr(), self.mc_ctas, side.cuda_stream)
@@ -391,7 +411,7 @@ class VaultTrainStep:
         self._mc_dirty = True
 
     def _get_slot(self, batch) -> _Slot:
-        key = tuple((k, tuple(batch[k].shape)) for k in _INPUT_KEYS if batch.get(k) is not None)
+        key = tuple((k, tuple(batch[k].shape), bool(batch[k].is_cuda)) for k in _INPUT_KEYS if batch.get(k) is not None)
         if key not in self._states:
             self._states[key] = [self._make_slot(batch), self._make_slot(batch)]
         self._turn ^= 1
@@ -404,12 +424,22 @@ class VaultTrainStep:
         cs = torch.cuda.current_stream(self.dev)
         on_host = not batch["pixel_values"].is_cuda
         if on_host:
+            nbytes = 0
             with torch.cuda.stream(self.copy_stream):
                 self.copy_stream.wait_event(s.free)
+                if s.host_hw:
+                    pm, P = batch["pixel_mask"], eng.patch
+                    s.free.synchronize()  # the pinned staging pair of this slot is reused: its previous copy must have been consumed
+                    s.hw_pinned[:, 0] = (pm[:, ::P, 0] != 0).sum(1)
+                    s.hw_pinned[:, 1] = (pm[:, 0, ::P] != 0).sum(1)
+                    s.buf["hw"].copy_(s.hw_pinned, non_blocking=True)
+                    nbytes += s.hw_pinned.numel() * 4
                 for k, dst in s.buf.items():
                     if k in batch and batch[k] is not None:
                         dst.copy_(batch[k], non_blocking=True)
+                        nbytes += dst.numel() * dst.element_size()
                 s.ready.record(self.copy_stream)
+            self.last_h2d_bytes = nbytes
             cs.wait_event(s.ready)
         else:
             for k, dst in s.buf.items():
@@ -439,6 +469,27 @@ class VaultTrainStep:
                 # stream (weight gradients, bias sums) keeps the default priority: pending chain CTAs are placed first, the rest fills in
                 cap_stream = torch.cuda.Stream(device=self.dev, priority=-1 if os.environ.get("VAULT_B200_CHAIN_PRIORITY", "0") != "0" else 0)
                 done = False
+                if self.mc_in_graph:
+                    g = torch.cuda.CUDAGraph()
+                    eng.comm_stream = self._comm_stream
+                    try:
+                        with torch.cuda.graph(g, pool=self._pool, stream=cap_stream):
+                            lo_c = 0
+                            for reached in it:
+                                lo_c = self._after_segment(lo_c, reached, hp, cap_stream)
+                            self._after_segment(lo_c, n_train, hp, cap_stream)
+                            with torch.cuda.stream(self._comm_stream):
+                                self.mc.barrier()  # every rank has stored every slice to every replica; gradients may be overwritten
+                            evc = torch.cuda.Event()
+                            evc.record(self._comm_stream)
+                            torch.cuda.current_stream(self.dev).wait_event(evc)
+                    finally:
+                        eng.comm_stream = None
+                    self._mc_dirty = False
+                    if self._pool is None:
+                        self._pool = g.pool()
+                    s.graphs.append((g, "whole_step"))
+                    done = True
                 while not done:
                     g = torch.cuda.CUDAGraph()
                     with torch.cuda.graph(g, pool=self._pool, stream=cap_stream):
@@ -454,6 +505,9 @@ class VaultTrainStep:
                 cs.wait_event(self._ev_lm)  # previous step's AdamW has finished the LM range
             for g, reached in s.graphs:
                 g.replay()
+                if reached == "whole_step":
+                    self._mc_stale = self.mc_shard_master
+                    continue
                 lo = self._after_segment(lo, reached, hp, cs)
         else:
             lo = 0

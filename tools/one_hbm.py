@@ -5,7 +5,8 @@ import torch
 sys.path.insert(0, os.path.dirname(os.path.dirname(os.path.abspath(__file__))))
 from vault_b200 import _abi
 dev = torch.device("cuda:0"); lib = _abi.lib(); st = torch.cuda.current_stream().cuda_stream
-rows, cols, n = 32 * 185 * 4, 768, 64 * 1024 * 1024
+rows = int(sys.argv[1]) if len(sys.argv) > 1 else 11808  # the target workload's own ViLT row count (32 x 369)
+cols, n = 768, (int(sys.argv[2]) if len(sys.argv) > 2 else 197_017_344 // 4 * 4)  # AdamW: the model's own trainable parameter count
 g, b = torch.ones(cols, device=dev), torch.zeros(cols, device=dev)
 dg, db, dc = (torch.zeros(cols, device=dev) for _ in range(3))
 sets = []

@@ -137,6 +137,55 @@ __device__ __forceinline__ float gelu_erf_grad(float x) {
   return fmaf(x * 0.39894228040143267794f, e, cdf);
 }
 
+// Two elements per instruction: Blackwell's packed fp32 pipe (fma/mul/add.f32x2 -> FFMA2 / FMUL2 / FADD2, IEEE rn per lane, so the results
+// are bit-identical to the scalar forms above).  The GELU epilogues are bound by issue slots and latency next to the MMA warps; the
+// polynomial part of a pair costs 10 instructions instead of 20 (MUFU, |x| and max stay per element).
+__device__ __forceinline__ float2 fma2(float2 a, float2 b, float2 c) {
+  float2 d;
+  asm("{ .reg .b64 ra, rb, rc, rd; mov.b64 ra, {%2, %3}; mov.b64 rb, {%4, %5}; mov.b64 rc, {%6, %7}; fma.rn.f32x2 rd, ra, rb, rc; mov.b64 {%0, %1}, rd; }"
+      : "=f"(d.x), "=f"(d.y)
+      : "f"(a.x), "f"(a.y), "f"(b.x), "f"(b.y), "f"(c.x), "f"(c.y));
+  return d;
+}
+__device__ __forceinline__ float2 mul2(float2 a, float2 b) {
+  float2 d;
+  asm("{ .reg .b64 ra, rb, rd; mov.b64 ra, {%2, %3}; mov.b64 rb, {%4, %5}; mul.rn.f32x2 rd, ra, rb; mov.b64 {%0, %1}, rd; }"
+      : "=f"(d.x), "=f"(d.y)
+      : "f"(a.x), "f"(a.y), "f"(b.x), "f"(b.y));
+  return d;
+}
+__device__ __forceinline__ float2 add2(float2 a, float2 b) {
+  float2 d;
+  asm("{ .reg .b64 ra, rb, rd; mov.b64 ra, {%2, %3}; mov.b64 rb, {%4, %5}; add.rn.f32x2 rd, ra, rb; mov.b64 {%0, %1}, rd; }"
+      : "=f"(d.x), "=f"(d.y)
+      : "f"(a.x), "f"(a.y), "f"(b.x), "f"(b.y));
+  return d;
+}
+__device__ __forceinline__ float2 splat2(float v) { return make_float2(v, v); }
+__device__ __forceinline__ float2 gelu_tail_h2(float2 ax, float2 e) {
+  const float2 d = fma2(splat2(0.23164189f), ax, splat2(1.0f));
+  const float2 t = make_float2(fast_rcp(d.x), fast_rcp(d.y));
+  float2 poly = fma2(splat2(0.5307027145f), t, splat2(-0.7265760135f));
+  poly = fma2(poly, t, splat2(0.7107068705f));
+  poly = fma2(poly, t, splat2(-0.142248368f));
+  poly = fma2(poly, t, splat2(0.127414796f));
+  return mul2(mul2(poly, t), e);
+}
+__device__ __forceinline__ float2 gelu_erf2(float2 x) {
+  const float2 a = mul2(mul2(x, x), splat2(-0.72134752044448170368f));
+  const float2 e = make_float2(fast_exp2(a.x), fast_exp2(a.y));
+  const float2 ax = make_float2(fabsf(x.x), fabsf(x.y));
+  const float2 h = gelu_tail_h2(ax, e);
+  return fma2(make_float2(-ax.x, -ax.y), h, make_float2(fmaxf(x.x, 0.0f), fmaxf(x.y, 0.0f)));
+}
+__device__ __forceinline__ float2 gelu_erf_grad2(float2 x) {
+  const float2 a = mul2(mul2(x, x), splat2(-0.72134752044448170368f));
+  const float2 e = make_float2(fast_exp2(a.x), fast_exp2(a.y));
+  const float2 h = gelu_tail_h2(make_float2(fabsf(x.x), fabsf(x.y)), e);
+  const float2 cdf = make_float2(x.x >= 0.0f ? 1.0f - h.x : h.x, x.y >= 0.0f ? 1.0f - h.y : h.y);
+  return fma2(mul2(x, splat2(0.39894228040143267794f)), e, cdf);
+}
+
 // ---- Philox4x32-10 (counter-based dropout masks: forward and backward regenerate the same bits) ------------------
 struct Philox {
   uint32_t k0, k1;

@@ -15,6 +15,9 @@
 #ifndef VB_EPI_DIRECT
 #define VB_EPI_DIRECT 0  // 1 = no smem transpose: every thread applies the epilogue to its own row (the TMEM lane) and stores 16-byte pieces
 #endif
+#ifndef VB_GELU_PACKED
+#define VB_GELU_PACKED 1  // GELU / GELU' epilogue arithmetic on the packed fp32 pipe (FFMA2 / FMUL2 / FADD2): 0 = scalar form, for A/B builds
+#endif
 #ifndef VB_EPI_WARPS
 #define VB_EPI_WARPS 8  // 16 (four warps per TMEM lane quadrant, 16-column chunks) measured 3-4 % SLOWER on every shape: kept for A/B builds
 #endif
@@ -108,9 +111,16 @@ __device__ __forceinline__ void epilogue4(const GemmParams& p, float4 acc, const
   if constexpr (EPI == VAULT_EPI_BIAS_BF16) {
     *reinterpret_cast<uint2*>(out) = make_uint2(pack_bf16x2(acc.x + b4.x, acc.y + b4.y), pack_bf16x2(acc.z + b4.z, acc.w + b4.w));
   } else if constexpr (EPI == VAULT_EPI_BIAS_GELU_BF16) {
+#if VB_GELU_PACKED
+    const float2 xa = add2(make_float2(acc.x, acc.y), make_float2(b4.x, b4.y)), xb = add2(make_float2(acc.z, acc.w), make_float2(b4.z, b4.w));
+    if (out2) *reinterpret_cast<uint2*>(out2) = make_uint2(pack_bf16x2(xa.x, xa.y), pack_bf16x2(xb.x, xb.y));
+    const float2 ga = gelu_erf2(xa), gb = gelu_erf2(xb);
+    *reinterpret_cast<uint2*>(out) = make_uint2(pack_bf16x2(ga.x, ga.y), pack_bf16x2(gb.x, gb.y));
+#else
     const float x0 = acc.x + b4.x, x1 = acc.y + b4.y, x2 = acc.z + b4.z, x3 = acc.w + b4.w;
     if (out2) *reinterpret_cast<uint2*>(out2) = make_uint2(pack_bf16x2(x0, x1), pack_bf16x2(x2, x3));
     *reinterpret_cast<uint2*>(out) = make_uint2(pack_bf16x2(gelu_erf(x0), gelu_erf(x1)), pack_bf16x2(gelu_erf(x2), gelu_erf(x3)));
+#endif
   } else if constexpr (EPI == VAULT_EPI_BIAS_RESID_F32) {
     float x0 = acc.x + b4.x, x1 = acc.y + b4.y, x2 = acc.z + b4.z, x3 = acc.w + b4.w;
     if (p.dropout_p > 0.f) {
@@ -126,8 +136,14 @@ __device__ __forceinline__ void epilogue4(const GemmParams& p, float4 acc, const
   } else if constexpr (EPI == VAULT_EPI_PLAIN_BF16) {
     *reinterpret_cast<uint2*>(out) = make_uint2(pack_bf16x2(acc.x, acc.y), pack_bf16x2(acc.z, acc.w));
   } else if constexpr (EPI == VAULT_EPI_DGELU_BF16) {
+#if VB_GELU_PACKED
+    const float2 da = mul2(make_float2(acc.x, acc.y), gelu_erf_grad2(make_float2(side.x, side.y)));
+    const float2 db = mul2(make_float2(acc.z, acc.w), gelu_erf_grad2(make_float2(side.z, side.w)));
+    *reinterpret_cast<uint2*>(out) = make_uint2(pack_bf16x2(da.x, da.y), pack_bf16x2(db.x, db.y));
+#else
     *reinterpret_cast<uint2*>(out) = make_uint2(pack_bf16x2(acc.x * gelu_erf_grad(side.x), acc.y * gelu_erf_grad(side.y)),
                                                 pack_bf16x2(acc.z * gelu_erf_grad(side.z), acc.w * gelu_erf_grad(side.w)));
+#endif
   } else if constexpr (EPI == VAULT_EPI_ATOMIC_F32) {
     asm volatile("red.global.add.v4.f32 [%0], {%1, %2, %3, %4};" ::"l"(out), "f"(acc.x), "f"(acc.y), "f"(acc.z), "f"(acc.w) : "memory");
   } else if constexpr (EPI == VAULT_EPI_ATOMIC_BIAS_DROP_F32) {

@@ -6,11 +6,12 @@ from vault_b200 import ops
 dev = torch.device("cuda:0")
 e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
 E = ops
-cases = [("qkv_fwd", 5920, 2304, 768, E.EPI_BIAS_BF16, 0), ("out_fwd_resid", 5920, 768, 768, E.EPI_BIAS_RESID_F32, 0),
-         ("mlp1_fwd_gelu", 5920, 3072, 768, E.EPI_BIAS_GELU_BF16, 0), ("mlp2_fwd_resid", 5920, 768, 3072, E.EPI_BIAS_RESID_F32, 0),
-         ("mlp2_dgrad_dgelu", 5920, 3072, 768, E.EPI_DGELU_BF16, 1), ("mlp1_dgrad", 5920, 768, 3072, E.EPI_PLAIN_BF16, 1),
-         ("qkv_dgrad", 5920, 768, 2304, E.EPI_PLAIN_BF16, 1), ("lm_out_resid", 1280, 768, 768, E.EPI_BIAS_RESID_F32, 0),
-         ("lm_mlp1_gelu", 1280, 3072, 768, E.EPI_BIAS_GELU_BF16, 0), ("lm_mlp2_resid", 1280, 768, 3072, E.EPI_BIAS_RESID_F32, 0)]
+MV, ML = int(os.environ.get("VB_M_VILT", "5920")), int(os.environ.get("VB_M_LM", "1280"))  # target shape: VB_M_VILT=11808 VB_M_LM=4096
+cases = [("qkv_fwd", MV, 2304, 768, E.EPI_BIAS_BF16, 0), ("out_fwd_resid", MV, 768, 768, E.EPI_BIAS_RESID_F32, 0),
+         ("mlp1_fwd_gelu", MV, 3072, 768, E.EPI_BIAS_GELU_BF16, 0), ("mlp2_fwd_resid", MV, 768, 3072, E.EPI_BIAS_RESID_F32, 0),
+         ("mlp2_dgrad_dgelu", MV, 3072, 768, E.EPI_DGELU_BF16, 1), ("mlp1_dgrad", MV, 768, 3072, E.EPI_PLAIN_BF16, 1),
+         ("qkv_dgrad", MV, 768, 2304, E.EPI_PLAIN_BF16, 1), ("lm_out_resid", ML, 768, 768, E.EPI_BIAS_RESID_F32, 0),
+         ("lm_mlp1_gelu", ML, 3072, 768, E.EPI_BIAS_GELU_BF16, 0), ("lm_dgelu", ML, 3072, 768, E.EPI_DGELU_BF16, 1), ("lm_mlp2_resid", ML, 768, 3072, E.EPI_BIAS_RESID_F32, 0)]
 res = {}
 tot = 0.0
 for name, M, N, K, epi, b_mn in cases:

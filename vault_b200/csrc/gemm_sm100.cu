@@ -16,7 +16,10 @@
 #define VB_EPI_DIRECT 0  // 1 = no smem transpose: every thread applies the epilogue to its own row (the TMEM lane) and stores 16-byte pieces
 #endif
 #ifndef VB_GELU_PACKED
-#define VB_GELU_PACKED 1  // GELU / GELU' epilogue arithmetic on the packed fp32 pipe (FFMA2 / FMUL2 / FADD2): 0 = scalar form, for A/B builds
+#define VB_GELU_PACKED 0  // 1 = GELU / GELU' epilogue arithmetic on the packed fp32 pipe (FFMA2 / FMUL2 / FADD2): 26 % fewer instructions per chunk,
+                          // yet measured EQUAL for the forward (64.6 vs 64.4 us at 11808x3072x768) and 6 us SLOWER for GELU' (71.9 -> 78.1 us):
+                          // these epilogues are not instruction-bound -- the forward writes two bf16 streams (145 MB per launch, 2.3 TB/s of
+                          // pure writes next to the operand reads), i.e. it sits on the HBM write roof, not on the issue slots
 #endif
 #ifndef VB_EPI_WARPS
 #define VB_EPI_WARPS 8  // 16 (four warps per TMEM lane quadrant, 16-column chunks) measured 3-4 % SLOWER on every shape: kept for A/B builds
@@ -567,6 +570,15 @@ gemm_bf16_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant_
       for (int c = part * kColsPerWarp; c < (part + 1) * kColsPerWarp; c += kCW) {
         uint32_t r[kCW];
         tmem_ld_cols(tmem_base + ((uint32_t)(q * 32) << 16) + (uint32_t)(as * BN + c), r);
+        // the chunk's bias columns are requested while the accumulators are on their way from TMEM (L1 / L2 latency off the chunk's chain)
+        const int col = n0 + c + (lane % kLPR) * 4;
+        float4 b4 = make_float4(0.f, 0.f, 0.f, 0.f);
+        if constexpr (EPI == VAULT_EPI_BIAS_BF16 || EPI == VAULT_EPI_BIAS_GELU_BF16 || EPI == VAULT_EPI_BIAS_RESID_F32 || EPI == VAULT_EPI_BIAS_F32) {
+          if (p.bias != nullptr && col < p.N) b4 = __ldg(reinterpret_cast<const float4*>(p.bias + col));
+        }
+        if constexpr (EPI == VAULT_EPI_ATOMIC_BIAS_DROP_F32) {
+          if (p.bias != nullptr && col < p.N && split == 0) b4 = __ldg(reinterpret_cast<const float4*>(p.bias + col));
+        }
         tmem_ld_wait();
 #if VB_EPI_DIRECT
         if (full_tile) epilogue_row<EPI, false>(p, r, (long long)m0 + q * 32 + lane, n0 + c, split, seed);
@@ -580,14 +592,6 @@ gemm_bf16_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant_
               make_float4(__uint_as_float(r[4 * j]), __uint_as_float(r[4 * j + 1]), __uint_as_float(r[4 * j + 2]), __uint_as_float(r[4 * j + 3]));
         }
         __syncwarp();
-        const int col = n0 + c + (lane % kLPR) * 4;
-        float4 b4 = make_float4(0.f, 0.f, 0.f, 0.f);
-        if constexpr (EPI == VAULT_EPI_BIAS_BF16 || EPI == VAULT_EPI_BIAS_GELU_BF16 || EPI == VAULT_EPI_BIAS_RESID_F32 || EPI == VAULT_EPI_BIAS_F32) {
-          if (p.bias != nullptr && col < p.N) b4 = __ldg(reinterpret_cast<const float4*>(p.bias + col));
-        }
-        if constexpr (EPI == VAULT_EPI_ATOMIC_BIAS_DROP_F32) {
-          if (p.bias != nullptr && col < p.N && split == 0) b4 = __ldg(reinterpret_cast<const float4*>(p.bias + col));
-        }
         const long long row0 = (long long)m0 + q * 32;
         if (full_tile) epilogue_chunk<EPI, false>(p, stg, lane, b4, seed, row0, col);
         else epilogue_chunk<EPI, true>(p, stg, lane, b4, seed, row0, col);

@@ -486,6 +486,15 @@ def main():
                                  model_tflops_per_gpu=B * 10 / (ms3 * 1e-3) * W3["train_gflop"] / 1e3))
         del host3, dev3
 
+    replicas_identical = None
+    if world > 1:
+        # after the run every replica must hold the same fp32 weights (synchronize() also consolidates sharded masters): compare a checksum
+        ts.synchronize()
+        mw = ts.engine.master[:ts.engine.n_train]
+        chk = torch.stack([mw.double().sum(), mw[::997].double().abs().sum()])
+        allc = [torch.empty_like(chk) for _ in range(world)]
+        dist.all_gather(allc, chk)
+        replicas_identical = bool(all(torch.equal(allc[0], c) for c in allc[1:]))
     if rank == 0:
         peaks = {}
         try:
@@ -524,6 +533,7 @@ def main():
             "hbm_kernels": hbm,
             "cpu_baseline": cpu,
             "loss_first_last": [losses[0], losses[-1]] if losses else None,
+            "replicas_identical": replicas_identical,
             "also": also,
         }
         print(json.dumps(out), flush=True)

@@ -95,6 +95,63 @@ def test_schedule_matches_oracle():
     assert ts.lr_at(0) == 0.0
 
 
+def test_multicast_slices_partition_every_gradient_range():
+    """Data-parallel multicast path (train.py): rank r owns slice r of every finished gradient range -- the slices are disjoint, cover the
+    range, and start / end on multiples of 8 parameters (one 32-byte unit of vault_mc_adamw_step) wherever the range does."""
+    from vault_b200.train import VaultTrainStep
+
+    for world in (2, 3, 4, 8):
+        for lo, hi in ((0, 64), (128, 128 + 8 * 1000), (64, 64 + 27_981_888), (0, 8), (192, 192 + 24)):
+            cover = []
+            for rank in range(world):
+                ts = VaultTrainStep.__new__(VaultTrainStep)
+                ts.world, ts.rank = world, rank
+                a, b = ts._mc_slice(lo, hi)
+                assert lo <= a <= b <= hi and (a - lo) % 8 == 0 and ((b - lo) % 8 == 0 or b == hi)
+                cover.append((a, b))
+            assert cover[0][0] == lo and cover[-1][1] == hi
+            assert all(cover[i][1] == cover[i + 1][0] for i in range(world - 1))
+
+
+def test_weight_gradient_tile_choice_fills_the_sms():
+    """_wgrad_cfg: 128x256 tiles with a power-of-two split-K where that fills the 148 SMs, 128x192 for the 2304 x 768 QKV gradient
+    (54 tiles x 2 = 108 CTAs -> 72 x 2 = 144)."""
+    d, m = tiny_model()
+    eng = m.engine
+    eng.sms = 148
+    assert eng._wgrad_cfg(2304, 768, 11808) == (192, 2)     # QKV
+    assert eng._wgrad_cfg(3072, 768, 11808) == (256, 2)     # MLP-1: 72 tiles x 2
+    assert eng._wgrad_cfg(768, 3072, 11808) == (256, 2)     # MLP-2
+    assert eng._wgrad_cfg(768, 768, 11808) == (256, 8)      # attention output: 18 tiles x 8
+    bn, split = eng._wgrad_cfg(768, 768, 100)               # two k-blocks only: no split
+    assert split == 1 and bn in (128, 192, 256)
+
+
+def test_shadow_only_bitmap_marks_dense_matrices_only():
+    """The multicast optimizer step leaves the fp32 masters of a 64-parameter block sharded iff its bit is set: set for the dense projection
+    matrices of the encoder layers (read through the bf16 shadow only), clear for everything a kernel reads in fp32."""
+    import types
+    from vault_b200.engine import ALIGN, Slot, VaultEngine
+
+    names = ["classifier.1.weight", "encoder.layer.1.attention.attention.query.bias", "encoder.layer.1.layernorm_before.weight",
+             "encoder.layer.1.attention.output.dense.weight", "encoder.layer.1.attention.attention.query.weight",
+             "encoder.layer.1.intermediate.dense.weight", "encoder.layer.1.output.dense.bias", "embeddings.position_embeddings",
+             "bert.encoder.layer.0.attention.self.value.weight", "bert.encoder.layer.0.output.LayerNorm.weight",
+             "bert.embeddings.word_embeddings.weight", "pooler.dense.weight"]
+    off, slots = 0, {}
+    for i, n in enumerate(names):
+        numel = 64 * (i + 1) + (8 if i % 2 else 0)
+        slots[n] = Slot(n, off, numel, (numel,), True)
+        off += (numel + ALIGN - 1) // ALIGN * ALIGN
+    fake = types.SimpleNamespace(slots=slots, n_train=off, device=torch.device("cpu"))
+    words = VaultEngine.shadow_only_bitmap(fake)
+    bits = [(int(words[b // 32]) >> (b % 32)) & 1 for b in range((off + ALIGN - 1) // ALIGN)]
+    for n, sl in slots.items():
+        dense = any(k in n for k in ("query.weight", "value.weight", "attention.output.dense.weight", "intermediate.dense.weight"))
+        blocks = range(sl.off // ALIGN, (sl.off + sl.numel + ALIGN - 1) // ALIGN)
+        assert all(bits[b] == int(dense) for b in blocks), n
+
+
 def _free_port():
     s = socket.socket()
     s.bind(("127.0.0.1", 0))

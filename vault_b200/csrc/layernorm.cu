@@ -7,8 +7,16 @@ namespace vb {
 
 constexpr int kLnWarps = 8;
 
+#ifndef VB_LN_FWD_CTAS
+#define VB_LN_FWD_CTAS 4  // resident CTAs per SM asked of the compiler: 4 (64 registers) 11.34 us at 11,808 x 768; 0 = its own choice (56 registers) 11.5; 5 (48 registers, spills) 12.9
+#endif
+#if VB_LN_FWD_CTAS > 0
+#define VB_LN_FWD_BOUNDS __launch_bounds__(kLnWarps * 32, VB_LN_FWD_CTAS)
+#else
+#define VB_LN_FWD_BOUNDS __launch_bounds__(kLnWarps * 32)
+#endif
 template <int VPL>  // float4 vectors per lane: cols = 128 * VPL
-__global__ void __launch_bounds__(kLnWarps * 32)
+__global__ void VB_LN_FWD_BOUNDS
 ln_fwd_kernel(const float* __restrict__ x, const float* __restrict__ gamma, const float* __restrict__ beta, bf16* __restrict__ y_bf16,
               float* __restrict__ y_f32, float* __restrict__ mean_out, float* __restrict__ rstd_out, long long rows, float eps,
               float drop_p, unsigned long long seed, const unsigned long long* seed_dev, unsigned site) {
@@ -75,22 +83,41 @@ ln_fwd_kernel(const float* __restrict__ x, const float* __restrict__ gamma, cons
 // and meet once per CTA: O(SMs * cols) fp32 atomics.
 constexpr int kLnBwdWarps = 8;    // consumer warps
 constexpr int kLnBwdSlots = 16;   // rows in flight per CTA
+#ifndef VB_LN_PRODUCERS
+#define VB_LN_PRODUCERS 4  // measured at 11,808 x 768: 1 lane 30.5 us, 2 lanes 29.6, 4 lanes 29.4
+#endif
+constexpr int kLnBwdProducers = VB_LN_PRODUCERS;  // producer lanes
 
+// The consumers' per-column partial sums (up to three sets: dgamma, dbeta, bias-gradient column sums) meet once per CTA: one trip through
+// shared memory for all sets together (two named barriers in total), then one red.global.add.v4 per 4 columns and set.
 template <int VPL>
-__device__ __forceinline__ void cta_colsum_flush(float4 (&acc)[VPL], float4 (*red)[32 * VPL + 1], float* __restrict__ dst, int warp, int lane) {
-  asm volatile("bar.sync 1, %0;" ::"n"(kLnBwdWarps * 32));
+__device__ __forceinline__ void cta_colsum_flush3(float4 (&a0)[VPL], float4 (&a1)[VPL], float4 (&a2)[VPL], float* __restrict__ d0,
+                                                  float* __restrict__ d1, float* __restrict__ d2, uint8_t* smem, int warp, int lane) {
+  constexpr int kRow = 32 * VPL + 1;
+  float4* red = reinterpret_cast<float4*>(smem);  // [3][kLnBwdWarps][kRow]
+  asm volatile("bar.sync 1, %0;" ::"n"(kLnBwdWarps * 32));  // every consumer is done with the ring
 #pragma unroll
-  for (int i = 0; i < VPL; ++i) red[warp][lane + 32 * i] = acc[i];
-  asm volatile("bar.sync 1, %0;" ::"n"(kLnBwdWarps * 32));
-  for (int c4 = warp * 32 + lane; c4 < 32 * VPL; c4 += kLnBwdWarps * 32) {
-    float4 a = red[0][c4];
-#pragma unroll
-    for (int w = 1; w < kLnBwdWarps; ++w) {
-      const float4 t = red[w][c4];
-      a.x += t.x; a.y += t.y; a.z += t.z; a.w += t.w;
-    }
-    asm volatile("red.global.add.v4.f32 [%0], {%1, %2, %3, %4};" ::"l"(dst + 4 * c4), "f"(a.x), "f"(a.y), "f"(a.z), "f"(a.w) : "memory");
+  for (int i = 0; i < VPL; ++i) {
+    if (d0) red[(0 * kLnBwdWarps + warp) * kRow + lane + 32 * i] = a0[i];
+    if (d1) red[(1 * kLnBwdWarps + warp) * kRow + lane + 32 * i] = a1[i];
+    if (d2) red[(2 * kLnBwdWarps + warp) * kRow + lane + 32 * i] = a2[i];
   }
+  asm volatile("bar.sync 1, %0;" ::"n"(kLnBwdWarps * 32));
+  auto reduce_set = [&](int s, float* __restrict__ dst) {
+    if (dst == nullptr) return;
+    for (int c4 = warp * 32 + lane; c4 < 32 * VPL; c4 += kLnBwdWarps * 32) {
+      float4 a = red[(s * kLnBwdWarps) * kRow + c4];
+#pragma unroll
+      for (int w = 1; w < kLnBwdWarps; ++w) {
+        const float4 t = red[(s * kLnBwdWarps + w) * kRow + c4];
+        a.x += t.x; a.y += t.y; a.z += t.z; a.w += t.w;
+      }
+      asm volatile("red.global.add.v4.f32 [%0], {%1, %2, %3, %4};" ::"l"(dst + 4 * c4), "f"(a.x), "f"(a.y), "f"(a.z), "f"(a.w) : "memory");
+    }
+  };
+  reduce_set(0, d0);
+  reduce_set(1, d1);
+  reduce_set(2, d2);
 }
 
 template <int VPL>
@@ -123,8 +150,9 @@ ln_bwd_kernel(const float* __restrict__ dy_f32, const bf16* __restrict__ dy_bf16
 
   if (warp == kLnBwdWarps) {
     // ===================== producer: bulk-copy rows into the ring =====================
-    if (lane == 0) {
-      for (long long k = 0; k < my_rows; ++k) {
+    if (lane < kLnBwdProducers) {  // lane l streams the rows k = l, l + P, ...: P issue threads in lock-step (one thread's wait + expect_tx + 3-4
+                                   // bulk copies per row is ~450 cycles, close to the ~540 cycles a row may take at full HBM rate)
+      for (long long k = lane; k < my_rows; k += kLnBwdProducers) {
         const int slot = (int)(k % kLnBwdSlots);
         const uint32_t ph = (uint32_t)((k / kLnBwdSlots) & 1);
         mbar_wait(bars + 8u * (kLnBwdSlots + slot), ph ^ 1u);
@@ -224,10 +252,7 @@ ln_bwd_kernel(const float* __restrict__ dy_f32, const bf16* __restrict__ dy_bf16
   }
   if (dgamma == nullptr && dbeta == nullptr && dcolsum == nullptr) return;
   // the ring is idle now (every row of this CTA has been consumed by the time all consumers pass the first bar.sync)
-  float4(*red)[32 * VPL + 1] = reinterpret_cast<float4(*)[32 * VPL + 1]>(ln_smem);
-  if (dgamma) cta_colsum_flush<VPL>(dg, red, dgamma, warp, lane);
-  if (dbeta) cta_colsum_flush<VPL>(db, red, dbeta, warp, lane);
-  if (dcolsum) cta_colsum_flush<VPL>(dcs, red, dcolsum, warp, lane);
+  cta_colsum_flush3<VPL>(dg, db, dcs, dgamma, dbeta, dcolsum, ln_smem, warp, lane);
 }
 
 template <int VPL>
@@ -245,7 +270,7 @@ int ln_bwd_launch(const float* dy_f32, const void* dy_bf16, const float* x, cons
   constexpr int cols = 128 * VPL;
   const int slot_bytes = cols * 4 + (dres ? cols * 4 : 0) + (dy_f32 ? cols * 4 : 0) + (dy_bf16 ? cols * 2 : 0);
   int smem = kLnBwdSlots * slot_bytes + 2 * kLnBwdSlots * 8;
-  const int red_bytes = kLnBwdWarps * (32 * VPL + 1) * 16;
+  const int red_bytes = 3 * kLnBwdWarps * (32 * VPL + 1) * 16;
   if (smem < red_bytes) smem = red_bytes;
   static int smem_set = 0;
   if (smem > smem_set) {

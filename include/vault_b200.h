@@ -55,7 +55,9 @@ enum {
   VAULT_EPI_ATOMIC_F32 = 5,      /* out(f32) += acc   (split-K partial sums; caller zero-fills)               */
   VAULT_EPI_BIAS_F32 = 6,        /* out(f32) = acc + bias (bias optional)                                    */
   VAULT_EPI_STORE_F32 = 7,       /* out(f32) = acc        (wgrad without split-K)                             */
-  VAULT_EPI_ATOMIC_BIAS_DROP_F32 = 8 /* out(f32) += dropout_p(acc + bias): split-K form of RESID, out already holds the residual */
+  VAULT_EPI_ATOMIC_BIAS_DROP_F32 = 8, /* out(f32) += dropout_p(acc + bias): split-K form of RESID, out already holds the residual */
+  VAULT_EPI_BIAS_GELU_GRAD_BF16 = 9,  /* training forward: out(bf16) = gelu_erf(acc + bias) ; out2(bf16, optional) = gelu_erf'(acc + bias)  */
+  VAULT_EPI_MUL_AUX_BF16 = 10         /* its backward: out(bf16) = acc * aux(bf16), aux = the derivative saved by epilogue 9                */
 };
 
 typedef struct vault_gemm_args {

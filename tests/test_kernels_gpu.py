@@ -98,6 +98,14 @@ def test_gemm_epilogues(dev, ops):
     gp = 0.5 * (1 + torch.erf(x / 2 ** 0.5)) + x * torch.exp(-0.5 * x * x) / (2 * math.pi) ** 0.5
     assert _rel(ops.gemm(a, b, ops.EPI_DGELU_BF16, aux=aux), acc * gp) < tol
     assert _rel(ops.gemm(a, b, ops.EPI_BIAS_F32, bias=bias), acc + bias) < 1e-4
+    # training pair: the forward saves gelu'(x) next to gelu(x), the backward epilogue multiplies by it
+    xr = (acc + bias).clone().requires_grad_(True)
+    torch.nn.functional.gelu(xr).sum().backward()
+    dact = torch.empty(M, N, device=dev, dtype=torch.bfloat16)
+    act2 = ops.gemm(a, b, ops.EPI_BIAS_GELU_GRAD_BF16, bias=bias, out2=dact)
+    assert _rel(act2, torch.nn.functional.gelu(acc + bias)) < tol and torch.equal(act2, act)
+    assert (dact.float() - xr.grad).abs().max().item() < 1e-2  # gelu' in [-0.13, 1.13], bf16 output
+    assert _rel(ops.gemm(a, b, ops.EPI_MUL_AUX_BF16, aux=aux), acc * aux.float()) < tol
 
 
 def test_gemm_dropout_epilogue_statistics(dev, ops):

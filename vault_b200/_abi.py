@@ -15,6 +15,7 @@ c_i32, c_i64, c_u32, c_u64, c_f32, c_p = C.c_int32, C.c_int64, C.c_uint32, C.c_u
 
 EPI_BIAS_BF16, EPI_BIAS_GELU_BF16, EPI_BIAS_RESID_F32, EPI_PLAIN_BF16 = 0, 1, 2, 3
 EPI_DGELU_BF16, EPI_ATOMIC_F32, EPI_BIAS_F32, EPI_STORE_F32 = 4, 5, 6, 7
+EPI_BIAS_GELU_GRAD_BF16, EPI_MUL_AUX_BF16 = 9, 10
 EPI_ATOMIC_BIAS_DROP_F32 = 8
 
 

@@ -137,6 +137,16 @@ __device__ __forceinline__ float gelu_erf_grad(float x) {
   return fmaf(x * 0.39894228040143267794f, e, cdf);
 }
 
+// value and derivative together (training forward): one exponential, one tail polynomial
+__device__ __forceinline__ void gelu_erf_both(float x, float& g, float& d) {
+  const float e = fast_exp2(x * x * -0.72134752044448170368f);
+  const float ax = fabsf(x);
+  const float h = gelu_tail_h(ax, e);
+  g = fmaf(-ax, h, fmaxf(x, 0.0f));
+  const float cdf = x >= 0.0f ? 1.0f - h : h;
+  d = fmaf(x * 0.39894228040143267794f, e, cdf);
+}
+
 // Two elements per instruction: Blackwell's packed fp32 pipe (fma/mul/add.f32x2 -> FFMA2 / FMUL2 / FADD2, IEEE rn per lane, so the results
 // are bit-identical to the scalar forms above).  The GELU epilogues are bound by issue slots and latency next to the MMA warps; the
 // polynomial part of a pair costs 10 instructions instead of 20 (MUFU, |x| and max stay per element).

@@ -21,8 +21,8 @@ from typing import Dict, List, Optional, Tuple
 import torch
 
 from . import _abi
-from ._abi import (EPI_ATOMIC_BIAS_DROP_F32, EPI_ATOMIC_F32, EPI_BIAS_BF16, EPI_BIAS_F32, EPI_BIAS_GELU_BF16, EPI_BIAS_RESID_F32,
-                   EPI_DGELU_BF16, EPI_PLAIN_BF16, EPI_STORE_F32, GemmArgs)
+from ._abi import (EPI_ATOMIC_BIAS_DROP_F32, EPI_ATOMIC_F32, EPI_BIAS_BF16, EPI_BIAS_F32, EPI_BIAS_GELU_BF16, EPI_BIAS_GELU_GRAD_BF16, EPI_BIAS_RESID_F32,
+                   EPI_MUL_AUX_BF16, EPI_PLAIN_BF16, EPI_STORE_F32, GemmArgs)
 
 ALIGN = 64  # elements; every slot starts on a 256-byte (fp32) / 128-byte (bf16) boundary -> TMA- and float4-safe
 
@@ -510,8 +510,13 @@ class VaultEngine:
         """resid_inplace: the caller does not need resid32 afterwards, so a split-K second GEMM may accumulate into it."""
         H, I = self.H, self.I
         act = self._new((M, I), torch.bfloat16)
-        pre = self._new((M, I), torch.bfloat16) if save is not None else None
-        self.linear_fwd(n16, M, nm["w1"], nm["b1"], I, H, EPI_BIAS_GELU_BF16, act, out2=pre.data_ptr() if pre is not None else 0, ldo2=I)
+        # training: the epilogue also writes gelu'(pre-activation) -- it shares the exponential and the tail polynomial with the value -- so the
+        # backward epilogue of the W2 dgrad only multiplies by it (saved in place of the pre-activation, which nothing else reads)
+        dact = self._new((M, I), torch.bfloat16) if save is not None else None
+        if dact is not None:
+            self.linear_fwd(n16, M, nm["w1"], nm["b1"], I, H, EPI_BIAS_GELU_GRAD_BF16, act, out2=dact.data_ptr(), ldo2=I)
+        else:
+            self.linear_fwd(n16, M, nm["w1"], nm["b1"], I, H, EPI_BIAS_GELU_BF16, act)
         # training only: atomic accumulation order makes the result run-to-run different in the last fp32 bit; inference stays bit-reproducible
         split = self._small_m_split(M, H, I) if (resid_inplace and save is not None) else 1
         if split > 1:
@@ -521,7 +526,7 @@ class VaultEngine:
             y32 = self._new((M, H), torch.float32)
             self.linear_fwd(act, M, nm["w2"], nm["b2"], H, I, EPI_BIAS_RESID_F32, y32, resid=resid32.data_ptr(), ldr=H, p=p_out, site=site)
         if save is not None:
-            save[f"{li}.pre"], save[f"{li}.act"] = pre, act
+            save[f"{li}.dact"], save[f"{li}.act"] = dact, act
         return y32
 
     # ---- ViLT (pre-LN) -----------------------------------------------------------------------------------------
@@ -544,7 +549,7 @@ class VaultEngine:
         li = f"v{i}"
         H, I = self.H, self.I
         dpre = self._new((M, I), torch.bfloat16)
-        self.linear_dgrad(g16, M, nm["w2"], H, I, EPI_DGELU_BF16, dpre, aux=sv[f"{li}.pre"].data_ptr(), ldaux=I)
+        self.linear_dgrad(g16, M, nm["w2"], H, I, EPI_MUL_AUX_BF16, dpre, aux=sv[f"{li}.dact"].data_ptr(), ldaux=I)
         self.linear_wgrad(g16, sv[f"{li}.act"], M, nm["w2"], nm["b2"], H, I, bias=False)  # db2: summed by the kernel that produced g16
         dn2 = self._new((M, H), torch.bfloat16)
         self.linear_dgrad(dpre, M, nm["w1"], I, H, EPI_PLAIN_BF16, dn2)
@@ -587,7 +592,7 @@ class VaultEngine:
         ds32, ds16 = self.ln_bwd(g32, gx16, sv[f"{li}.s"], sv[f"{li}.st2"], M, nm["ln2"] + ".weight", nm["ln2"] + ".bias", out_p=p,
                                  out_site=self._site(i, 2), colsum_to=nm["b2"])
         dpre = self._new((M, I), torch.bfloat16)
-        self.linear_dgrad(ds16, M, nm["w2"], H, I, EPI_DGELU_BF16, dpre, aux=sv[f"{li}.pre"].data_ptr(), ldaux=I)
+        self.linear_dgrad(ds16, M, nm["w2"], H, I, EPI_MUL_AUX_BF16, dpre, aux=sv[f"{li}.dact"].data_ptr(), ldaux=I)
         self.linear_wgrad(ds16, sv[f"{li}.act"], M, nm["w2"], nm["b2"], H, I, bias=False)
         split = self._small_m_split(M, H, I)
         if split > 1:

@@ -8,8 +8,8 @@ from typing import Optional
 import torch
 
 from . import _abi
-from ._abi import (EPI_ATOMIC_BIAS_DROP_F32, EPI_ATOMIC_F32, EPI_BIAS_BF16, EPI_BIAS_F32, EPI_BIAS_GELU_BF16, EPI_BIAS_RESID_F32,
-                   EPI_DGELU_BF16, EPI_PLAIN_BF16, EPI_STORE_F32, GemmArgs)
+from ._abi import (EPI_ATOMIC_BIAS_DROP_F32, EPI_ATOMIC_F32, EPI_BIAS_BF16, EPI_BIAS_F32, EPI_BIAS_GELU_BF16, EPI_BIAS_GELU_GRAD_BF16, EPI_BIAS_RESID_F32,
+                   EPI_DGELU_BF16, EPI_MUL_AUX_BF16, EPI_PLAIN_BF16, EPI_STORE_F32, GemmArgs)
 
 _OUT_F32 = {EPI_BIAS_RESID_F32, EPI_ATOMIC_F32, EPI_BIAS_F32, EPI_STORE_F32, EPI_ATOMIC_BIAS_DROP_F32}
 

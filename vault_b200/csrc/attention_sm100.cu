@@ -191,17 +191,24 @@ attn_sm100_kernel(const __grid_constant__ CUtensorMap tmQKV, const __grid_consta
   // sequences the next item's blocks land in free slots while the current item is still being worked on)
   auto rslot = [&](int it, int b) { return (it * nblk + b) % 3; };
   auto rpar = [&](int it, int b) { return (uint32_t)(((it * nblk + b) / 3) & 1); };
-  const int my_items = ((int)p.n_items - (int)blockIdx.x + (int)gridDim.x - 1) / (int)gridDim.x;
+  // Work of this CTA: a contiguous range [t0, t1) of the launch's n_items x ntiles tiles, balanced to one tile (S = 369: 1,152 tiles over 148
+  // CTAs = 7 or 8 each, where whole items gave 6 or 9).  An item may be shared by two CTAs; each then loads the item's resident blocks itself.
+  const long long Tt = (long long)p.n_items * ntiles;
+  const int t0 = (int)(Tt * blockIdx.x / gridDim.x), t1 = (int)(Tt * (blockIdx.x + 1) / gridDim.x);
+  const int item0 = t0 / ntiles;
+  const int my_items = t1 > t0 ? (t1 - 1) / ntiles - item0 + 1 : 0;
+  auto tile_lo = [&](int it) { return it == 0 ? t0 - item0 * ntiles : 0; };
+  auto tile_hi = [&](int it) { return it == my_items - 1 ? t1 - (item0 + it) * ntiles : ntiles; };
 
   if (warp == 0) {
     // =========================================== TMA producer ===========================================
     if (lane == 0) {
       int nt = 0;
       for (int it = 0; it < my_items; ++it) {
-        const int item = (int)blockIdx.x + it * (int)gridDim.x;
+        const int item = item0 + it;
         const int b_ = item / p.heads, h_ = item % p.heads;
         const int row0 = b_ * S;
-        for (int tile = 0; tile < ntiles; ++tile, ++nt) {
+        for (int tile = tile_lo(it), tile_end = tile_hi(it); tile < tile_end; ++tile, ++nt) {
           const int ts = MODE == MODE_F ? (nt & 1) : 0;
           const uint32_t tpar = (uint32_t)((MODE == MODE_F ? (nt >> 1) : nt) & 1);
           mbar_wait(bar(bTE + ts), tpar ^ 1u);
@@ -226,7 +233,7 @@ attn_sm100_kernel(const __grid_constant__ CUtensorMap tmQKV, const __grid_consta
               tma_load_2d(d + kBlk + 8192u, &tmQKV, fb, 2 * H + h_ * 64, r + 64);
             }
           }
-          if (tile == 0) {
+          if (tile == tile_lo(it)) {
             // resident blocks in the order the item's first tile needs them (= the order the previous item released them)
             const int dir0 = MODE == MODE_F ? (nt & 1) : 0;
             auto load_r = [&](int which, int bb) {  // which 0: R1 (F / BQ: K_b, BKV: Q_b); 1: R2 (F / BQ: V_b, BKV: dO_b)
@@ -263,9 +270,9 @@ attn_sm100_kernel(const __grid_constant__ CUtensorMap tmQKV, const __grid_consta
       int n = 0, nt = 0, tr_n = 0;
       for (int it = 0; it < my_items; ++it) {
         uint32_t seen = 0;  // bit b: R1_b of this item already waited for, bit 4 + b: R2_b
-        for (int tile = 0; tile < ntiles; ++tile, ++nt) {
+        for (int tile = tile_lo(it), tile_end = tile_hi(it); tile < tile_end; ++tile, ++nt) {
           const int ts = MODE == MODE_F ? (nt & 1) : 0;
-          const bool last_tile = tile == ntiles - 1;
+          const bool last_tile = tile == tile_end - 1;
           for (int j = 0; j < L; ++j, ++n) {
             const int b = blk_of(j, nt), kind = kind_of(j);
             const int sl = n % kRing, rs = rslot(it, b);
@@ -312,8 +319,8 @@ attn_sm100_kernel(const __grid_constant__ CUtensorMap tmQKV, const __grid_consta
       (void)tr_n;
       for (int it = 0; it < my_items; ++it) {
         uint32_t seen = 0;
-        for (int tile = 0; tile < ntiles; ++tile, ++nt) {
-          const bool last_tile = tile == ntiles - 1;
+        for (int tile = tile_lo(it), tile_end = tile_hi(it); tile < tile_end; ++tile, ++nt) {
+          const bool last_tile = tile == tile_end - 1;
           const int ob = nt & 1;
           for (int j = 0; j < L; ++j) {
             const int b = blk_of(j, nt), kind = kind_of(j);
@@ -434,11 +441,12 @@ attn_sm100_kernel(const __grid_constant__ CUtensorMap tmQKV, const __grid_consta
       const int key = 32 * w + lane;
       return (key < S && p.key_mask[(long long)(item / p.heads) * S + key] != 0) ? 1u : 0u;
     };
-    uint32_t nx0 = mask_bytes((int)blockIdx.x, ew), nx1 = mask_bytes((int)blockIdx.x, ew + 8);
+    const int first_item = my_items > 0 ? item0 : p.n_items;
+    uint32_t nx0 = mask_bytes(first_item, ew), nx1 = mask_bytes(first_item, ew + 8);
 
     int n = 0, nt = 0;
     for (int it = 0; it < my_items; ++it) {
-      const int item = (int)blockIdx.x + it * (int)gridDim.x;
+      const int item = item0 + it;
       const int b_ = item / p.heads, h_ = item % p.heads;
       const long long bh = (long long)b_ * p.heads + h_;
       {
@@ -447,14 +455,14 @@ attn_sm100_kernel(const __grid_constant__ CUtensorMap tmQKV, const __grid_consta
           mws[(it & 1) * 12 + ew] = w0;
           if (ew + 8 < 12) mws[(it & 1) * 12 + ew + 8] = w1;
         }
-        const int nitem = item + (int)gridDim.x;
+        const int nitem = it + 1 < my_items ? item + 1 : p.n_items;
         nx0 = mask_bytes(nitem, ew);
         nx1 = mask_bytes(nitem, ew + 8);
         bar_sync_256();
       }
       const uint32_t* mw_item = mws + (it & 1) * 12;
 
-      for (int tile = 0; tile < ntiles; ++tile, ++nt) {
+      for (int tile = tile_lo(it), tile_end = tile_hi(it); tile < tile_end; ++tile, ++nt) {
         const bool warp_active = MODE == MODE_BKV ? true : (tile * 128 + q * 32 < S);  // warp-uniform
         float m_run = -INFINITY, msc = 0.f, l = 0.f;
         float lse2 = INFINITY, dl = 0.f;
@@ -1190,7 +1198,9 @@ int attn_fwd_sm100(const void* qkv, const uint8_t* key_mask, void* ctx, float* l
   CUtensorMap tm;
   int rc = encode_tmap_2d(&tm, CU_TENSOR_MAP_DATA_TYPE_BFLOAT16, 2, qkv, (uint64_t)3 * H, (uint64_t)B * S, (uint64_t)3 * H, 64, 64);
   if (rc) return rc;
-  const int grid = p.n_items < device_sm_count() ? p.n_items : device_sm_count();
+  const int grid_pp = p.n_items < device_sm_count() ? p.n_items : device_sm_count();
+  const long long tiles = (long long)p.n_items * p.nblk;  // the shared-tile kernels split the launch's tiles, not its items, over the CTAs
+  const int grid = (int)(tiles < device_sm_count() ? tiles : device_sm_count());
   p.trace = trace_buf();
   // g_attn_fwd_pp (vault_attn_set_impl(4)): the forward with one tile per warpgroup instead of the shared-tile MODE_F.  Measured on B200
   // (B = 32, 12 heads): S = 369 60.5 us against 56.0 us, S = 209 (B = 64) 49.1 against 53.4 us -- the warpgroups do drift apart as intended,
@@ -1200,10 +1210,10 @@ int attn_fwd_sm100(const void* qkv, const uint8_t* key_mask, void* ctx, float* l
   if (g_attn_fwd_pp) {
     if (dropout_p > 0.f) {
       if ((rc = set_smem_a(attn_fwd_pp_kernel<true>))) return rc;
-      launch(attn_fwd_pp_kernel<true>, dim3(grid), dim3(kThreadsA), (size_t)kSmemA, st, tm, p);
+      launch(attn_fwd_pp_kernel<true>, dim3(grid_pp), dim3(kThreadsA), (size_t)kSmemA, st, tm, p);
     } else {
       if ((rc = set_smem_a(attn_fwd_pp_kernel<false>))) return rc;
-      launch(attn_fwd_pp_kernel<false>, dim3(grid), dim3(kThreadsA), (size_t)kSmemA, st, tm, p);
+      launch(attn_fwd_pp_kernel<false>, dim3(grid_pp), dim3(kThreadsA), (size_t)kSmemA, st, tm, p);
     }
   } else if (dropout_p > 0.f) {
     if ((rc = set_smem_a(attn_sm100_kernel<MODE_F, true>))) return rc;
@@ -1235,7 +1245,8 @@ int attn_bwd_sm100(const void* qkv, const uint8_t* key_mask, const void* ctx, co
   launch(attn_delta_kernel, dim3((unsigned)((total + 255) / 256)), dim3(256), 0, st, reinterpret_cast<const bf16*>(ctx), reinterpret_cast<const bf16*>(dctx), delta,
          B, S, heads);
   if ((rc = check_launch("attn_delta_kernel"))) return rc;
-  const int grid = p.n_items < device_sm_count() ? p.n_items : device_sm_count();
+  const long long tiles = (long long)p.n_items * p.nblk;
+  const int grid = (int)(tiles < device_sm_count() ? tiles : device_sm_count());
   p.trace = trace_buf();
   if (drop) launch(attn_sm100_kernel<MODE_BQ, true>, dim3(grid), dim3(kThreadsA), (size_t)kSmemA, st, tmQ, tmD, p);
   else launch(attn_sm100_kernel<MODE_BQ, false>, dim3(grid), dim3(kThreadsA), (size_t)kSmemA, st, tmQ, tmD, p);

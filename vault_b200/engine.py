@@ -103,6 +103,7 @@ class VaultEngine:
         self.wgrad_side_stream = os.environ.get("VAULT_B200_WGRAD_SIDE", "1") != "0"
         self.small_m_split_k = os.environ.get("VAULT_B200_SMALL_M_SPLITK", "1") != "0"
         self.comm_stream = None  # see _cut()
+        self.prezeroed = False
         self.flat_alloc = None  # optional allocator of the flat master / shadow / gradient buffers (see ensure_packed)
         self.fuse_bias_grad = os.environ.get("VAULT_B200_FUSE_BIAS_GRAD", "1") != "0"  # A/B switch: 0 = separate vault_colsum_bf16 launches
         self.patch_wgrad_tma = os.environ.get("VAULT_B200_PATCH_WGRAD_TMA", "1") != "0"  # 0: bf16 im2col + GEMM (A/B switch)
@@ -903,7 +904,10 @@ class VaultEngine:
         pending = first and self.grads_pending(exclude_prefix="classifier.")
         if first:
             if not pending:
-                self.zero_accumulated_grads()
+                if self.prezeroed:
+                    self.prezeroed = False  # the caller zero-filled the accumulated ranges already (train.py: on the side stream, under the forward)
+                else:
+                    self.zero_accumulated_grads()
             self._gen = tape.gen + 1
         self._accumulate = (not first) or pending
         if dlhs is not None:

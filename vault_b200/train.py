@@ -301,9 +301,19 @@ class VaultTrainStep:
         else:
             b["hw"][:, 0] = gh
             b["hw"][:, 1] = gw
+        # gradient zero-fill (the accumulated ranges, ~0.8 GB) on the side stream: it runs under the LM forward instead of in front of the backward
+        if not (segments and self.split_lm):  # (that opt-in mode ends a graph right after the LM forward: nothing may be in flight on the side stream there)
+            ev0 = torch.cuda.Event()
+            ev0.record(torch.cuda.current_stream(self.dev))
+            eng._side.wait_event(ev0)
+            with torch.cuda.stream(eng._side):
+                eng.zero_accumulated_grads()
+            eng._side_dirty = True
+            eng.prezeroed = True
         lhs, pooled, key_mask, tape = yield from eng.forward_iter(b["input_ids"], b.get("attention_mask"), b.get("token_type_ids"), b["pixel_values"],
                                                                   None, training=train, need_grad=True, hw=b["hw"], pmax=gh * gw,
                                                                   split_lm=segments and self.split_lm)
+        eng._join_side()  # the zero-fill (and the image branch) have landed before the first gradient is written
         # ---- head: Linear(Dropout(pooled)) -> CE mean; dlogits = (softmax - onehot) / B_local (DP averaging is applied in AdamW's grad_scale)
         p = self.head_p if train else 0.0
         x = pooled

@@ -350,6 +350,35 @@ def test_adamw_matches_hf_rule(dev, correct_bias, wd):
     assert torch.equal(sh[:n].cpu(), pd[:n].cpu().to(torch.bfloat16))
 
 
+@pytest.mark.parametrize("B,T,H,n_types", [(32, 128, 768, 2), (3, 17, 128, 1), (8, 40, 768, 4), (2, 9, 1152, 2)])
+def test_embedding_backward_scatter_adds(dev, B, T, H, n_types):
+    """lm_embed_bwd / vilt_text_embed_bwd: word / token-type / position table gradients == torch index_add_ of the row gradients
+    (token types 0 and 1 are summed per CTA in registers + shared memory, other types and rows wider than 1,024 take direct atomics)."""
+    from vault_b200 import _abi
+    torch.manual_seed(B * T + H)
+    V = 97
+    ids = torch.randint(1, V, (B, T), device=dev)
+    ids[:, -2:] = 0  # padding id: no word gradient
+    tt = torch.randint(0, n_types, (B, T), device=dev)
+    dx = torch.randn(B * T, H, device=dev)
+    st = torch.cuda.current_stream().cuda_stream
+    dword, dtype, dpos = torch.zeros(V, H, device=dev), torch.zeros(n_types, H, device=dev), torch.zeros(T, H, device=dev)
+    _abi.call("vault_lm_embed_bwd", ids.data_ptr(), tt.data_ptr(), dx.data_ptr(), dword.data_ptr(), dtype.data_ptr(), dpos.data_ptr(), B, T, H, -1, 0, st)
+    rw = torch.zeros(V, H, device=dev).index_add_(0, ids.flatten(), dx)
+    rw[0] = 0
+    rt = torch.zeros(n_types, H, device=dev).index_add_(0, tt.flatten(), dx)
+    rp = torch.zeros(T, H, device=dev).index_add_(0, torch.arange(T, device=dev).repeat(B), dx)
+    for got, ref in ((dword, rw), (dtype, rt), (dpos, rp)):
+        assert (got - ref).abs().max().item() <= 1e-4 * max(1.0, ref.abs().max().item())
+    dtype2, dpos2 = torch.zeros(n_types, H, device=dev), torch.zeros(T, H, device=dev)
+    _abi.call("vault_vilt_text_embed_bwd", tt.data_ptr(), dx.data_ptr(), dtype2.data_ptr(), dpos2.data_ptr(), B, T, H, st)
+    for got, ref in ((dtype2, rt), (dpos2, rp)):
+        assert (got - ref).abs().max().item() <= 1e-4 * max(1.0, ref.abs().max().item())
+    dtype3 = torch.zeros(n_types, H, device=dev)
+    _abi.call("vault_vilt_text_embed_bwd", None, dx.data_ptr(), dtype3.data_ptr(), None, B, T, H, st)  # no token types: everything is type 0
+    assert (dtype3[0] - dx.sum(0)).abs().max().item() <= 1e-4 * max(1.0, dx.sum(0).abs().max().item())
+
+
 def test_ce_loss_and_colsum(dev):
     from vault_b200 import _abi
 

@@ -45,27 +45,75 @@ lm_embed_fwd_kernel(const int64_t* __restrict__ ids, const int64_t* __restrict__
   for (int c = lane; c < H / 4; c += 32) o[c] = f4add(f4add(__ldg(w + c), __ldg(ty4 + c)), __ldg(p4 + c));
 }
 
+// Token-type rows are shared by (nearly) every token: thousands of atomics on the same 1-2 table rows serialise in the L2 (the kernel took
+// 86 us for 4,096 rows).  A warp therefore walks several rows and keeps the sums of types 0 and 1 in registers; the CTA's eight warps meet in
+// shared memory and issue ONE red.global.add.v4 per 4 columns and type.  Word / position rows see little contention and keep direct atomics.
+constexpr int kEmbMaxV = 8;  // float4 per lane: H <= 1024 on the register path (wider rows fall back to direct atomics)
+
+template <int NT>
+__device__ __forceinline__ void type_sums_flush(float4 (&acc)[NT][kEmbMaxV], float* __restrict__ dtype, int H, int warp, int lane) {
+  __shared__ float4 red[kEmbWarps][kEmbMaxV * 32];  // 32 KB: one token type at a time
+  const int nv = H / 4;
+#pragma unroll
+  for (int ty = 0; ty < NT; ++ty) {
+#pragma unroll
+    for (int k = 0; k < kEmbMaxV; ++k)
+      if (lane + 32 * k < nv) red[warp][lane + 32 * k] = acc[ty][k];
+    __syncthreads();
+    for (int c = threadIdx.x; c < nv; c += kEmbWarps * 32) {
+      float4 a = red[0][c];
+#pragma unroll
+      for (int w = 1; w < kEmbWarps; ++w) a = f4add(a, red[w][c]);
+      if (a.x != 0.f || a.y != 0.f || a.z != 0.f || a.w != 0.f) atomic_add4(dtype + (long long)ty * H + 4 * c, a);
+    }
+    __syncthreads();
+  }
+}
+
 __global__ void __launch_bounds__(kEmbWarps * 32)
 lm_embed_bwd_kernel(const int64_t* __restrict__ ids, const int64_t* __restrict__ tt, const float* __restrict__ dx, float* __restrict__ dword,
                     float* __restrict__ dtype, float* __restrict__ dpos, int B, int T, int H, int roberta_pad, int word_pad) {
   pdl_enter();
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
-  const long long row = (long long)blockIdx.x * kEmbWarps + warp;
-  if (row >= (long long)B * T) return;
-  const int b = (int)(row / T), t = (int)(row % T);
-  const long long id = ids[row];
-  const long long ty = tt ? tt[row] : 0;
-  const int pid = roberta_pad >= 0 ? roberta_pos(ids + (long long)b * T, t, roberta_pad, lane) : t;
-  const float4* g = reinterpret_cast<const float4*>(dx + row * H);
-  // nn.Embedding(padding_idx=...) rows receive no gradient (word table: pad_token_id; RoBERTa position table: pad id too)
-  const bool do_word = dword != nullptr && id != word_pad;
-  const bool do_pos = dpos != nullptr && !(roberta_pad >= 0 && pid == roberta_pad);
-  for (int c = lane; c < H / 4; c += 32) {
-    const float4 v = __ldg(g + c);
-    if (do_word) atomic_add4(dword + id * H + 4 * c, v);
-    if (dtype) atomic_add4(dtype + ty * H + 4 * c, v);
-    if (do_pos) atomic_add4(dpos + (long long)pid * H + 4 * c, v);
+  const bool reg_path = dtype != nullptr && H <= kEmbMaxV * 128;
+  float4 acc[2][kEmbMaxV];
+#pragma unroll
+  for (int k = 0; k < kEmbMaxV; ++k) acc[0][k] = acc[1][k] = make_float4(0.f, 0.f, 0.f, 0.f);
+  for (long long row = (long long)blockIdx.x * kEmbWarps + warp; row < (long long)B * T; row += (long long)gridDim.x * kEmbWarps) {
+    const int b = (int)(row / T), t = (int)(row % T);
+    const long long id = ids[row];
+    const long long ty = tt ? tt[row] : 0;
+    const int pid = roberta_pad >= 0 ? roberta_pos(ids + (long long)b * T, t, roberta_pad, lane) : t;
+    const float4* g = reinterpret_cast<const float4*>(dx + row * H);
+    // nn.Embedding(padding_idx=...) rows receive no gradient (word table: pad_token_id; RoBERTa position table: pad id too)
+    const bool do_word = dword != nullptr && id != word_pad;
+    const bool do_pos = dpos != nullptr && !(roberta_pad >= 0 && pid == roberta_pad);
+    const bool ty_reg = reg_path && ty < 2;  // warp-uniform
+#pragma unroll
+    for (int k = 0; k < kEmbMaxV; ++k) {
+      const int c = lane + 32 * k;
+      if (c < H / 4) {
+        const float4 v = __ldg(g + c);
+        if (do_word) atomic_add4(dword + id * H + 4 * c, v);
+        if (do_pos) atomic_add4(dpos + (long long)pid * H + 4 * c, v);
+        if (ty_reg) {
+          if (ty == 0) acc[0][k] = f4add(acc[0][k], v);
+          else acc[1][k] = f4add(acc[1][k], v);
+        } else if (dtype) {
+          atomic_add4(dtype + ty * H + 4 * c, v);
+        }
+      }
+    }
+    if (H > kEmbMaxV * 128) {  // columns beyond the register path
+      for (int c = lane + 32 * kEmbMaxV; c < H / 4; c += 32) {
+        const float4 v = __ldg(g + c);
+        if (do_word) atomic_add4(dword + id * H + 4 * c, v);
+        if (do_pos) atomic_add4(dpos + (long long)pid * H + 4 * c, v);
+        if (dtype) atomic_add4(dtype + ty * H + 4 * c, v);
+      }
+    }
   }
+  if (reg_path) type_sums_flush<2>(acc, dtype, H, warp, lane);
 }
 
 __global__ void __launch_bounds__(kEmbWarps * 32)
@@ -92,16 +140,32 @@ vilt_text_embed_bwd_kernel(const int64_t* __restrict__ tt, const float* __restri
                            int T, int H) {
   pdl_enter();
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
-  const long long row = (long long)blockIdx.x * kEmbWarps + warp;
-  if (row >= (long long)B * T) return;
-  const int t = (int)(row % T);
-  const long long ty = tt ? tt[row] : 0;
-  const float4* g = reinterpret_cast<const float4*>(dx + row * H);
-  for (int c = lane; c < H / 4; c += 32) {
-    const float4 v = __ldg(g + c);
-    if (dtype) atomic_add4(dtype + ty * H + 4 * c, v);
-    if (dpos) atomic_add4(dpos + (long long)t * H + 4 * c, v);
+  const bool reg_path = dtype != nullptr && H <= kEmbMaxV * 128;
+  float4 acc[2][kEmbMaxV];
+#pragma unroll
+  for (int k = 0; k < kEmbMaxV; ++k) acc[0][k] = acc[1][k] = make_float4(0.f, 0.f, 0.f, 0.f);
+  for (long long row = (long long)blockIdx.x * kEmbWarps + warp; row < (long long)B * T; row += (long long)gridDim.x * kEmbWarps) {
+    const int t = (int)(row % T);
+    const long long ty = tt ? tt[row] : 0;
+    const float4* g = reinterpret_cast<const float4*>(dx + row * H);
+    const bool ty_reg = reg_path && ty < 2;  // warp-uniform
+    for (int c = lane; c < H / 4; c += 32) {
+      const float4 v = __ldg(g + c);
+      const int k = c >> 5;
+      if (ty_reg && k < kEmbMaxV) {
+#pragma unroll
+        for (int kk = 0; kk < kEmbMaxV; ++kk)
+          if (kk == k) {
+            if (ty == 0) acc[0][kk] = f4add(acc[0][kk], v);
+            else acc[1][kk] = f4add(acc[1][kk], v);
+          }
+      } else if (dtype) {
+        atomic_add4(dtype + ty * H + 4 * c, v);
+      }
+      if (dpos) atomic_add4(dpos + (long long)t * H + 4 * c, v);
+    }
   }
+  if (reg_path) type_sums_flush<2>(acc, dtype, H, warp, lane);
 }
 
 // h_b = #valid patch rows in patch column 0, w_b = #valid patch columns in patch row 0 (nearest down-sampling: pixel (P*i, P*j))
@@ -376,6 +440,11 @@ patchify_kernel(const float* __restrict__ px, bf16* __restrict__ out, int B, int
 }
 
 static inline unsigned rows_grid(long long rows) { return (unsigned)((rows + kEmbWarps - 1) / kEmbWarps); }
+// embedding backward: at most one CTA per SM, so the per-CTA token-type sums meet in <= 148 atomics per address
+static inline unsigned bwd_rows_grid(long long rows) {
+  const long long g = (rows + kEmbWarps - 1) / kEmbWarps, cap = device_sm_count();
+  return (unsigned)(g < cap ? g : cap);
+}
 
 }  // namespace vb
 
@@ -395,7 +464,7 @@ extern "C" int vault_lm_embed_bwd(const int64_t* ids, const int64_t* tt, const f
                                   int32_t T, int32_t H, int32_t roberta_pad, int32_t word_pad, void* stream) {
   VB_REQUIRE(ids && dx, "lm_embed_bwd: null pointer");
   VB_REQUIRE(B > 0 && T > 0 && H % 4 == 0, "lm_embed_bwd: bad shape");
-  launch(lm_embed_bwd_kernel, dim3(rows_grid((long long)B * T)), dim3(kEmbWarps * 32), 0, (cudaStream_t)stream, ids, tt, dx, dword, dtype, dpos, B, T, H, roberta_pad,
+  launch(lm_embed_bwd_kernel, dim3(bwd_rows_grid((long long)B * T)), dim3(kEmbWarps * 32), 0, (cudaStream_t)stream, ids, tt, dx, dword, dtype, dpos, B, T, H, roberta_pad,
                                                                                                 word_pad);
   return check_launch("lm_embed_bwd_kernel");
 }
@@ -412,7 +481,7 @@ extern "C" int vault_vilt_text_embed_bwd(const int64_t* tt, const float* dx, flo
                                          void* stream) {
   VB_REQUIRE(dx, "vilt_text_embed_bwd: null pointer");
   if (!dtype && !dpos) return VAULT_OK;
-  launch(vilt_text_embed_bwd_kernel, dim3(rows_grid((long long)B * T)), dim3(kEmbWarps * 32), 0, (cudaStream_t)stream, tt, dx, dtype, dpos, B, T, H);
+  launch(vilt_text_embed_bwd_kernel, dim3(bwd_rows_grid((long long)B * T)), dim3(kEmbWarps * 32), 0, (cudaStream_t)stream, tt, dx, dtype, dpos, B, T, H);
   return check_launch("vilt_text_embed_bwd_kernel");
 }
 

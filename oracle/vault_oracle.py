@@ -181,6 +181,7 @@ def vault_forward(
     use_vilt_position_embeddings: bool = False,
     image_token_type_idx: int = 1,
     inputs_embeds: Optional[Tensor] = None,
+    output_hidden_states: bool = False,
 ) -> Dict[str, Tensor]:
     """VaultMixin.forward (ref:vault/models/vault/model.py:151-218) -> ViltModel.forward
     (HF:models/vilt/modeling_vilt.py:550-660) -> ViltPooler (:663-675).  ``inputs_embeds`` with ``input_ids=None``: the text
@@ -202,15 +203,21 @@ def vault_forward(
     img = img + mod[image_token_type_idx]
     x = torch.cat([text, img], dim=1)
     mask = torch.cat([attention_mask.to(torch.int64), img_mask], dim=1)
+    hidden = []  # ViltEncoder with output_hidden_states (HF:models/vilt/modeling_vilt.py:505-540): input of every layer, then the last output
     for i in range(d.layers):
+        hidden.append(x)
         pre = f"encoder.layer.{i}."
         ctx = _self_attention(_ln(x, sd, pre + "layernorm_before", d.vilt_eps), mask, sd, pre + "attention.attention.", d.heads, 0.0, False)
         h = x + _lin(ctx, sd, pre + "attention.output.dense")
         m = F.gelu(_lin(_ln(h, sd, pre + "layernorm_after", d.vilt_eps), sd, pre + "intermediate.dense"))
         x = h + _lin(m, sd, pre + "output.dense")
+    hidden.append(x)
     x = _ln(x, sd, "layernorm", d.vilt_eps)
     pooled = torch.tanh(_lin(x[:, 0], sd, "pooler.dense"))
-    return dict(last_hidden_state=x, pooler_output=pooled, mask=mask, patch_index=patch_index)
+    out = dict(last_hidden_state=x, pooler_output=pooled, mask=mask, patch_index=patch_index)
+    if output_hidden_states:
+        out["hidden_states"] = tuple(hidden)
+    return out
 
 
 def tmsc_logits(sd, d: Dims, pooled: Tensor, train: bool = False) -> Tensor:

@@ -3,7 +3,7 @@
 import pytest
 import torch
 
-from oracle import vault_oracle as O
+from oracle import synth, vault_oracle as O
 from tests.golden_utils import cosine, golden_names, load_case, rel_err
 
 FWD_KEYS = ("input_ids", "attention_mask", "token_type_ids", "pixel_values", "pixel_mask")
@@ -130,3 +130,22 @@ def test_text_inputs_embeds_matches_reference(kind):
         assert cosine(params[k].grad, g_ref) > 1 - 1e-6, k
     word = "bert.embeddings.word_embeddings.weight" if kind != "nolm" else "embeddings.text_embeddings.word_embeddings.weight"
     assert params[word].grad is None  # the lookup never ran
+
+
+def test_hidden_states_match_reference():
+    """output_hidden_states: the restatement's per-layer ViLT hidden states against the REAL reference's (fixture written by
+    oracle/make_golden_hidden.py: text rows, image CLS row, valid image rows un-permuted into raster order)."""
+    import os
+
+    g = torch.load(os.path.join(os.path.dirname(os.path.abspath(__file__)), "golden", "heads", "hidden_states_tiny.pt"), weights_only=False)
+    d = getattr(synth.Dims, g["case"]["dims_factory"])()
+    sd = synth.make_state_dict(d, seed=0)
+    inp = synth.make_inputs(d, seed=g["seed"], **g["case"]["input_kwargs"])
+    o = O.vault_forward(sd, d, output_hidden_states=True, **{k: inp[k] for k in ("input_ids", "attention_mask", "token_type_ids", "pixel_values", "pixel_mask")})
+    T = inp["input_ids"].shape[1]
+    assert len(o["hidden_states"]) == g["n_hidden"] == d.layers + 1
+    for k, h in enumerate(o["hidden_states"]):
+        assert (h[:, :T] - g["text"][k]).abs().max().item() < 1e-5 and (h[:, T] - g["image_cls"][k]).abs().max().item() < 1e-5
+        for b in range(h.shape[0]):
+            nv = int(g["n_valid_patches"][b])
+            assert (h[b, T + 1:T + 1 + nv] - g["image_raster"][k][b]).abs().max().item() < 1e-5

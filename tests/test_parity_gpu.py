@@ -92,6 +92,33 @@ def test_backward_vs_oracle(name):
     assert dot / (n1 ** 0.5 * n2 ** 0.5) >= 0.999
 
 
+def test_output_hidden_states_vs_reference_fixture():
+    """model(..., output_hidden_states=True): the ViLT encoder's hidden states (embedding output + every layer's output, image rows in raster
+    order) against the REAL reference's (tests/golden/heads/hidden_states_tiny.pt), tuple layout as HF's BaseModelOutputWithPooling."""
+    import os
+
+    g = torch.load(os.path.join(os.path.dirname(os.path.abspath(__file__)), "golden", "heads", "hidden_states_tiny.pt"), weights_only=False)
+    d = getattr(synth.Dims, g["case"]["dims_factory"])()
+    sd = synth.make_state_dict(d, seed=0)
+    inp = synth.make_inputs(d, seed=g["seed"], **g["case"]["input_kwargs"])
+    m = build(d, sd)
+    cu = {k: inp[k].to(DEV) for k in FWD}
+    T = inp["input_ids"].shape[1]
+    with torch.no_grad():
+        out = m.__class__.__mro__[1].forward(m, output_hidden_states=True, **cu)
+        tup = m.__class__.__mro__[1].forward(m, output_hidden_states=True, return_dict=False, **cu)
+        plain = m.__class__.__mro__[1].forward(m, **cu)
+    assert plain.hidden_states is None and len(tup) == 3 and len(tup[2]) == g["n_hidden"] == len(out.hidden_states)
+    for k, h in enumerate(out.hidden_states):
+        h = h.float().cpu()
+        scale = max(1.0, g["text"][k].abs().max().item())
+        assert (h[:, :T] - g["text"][k]).abs().max().item() <= 2e-2 * scale and (h[:, T] - g["image_cls"][k]).abs().max().item() <= 2e-2 * scale
+        for b in range(h.shape[0]):
+            nv = int(g["n_valid_patches"][b])
+            assert (h[b, T + 1:T + 1 + nv] - g["image_raster"][k][b]).abs().max().item() <= 2e-2 * scale
+    assert torch.equal(out.last_hidden_state, plain.last_hidden_state)
+
+
 def test_train_step_matches_oracle_one_step():
     """VaultTrainStep (CUDA graph, fused CE head, fused AdamW) vs the oracle's train_step: loss and post-step weight delta."""
     from vault_b200 import VaultTrainStep

@@ -647,8 +647,9 @@ class VaultEngine:
     def forward_iter(self, input_ids, attention_mask, token_type_ids, pixel_values, pixel_mask, image_token_type_idx=1, training=False,
                      need_grad=False, hw: Optional[torch.Tensor] = None, pmax: Optional[int] = None, split_lm: bool = False,
                      image_embeds: Optional[torch.Tensor] = None, inputs_embeds: Optional[torch.Tensor] = None,
-                     seed_snapshot: Optional[torch.Tensor] = None):
-        """Generator form of forward.  With split_lm it yields "lm_done" once the language model's forward is enqueued and before
+                     seed_snapshot: Optional[torch.Tensor] = None, hidden_out: Optional[list] = None):
+        """Generator form of forward.  hidden_out: a list that receives detached copies of the ViLT encoder's hidden states (embedding output,
+        then the output of every layer: what ViltEncoder collects with output_hidden_states=True, HF:models/vilt/modeling_vilt.py:505-540).  With split_lm it yields "lm_done" once the language model's forward is enqueued and before
         anything reads a ViLT parameter, so a caller can start the LM while the previous step's AdamW is still updating the
         ViLT range (VaultTrainStep); the return value (StopIteration.value) is forward()'s tuple."""
         embeds_mode = image_embeds is not None  # pre-embedded image tokens [B,P,H] (+ pixel_mask flattened to [B,P]) instead of pixels
@@ -831,7 +832,11 @@ class VaultEngine:
         # ---------------- ViLT encoder, final LN, pooler ----------------
         x32 = X.view(M, H)
         for i in range(self.L):
+            if hidden_out is not None:
+                hidden_out.append(x32.view(B, S, H).clone())
             x32 = self.vilt_layer_fwd(i, x32, M, B, S, key_mask, sv)
+        if hidden_out is not None:
+            hidden_out.append(x32.view(B, S, H).clone())
         _, lhs, st_f = self.ln_fwd(x32, M, "layernorm.weight", "layernorm.bias", self.vilt_eps, want16=False, want32=True)
         pooled = None
         if self.has("pooler.dense.weight"):

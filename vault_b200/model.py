@@ -17,7 +17,8 @@ forward and backward goes through ``vault_b200.engine.VaultEngine`` -> C ABI -> 
 Differences from the reference, all deliberate:
   * image tokens come out in raster order (valid patches first) instead of a random permutation -- ``pooler_output`` and the
     text rows are unaffected, image rows match after un-permuting the reference with its ``patch_index``;
-  * ``head_mask``, ``output_attentions`` and ``output_hidden_states`` are not on the hot path and raise ``NotImplementedError``
+  * ``head_mask`` and ``output_attentions`` are not on the hot path and raise ``NotImplementedError``; ``output_hidden_states=True``
+    returns detached copies of the encoder's hidden states
     (``image_embeds`` and text ``inputs_embeds`` are served by the kernels, gradients to the caller's tensors included);
   * gradients are written into one flat fp32 buffer and ``p.grad`` are views of it: zero (or ``None``) them between backward
     calls as the reference trainer does (ref:vault/tmsc_utils/trainer.py:364); if a caller keeps ``p.grad`` across backward calls the next backward adds to it (torch semantics).
@@ -270,8 +271,11 @@ class VaultMixin(nn.Module, ABC):
     def _trunk(self, input_ids=None, attention_mask=None, token_type_ids=None, pixel_values=None, pixel_mask=None, head_mask=None,
                inputs_embeds=None, image_embeds=None, image_token_type_idx=None, output_attentions=None, output_hidden_states=None,
                return_dict=None, **extra):
-        if head_mask is not None or output_attentions or output_hidden_states:
-            raise NotImplementedError("vault_b200: head_mask / output_attentions / output_hidden_states are not on the hot path")
+        if head_mask is not None or output_attentions:
+            raise NotImplementedError("vault_b200: head_mask / output_attentions are not on the hot path (attention probabilities are never materialised)")
+        # output_hidden_states: detached copies of the encoder's hidden states (image rows in raster order); left in self._hidden_states
+        hs = [] if output_hidden_states else None
+        self.__dict__["_hidden_states"] = hs
         if input_ids is not None and inputs_embeds is not None:
             raise ValueError("You cannot specify both input_ids and inputs_embeds at the same time")
         if (input_ids is None and inputs_embeds is None) or (pixel_values is None and image_embeds is None):
@@ -286,6 +290,8 @@ class VaultMixin(nn.Module, ABC):
                   pixel_mask=pixel_mask, image_token_type_idx=1 if image_token_type_idx is None else image_token_type_idx,
                   training=self.training)
         kw.update({k: v for k, v in extra.items() if k in ("hw", "pmax")})
+        if hs is not None:
+            kw["hidden_out"] = hs
         dev = (pixel_values if pixel_values is not None else image_embeds).device
         need_grad = need_grad or (torch.is_grad_enabled() and any(e is not None and e.requires_grad for e in (image_embeds, inputs_embeds)))
         if need_grad:
@@ -321,9 +327,11 @@ class VaultMixin(nn.Module, ABC):
             finally:
                 self.__dict__["_seed_held"] = False
         lhs, pooled, _ = self._trunk(*args, **kwargs)
+        hs = self.__dict__.pop("_hidden_states", None)
+        hs = tuple(hs) if hs is not None else None
         if kwargs.get("return_dict") is False:
-            return (lhs, pooled)
-        return BaseModelOutputWithPooling(last_hidden_state=lhs, pooler_output=pooled)
+            return (lhs, pooled) + ((hs,) if hs is not None else ())
+        return BaseModelOutputWithPooling(last_hidden_state=lhs, pooler_output=pooled, hidden_states=hs)
 
 
 class _KernelTrunk(ViltModel):
@@ -337,9 +345,11 @@ class _KernelTrunk(ViltModel):
                                       pixel_mask=pixel_mask, head_mask=head_mask, inputs_embeds=inputs_embeds, image_embeds=image_embeds,
                                       image_token_type_idx=image_token_type_idx, output_attentions=output_attentions,
                                       output_hidden_states=output_hidden_states)
+        hs = owner.__dict__.pop("_hidden_states", None)
+        hs = tuple(hs) if hs is not None else None
         if return_dict is False:
-            return (lhs, pooled)
-        return BaseModelOutputWithPooling(last_hidden_state=lhs, pooler_output=pooled)
+            return (lhs, pooled) + ((hs,) if hs is not None else ())
+        return BaseModelOutputWithPooling(last_hidden_state=lhs, pooler_output=pooled, hidden_states=hs)
 
 
 class VaultModel(VaultMixin, ViltModel):

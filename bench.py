@@ -283,16 +283,16 @@ def gemm_roofline(torch, ts, batch_dev, peaks):
     lib = _abi.lib()
     st = torch.cuda.current_stream().cuda_stream
     # forward-type GEMMs only write outputs, so replay is idempotent except split-K atomics (harmless: gradients are recomputed)
-    flops = sum(2.0 * g.M * g.N * g.K for g in gemms)
+    flops = sum(_abi.gemm_flops(g) for g in gemms)  # grouped weight-gradient launches count all their problems
     reps = 5
     for g in gemms:
-        lib.vault_gemm_bf16(C.byref(g), st)
+        _abi.replay_gemm(g, st)
     torch.cuda.synchronize()
     e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
     e0.record()
     for _ in range(reps):
         for g in gemms:
-            lib.vault_gemm_bf16(C.byref(g), st)
+            _abi.replay_gemm(g, st)
     e1.record()
     torch.cuda.synchronize()
     ms = e0.elapsed_time(e1) / reps
@@ -300,7 +300,7 @@ def gemm_roofline(torch, ts, batch_dev, peaks):
     peak = peaks.get("bf16_tflops_sustained") or 1400.0
     del keep
     tr = NCU_TRAFFIC.get("gemm")  # one `ncu --set full` capture of this round (profiles/r02_ncu_traffic.json), per launch; None if not captured
-    return dict(bound="tensor", kernel="vb::gemm_bf16_kernel (tcgen05/TMEM/TMA)", achieved=achieved, peak=peak, unit="TFLOP/s", frac=achieved / peak,
+    return dict(bound="tensor", kernel="vb::gemm_bf16_kernel + vb::gemm_wgrad_grouped_kernel (tcgen05/TMEM/TMA)", achieved=achieved, peak=peak, unit="TFLOP/s", frac=achieved / peak,
                 traffic=(tr or {}).get("dram_bytes_per_launch"), traffic_note=tr,
                 launches_per_step=len(gemms), gemm_ms_per_step=ms, flops_per_step=flops,
                 peak_source="MEASURED_PEAKS.json bf16_tflops_sustained (kernel replayed inside a multi-ms dense run)" if "bf16_tflops_sustained" in peaks

@@ -95,6 +95,11 @@ typedef struct vault_gemm_args {
 } vault_gemm_args;
 
 int vault_gemm_bf16(const vault_gemm_args* args, void* stream);
+/* Up to 4 weight-gradient problems (a_mn = b_mn = 1, VAULT_EPI_ATOMIC_F32, per-problem split_k and optional a_colsum; 128x256 tiles) as ONE
+ * persistent launch over the pooled tile list: the four dW of a transformer layer (QKV, attention output, MLP-1, MLP-2: same tokens as
+ * the contraction) share one launch head / tail and fill the SMs in whole waves.  Fields other than M, N, K, A, lda, B, ldb, out, ldo,
+ * split_k, a_colsum (and max_ctas of problem 0) are ignored.  Same results as the single launches (fp32 atomics: same values, any order). */
+int vault_gemm_wgrad_grouped(const vault_gemm_args* args, int32_t n, void* stream);
 
 /* Patch embedding, im2col-free: Conv2d(C,N,k=32,s=32) as a TF32 tcgen05 GEMM whose A tiles are 5-D TMA boxes taken straight
  * from the NCHW fp32 pixels (no patch matrix is materialised).  Replaces ViltPatchEmbeddings.forward,

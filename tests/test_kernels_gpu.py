@@ -71,6 +71,29 @@ def test_gemm_wgrad_fused_bias_gradient(dev, ops, n_out, k_in, tokens, split, bn
         assert _rel(gb, ref_b) < 1e-5, (max_ctas, (gb - ref_b).abs().max().item())
 
 
+@pytest.mark.parametrize("tokens,max_ctas", [(11808, 0), (4096, 0), (1000, 0), (200, 5), (64, 0)])
+def test_gemm_wgrad_grouped(dev, ops, tokens, max_ctas):
+    """The four weight gradients of a layer as ONE persistent launch over their pooled tiles == the four fp32 products, with the fused bias
+    gradients of the QKV / MLP-1 problems; ragged token counts, few CTAs (many tiles per CTA across problem boundaries), a lone k-block."""
+    torch.manual_seed(tokens)
+    H, I = 768, 3072
+    shapes = [(3 * H, H, True), (H, H, False), (I, H, True), (H, I, False)]  # (n_out, k_in, bias gradient?)
+    probs, refs = [], []
+    for n_out, k_in, bias in shapes:
+        dy, x = _rnd(dev, tokens, n_out, scale=0.5), _rnd(dev, tokens, k_in, scale=0.5)
+        dw = torch.zeros(n_out, k_in, device=dev)
+        db = torch.zeros(n_out, device=dev) if bias else None
+        probs.append((dy, x, dw, 2, db))
+        refs.append((dy.float().t() @ x.float(), dy.float().sum(0)))
+    ops.gemm_wgrad_grouped(probs, max_ctas=max_ctas)
+    for (dy, x, dw, _, db), (rw, rb) in zip(probs, refs):
+        assert _rel(dw, rw) < 1e-4
+        if db is not None:
+            assert _rel(db, rb) < 1e-5
+    ops.gemm_wgrad_grouped(probs[2:3], max_ctas=max_ctas)  # a group of one; accumulates on top
+    assert _rel(probs[2][2], 2 * refs[2][0]) < 1e-4
+
+
 @pytest.mark.parametrize("split", [2, 4, 8])
 def test_gemm_split_k_atomic(dev, ops, split):
     a, b = _rnd(dev, 768, 5920, scale=0.5), _rnd(dev, 768, 5920, scale=0.5)

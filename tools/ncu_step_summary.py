@@ -52,7 +52,7 @@ def pick(pred):
     n = sum(f["launches"] for f in sel)
     return None if not n else dict(dram_bytes_per_launch=sum(f["rd"] + f["wr"] for f in sel) / n, launches=n, share_of_step=sum(f["us"] for f in sel) / tot,
                                    source=f"{out_md} (ncu dram__bytes_read.sum + dram__bytes_write.sum, average over every launch of the kernel in one eager {workload} step)")
-res = dict(workload=workload, gemm=pick(lambda k: k.startswith("gemm_bf16_kernel")), layernorm_fwd=pick(lambda k: k.startswith("ln_fwd")),
+res = dict(workload=workload, gemm=pick(lambda k: k.startswith("gemm_bf16_kernel") or k.startswith("gemm_wgrad_grouped_kernel")), layernorm_fwd=pick(lambda k: k.startswith("ln_fwd")),
            layernorm_bwd=pick(lambda k: k.startswith("ln_bwd")), adamw=pick(lambda k: k.startswith("adamw")),
            attention=pick(lambda k: k.startswith("attn_")))
 json.dump(res, open(out_json, "w"), indent=1)

@@ -43,6 +43,8 @@ _abi.uninstall_counter()
 fams = {
     "gemm_vilt": lambda n, a: n == "vault_gemm_bf16" and max(a[0].M, a[0].K if a[0].a_mn else 0) >= 4500,
     "gemm_lm": lambda n, a: n == "vault_gemm_bf16" and max(a[0].M, a[0].K if a[0].a_mn else 0) < 4500,
+    "gemm_wgrad_grouped_vilt": lambda n, a: n == "vault_gemm_wgrad_grouped" and a[0][0].K >= 4500,
+    "gemm_wgrad_grouped_lm": lambda n, a: n == "vault_gemm_wgrad_grouped" and a[0][0].K < 4500,
     "attn_fwd_vilt": lambda n, a: n == "vault_attn_fwd" and int(a[5]) != W["text_len"],
     "attn_bwd_vilt": lambda n, a: n == "vault_attn_bwd" and int(a[8]) != W["text_len"],
     "attn_fwd_lm": lambda n, a: n == "vault_attn_fwd" and int(a[5]) == W["text_len"],
@@ -50,7 +52,7 @@ fams = {
     "ln_fwd": lambda n, a: n == "vault_layernorm_fwd_drop",
     "ln_bwd": lambda n, a: n == "vault_layernorm_bwd_drop",
     "colsum": lambda n, a: n == "vault_colsum_bf16",
-    "other": lambda n, a: n not in ("vault_gemm_bf16", "vault_attn_fwd", "vault_attn_bwd", "vault_layernorm_fwd_drop", "vault_layernorm_bwd_drop", "vault_colsum_bf16"),
+    "other": lambda n, a: n not in ("vault_gemm_bf16", "vault_gemm_wgrad_grouped", "vault_attn_fwd", "vault_attn_bwd", "vault_layernorm_fwd_drop", "vault_layernorm_bwd_drop", "vault_colsum_bf16"),
     "all": lambda n, a: True,
 }
 res = {}

@@ -34,22 +34,26 @@ if "--gemms" in sys.argv:
     lib = _abi.lib(); st = torch.cuda.current_stream().cuda_stream
     groups = {}
     for g in gemms:
-        key = (g.M, g.N, g.K, g.a_mn, g.b_mn, g.epilogue, g.split_k, g.block_n)
+        if isinstance(g, _abi.GemmArgs):
+            key = (g.M, g.N, g.K, g.a_mn, g.b_mn, g.epilogue, g.split_k, g.block_n)
+        else:  # grouped weight-gradient launch: one row per distinct group shape
+            key = ("grouped", tuple((x.M, x.N, x.K) for x in g), 0, 1, 1, 5, g[0].split_k, 256)
         groups.setdefault(key, []).append(g)
     rows = []
     e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
     for key, gs in groups.items():
         for _ in range(2):
-            for g in gs: lib.vault_gemm_bf16(C.byref(g), st)
+            for g in gs: _abi.replay_gemm(g, st)
         torch.cuda.synchronize(); e0.record()
         reps = 5
         for _ in range(reps):
-            for g in gs: lib.vault_gemm_bf16(C.byref(g), st)
+            for g in gs: _abi.replay_gemm(g, st)
         e1.record(); torch.cuda.synchronize()
         us = e0.elapsed_time(e1) * 1e3 / reps / len(gs)
         M, N, K = key[:3]
+        fl = _abi.gemm_flops(gs[0])
         rows.append(dict(M=M, N=N, K=K, a_mn=key[3], b_mn=key[4], epi=key[5], split=key[6], bn=key[7], count=len(gs), us=round(us, 2),
-                         tflops=round(2.0 * M * N * K / us / 1e6, 1), total_us=round(us * len(gs), 1)))
+                         tflops=round(fl / us / 1e6, 1), total_us=round(us * len(gs), 1)))
     rows.sort(key=lambda r: -r["total_us"])
     for r in rows: print(json.dumps(r))
     print(json.dumps(dict(total_ms=sum(r["total_us"] for r in rows) / 1e3)))

@@ -40,6 +40,7 @@ SIGNATURES = {
     "vault_last_error": [C.c_char_p, C.c_size_t],
     "vault_check_device": [c_i32],
     "vault_gemm_bf16": [C.POINTER(GemmArgs), c_p],
+    "vault_gemm_wgrad_grouped": [C.POINTER(GemmArgs), c_i32, c_p],
     "vault_patch_embed_fwd": [c_p, c_p, c_p, c_p, c_i32, c_i32, c_i32, c_i32, c_i32, c_i32, c_p],
     "vault_patch_embed_wgrad_ok": [c_i32, c_i32, c_i32, c_i32, c_i32],
     "vault_patch_embed_wgrad": [c_p, c_p, c_p, c_i32, c_i32, c_i32, c_i32, c_i32, c_i32, c_p],
@@ -165,6 +166,12 @@ class CountingLib:
                 C.memmove(C.byref(cp), C.byref(src), C.sizeof(GemmArgs))
                 self.gemms.append(cp)
                 self.trace.append((name, (cp,)))
+            elif name == "vault_gemm_wgrad_grouped":
+                n_prob = int(args[1])
+                cp = (GemmArgs * n_prob)()
+                C.memmove(cp, args[0], C.sizeof(GemmArgs) * n_prob)
+                self.gemms.append(cp)  # a ctypes ARRAY of GemmArgs = one grouped launch (replay_gemm() tells them apart)
+                self.trace.append((name, (cp, n_prob)))
             else:
                 self.trace.append((name, args[:-1]))
             return fn(*args)
@@ -184,6 +191,19 @@ def uninstall_counter():
     global _lib
     if isinstance(_lib, CountingLib):
         _lib = _lib._inner
+
+
+def replay_gemm(g, stream: int):
+    """Re-issue one recorded GEMM launch: a GemmArgs (vault_gemm_bf16) or a GemmArgs array (vault_gemm_wgrad_grouped)."""
+    l = lib()
+    inner = l._inner if isinstance(l, CountingLib) else l
+    if isinstance(g, GemmArgs):
+        return inner.vault_gemm_bf16(C.byref(g), stream)
+    return inner.vault_gemm_wgrad_grouped(g, len(g), stream)
+
+
+def gemm_flops(g) -> float:
+    return 2.0 * g.M * g.N * g.K if isinstance(g, GemmArgs) else sum(2.0 * x.M * x.N * x.K for x in g)
 
 
 def replay_trace(trace, stream: int, only=None):

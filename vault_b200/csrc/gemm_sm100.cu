@@ -642,6 +642,240 @@ gemm_bf16_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant_
   }
 }
 
+// ---- grouped weight-gradient launch ------------------------------------------------------------------------------------
+// The four weight gradients of a transformer layer (QKV, attention output, MLP-1, MLP-2) have the same contraction (the layer's tokens)
+// and nothing in common otherwise.  As four launches each pays its own head (barrier set-up, first loads: ~3 us) and tail (the last
+// epilogue cannot overlap anything: most of these launches are ONE tile per CTA) -- 8-10 us on 20-50 us kernels.  Here the tiles of
+// all problems form one list walked by one persistent grid: a CTA's epilogue of tile i runs under the main loop of its tile i+1
+// whichever problem that belongs to, and the 216 x split-K tiles of a layer fill the 148 SMs in whole waves (432 = 2.92 waves) where the
+// single launches left 4-40 SMs idle.  Same pipeline as gemm_bf16_kernel, specialised: both operands MN-major (dy and x read
+// un-transposed), 128x256 tiles, fp32 red.global.add epilogue, optional fused bias gradient (a_colsum) per problem.
+constexpr int kMaxGroup = 4;
+struct GroupProblem {
+  CUtensorMap tmA, tmB;
+  int M, N;                                                     // dW is [M, N]: M = output features of the Linear, N = its input features
+  int num_m_blocks, num_n_blocks, num_k_blocks, split_k, kb_per_split;
+  int tile_begin;                                               // first tile of this problem in the launch's tile list
+  float* out;
+  long long ldo;
+  float* a_colsum;
+};
+struct GroupedParams {
+  int n, total_tiles;
+  GroupProblem pr[kMaxGroup];
+};
+
+__global__ void __launch_bounds__(kThreads, 1) gemm_wgrad_grouped_kernel(const __grid_constant__ GroupedParams gp) {
+  constexpr int BN = 256, EPI = VAULT_EPI_ATOMIC_F32;
+  constexpr int kAStage = BM * BK * 2, kBStage = BN * BK * 2, kStage = kAStage + kBStage;
+  constexpr int kStages = kRingBytes / kStage;
+  constexpr uint32_t kTmemCols = 2u * BN;
+  extern __shared__ uint8_t smem_raw[];
+  const uint32_t smem_base = (smem_u32(smem_raw) + 1023u) & ~1023u;
+  uint8_t* smem_gen = smem_raw + (smem_base - smem_u32(smem_raw));
+  const uint32_t ring = smem_base;
+  uint8_t* staging_gen = smem_gen + kRingBytes;
+  const uint32_t bars = smem_base + kRingBytes + kStagingBytes;
+  // barrier slots: full[kStages] | empty[kStages] | tmem_full[2] | tmem_empty[2] | tmem ptr | csfull[kStages] | csdone[kStages]
+  auto full_bar = [&](int s) { return bars + 8u * s; };
+  auto empty_bar = [&](int s) { return bars + 8u * (kStages + s); };
+  auto tfull_bar = [&](int s) { return bars + 8u * (2 * kStages + s); };
+  auto tempty_bar = [&](int s) { return bars + 8u * (2 * kStages + 2 + s); };
+  const uint32_t tmem_slot = bars + 8u * (2 * kStages + 4);
+  volatile uint32_t* tmem_slot_gen = reinterpret_cast<volatile uint32_t*>(smem_gen + kRingBytes + kStagingBytes + 8 * (2 * kStages + 4));
+  auto csfull_bar = [&](int s) { return bars + 8u * (2 * kStages + 5 + s); };
+  auto csdone_bar = [&](int s) { return bars + 8u * (3 * kStages + 5 + s); };
+  static_assert(8 * (4 * kStages + 5) <= 384, "barrier block overflows its 384 bytes");
+
+  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+  if (warp == 0 && lane == 0) {
+    for (int q = 0; q < gp.n; ++q) {
+      tma_prefetch_desc(&gp.pr[q].tmA);
+      tma_prefetch_desc(&gp.pr[q].tmB);
+    }
+  }
+  if (warp == 1 && lane == 0) {
+    for (int s = 0; s < kStages; ++s) {
+      mbar_init(full_bar(s), 1);
+      mbar_init(empty_bar(s), 1);
+      mbar_init(csfull_bar(s), 1);
+      mbar_init(csdone_bar(s), kEpiWarps);
+    }
+    for (int s = 0; s < 2; ++s) {
+      mbar_init(tfull_bar(s), 1);
+      mbar_init(tempty_bar(s), kEpiWarps);
+    }
+    mbar_fence_init();
+  }
+  if (warp == 2) tmem_alloc(tmem_slot, kTmemCols);
+  tc_fence_before();
+  __syncthreads();
+  tc_fence_after();
+  const uint32_t tmem_base = *tmem_slot_gen;
+  pdl_enter();
+
+  // tile t of the launch -> (problem, split, m block, n block): the same arithmetic in the three roles
+  struct Tile {
+    int q, split, m0, n0, kb0, kb1, cs_first, n_units;
+  };
+  auto decode = [&](int t) {
+    int q = 0;
+#pragma unroll
+    for (int i = 1; i < kMaxGroup; ++i)
+      if (i < gp.n && t >= gp.pr[i].tile_begin) q = i;
+    const GroupProblem& P = gp.pr[q];
+    const int tl = t - P.tile_begin, tiles_mn = P.num_m_blocks * P.num_n_blocks;
+    Tile r;
+    r.q = q;
+    r.split = tl / tiles_mn;
+    const int rem = tl - r.split * tiles_mn;
+    r.n_units = P.num_n_blocks;
+    r.m0 = (rem / P.num_n_blocks) * BM;
+    const int nblk = rem % P.num_n_blocks;
+    r.n0 = nblk * BN;
+    r.kb0 = r.split * P.kb_per_split;
+    r.kb1 = min(r.kb0 + P.kb_per_split, P.num_k_blocks);
+    // fused bias gradient: tile j of an m block adds up the A tiles of the k-blocks with kb % n_units == j (-1: none)
+    r.cs_first = P.a_colsum != nullptr ? r.kb0 + ((nblk - r.kb0 % P.num_n_blocks) + P.num_n_blocks) % P.num_n_blocks : -1;
+    return r;
+  };
+
+  if (warp == 0) {
+    // ===================== TMA producer =====================
+    if (lane == 0) {
+      int stage = 0;
+      uint32_t phase = 0, cs_pending = 0, cs_phase = 0;
+      for (int t = (int)blockIdx.x; t < gp.total_tiles; t += (int)gridDim.x) {
+        const Tile T = decode(t);
+        const CUtensorMap* ta = &gp.pr[T.q].tmA;
+        const CUtensorMap* tb = &gp.pr[T.q].tmB;
+        int cs_next = T.cs_first;
+        for (int kb = T.kb0; kb < T.kb1; ++kb) {
+          mbar_wait(empty_bar(stage), phase ^ 1u);
+          if ((cs_pending >> stage) & 1u) {  // the slot fed the column sums: the epilogue warps must have let go of it too
+            mbar_wait(csdone_bar(stage), (cs_phase >> stage) & 1u);
+            cs_phase ^= 1u << stage;
+            cs_pending &= ~(1u << stage);
+          }
+          if (kb == cs_next) {
+            cs_pending |= 1u << stage;
+            cs_next += T.n_units;
+          }
+          const uint32_t sA = ring + stage * kStage, sB = sA + kAStage, fb = full_bar(stage);
+          mbar_expect_tx(fb, kStage);
+          const int k0 = kb * BK;
+#pragma unroll
+          for (int j = 0; j < BM / 64; ++j) tma_load_2d(sA + j * 8192, ta, fb, T.m0 + 64 * j, k0);  // box {64 m, 64 k-rows}
+#pragma unroll
+          for (int j = 0; j < BN / 64; ++j) tma_load_2d(sB + j * 8192, tb, fb, T.n0 + 64 * j, k0);
+          if (++stage == kStages) { stage = 0; phase ^= 1u; }
+        }
+      }
+    }
+  } else if (warp == 1) {
+    // ===================== MMA issuer (single thread) =====================
+    if (lane == 0) {
+      const uint32_t idesc = umma_idesc(1u, BM, BN, 1u, 1u);
+      int stage = 0, as = 0;
+      uint32_t phase = 0, aphase = 0;
+      for (int t = (int)blockIdx.x; t < gp.total_tiles; t += (int)gridDim.x) {
+        const Tile T = decode(t);
+        int cs_next = T.cs_first;
+        mbar_wait(tempty_bar(as), aphase ^ 1u);
+        tc_fence_after();
+        const uint32_t d_tmem = tmem_base + (uint32_t)(as * BN);
+        for (int kb = T.kb0; kb < T.kb1; ++kb) {
+          mbar_wait(full_bar(stage), phase);
+          if (kb == cs_next) {
+            mbar_arrive(csfull_bar(stage));
+            cs_next += T.n_units;
+          }
+          tc_fence_after();
+          const uint32_t sA = ring + stage * kStage, sB = sA + kAStage;
+#pragma unroll
+          for (int k = 0; k < BK / UMMA_K; ++k)
+            tc_mma_f16(d_tmem, umma_desc_sw128(sA + k * (UMMA_K * 128u), 8192u, 1024u), umma_desc_sw128(sB + k * (UMMA_K * 128u), 8192u, 1024u), idesc,
+                       (kb > T.kb0 || k > 0) ? 1u : 0u);
+          tc_commit(empty_bar(stage));
+          if (++stage == kStages) { stage = 0; phase ^= 1u; }
+        }
+        tc_commit(tfull_bar(as));
+        as ^= 1;
+        if (as == 0) aphase ^= 1u;
+      }
+    }
+  } else if (warp >= 4) {
+    // ===================== epilogue warps (+ the bias-gradient sums during the main loop) =====================
+    const int ew = warp - 4, q4 = warp & 3, part = ew >> 2;
+    constexpr int kColsPerWarp = BN / (kEpiWarps / 4);
+    float4* stg = reinterpret_cast<float4*>(staging_gen + ew * (32 * kCW * 4));
+    int as = 0;
+    uint32_t aphase = 0, gkb = 0, csf_phase = 0;
+    for (int t = (int)blockIdx.x; t < gp.total_tiles; t += (int)gridDim.x) {
+      const Tile T = decode(t);
+      const GroupProblem& P = gp.pr[T.q];
+      if (T.cs_first >= 0) {
+        constexpr int kRowsPerWarp = 64 / (kEpiWarps / 2);
+        const int box = ew & 1, r0 = (ew >> 1) * kRowsPerWarp;
+        float s0 = 0.f, s1 = 0.f;
+        for (int kb = T.cs_first; kb < T.kb1; kb += T.n_units) {
+          const int stage = (int)((gkb + (uint32_t)(kb - T.kb0)) % (uint32_t)kStages);
+          mbar_wait(csfull_bar(stage), (csf_phase >> stage) & 1u);
+          csf_phase ^= 1u << stage;
+          const uint32_t sA = ring + stage * kStage + box * 8192;
+#pragma unroll
+          for (int r = r0; r < r0 + kRowsPerWarp; ++r) {
+            const float2 v = unpack_bf16x2(lds_u32(sA + r * 128 + ((((lane >> 2) ^ (r & 7))) << 4) + (lane & 3) * 4));
+            s0 += v.x;
+            s1 += v.y;
+          }
+          __syncwarp();
+          if (lane == 0) mbar_arrive(csdone_bar(stage));
+        }
+        const int m = T.m0 + box * 64 + 2 * lane;
+        if (m < P.M) {
+          atomicAdd(P.a_colsum + m, s0);
+          atomicAdd(P.a_colsum + m + 1, s1);
+        }
+      }
+      gkb += (uint32_t)(T.kb1 - T.kb0);
+      GemmParams lp{};  // what the shared epilogue code reads of the problem
+      lp.M = P.M; lp.N = P.N; lp.out = P.out; lp.ldo = P.ldo;
+      mbar_wait(tfull_bar(as), aphase);
+      tc_fence_after();
+      const bool full_tile = (T.m0 + BM <= P.M) && (T.n0 + BN <= P.N);
+#pragma unroll 1
+      for (int c = part * kColsPerWarp; c < (part + 1) * kColsPerWarp; c += kCW) {
+        uint32_t r[kCW];
+        tmem_ld_cols(tmem_base + ((uint32_t)(q4 * 32) << 16) + (uint32_t)(as * BN + c), r);
+        tmem_ld_wait();
+#pragma unroll
+        for (int j = 0; j < kLPR; ++j)
+          stg[lane * kLPR + (j ^ stg_swz(lane))] =
+              make_float4(__uint_as_float(r[4 * j]), __uint_as_float(r[4 * j + 1]), __uint_as_float(r[4 * j + 2]), __uint_as_float(r[4 * j + 3]));
+        __syncwarp();
+        const int col = T.n0 + c + (lane % kLPR) * 4;
+        const float4 b4 = make_float4(0.f, 0.f, 0.f, 0.f);
+        const long long row0 = (long long)T.m0 + q4 * 32;
+        if (full_tile) epilogue_chunk<EPI, false>(lp, stg, lane, b4, 0ull, row0, col);
+        else epilogue_chunk<EPI, true>(lp, stg, lane, b4, 0ull, row0, col);
+        __syncwarp();
+      }
+      tc_fence_before();
+      __syncwarp();
+      if (lane == 0) mbar_arrive(tempty_bar(as));
+      as ^= 1;
+      if (as == 0) aphase ^= 1u;
+    }
+  }
+  tc_fence_before();
+  __syncthreads();
+  if (warp == 2) {
+    tc_fence_after();
+    tmem_dealloc(tmem_base, kTmemCols);
+  }
+}
+
 // ---- host side -----------------------------------------------------------------------------------------------------
 typedef CUresult (*EncodeTiledFn)(CUtensorMap*, CUtensorMapDataType, cuuint32_t, void*, const cuuint64_t*, const cuuint64_t*,
                                   const cuuint32_t*, const cuuint32_t*, CUtensorMapInterleave, CUtensorMapSwizzle,
@@ -818,4 +1052,44 @@ extern "C" int vault_gemm_bf16(const vault_gemm_args* a, void* stream) {
     case VAULT_EPI_MUL_AUX_BF16: return dispatch_bn<VAULT_EPI_MUL_AUX_BF16>(bn, tmA, tmB, p, grid, st);
   }
   return fail(VAULT_ERR_INVALID, "vault_gemm_bf16: unknown epilogue %d", a->epilogue);
+}
+
+extern "C" int vault_gemm_wgrad_grouped(const vault_gemm_args* args, int32_t n, void* stream) {
+  using namespace vb;
+  VB_REQUIRE(args != nullptr && n >= 1 && n <= kMaxGroup, "vault_gemm_wgrad_grouped: 1..%d problems (got %d)", kMaxGroup, n);
+  GroupedParams gp;  // ~1.4 KB of kernel parameters (the tensor maps travel as __grid_constant__ data)
+  gp.n = n;
+  int tiles = 0;
+  for (int i = 0; i < n; ++i) {
+    const vault_gemm_args* a = args + i;
+    VB_REQUIRE(a->M > 0 && a->N > 0 && a->K > 0 && a->A && a->B && a->out, "vault_gemm_wgrad_grouped: problem %d: empty or null", i);
+    VB_REQUIRE(a->a_mn == 1 && a->b_mn == 1 && a->epilogue == VAULT_EPI_ATOMIC_F32,
+               "vault_gemm_wgrad_grouped: problem %d: needs MN-major operands and EPI_ATOMIC_F32 (the weight-gradient form)", i);
+    VB_REQUIRE(a->N % 8 == 0 && a->M % 2 == 0 && a->ldo % 4 == 0 && a->split_k >= 1, "vault_gemm_wgrad_grouped: problem %d: bad shape", i);
+    GroupProblem& P = gp.pr[i];
+    int rc = encode_tmap_2d(&P.tmA, CU_TENSOR_MAP_DATA_TYPE_BFLOAT16, 2, a->A, (uint64_t)a->M, (uint64_t)a->K, (uint64_t)a->lda, 64, BK);
+    if (rc) return rc;
+    rc = encode_tmap_2d(&P.tmB, CU_TENSOR_MAP_DATA_TYPE_BFLOAT16, 2, a->B, (uint64_t)a->N, (uint64_t)a->K, (uint64_t)a->ldb, 64, BK);
+    if (rc) return rc;
+    P.M = a->M; P.N = a->N;
+    P.num_m_blocks = (a->M + BM - 1) / BM;
+    P.num_n_blocks = (a->N + 255) / 256;
+    P.num_k_blocks = (a->K + BK - 1) / BK;
+    int split = a->split_k < P.num_k_blocks ? a->split_k : P.num_k_blocks;
+    P.kb_per_split = (P.num_k_blocks + split - 1) / split;
+    P.split_k = (P.num_k_blocks + P.kb_per_split - 1) / P.kb_per_split;
+    P.tile_begin = tiles;
+    tiles += P.num_m_blocks * P.num_n_blocks * P.split_k;
+    P.out = reinterpret_cast<float*>(a->out); P.ldo = a->ldo; P.a_colsum = a->a_colsum;
+  }
+  gp.total_tiles = tiles;
+  static bool attr_set = false;
+  if (!attr_set) {
+    cudaError_t e = cudaFuncSetAttribute(gemm_wgrad_grouped_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, kSmemBytes);
+    if (e != cudaSuccess) return fail(VAULT_ERR_LAUNCH, "cudaFuncSetAttribute(smem=%d): %s", kSmemBytes, cudaGetErrorString(e));
+    attr_set = true;
+  }
+  const int sms = args[0].max_ctas > 0 ? args[0].max_ctas : device_sm_count();
+  launch(gemm_wgrad_grouped_kernel, dim3((unsigned)(tiles < sms ? tiles : sms)), dim3(kThreads), kSmemBytes, reinterpret_cast<cudaStream_t>(stream), gp);
+  return check_launch("gemm_wgrad_grouped_kernel");
 }

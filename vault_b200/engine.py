@@ -103,6 +103,8 @@ class VaultEngine:
         self.wgrad_side_stream = os.environ.get("VAULT_B200_WGRAD_SIDE", "1") != "0"
         self.small_m_split_k = os.environ.get("VAULT_B200_SMALL_M_SPLITK", "1") != "0"
         self.comm_stream = None  # see _cut()
+        self._wgrad_group = None
+        self.group_wgrads = os.environ.get("VAULT_B200_GROUP_WGRADS", "1") != "0"  # A/B switch: 0 = one launch per weight gradient
         self.prezeroed = False
         self.flat_alloc = None  # optional allocator of the flat master / shadow / gradient buffers (see ensure_packed)
         self.fuse_bias_grad = os.environ.get("VAULT_B200_FUSE_BIAS_GRAD", "1") != "0"  # A/B switch: 0 = separate vault_colsum_bf16 launches
@@ -381,6 +383,10 @@ class VaultEngine:
         gb = self.g32(bname) if bias else 0
         if not gw and not gb:
             return
+        if self._wgrad_group is not None and gw and N_out % 2 == 0 and K_in % 8 == 0 and (not gb or self.fuse_bias_grad):
+            # inside a layer's backward: queued, launched with the layer's other weight gradients as one grouped GEMM (_wgrad_flush)
+            self._wgrad_group.append((dy16, x16, M, gw, gb, N_out, K_in))
+            return
         st = self._st
         if self.wgrad_side_stream:
             # weight gradients are off the critical path (nothing downstream in backward reads them): run them on a side stream
@@ -405,6 +411,48 @@ class VaultEngine:
             rc = self._lib.vault_colsum_bf16(dy16.data_ptr(), N_out, gb, M, N_out, st)
             if rc:
                 _abi.check(rc, "vault_colsum_bf16")
+
+    def _wgrad_begin(self):
+        """Start collecting the weight gradients of one transformer layer (same token count = same contraction)."""
+        self._wgrad_group = [] if self.group_wgrads else None
+
+    def _wgrad_flush(self):
+        """The queued weight gradients of a layer as ONE persistent launch over their pooled 128x256 tiles (vault_gemm_wgrad_grouped): one launch
+        head / tail instead of four, every CTA's epilogue hidden under its next tile, the SMs filled in whole waves."""
+        grp, self._wgrad_group = self._wgrad_group, None
+        if not grp:
+            return
+        st = self._st
+        if self.wgrad_side_stream:
+            ev = torch.cuda.Event()
+            ev.record(torch.cuda.current_stream(self.device))
+            self._side.wait_event(ev)
+            st = self._side.cuda_stream
+            self._side_keep.append(tuple(t for g in grp for t in g[:2]))  # keep the operands alive until the join
+            self._side_dirty = True
+        for a in range(0, len(grp), 4):
+            chunk = grp[a:a + 4]
+            tiles = sum(-(-n_out // 128) * -(-k_in // 256) for (_, _, _, _, _, n_out, k_in) in chunk)
+            nkb = -(-chunk[0][2] // 64)
+            # split-K of the whole group: the pooled tile count should come out as whole waves of SMs (fewest splits among the best fills)
+            best, split = -1.0, 1
+            for sk in (1, 2, 4, 8):
+                if sk > 1 and nkb // sk < 2:
+                    break
+                fill = tiles * sk / (-(-(tiles * sk) // self.sms) * self.sms)
+                if fill > best + 0.02:
+                    best, split = fill, sk
+            arr = (GemmArgs * len(chunk))()
+            for g, (dy16, x16, M, gw, gb, n_out, k_in) in zip(arr, chunk):
+                g.M, g.N, g.K = n_out, k_in, M
+                g.A, g.lda, g.a_mn = dy16.data_ptr(), n_out, 1
+                g.B, g.ldb, g.b_mn = x16.data_ptr(), k_in, 1
+                g.epilogue, g.out, g.ldo = EPI_ATOMIC_F32, gw, k_in
+                g.split_k, g.max_ctas = split, self.gemm_max_ctas
+                g.a_colsum = gb or None
+            rc = self._lib.vault_gemm_wgrad_grouped(arr, len(chunk), st)
+            if rc:
+                _abi.check(rc, "vault_gemm_wgrad_grouped")
 
     def _cut(self):
         """A gradient range is complete once the chain AND the weight-gradient stream get here.  Default: the chain waits for the side
@@ -549,6 +597,7 @@ class VaultEngine:
         nm = self._names("", i, True)
         li = f"v{i}"
         H, I = self.H, self.I
+        self._wgrad_begin()
         dpre = self._new((M, I), torch.bfloat16)
         self.linear_dgrad(g16, M, nm["w2"], H, I, EPI_MUL_AUX_BF16, dpre, aux=sv[f"{li}.dact"].data_ptr(), ldaux=I)
         self.linear_wgrad(g16, sv[f"{li}.act"], M, nm["w2"], nm["b2"], H, I, bias=False)  # db2: summed by the kernel that produced g16
@@ -564,6 +613,7 @@ class VaultEngine:
         dn1 = self._new((M, H), torch.bfloat16)
         self.linear_dgrad(dqkv, M, nm["qkv_w"], 3 * H, H, EPI_PLAIN_BF16, dn1)
         self.linear_wgrad(dqkv, sv[f"{li}.n1"], M, nm["qkv_w"], nm["qkv_b"], 3 * H, H)
+        self._wgrad_flush()
         below_b2 = self._names("", i - 1, True)["b2"] if i > 0 else None  # this output is the dy of the layer below's MLP-2
         return self.ln_bwd(None, dn1, sv[f"{li}.x"], sv[f"{li}.st1"], M, nm["ln1"] + ".weight", nm["ln1"] + ".bias", dres32=g2_32, colsum_to=below_b2)
 
@@ -590,6 +640,7 @@ class VaultEngine:
         li = f"l{i}"
         H, I = self.H, self.I
         p, pa = (self.lm_p, self.lm_p_attn) if train else (0.0, 0.0)
+        self._wgrad_begin()
         ds32, ds16 = self.ln_bwd(g32, gx16, sv[f"{li}.s"], sv[f"{li}.st2"], M, nm["ln2"] + ".weight", nm["ln2"] + ".bias", out_p=p,
                                  out_site=self._site(i, 2), colsum_to=nm["b2"])
         dpre = self._new((M, I), torch.bfloat16)
@@ -613,6 +664,7 @@ class VaultEngine:
         gx = self._new((M, H), torch.bfloat16)
         self.linear_dgrad(dqkv, M, nm["qkv_w"], 3 * H, H, EPI_PLAIN_BF16, gx)
         self.linear_wgrad(dqkv, sv[f"{li}.x16"], M, nm["qkv_w"], nm["qkv_b"], 3 * H, H)
+        self._wgrad_flush()
         return dt32, gx
 
     # ------------------------------------------------------------------------------------------------------------

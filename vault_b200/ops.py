@@ -83,3 +83,20 @@ def layernorm_bwd(dy_f32, dy_bf16, x, mean, rstd, gamma, dres, dgamma, dbeta, *,
               _ptr(dres), dx32.data_ptr(), _ptr(dx16), _ptr(dgamma), _ptr(dbeta), _ptr(dcolsum), rows, cols, in_p, in_site, out_p, out_site, seed, None,
               _stream())
     return dx32, dx16
+
+
+def gemm_wgrad_grouped(problems, max_ctas: int = 0):
+    """problems: list of (dy [tokens, n_out] bf16, x [tokens, k_in] bf16, dW [n_out, k_in] fp32 (accumulated into), split_k, db [n_out] fp32 or None).
+    One persistent launch over all their 128x256 tiles (include/vault_b200.h: vault_gemm_wgrad_grouped)."""
+    arr = (GemmArgs * len(problems))()
+    for g, (dy, x, dw, split, db) in zip(arr, problems):
+        _cuda(dy, x, dw, db)
+        assert dy.dtype == torch.bfloat16 and x.dtype == torch.bfloat16 and dw.dtype == torch.float32 and dy.shape[0] == x.shape[0]
+        g.M, g.N, g.K = dy.shape[1], x.shape[1], dy.shape[0]
+        g.A, g.lda, g.a_mn = dy.data_ptr(), dy.stride(0), 1
+        g.B, g.ldb, g.b_mn = x.data_ptr(), x.stride(0), 1
+        g.epilogue = EPI_ATOMIC_F32
+        g.out, g.ldo = dw.data_ptr(), dw.stride(0)
+        g.split_k, g.max_ctas = split, max_ctas
+        g.a_colsum = _ptr(db)
+    _abi.call("vault_gemm_wgrad_grouped", arr, len(problems), _stream())

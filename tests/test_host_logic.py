@@ -125,6 +125,11 @@ def test_weight_gradient_tile_choice_fills_the_sms():
     assert eng._wgrad_cfg(768, 768, 11808) == (256, 8)      # attention output: 18 tiles x 8
     bn, split = eng._wgrad_cfg(768, 768, 100)               # two k-blocks only: no split
     assert split == 1 and bn in (128, 192, 256)
+    # grouped launch of a layer's four weight gradients: 54 + 18 + 72 + 72 = 216 tiles -> x2 = 432 = 2.92 waves of 148 SMs
+    assert eng._group_split(216, 185) == 2 and eng._group_split(216, 64) == 2
+    assert eng._group_split(216, 3) == 1        # too few k-blocks to split
+    assert eng._group_split(148, 100) == 1      # one full wave as it is
+    assert eng._group_split(30, 100) == 4       # 120 of 148 SMs (0.81); eight splits would leave a 62 % second wave
 
 
 def test_shadow_only_bitmap_marks_dense_matrices_only():

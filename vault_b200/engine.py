@@ -416,6 +416,18 @@ class VaultEngine:
         """Start collecting the weight gradients of one transformer layer (same token count = same contraction)."""
         self._wgrad_group = [] if self.group_wgrads else None
 
+    def _group_split(self, tiles: int, k_blocks: int) -> int:
+        """Split-K of a grouped weight-gradient launch: the pooled 128x256 tile count times the split should come out as whole waves of SMs
+        (a layer's 216 tiles: x2 = 432 = 2.92 waves of 148); the fewest splits among the best fills, at least two k-blocks per split."""
+        best, split = -1.0, 1
+        for sk in (1, 2, 4, 8):
+            if sk > 1 and k_blocks // sk < 2:
+                break
+            fill = tiles * sk / (-(-(tiles * sk) // self.sms) * self.sms)
+            if fill > best + 0.02:
+                best, split = fill, sk
+        return split
+
     def _wgrad_flush(self):
         """The queued weight gradients of a layer as ONE persistent launch over their pooled 128x256 tiles (vault_gemm_wgrad_grouped): one launch
         head / tail instead of four, every CTA's epilogue hidden under its next tile, the SMs filled in whole waves."""
@@ -433,15 +445,7 @@ class VaultEngine:
         for a in range(0, len(grp), 4):
             chunk = grp[a:a + 4]
             tiles = sum(-(-n_out // 128) * -(-k_in // 256) for (_, _, _, _, _, n_out, k_in) in chunk)
-            nkb = -(-chunk[0][2] // 64)
-            # split-K of the whole group: the pooled tile count should come out as whole waves of SMs (fewest splits among the best fills)
-            best, split = -1.0, 1
-            for sk in (1, 2, 4, 8):
-                if sk > 1 and nkb // sk < 2:
-                    break
-                fill = tiles * sk / (-(-(tiles * sk) // self.sms) * self.sms)
-                if fill > best + 0.02:
-                    best, split = fill, sk
+            split = self._group_split(tiles, -(-chunk[0][2] // 64))
             arr = (GemmArgs * len(chunk))()
             for g, (dy16, x16, M, gw, gb, n_out, k_in) in zip(arr, chunk):
                 g.M, g.N, g.K = n_out, k_in, M
@@ -953,6 +957,7 @@ class VaultEngine:
             raise RuntimeError("vault_b200: backward called twice on the same forward (activations already released)")
         self._lib, self._st = _abi.lib(), self._stream()
         lib, st = self._lib, self._st
+        self._wgrad_group = None  # (a backward that raised mid-layer must not leave its queue behind)
         sv, mt = tape.t, tape.meta
         self._seed_buf = mt.get("seed_buf", self.seed_dev)
         B, T, S, pmax, gh, gw = mt["B"], mt["T"], mt["S"], mt["pmax"], mt["gh"], mt["gw"]

@@ -78,9 +78,9 @@ __device__ __forceinline__ void adam4(float4& p, const float4& g, float4& m, flo
 }
 
 constexpr int kMcThreads = 512;
-constexpr int kMcUnrollMax = 8;  // (per-kernel unroll: 4 fp32 / 8 bf16 units) independent gradient pulls in flight per thread: an NVLink round trip through the switch is microseconds,
-                              // so the kernel is sized by bytes in flight -- 2 CTAs/SM x 512 threads x 128 B = 128 KB per SM, ~30 SMs cover the
-                              // bandwidth-latency product of the link and the rest of the GPU stays with the backward pass
+// Sizing: an NVLink round trip through the switch is microseconds, so the kernel is sized by bytes in flight -- every thread has 128 bytes of
+// gradient pulls outstanding (4 fp32 units or 8 bf16 units of 8 parameters), 2 CTAs/SM x 512 threads = 128 KB per SM; ~30 SMs cover the
+// bandwidth-latency product of the link and the rest of the GPU stays with the backward pass (grid bounded by the caller: `ctas`).
 
 template <bool G16>
 __global__ void __launch_bounds__(kMcThreads, 2) mc_adamw_kernel(const McAdamParams a) {

@@ -45,7 +45,8 @@ class _McBuffers:
     gradients are allocated with torch.distributed._symmetric_memory.empty, exchanged with rendezvous() (CUDA VMM handles + one NVSwitch
     multicast object per buffer) and addressed through `multicast_ptr` by vault_mc_adamw_step."""
 
-    BARRIER_TIMEOUT_MS = 60000
+    # a rank that waits longer than this at a gradient-range barrier traps (CUDA error) instead of hanging: same order as NCCL's watchdog
+    BARRIER_TIMEOUT_MS = int(os.environ.get("VAULT_B200_MC_BARRIER_TIMEOUT_MS", "600000"))
 
     def __init__(self):
         self.master_mc = self.shadow_mc = self.grad_mc = self.grad16_mc = 0
